@@ -1,0 +1,240 @@
+/*
+ * vlb_bake.h — C ABI of the B200-native light-probe baker (libvlb_bake.so).
+ *
+ * This is the drop-in boundary for the bake path of Reefufui/vulkan-light-bakery.
+ * The reference has no FFI layer of its own (its entry points are C++ classes), so every
+ * function below cites the reference interface it replaces (paths relative to the reference
+ * repository root). Plain pointers and sizes only; no C++/torch/CUDA types cross this boundary.
+ *
+ * Conventions
+ *   - every call returns a vlb_status (0 = ok, <0 = error); the text of the last error is
+ *     available from vlb_last_error(). Nothing throws or aborts across the ABI.
+ *   - the caller owns every host buffer passed in or out; the library owns all device memory
+ *     inside a vlb_ctx. A ctx is bound to ONE CUDA device; it is not thread-safe, distinct
+ *     contexts are independent (one ctx per GPU / per rank).
+ *   - functions without a `_device` suffix take HOST pointers and are synchronous (they return
+ *     after the ctx stream has drained), mirroring the reference's blocking submits
+ *     (src/application.cpp:255-277). `_device` variants take DEVICE pointers, enqueue on the
+ *     ctx stream and return without synchronising.
+ *   - there is no CPU fallback: every compute entry point fails with VLB_ERR_NO_DEVICE when no
+ *     CUDA device is usable.
+ */
+#ifndef VLB_BAKE_H
+#define VLB_BAKE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VLB_ABI_VERSION 1
+
+typedef struct vlb_ctx vlb_ctx;
+
+typedef enum vlb_status {
+    VLB_OK              =  0,
+    VLB_ERR_INVALID     = -1,  /* bad argument                                   */
+    VLB_ERR_CUDA        = -2,  /* CUDA runtime error (text in vlb_last_error)     */
+    VLB_ERR_NO_DEVICE   = -3,  /* no usable CUDA device                          */
+    VLB_ERR_STATE       = -4,  /* call order violated (e.g. bake before scene)   */
+    VLB_ERR_IO          = -5,  /* file could not be read / written               */
+    VLB_ERR_UNSUPPORTED = -6,  /* valid glTF / format feature that is not handled*/
+    VLB_ERR_NOMEM       = -7
+} vlb_status;
+
+/* ------------------------------------------------------------------------------------------
+ * Layouts shared with the reference's shaders (shaders/structures.h:13-71, scalar layout).
+ * They are accepted verbatim, so a maintainer can pass the very std::vectors that
+ * Scene_t::fetchVertices / loadMaterials build (src/scene_manager.cpp:257-290, 695-857).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct vlb_vertex {      /* shader::Vertex, 44 bytes (structures.h:20-26) */
+    float position[4];
+    float normal[3];
+    float uv0[2];
+    float uv1[2];
+} vlb_vertex;
+
+typedef struct vlb_texture_ref { /* shader::Texture (structures.h:46-50) */
+    int32_t index;               /* -1 = none */
+    int32_t coord_set;
+} vlb_texture_ref;
+
+typedef struct vlb_material {    /* shader::Material, 144 bytes (structures.h:28-71) */
+    /* Textures (64 B) */
+    vlb_texture_ref normal, occlusion, base_color, metallic_roughness, emissive,
+                    diffuse_ext, specular_ext, dummy;
+    /* Factors (80 B) */
+    float base_color_factor[4];
+    float emissive_factor[4];
+    float diffuse_factor[4];
+    float specular_factor[3];
+    float metallic;
+    float roughness;
+    float alpha_cutoff;
+    float pad[2];
+} vlb_material;
+
+/* One reference "instance" = one glTF primitive placed by its node's world matrix
+ * (src/scene_manager.cpp:385-443: one BLAS per primitive, instance transform =
+ * Node_t::getMatrix() :445-461, customIndex = running instance id). Indices are relative to
+ * `first_vertex`, as each reference primitive owns its own vertex buffer. */
+typedef struct vlb_instance {
+    uint32_t first_index;        /* offset into the index array                              */
+    uint32_t index_count;        /* triangles = index_count / 3 (scene_manager.cpp:236)      */
+    uint32_t first_vertex;       /* offset into the vertex array                             */
+    uint32_t vertex_count;
+    uint32_t material_index;
+    float    transform[12];      /* object->world, 3x4 row-major (VkTransformMatrixKHR)      */
+} vlb_instance;
+
+typedef enum vlb_texel_format {
+    VLB_FMT_RGBA8   = 0,         /* reference skyboxes: stb RGBA8, value/255, no sRGB decode
+                                    (src/skybox_manager.cpp:18, src/application.cpp:690,779)  */
+    VLB_FMT_RGBA32F = 1          /* BASELINE configs: float4 texels                           */
+} vlb_texel_format;
+
+/* ------------------------------------------------------------------------------------------
+ * Bake settings. Defaults (vlb_bake_settings_default) are the reference's hard-coded
+ * constants: 7x7x7 probes (src/baker/light_baker.cpp:38), 3141x1000 directions
+ * (light_baker.cpp:65, src/baker/env_map_generator.cpp:24-28), 16 coefficients
+ * (light_baker.cpp:294), light (1,10,1), bias .005, Cdiffuse/Cspecular .5, gloss 16,
+ * ambient 0 (shaders/env_map.rchit:25,75-96), tmin 1e-3 / tmax 1e4 (shaders/env_map.rgen:22-23).
+ * ---------------------------------------------------------------------------------------- */
+enum {
+    VLB_BAKE_SHADOW_RAYS             = 1u << 0, /* env_map.rchit:83-88                        */
+    VLB_BAKE_SKYBOX_ON_MISS          = 1u << 1, /* main.rmiss:18-40 (intent)  */
+    VLB_BAKE_SRGB_ENCODE             = 1u << 2, /* env_map.rchit:101, main.rmiss:40           */
+    VLB_BAKE_QUANTIZE_RGBA8          = 1u << 3, /* rgba8 storage image, env_map_generator.hpp:39 */
+    VLB_BAKE_REFERENCE_PROBE_ORDER   = 1u << 4, /* writer order of light_baker.cpp:80-101     */
+    VLB_BAKE_ACCUMULATE_ACROSS_PROBES= 1u << 5, /* literal light_baker.cpp:110-121 behaviour  */
+    VLB_BAKE_SH_WORLD_FRAME          = 1u << 6  /* evaluate SH on the world ray dir (App. B-6) */
+};
+
+typedef struct vlb_bake_settings {
+    int32_t  probes[3];          /* probe grid counts Nx,Ny,Nz                                */
+    float    origin[3];          /* position of probe (0,0,0) = bounds min                    */
+    float    step[3];            /* gridStep = (max-min)/(N-1) (light_baker.cpp:85)           */
+    int32_t  dir_w, dir_h;       /* equirect direction grid (env_map.rgen:20-21)              */
+    int32_t  sh_order;           /* 2 -> 9 coefficients written, 3 -> 16                      */
+    float    light_pos[3];
+    float    shadow_bias;
+    float    c_diffuse;
+    float    c_specular;
+    float    gloss;
+    float    ambient;
+    float    tmin, tmax;
+    uint32_t flags;
+    int32_t  slab_k0, slab_k1;   /* bake only z-slices k0 <= k < k1; k1 < 0 = whole grid      */
+    int32_t  reserved[4];
+} vlb_bake_settings;
+
+#define VLB_SH_STRIDE 48         /* floats per probe: vec3 coeffs[16] (shaders/sh.comp:21)     */
+
+typedef struct vlb_bvh_stats {
+    uint64_t n_triangles;
+    uint64_t n_nodes;            /* traversal nodes emitted                                   */
+    uint32_t max_leaf_size;
+    uint32_t reserved;
+    float    bounds[6];          /* tight world AABB min xyz, max xyz                         */
+    float    build_ms;           /* device time of the whole build                            */
+    float    sort_ms;
+} vlb_bvh_stats;
+
+typedef struct vlb_bake_stats {
+    uint64_t n_probes;           /* probes baked by this call (slab)                          */
+    uint64_t n_primary_rays;
+    uint64_t n_shadow_rays;      /* shadow rays actually traced (sDotN != 0)                  */
+    uint64_t n_nodes_visited;    /* filled only by the instrumented build      */
+    uint64_t n_tris_tested;
+    float    kernel_ms;          /* device time of the bake kernel(s) of the last call        */
+    float    total_ms;           /* device time of the whole call                             */
+} vlb_bake_stats;
+
+/* --- context ---------------------------------------------------------------------------- */
+/* Replaces vlb::Application's device bring-up (src/application.cpp:540-556). */
+int  vlb_ctx_create(int device_id, vlb_ctx** out);
+void vlb_ctx_destroy(vlb_ctx* ctx);
+/* Use an existing CUDA stream (a cudaStream_t passed as an integer handle); 0 restores the
+ * ctx's own stream. */
+int  vlb_ctx_set_stream(vlb_ctx* ctx, uint64_t cuda_stream_handle);
+int  vlb_ctx_synchronize(vlb_ctx* ctx);
+/* Last error text of this ctx (or of the calling thread when ctx == NULL). Never NULL. */
+const char* vlb_last_error(const vlb_ctx* ctx);
+int  vlb_abi_version(void);
+/* Names of the CUDA kernels this library launched since the ctx was created, and how many
+ * launches in total (bench.py's gpu_launches). */
+uint64_t vlb_ctx_launch_count(const vlb_ctx* ctx);
+
+/* --- scene (replaces Scene_t ingest output + buildAccelerationStructures) --------------- */
+/* SceneManager::pushScene -> Scene_t::loadNode output (src/scene_manager.cpp:479-538). */
+int vlb_scene_set_triangles(vlb_ctx* ctx,
+                            const vlb_vertex* vertices, uint64_t n_vertices,
+                            const uint32_t* indices, uint64_t n_indices,
+                            const vlb_instance* instances, uint32_t n_instances,
+                            const vlb_material* materials, uint32_t n_materials);
+/* Scene_t::getBounds (src/scene_manager.cpp:214-217). mode 0: the reference's semantics
+ * (bounds start at the origin, only the two local AABB corners are transformed,
+ * scene_manager.cpp:497-507); mode 1: tight world-space AABB of all triangles. */
+int vlb_scene_bounds(vlb_ctx* ctx, int tight, float out_min_max[6]);
+/* Scene_t::buildAccelerationStructures (src/scene_manager.cpp:385-443) -> software LBVH. */
+int vlb_bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats_or_null);
+
+/* --- skybox (replaces Skybox_t) ---------------------------------------------------------- */
+/* Skybox_t::createTexture (src/skybox_manager.cpp:49-63): the map sampled on ray miss. */
+int vlb_skybox_set(vlb_ctx* ctx, const void* texels, int format, int width, int height);
+/* Skybox_t::createSHBuffer + computeSH (src/skybox_manager.cpp:65-76,107-130), i.e. one
+ * dispatch of shaders/skybox_sh.comp. out = vec3 coeffs[16] (48 floats); order 2 fills
+ * entries 0..8 and zero-fills 9..15. */
+int vlb_skybox_project_sh(vlb_ctx* ctx, const void* texels, int format, int width, int height,
+                          int sh_order, float* out48);
+/* n maps of identical size; maps[i] are host pointers; out = n x 48 floats. */
+int vlb_skybox_project_sh_batched(vlb_ctx* ctx, const void* const* maps, uint32_t n_maps,
+                                  int format, int width, int height, int sh_order, float* out);
+/* Device-resident variant: n maps at d_texels + i*map_stride_bytes, d_out = n x 48 floats. */
+int vlb_skybox_project_sh_device(vlb_ctx* ctx, const void* d_texels, uint64_t map_stride_bytes,
+                                 uint32_t n_maps, int format, int width, int height,
+                                 int sh_order, float* d_out);
+/* shaders/sh.comp applied to a caller-supplied environment image (the reference's image-input
+ * debug path, src/baker/light_baker.cpp:68-73): SH argument is the un-swizzled toVector. */
+int vlb_envmap_project_sh(vlb_ctx* ctx, const void* texels, int format, int width, int height,
+                          int sh_order, float* out48);
+
+/* --- bake (replaces LightBaker::bake's per-probe getMap + dispatchBakingKernel loop) ----- */
+void vlb_bake_settings_default(vlb_bake_settings* s);
+/* LightBaker::probePositionsFromBoudingBox (src/baker/light_baker.cpp:80-101): fills
+ * origin/step from bounds and probes[]. */
+int vlb_bake_settings_from_bounds(vlb_bake_settings* s, const float bounds_min_max[6]);
+/* Probe positions in OUTPUT order (x-fastest, or the reference writer's order under
+ * VLB_BAKE_REFERENCE_PROBE_ORDER); out = Nx*Ny*Nz*3 floats. Host-only helper. */
+int vlb_probe_positions(const vlb_bake_settings* s, float* out_xyz);
+/* LightBaker::bake (src/baker/light_baker.cpp:287-328). out = n_slab_probes x 48 floats
+ * (float[probe][16][3], light_baker.cpp:294-322). */
+int vlb_bake_probes(vlb_ctx* ctx, const vlb_bake_settings* s, float* out);
+int vlb_bake_probes_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out);
+int vlb_bake_last_stats(vlb_ctx* ctx, vlb_bake_stats* out);
+
+/* --- validation entry points (BVH hit IDs bit-exact vs brute force) --------------------- */
+enum { VLB_TRACE_BVH = 0, VLB_TRACE_BRUTE_FORCE = 1 };
+enum { VLB_TRACE_CLOSEST = 0, VLB_TRACE_ANY = 1 };
+/* origins/dirs: n x 3 floats (host). hit_ids: flat triangle id (instance prefix sum +
+ * primitive id) or -1; hit_tuv: n x 3 floats (t, u, v) or NULL. */
+int vlb_trace_rays(vlb_ctx* ctx, const float* origins, const float* dirs, uint64_t n,
+                   float tmin, float tmax, int accel, int kind,
+                   int32_t* hit_ids, float* hit_tuv);
+
+/* --- on-disk format (LightBaker::serialize, src/baker/light_baker.cpp:375-402; reader
+ * Scene_t::loadBakedLight, src/scene_manager.cpp:613-648) -------------------------------- */
+int vlb_bake_serialize_gltf(const char* in_gltf_path, const char* out_gltf_path,
+                            const float* coeffs, uint64_t n_probes,
+                            const vlb_bake_settings* s);
+/* Reads back what vlb_bake_serialize_gltf (or the reference) wrote. coeffs may be NULL to
+ * query n_probes_out first. */
+int vlb_bake_deserialize_gltf(const char* gltf_path, float* coeffs, uint64_t capacity_floats,
+                              uint64_t* n_floats_out, float grid_step_out[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLB_BAKE_H */

@@ -1,0 +1,208 @@
+"""ctypes binding of the CPU oracle (oracle/libvlb_oracle.so) and of the reference-header shim
+(oracle/_ref/libvlb_refsh.so). TEST INFRASTRUCTURE: imported only by tests/, by
+__graft_entry__.smoke() and by bench.py's cpu_baseline / `--impl reference` legs."""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(_HERE, "libvlb_oracle.so")
+REF_SO = os.path.join(_HERE, "_ref", "libvlb_refsh.so")
+
+_vp, _u64, _i32, _f32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_float
+_lib = None
+_ref = None
+
+
+def _p(a):
+    return a.ctypes.data_as(_vp) if a is not None else None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            from . import build_oracle  # noqa: F401  (package-relative when imported as oracle.oracle_api)
+            build_oracle.build_oracle()
+        L = ctypes.CDLL(ORACLE_SO)
+        L.vo_num_threads.restype = _i32
+        L.vo_set_num_threads.argtypes = [_i32]
+        L.vo_sh_basis.argtypes = [_vp, _u64, _vp]
+        L.vo_x2phi.restype = _f32
+        L.vo_x2phi.argtypes = [_i32, _i32]
+        L.vo_y2theta.restype = _f32
+        L.vo_y2theta.argtypes = [_i32, _i32]
+        L.vo_to_vector.argtypes = [_f32, _f32, _vp]
+        L.vo_srgb.restype = _f32
+        L.vo_srgb.argtypes = [_f32]
+        L.vo_probe_dirs.argtypes = [_i32, _i32, _vp, _vp, _vp]
+        L.vo_skybox_project.argtypes = [_vp, _i32, _i32, _i32, _i32, _vp]
+        L.vo_envmap_project.argtypes = [_vp, _i32, _i32, _i32, _i32, _vp]
+        L.vo_sh_reconstruct.argtypes = [_vp, _i32, _i32, _i32, _vp]
+        L.vo_probe_positions.argtypes = [_vp, _vp]
+        L.vo_probe_positions_literal.restype = _u64
+        L.vo_probe_positions_literal.argtypes = [_vp, _vp, _vp, _vp]
+        L.vo_scene_create.restype = _vp
+        L.vo_scene_create.argtypes = [_vp, _u64, _vp, _u64, _vp, ctypes.c_uint32, _vp, ctypes.c_uint32]
+        L.vo_scene_destroy.argtypes = [_vp]
+        L.vo_scene_num_triangles.restype = _u64
+        L.vo_scene_num_triangles.argtypes = [_vp]
+        L.vo_scene_bounds.argtypes = [_vp, _i32, _vp]
+        L.vo_scene_set_skybox.argtypes = [_vp, _vp, _i32, _i32, _i32]
+        L.vo_scene_triangles.argtypes = [_vp, _vp]
+        L.vo_trace_rays.argtypes = [_vp, _vp, _vp, _u64, _f32, _f32, _i32, _i32, _vp, _vp]
+        L.vo_bake_probes.restype = _u64
+        L.vo_bake_probes.argtypes = [_vp, _vp, _vp, _u64, _i32, _vp]
+        L.vo_probe_envmap.argtypes = [_vp, _vp, _vp, _i32, _vp, _vp]
+        _lib = L
+    return _lib
+
+
+def ref_lib():
+    """The reference's own sh_common.h compiled by oracle/build_oracle.py; None if unavailable."""
+    global _ref
+    if _ref is None and os.path.exists(REF_SO):
+        R = ctypes.CDLL(REF_SO)
+        R.ref_SH.restype = _f32
+        R.ref_SH.argtypes = [_i32, _i32, _f32, _f32, _f32]
+        R.ref_x2phi.restype = _f32
+        R.ref_x2phi.argtypes = [_i32, _i32]
+        R.ref_y2theta.restype = _f32
+        R.ref_y2theta.argtypes = [_i32, _i32]
+        R.ref_toVector.argtypes = [_f32, _f32, _vp]
+        R.ref_PI.restype = _f32
+        _ref = R
+    return _ref
+
+
+def num_threads():
+    return int(lib().vo_num_threads())
+
+
+def set_num_threads(n):
+    lib().vo_set_num_threads(int(n))
+
+
+def sh_basis(dirs):
+    d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+    out = np.zeros((d.shape[0], 25), np.float32)
+    lib().vo_sh_basis(_p(d), d.shape[0], _p(out))
+    return out
+
+
+def probe_dirs(W, H):
+    t = np.zeros((H, W, 3), np.float32)
+    r = np.zeros((H, W, 3), np.float32)
+    w = np.zeros((H, W), np.float32)
+    lib().vo_probe_dirs(W, H, _p(t), _p(r), _p(w))
+    return t, r, w
+
+
+def _texels(texels):
+    t = np.ascontiguousarray(texels)
+    assert t.ndim == 3 and t.shape[2] == 4 and t.dtype in (np.uint8, np.float32)
+    return t, (0 if t.dtype == np.uint8 else 1)
+
+
+def skybox_project(texels, order=3):
+    t, fmt = _texels(texels)
+    out = np.zeros((16, 3), np.float32)
+    lib().vo_skybox_project(_p(t), fmt, t.shape[1], t.shape[0], order, _p(out))
+    return out
+
+
+def envmap_project(texels, order=3):
+    t, fmt = _texels(texels)
+    out = np.zeros((16, 3), np.float32)
+    lib().vo_envmap_project(_p(t), fmt, t.shape[1], t.shape[0], order, _p(out))
+    return out
+
+
+def sh_reconstruct(coeffs, order, W, H):
+    c = np.ascontiguousarray(coeffs, np.float32).reshape(48)
+    out = np.zeros((H, W, 3), np.float32)
+    lib().vo_sh_reconstruct(_p(c), order, W, H, _p(out))
+    return out
+
+
+def probe_positions(settings):
+    n = settings.probes[0] * settings.probes[1] * settings.probes[2]
+    out = np.zeros((n, 3), np.float32)
+    lib().vo_probe_positions(ctypes.byref(settings), _p(out))
+    return out
+
+
+def probe_positions_literal(bounds, counts):
+    b = np.ascontiguousarray(bounds, np.float32).reshape(6)
+    c = np.ascontiguousarray(counts, np.int32).reshape(3)
+    out = np.zeros((int(np.prod(c)), 3), np.float32)
+    step = np.zeros(3, np.float32)
+    n = lib().vo_probe_positions_literal(_p(b), _p(c), _p(out), _p(step))
+    assert n == out.shape[0]
+    return out, step
+
+
+class Scene:
+    def __init__(self, scene):
+        self._keep = [np.ascontiguousarray(scene[k]) for k in ("vertices", "indices", "instances", "materials")]
+        v, i, inst, m = self._keep
+        self._h = lib().vo_scene_create(_p(v), v.size, _p(i), i.size, _p(inst), inst.size, _p(m), m.size)
+
+    def close(self):
+        if self._h:
+            lib().vo_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n_triangles(self):
+        return int(lib().vo_scene_num_triangles(self._h))
+
+    def bounds(self, tight=False):
+        out = np.zeros(6, np.float32)
+        lib().vo_scene_bounds(self._h, int(bool(tight)), _p(out))
+        return out
+
+    def triangles(self):
+        out = np.zeros((self.n_triangles, 9), np.float32)
+        lib().vo_scene_triangles(self._h, _p(out))
+        return out
+
+    def set_skybox(self, texels):
+        t, fmt = _texels(texels)
+        lib().vo_scene_set_skybox(self._h, _p(t), fmt, t.shape[1], t.shape[0])
+
+    def trace_rays(self, origins, dirs, tmin=0.001, tmax=10000.0, accel=0, kind=0):
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        ids = np.zeros(o.shape[0], np.int32)
+        tuv = np.zeros((o.shape[0], 3), np.float32)
+        lib().vo_trace_rays(self._h, _p(o), _p(d), o.shape[0], tmin, tmax, accel, kind, _p(ids), _p(tuv))
+        return ids, tuv
+
+    def bake_probes(self, settings, probe_ids=None, brute=False):
+        """Whole slab (probe_ids None) or the listed x-fastest grid indices. Returns (coeffs, n_shadow_rays)."""
+        if probe_ids is None:
+            k1 = settings.probes[2] if settings.slab_k1 < 0 else settings.slab_k1
+            k0 = 0 if settings.slab_k1 < 0 else settings.slab_k0
+            n = settings.probes[0] * settings.probes[1] * (k1 - k0)
+            ids = None
+        else:
+            ids = np.ascontiguousarray(probe_ids, np.int64)
+            n = ids.size
+        out = np.zeros((n, 16, 3), np.float32)
+        sr = lib().vo_bake_probes(self._h, ctypes.byref(settings), _p(ids), n, int(bool(brute)), _p(out))
+        return out, int(sr)
+
+    def probe_envmap(self, settings, pos, brute=False):
+        img = np.zeros((settings.dir_h, settings.dir_w, 3), np.float32)
+        sh = np.zeros((16, 3), np.float32)
+        p = np.ascontiguousarray(pos, np.float32).reshape(3)
+        lib().vo_probe_envmap(self._h, ctypes.byref(settings), _p(p), int(bool(brute)), _p(img), _p(sh))
+        return img, sh

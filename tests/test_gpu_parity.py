@@ -1,0 +1,228 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle.
+Tolerances are BASELINE.json's: max relative L2 <= 1e-4 per skybox SH vector, <= 1e-3 per probe SH
+vector; BVH hit ids bit-exact against the brute-force CUDA intersector (and the oracle)."""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+SKY_TOL = 1e-4
+PROBE_TOL = 1e-3
+
+
+def _rays(n, lo, hi, seed=0):
+    rng = np.random.default_rng(seed)
+    o = rng.uniform(lo, hi, (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    return o, d.astype(np.float32)
+
+
+# ---------------------------------------------------------------- skybox projection ----------
+@pytest.mark.parametrize("order", [2, 3])
+@pytest.mark.parametrize("shape", [(32, 64), (256, 512), (100, 314), (7, 13), (1, 1)])
+def test_skybox_rgba32f_vs_oracle(ctx, oa, scenes, order, shape):
+    img = scenes.hdr_sky(shape[1], shape[0], seed=5)
+    got = ctx.skybox_project_sh(img, order)
+    ref = oa.skybox_project(img, order)
+    assert rel_l2(got, ref) <= SKY_TOL
+    if order == 2:
+        assert np.all(got[9:] == 0)
+
+
+@pytest.mark.parametrize("order", [2, 3])
+def test_skybox_rgba8_vs_oracle(ctx, oa, order):
+    rng = np.random.default_rng(11)
+    img = rng.integers(0, 256, (96, 200, 4), dtype=np.uint8)
+    assert rel_l2(ctx.skybox_project_sh(img, order), oa.skybox_project(img, order)) <= SKY_TOL
+
+
+@pytest.mark.parametrize("order", [2, 3])
+def test_envmap_vs_oracle(ctx, oa, scenes, order):
+    img = scenes.hdr_sky(314, 100, seed=2)        # sh.comp on a (scaled-down) 3141x1000-shaped map
+    assert rel_l2(ctx.envmap_project_sh(img, order), oa.envmap_project(img, order)) <= SKY_TOL
+
+
+def test_skybox_constant_image_kat(ctx):
+    # analytic: constant radiance c projects to c00 = 2*sqrt(pi)*c, everything else ~ 0
+    img = np.ones((1024, 2048, 4), np.float32)
+    img[..., 1] = 0.5
+    got = ctx.skybox_project_sh(img, 3)
+    assert np.allclose(got[0], 2 * np.sqrt(np.pi) * np.array([1, 0.5, 1]), rtol=2e-5)
+    assert np.abs(got[1:]).max() < 2e-5
+
+
+def test_skybox_batched_equals_single(ctx, scenes):
+    maps = [scenes.hdr_sky(128, 64, seed=100 + i) for i in range(9)]
+    got = ctx.skybox_project_sh_batched(maps, 3)
+    for i, m in enumerate(maps):
+        assert rel_l2(got[i], ctx.skybox_project_sh(m, 3)) <= 1e-6
+
+
+def test_skybox_full_size_c1(ctx, oa, scenes):
+    img = scenes.hdr_sky(2048, 1024, seed=1)      # BASELINE config 1
+    assert rel_l2(ctx.skybox_project_sh(img, 2), oa.skybox_project(img, 2)) <= SKY_TOL
+
+
+def test_skybox_deterministic(ctx, scenes):
+    img = scenes.hdr_sky(512, 256, seed=3)
+    a = ctx.skybox_project_sh(img, 3)
+    for _ in range(3):
+        assert np.array_equal(a, ctx.skybox_project_sh(img, 3))
+
+
+# ---------------------------------------------------------------- BVH hit ids ----------------
+@pytest.fixture(scope="module")
+def room(ctx, oa, scenes):
+    sc = scenes.small_room()
+    ctx.set_scene(sc)
+    ctx.build_bvh()
+    return sc, oa.Scene(sc)
+
+
+def test_hit_ids_room_bvh_vs_brute_vs_oracle(ctx, vlb, room):
+    sc, osc = room
+    ctx.set_scene(sc)
+    o, d = _rays(50000, 0.1, 3.9, seed=1)
+    ib, tb = ctx.trace_rays(o, d, accel=vlb.TRACE_BRUTE_FORCE)
+    iv, tv = ctx.trace_rays(o, d, accel=vlb.TRACE_BVH)
+    io, to = osc.trace_rays(o, d, accel=1)
+    assert np.array_equal(ib, iv) and np.array_equal(tb, tv)
+    assert np.array_equal(ib, io) and np.array_equal(tb, to)
+    assert 0.02 < (ib < 0).mean() < 0.9
+
+
+def test_any_hit_room(ctx, vlb, room):
+    sc, osc = room
+    ctx.set_scene(sc)
+    o, d = _rays(20000, 0.1, 3.9, seed=2)
+    a, _ = ctx.trace_rays(o, d, tmin=0.0, tmax=1.5, accel=vlb.TRACE_BVH, kind=vlb.TRACE_ANY)
+    b, _ = ctx.trace_rays(o, d, tmin=0.0, tmax=1.5, accel=vlb.TRACE_BRUTE_FORCE, kind=vlb.TRACE_ANY)
+    c, _ = osc.trace_rays(o, d, tmin=0.0, tmax=1.5, accel=1, kind=1)
+    assert np.array_equal(a >= 0, b >= 0) and np.array_equal(a >= 0, c >= 0)
+
+
+# ---------------------------------------------------------------- bake -----------------------
+def _room_settings(vlb, ctx, flags, order=3, probes=(3, 2, 3), dirs=(32, 16)):
+    s = vlb.default_settings()
+    s.probes[:] = probes
+    s.dir_w, s.dir_h = dirs
+    s.sh_order = order
+    s.light_pos[:] = (2.0, 3.5, 2.0)
+    s.flags = flags
+    vlb.settings_from_bounds(s, ctx.scene_bounds(tight=True))
+    return s
+
+
+@pytest.mark.parametrize("order", [2, 3])
+@pytest.mark.parametrize("flags", ["base", "quant", "noshadow", "linear", "nosky", "world"])
+def test_bake_room_vs_oracle(ctx, vlb, scenes, room, order, flags):
+    sc, osc = room
+    ctx.set_scene(sc)
+    sky = scenes.hdr_sky(64, 32, seed=4)
+    ctx.set_skybox(sky)
+    osc.set_skybox(sky)
+    base = vlb.SHADOW_RAYS | vlb.SKYBOX_ON_MISS | vlb.SRGB_ENCODE
+    f = {"base": base, "quant": base | vlb.QUANTIZE_RGBA8, "noshadow": base & ~vlb.SHADOW_RAYS,
+         "linear": base & ~vlb.SRGB_ENCODE, "nosky": base & ~vlb.SKYBOX_ON_MISS,
+         "world": base | vlb.SH_WORLD_FRAME}[flags]
+    s = _room_settings(vlb, ctx, f, order)
+    got = ctx.bake_probes(s)
+    ref, n_shadow = osc.bake_probes(s)
+    assert rel_l2(got, ref) <= PROBE_TOL
+    st = ctx.last_bake_stats()
+    assert st.n_primary_rays == s.n_probes * s.dir_w * s.dir_h
+    assert st.n_shadow_rays == n_shadow
+    if order == 2:
+        assert np.all(got[:, 9:] == 0)
+
+
+def test_bake_slab_union_is_bitwise_full(ctx, vlb, scenes, room):
+    sc, _ = room
+    ctx.set_scene(sc)
+    ctx.set_skybox(scenes.hdr_sky(64, 32, seed=4))
+    s = _room_settings(vlb, ctx, vlb.SHADOW_RAYS | vlb.SKYBOX_ON_MISS | vlb.SRGB_ENCODE, probes=(3, 2, 4))
+    full = ctx.bake_probes(s)
+    parts = []
+    for k0, k1 in ((0, 1), (1, 3), (3, 4)):
+        p = s.copy()
+        p.slab_k0, p.slab_k1 = k0, k1
+        parts.append(ctx.bake_probes(p))
+    assert np.array_equal(full, np.concatenate(parts))
+
+
+def test_bake_reference_probe_order_and_accumulate(ctx, vlb, oa, scenes, room):
+    sc, osc = room
+    ctx.set_scene(sc)
+    sky = scenes.hdr_sky(64, 32, seed=4)
+    ctx.set_skybox(sky)
+    osc.set_skybox(sky)
+    base = vlb.SHADOW_RAYS | vlb.SKYBOX_ON_MISS | vlb.SRGB_ENCODE
+    s = _room_settings(vlb, ctx, base, probes=(3, 2, 3))
+    x_fast = ctx.bake_probes(s)
+    r = s.copy()
+    r.flags = base | vlb.REFERENCE_PROBE_ORDER
+    ref_order = ctx.bake_probes(r)
+    # same probes, permuted: match positions
+    px, pr = vlb.probe_positions(s), vlb.probe_positions(r)
+    for i in range(len(pr)):
+        j = int(np.where((px == pr[i]).all(axis=1))[0][0])
+        assert np.array_equal(ref_order[i], x_fast[j])
+    a = r.copy()
+    a.flags = r.flags | vlb.ACCUMULATE_ACROSS_PROBES
+    acc = ctx.bake_probes(a)
+    assert rel_l2(acc, osc.bake_probes(a)[0]) <= PROBE_TOL
+
+
+def test_bake_errors(vlb, scenes):
+    with vlb.Context(0) as c:
+        s = vlb.default_settings()
+        with pytest.raises(vlb.VlbError) as e:
+            c.bake_probes(s)
+        assert e.value.code == vlb.ERR_STATE
+        c.set_scene(scenes.default_cube())
+        with pytest.raises(vlb.VlbError) as e:      # SKYBOX_ON_MISS without a skybox
+            c.bake_probes(s)
+        assert e.value.code == vlb.ERR_STATE
+        s.sh_order = 5
+        with pytest.raises(vlb.VlbError) as e:
+            c.bake_probes(s)
+        assert e.value.code == vlb.ERR_INVALID
+
+
+def test_bake_empty_scene_sees_only_sky(ctx, vlb, oa, scenes):
+    sc = scenes.default_cube()
+    empty = {k: v[:0] if k != "materials" else v for k, v in sc.items()}
+    with vlb.Context(0) as c:
+        c.set_scene(empty)
+        sky = scenes.hdr_sky(64, 32, seed=9)
+        c.set_skybox(sky)
+        s = vlb.default_settings()
+        s.probes[:] = (1, 1, 1)
+        s.dir_w, s.dir_h = 64, 32
+        s.flags = vlb.SKYBOX_ON_MISS
+        got = c.bake_probes(s)
+        osc = oa.Scene(empty)
+        osc.set_skybox(sky)
+        assert rel_l2(got, osc.bake_probes(s)[0]) <= PROBE_TOL
+
+
+def test_bake_cube_reference_defaults_scaled(ctx, vlb, oa, scenes):
+    # the reference's own scene (default cube), its 7x7x7 grid and default flags, direction grid
+    # scaled down from 3141x1000 so the oracle finishes in seconds
+    sc = scenes.default_cube()
+    with vlb.Context(0) as c:
+        c.set_scene(sc)
+        sky = scenes.hdr_sky(64, 32, seed=6)
+        c.set_skybox(sky)
+        s = vlb.default_settings()
+        s.dir_w, s.dir_h = 157, 50
+        vlb.settings_from_bounds(s, c.scene_bounds(tight=False))
+        assert np.allclose(c.scene_bounds(False), [-1, -1, -1, 1, 1, 1])
+        assert np.allclose(list(s.step), [2 / 6] * 3)
+        got = c.bake_probes(s)
+        osc = oa.Scene(sc)
+        osc.set_skybox(sky)
+        assert rel_l2(got, osc.bake_probes(s)[0]) <= PROBE_TOL

@@ -1,0 +1,323 @@
+"""vulkan-light-bakery_b200 — host-side Python mirror of the reference's bake interface over
+the C ABI of libvlb_bake.so (include/vlb_bake.h).
+
+The reference's host code is C++ (src/baker, src/scene_manager.cpp, src/skybox_manager.cpp); the
+C++ mirror of those classes lives in host/. This module is the thin ctypes layer the parity tests
+and bench.py use: same entry points, same argument meaning, same error behaviour (a failing call
+raises VlbError carrying vlb_last_error(), as the reference throws std::runtime_error).
+
+There is NO CPU fallback: if libvlb_bake.so is missing or no CUDA device is usable, every compute
+entry point raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvlb_bake.so")
+
+# ---- layouts shared with shaders/structures.h (scalar layout) ------------------------------
+VERTEX_DTYPE = np.dtype([("position", "<f4", (4,)), ("normal", "<f4", (3,)), ("uv0", "<f4", (2,)),
+                         ("uv1", "<f4", (2,))])
+INSTANCE_DTYPE = np.dtype([("first_index", "<u4"), ("index_count", "<u4"), ("first_vertex", "<u4"),
+                           ("vertex_count", "<u4"), ("material_index", "<u4"), ("transform", "<f4", (12,))])
+MATERIAL_DTYPE = np.dtype([("textures", "<i4", (8, 2)), ("base_color_factor", "<f4", (4,)),
+                           ("emissive_factor", "<f4", (4,)), ("diffuse_factor", "<f4", (4,)),
+                           ("specular_factor", "<f4", (3,)), ("metallic", "<f4"), ("roughness", "<f4"),
+                           ("alpha_cutoff", "<f4"), ("pad", "<f4", (2,))])
+assert VERTEX_DTYPE.itemsize == 44 and INSTANCE_DTYPE.itemsize == 68 and MATERIAL_DTYPE.itemsize == 144
+
+FMT_RGBA8, FMT_RGBA32F = 0, 1
+SH_STRIDE = 48
+
+SHADOW_RAYS = 1 << 0
+SKYBOX_ON_MISS = 1 << 1
+SRGB_ENCODE = 1 << 2
+QUANTIZE_RGBA8 = 1 << 3
+REFERENCE_PROBE_ORDER = 1 << 4
+ACCUMULATE_ACROSS_PROBES = 1 << 5
+SH_WORLD_FRAME = 1 << 6
+
+TRACE_BVH, TRACE_BRUTE_FORCE = 0, 1
+TRACE_CLOSEST, TRACE_ANY = 0, 1
+
+OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_STATE, ERR_IO, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6, -7
+
+
+class BakeSettings(ctypes.Structure):
+    """vlb_bake_settings (include/vlb_bake.h); defaults = the reference's hard-coded constants."""
+    _fields_ = [("probes", ctypes.c_int32 * 3), ("origin", ctypes.c_float * 3), ("step", ctypes.c_float * 3),
+                ("dir_w", ctypes.c_int32), ("dir_h", ctypes.c_int32), ("sh_order", ctypes.c_int32),
+                ("light_pos", ctypes.c_float * 3), ("shadow_bias", ctypes.c_float), ("c_diffuse", ctypes.c_float),
+                ("c_specular", ctypes.c_float), ("gloss", ctypes.c_float), ("ambient", ctypes.c_float),
+                ("tmin", ctypes.c_float), ("tmax", ctypes.c_float), ("flags", ctypes.c_uint32),
+                ("slab_k0", ctypes.c_int32), ("slab_k1", ctypes.c_int32), ("reserved", ctypes.c_int32 * 4)]
+
+    def copy(self):
+        c = BakeSettings()
+        ctypes.memmove(ctypes.byref(c), ctypes.byref(self), ctypes.sizeof(self))
+        return c
+
+    @property
+    def n_probes(self):
+        return self.probes[0] * self.probes[1] * self.probes[2]
+
+    @property
+    def slab(self):
+        k1 = self.probes[2] if self.slab_k1 < 0 else self.slab_k1
+        k0 = 0 if self.slab_k1 < 0 else self.slab_k0
+        return k0, k1
+
+
+class BvhStats(ctypes.Structure):
+    _fields_ = [("n_triangles", ctypes.c_uint64), ("n_nodes", ctypes.c_uint64), ("max_leaf_size", ctypes.c_uint32),
+                ("reserved", ctypes.c_uint32), ("bounds", ctypes.c_float * 6), ("build_ms", ctypes.c_float),
+                ("sort_ms", ctypes.c_float)]
+
+
+class BakeStats(ctypes.Structure):
+    _fields_ = [("n_probes", ctypes.c_uint64), ("n_primary_rays", ctypes.c_uint64), ("n_shadow_rays", ctypes.c_uint64),
+                ("n_nodes_visited", ctypes.c_uint64), ("n_tris_tested", ctypes.c_uint64), ("kernel_ms", ctypes.c_float),
+                ("total_ms", ctypes.c_float)]
+
+
+class VlbError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__("vlb error %d: %s" % (code, message))
+        self.code = code
+
+
+# every symbol include/vlb_bake.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "vlb_abi_version", "vlb_ctx_create", "vlb_ctx_destroy", "vlb_ctx_set_stream", "vlb_ctx_synchronize",
+    "vlb_last_error", "vlb_ctx_launch_count", "vlb_scene_set_triangles", "vlb_scene_bounds", "vlb_bvh_build",
+    "vlb_skybox_set", "vlb_skybox_project_sh", "vlb_skybox_project_sh_batched", "vlb_skybox_project_sh_device",
+    "vlb_envmap_project_sh", "vlb_bake_settings_default", "vlb_bake_settings_from_bounds", "vlb_probe_positions",
+    "vlb_bake_probes", "vlb_bake_probes_device", "vlb_bake_last_stats", "vlb_trace_rays",
+    "vlb_bake_serialize_gltf", "vlb_bake_deserialize_gltf",
+]
+
+_lib = None
+
+
+def load_library():
+    """dlopen libvlb_bake.so; fails loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: run `python __graft_entry__.py` (build()) first; there is no CPU fallback"
+                          % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, u64, u32, i32, f32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int, ctypes.c_float
+    S = ctypes.POINTER(BakeSettings)
+    sig = {
+        "vlb_abi_version": (i32, []),
+        "vlb_ctx_create": (i32, [i32, ctypes.POINTER(vp)]),
+        "vlb_ctx_destroy": (None, [vp]),
+        "vlb_ctx_set_stream": (i32, [vp, u64]),
+        "vlb_ctx_synchronize": (i32, [vp]),
+        "vlb_last_error": (ctypes.c_char_p, [vp]),
+        "vlb_ctx_launch_count": (u64, [vp]),
+        "vlb_scene_set_triangles": (i32, [vp, vp, u64, vp, u64, vp, u32, vp, u32]),
+        "vlb_scene_bounds": (i32, [vp, i32, vp]),
+        "vlb_bvh_build": (i32, [vp, ctypes.POINTER(BvhStats)]),
+        "vlb_skybox_set": (i32, [vp, vp, i32, i32, i32]),
+        "vlb_skybox_project_sh": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+        "vlb_skybox_project_sh_batched": (i32, [vp, vp, u32, i32, i32, i32, i32, vp]),
+        "vlb_skybox_project_sh_device": (i32, [vp, vp, u64, u32, i32, i32, i32, i32, vp]),
+        "vlb_envmap_project_sh": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+        "vlb_bake_settings_default": (None, [S]),
+        "vlb_bake_settings_from_bounds": (i32, [S, vp]),
+        "vlb_probe_positions": (i32, [S, vp]),
+        "vlb_bake_probes": (i32, [vp, S, vp]),
+        "vlb_bake_probes_device": (i32, [vp, S, vp]),
+        "vlb_bake_last_stats": (i32, [vp, ctypes.POINTER(BakeStats)]),
+        "vlb_trace_rays": (i32, [vp, vp, vp, u64, f32, f32, i32, i32, vp, vp]),
+        "vlb_bake_serialize_gltf": (i32, [ctypes.c_char_p, ctypes.c_char_p, vp, u64, S]),
+        "vlb_bake_deserialize_gltf": (i32, [ctypes.c_char_p, vp, u64, ctypes.POINTER(u64), vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def default_settings():
+    s = BakeSettings()
+    load_library().vlb_bake_settings_default(ctypes.byref(s))
+    return s
+
+
+def settings_from_bounds(s, bounds):
+    b = np.ascontiguousarray(bounds, np.float32).reshape(6)
+    r = load_library().vlb_bake_settings_from_bounds(ctypes.byref(s), _ptr(b))
+    if r:
+        raise VlbError(r, "vlb_bake_settings_from_bounds: bad probe counts")
+    return s
+
+
+def probe_positions(s):
+    out = np.zeros((s.n_probes, 3), np.float32)
+    r = load_library().vlb_probe_positions(ctypes.byref(s), _ptr(out))
+    if r:
+        raise VlbError(r, "vlb_probe_positions: bad settings")
+    return out
+
+
+class Context:
+    """One baker context bound to one CUDA device (mirrors vlb::LightBaker's device ownership,
+    src/baker/light_baker.cpp:20-74)."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        h = ctypes.c_void_p()
+        r = self._lib.vlb_ctx_create(int(device), ctypes.byref(h))
+        if r:
+            raise VlbError(r, self._lib.vlb_last_error(None).decode())
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.vlb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, r):
+        if r:
+            raise VlbError(r, self._lib.vlb_last_error(self._h).decode())
+
+    # -- plumbing
+    def set_stream(self, handle):
+        self._check(self._lib.vlb_ctx_set_stream(self._h, int(handle)))
+
+    def synchronize(self):
+        self._check(self._lib.vlb_ctx_synchronize(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.vlb_ctx_launch_count(self._h))
+
+    # -- scene (SceneManager::pushScene output)
+    def set_scene(self, scene):
+        v = np.ascontiguousarray(scene["vertices"], VERTEX_DTYPE)
+        i = np.ascontiguousarray(scene["indices"], np.uint32)
+        inst = np.ascontiguousarray(scene["instances"], INSTANCE_DTYPE)
+        m = np.ascontiguousarray(scene["materials"], MATERIAL_DTYPE)
+        self._check(self._lib.vlb_scene_set_triangles(self._h, _ptr(v), v.size, _ptr(i), i.size, _ptr(inst), inst.size,
+                                                      _ptr(m), m.size))
+
+    def scene_bounds(self, tight=False):
+        out = np.zeros(6, np.float32)
+        self._check(self._lib.vlb_scene_bounds(self._h, int(bool(tight)), _ptr(out)))
+        return out
+
+    def build_bvh(self):
+        st = BvhStats()
+        self._check(self._lib.vlb_bvh_build(self._h, ctypes.byref(st)))
+        return st
+
+    # -- skybox (Skybox_t)
+    @staticmethod
+    def _texels(texels):
+        t = np.ascontiguousarray(texels)
+        if t.ndim != 3 or t.shape[2] != 4 or t.dtype not in (np.uint8, np.float32):
+            raise ValueError("texels must be HxWx4 uint8 or float32")
+        return t, (FMT_RGBA8 if t.dtype == np.uint8 else FMT_RGBA32F)
+
+    def set_skybox(self, texels):
+        t, fmt = self._texels(texels)
+        self._check(self._lib.vlb_skybox_set(self._h, _ptr(t), fmt, t.shape[1], t.shape[0]))
+
+    def skybox_project_sh(self, texels, order=3):
+        t, fmt = self._texels(texels)
+        out = np.zeros((16, 3), np.float32)
+        self._check(self._lib.vlb_skybox_project_sh(self._h, _ptr(t), fmt, t.shape[1], t.shape[0], order, _ptr(out)))
+        return out
+
+    def envmap_project_sh(self, texels, order=3):
+        t, fmt = self._texels(texels)
+        out = np.zeros((16, 3), np.float32)
+        self._check(self._lib.vlb_envmap_project_sh(self._h, _ptr(t), fmt, t.shape[1], t.shape[0], order, _ptr(out)))
+        return out
+
+    def skybox_project_sh_batched(self, maps, order=3):
+        ts = [self._texels(m) for m in maps]
+        fmt, shape = ts[0][1], ts[0][0].shape
+        if any(t.shape != shape or f != fmt for t, f in ts):
+            raise ValueError("all maps must have the same size and format")
+        arr = (ctypes.c_void_p * len(ts))(*[t.ctypes.data for t, _ in ts])
+        out = np.zeros((len(ts), 16, 3), np.float32)
+        self._check(self._lib.vlb_skybox_project_sh_batched(self._h, arr, len(ts), fmt, shape[1], shape[0], order, _ptr(out)))
+        return out
+
+    def skybox_project_sh_device(self, d_texels, map_stride, n_maps, fmt, width, height, order, d_out):
+        self._check(self._lib.vlb_skybox_project_sh_device(self._h, int(d_texels), int(map_stride), int(n_maps), fmt,
+                                                           width, height, order, int(d_out)))
+
+    # -- bake (LightBaker::bake)
+    def bake_probes(self, s):
+        k0, k1 = s.slab
+        n = s.probes[0] * s.probes[1] * (k1 - k0)
+        out = np.zeros((n, 16, 3), np.float32)
+        self._check(self._lib.vlb_bake_probes(self._h, ctypes.byref(s), _ptr(out)))
+        return out
+
+    def bake_probes_device(self, s, d_out):
+        self._check(self._lib.vlb_bake_probes_device(self._h, ctypes.byref(s), int(d_out)))
+
+    def last_bake_stats(self):
+        st = BakeStats()
+        self._check(self._lib.vlb_bake_last_stats(self._h, ctypes.byref(st)))
+        return st
+
+    # -- validation
+    def trace_rays(self, origins, dirs, tmin=0.001, tmax=10000.0, accel=TRACE_BVH, kind=TRACE_CLOSEST):
+        o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        ids = np.full(o.shape[0], -2, np.int32)
+        tuv = np.zeros((o.shape[0], 3), np.float32)
+        self._check(self._lib.vlb_trace_rays(self._h, _ptr(o), _ptr(d), o.shape[0], tmin, tmax, accel, kind, _ptr(ids),
+                                             _ptr(tuv)))
+        return ids, tuv
+
+
+def serialize_gltf(in_path, out_path, coeffs, settings):
+    c = np.ascontiguousarray(coeffs, np.float32).reshape(-1, SH_STRIDE)
+    lib = load_library()
+    r = lib.vlb_bake_serialize_gltf(os.fsencode(in_path), os.fsencode(out_path), _ptr(c), c.shape[0], ctypes.byref(settings))
+    if r:
+        raise VlbError(r, lib.vlb_last_error(None).decode())
+
+
+def deserialize_gltf(path):
+    lib = load_library()
+    n = ctypes.c_uint64()
+    step = np.zeros(3, np.float32)
+    r = lib.vlb_bake_deserialize_gltf(os.fsencode(path), None, 0, ctypes.byref(n), _ptr(step))
+    if r:
+        raise VlbError(r, lib.vlb_last_error(None).decode())
+    out = np.zeros(n.value, np.float32)
+    r = lib.vlb_bake_deserialize_gltf(os.fsencode(path), _ptr(out), out.size, ctypes.byref(n), _ptr(step))
+    if r:
+        raise VlbError(r, lib.vlb_last_error(None).decode())
+    return out.reshape(-1, 16, 3), step

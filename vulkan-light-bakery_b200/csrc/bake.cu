@@ -1,0 +1,347 @@
+// bake.cu — the probe bake: replaces the reference's per-probe pair
+//   EnvMapGenerator::getMap  (src/baker/env_map_generator.cpp:325-359; shaders env_map.rgen/.rchit,
+//                             main.rmiss, shadow.rmiss)          and
+//   LightBaker::dispatchBakingKernel (src/baker/light_baker.cpp:269-285; shaders/sh.comp)
+// with ONE persistent launch over all probes of the slab: every warp pulls (probe, direction
+// chunk) items from a global counter, fires the probe's fixed equirect directions plus shadow
+// rays through the software LBVH, and projects the radiance onto SH in registers. Per-ray
+// radiance never goes to HBM; the only global writes are 192 bytes per probe.
+#include <algorithm>
+
+#include "vlb_context.h"
+#include "vlb_shade.cuh"
+#include "vlb_warp.cuh"
+
+namespace vlb {
+
+constexpr int kBakeBlock = 128;
+constexpr int kTileW = 8, kTileH = 4;   // one warp = an 8x4 tile of adjacent direction texels
+
+struct BakeParams {
+    BvhView bvh;
+    ShadeView shade;
+    BakeConsts c;
+    const float* px; const float* py; const float* pz;   // probe axis coordinates
+    const float2* row_sc;                                // (sin, cos) theta per direction row
+    const float2* col_cs;                                // (cos, sin) phi per direction column
+    int Nx, Ny, Nz, k0;
+    int W, H, tiles_x, n_tiles;
+    int chunks, tiles_per_chunk;
+    uint32_t n_items;
+    float pixel_area;
+    float* out;                  // chunks == 1: final [slot][48]; else partials [item][48]
+    unsigned int* work_counter;
+    unsigned long long* stats;   // [0] shadow rays, [1] nodes visited, [2] triangles tested
+    int ref_order, world_frame;
+};
+
+__device__ __forceinline__ size_t out_slot(const BakeParams& p, uint32_t q) {
+    if (!p.ref_order) return q;
+    const int i = q % p.Nx, j = (q / p.Nx) % p.Ny, k = q / (p.Nx * p.Ny);
+    // writer order of LightBaker::probePositionsFromBoudingBox (light_baker.cpp:87-98)
+    const size_t s = (j == 0) ? (size_t)i : (size_t)p.Nx + (size_t)i * (p.Ny - 1) + (j - 1);
+    return (k == 0) ? s : (size_t)p.Nx * p.Ny + s * (p.Nz - 1) + (k - 1);
+}
+
+template <int K, bool COUNT>
+__global__ void __launch_bounds__(kBakeBlock) k_bake(const BakeParams p) {
+    constexpr int V = (K * 3 <= 32) ? 32 : 64;
+    const int lane = threadIdx.x & 31;
+    TraceCounters cnt; cnt.nodes = 0; cnt.tris = 0;
+    uint32_t shadow = 0;
+    for (;;) {
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(p.work_counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= p.n_items) break;
+        const uint32_t q = item / (uint32_t)p.chunks, chunk = item % (uint32_t)p.chunks;
+        const uint32_t g = q + (uint32_t)p.k0 * (uint32_t)(p.Nx * p.Ny);
+        const Vec3 o = mk3(p.px[g % p.Nx], p.py[(g / p.Nx) % p.Ny], p.pz[g / (p.Nx * p.Ny)]);
+        float acc[V];
+#pragma unroll
+        for (int i = 0; i < V; ++i) acc[i] = 0.f;
+        const int t0 = chunk * p.tiles_per_chunk;
+        const int t1 = min(t0 + p.tiles_per_chunk, p.n_tiles);
+        for (int tile = t0; tile < t1; ++tile) {
+            const int x = (tile % p.tiles_x) * kTileW + (lane & (kTileW - 1));
+            const int y = (tile / p.tiles_x) * kTileH + (lane / kTileW);
+            if (x < p.W && y < p.H) {
+                const float2 row = __ldg(p.row_sc + y), col = __ldg(p.col_cs + x);
+                const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);   // sh_common.h:8-12
+                const Vec3 r = mk3(t.x, t.z, t.y);                         // env_map.rgen:21 .xzy
+                float rgb[3];
+                probe_ray_radiance<COUNT>(p.bvh, p.shade, p.c, o, r, rgb, &cnt, &shadow);
+                const float w = p.pixel_area * row.x;                      // sh.comp:32-33
+                float b[K];
+                sh_basis<K>(p.world_frame ? r : t, b);                     // sh.comp:30,39
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    const float bw = b[i] * w;
+                    acc[3 * i + 0] = fmaf(bw, rgb[0], acc[3 * i + 0]);
+                    acc[3 * i + 1] = fmaf(bw, rgb[1], acc[3 * i + 1]);
+                    acc[3 * i + 2] = fmaf(bw, rgb[2], acc[3 * i + 2]);
+                }
+            }
+            __syncwarp();
+        }
+        warp_transpose_reduce<V>(acc, lane);
+        float* dst = p.out + (p.chunks == 1 ? out_slot(p, q) : (size_t)item) * VLB_SH_STRIDE;
+        if (V == 32) {
+            if (lane < K * 3) dst[lane] = acc[0];
+            if (lane + 32 < VLB_SH_STRIDE) dst[lane + 32] = 0.f;
+            if (lane >= K * 3) dst[lane] = 0.f;
+        } else {
+            if (2 * lane < VLB_SH_STRIDE) {
+                dst[2 * lane] = acc[0];
+                dst[2 * lane + 1] = acc[1];
+            }
+        }
+    }
+    // statistics: one atomic per warp
+    unsigned long long s = shadow, nn = cnt.nodes, nt = cnt.tris;
+    for (int off = 16; off > 0; off >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (COUNT) { nn += __shfl_xor_sync(0xffffffffu, nn, off); nt += __shfl_xor_sync(0xffffffffu, nt, off); }
+    }
+    if (lane == 0) {
+        atomicAdd(p.stats + 0, s);
+        if (COUNT) { atomicAdd(p.stats + 1, nn); atomicAdd(p.stats + 2, nt); }
+    }
+}
+
+// chunks > 1: per-probe sum of the chunk partials in chunk order (fixed order => deterministic).
+__global__ void k_sum_partials(const BakeParams p, const float* __restrict__ partials, uint32_t n_probes, float* out) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_probes * VLB_SH_STRIDE) return;
+    const uint32_t q = idx / VLB_SH_STRIDE, c = idx % VLB_SH_STRIDE;
+    float s = 0.f;
+    for (int k = 0; k < p.chunks; ++k) s += partials[((size_t)q * p.chunks + k) * VLB_SH_STRIDE + c];
+    out[out_slot(p, q) * VLB_SH_STRIDE + c] = s;
+}
+
+// VLB_BAKE_ACCUMULATE_ACROSS_PROBES: the reference never re-zeroes its SSBO (light_baker.cpp:110-121),
+// so probe i holds the running total of probes 0..i in bake order. Forensic mode only.
+__global__ void k_running_total(float* out, uint32_t n_probes) {
+    const int c = threadIdx.x;
+    if (c >= VLB_SH_STRIDE) return;
+    float s = 0.f;
+    for (uint32_t q = 0; q < n_probes; ++q) { s += out[(size_t)q * VLB_SH_STRIDE + c]; out[(size_t)q * VLB_SH_STRIDE + c] = s; }
+}
+
+static int env_flag(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out) {
+    cudaStream_t st = ctx->stream;
+    const int Nx = s->probes[0], Ny = s->probes[1], Nz = s->probes[2];
+    const int k0 = s->slab_k1 < 0 ? 0 : s->slab_k0, k1 = s->slab_k1 < 0 ? Nz : s->slab_k1;
+    const uint64_t n_probes = (uint64_t)Nx * Ny * (uint64_t)(k1 - k0);
+    ctx->last_bake = vlb_bake_stats{};
+    if (n_probes == 0) return VLB_OK;
+    const int W = s->dir_w, H = s->dir_h;
+
+    // tables: probe axis coordinates and the equirect sin/cos tables (host_tables.cpp)
+    std::vector<float> axis((size_t)Nx + Ny + Nz), row(2 * (size_t)H), col(2 * (size_t)W);
+    host_axis_coords(s->origin[0], s->step[0], Nx, axis.data());
+    host_axis_coords(s->origin[1], s->step[1], Ny, axis.data() + Nx);
+    host_axis_coords(s->origin[2], s->step[2], Nz, axis.data() + Nx + Ny);
+    if (ctx->dir_w != W || ctx->dir_h != H) {
+        host_dir_tables(W, H, 0.f, row.data(), col.data());
+        VLB_CUDA(ctx, ctx->d_row_sc.reserve(row.size() * sizeof(float)));
+        VLB_CUDA(ctx, ctx->d_col_sc.reserve(col.size() * sizeof(float)));
+        VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_row_sc.p, row.data(), row.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_col_sc.p, col.data(), col.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        VLB_CUDA(ctx, cudaStreamSynchronize(st));
+        ctx->dir_w = W; ctx->dir_h = H;
+    }
+    VLB_CUDA(ctx, ctx->d_axis.reserve(axis.size() * sizeof(float)));
+    VLB_CUDA(ctx, ctx->d_work_counter.reserve(16));
+    VLB_CUDA(ctx, ctx->d_stats.reserve(4 * sizeof(unsigned long long)));
+    VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_axis.p, axis.data(), axis.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    VLB_CUDA(ctx, cudaMemsetAsync(ctx->d_work_counter.p, 0, 16, st));
+    VLB_CUDA(ctx, cudaMemsetAsync(ctx->d_stats.p, 0, 4 * sizeof(unsigned long long), st));
+
+    BakeParams p{};
+    p.bvh.nodes = ctx->d_nodes.as<float4>(); p.bvh.tris = ctx->d_tris.as<float4>(); p.bvh.n_tris = (uint32_t)ctx->n_tris;
+    p.shade.tri_shade = ctx->d_tri_shade.as<float4>(); p.shade.inst = ctx->d_inst.as<float4>();
+    p.shade.base_color = ctx->d_base_color.as<float4>();
+    p.shade.sky = ctx->sky_w ? ctx->d_sky.as<float4>() : nullptr; p.shade.sky_w = ctx->sky_w; p.shade.sky_h = ctx->sky_h;
+    for (int k = 0; k < 3; ++k) p.c.light[k] = s->light_pos[k];
+    p.c.shadow_bias = s->shadow_bias; p.c.c_diffuse = s->c_diffuse; p.c.c_specular = s->c_specular;
+    p.c.gloss = s->gloss; p.c.ambient = s->ambient; p.c.tmin = s->tmin; p.c.tmax = s->tmax; p.c.flags = s->flags;
+    p.px = ctx->d_axis.as<float>(); p.py = p.px + Nx; p.pz = p.py + Ny;
+    p.row_sc = ctx->d_row_sc.as<float2>(); p.col_cs = ctx->d_col_sc.as<float2>();
+    p.Nx = Nx; p.Ny = Ny; p.Nz = Nz; p.k0 = k0; p.W = W; p.H = H;
+    p.tiles_x = (W + kTileW - 1) / kTileW;
+    p.n_tiles = p.tiles_x * ((H + kTileH - 1) / kTileH);
+    // Work decomposition: a function of the WHOLE grid and the direction grid only (never of the
+    // slab), so that a probe's coefficients are bit-identical however the grid is sharded.
+    // Probes are split into direction chunks until there are >= 32768 items in the whole grid.
+    const uint64_t total_probes = (uint64_t)Nx * Ny * Nz;
+    int chunks = 1;
+    while (total_probes * (uint64_t)chunks < 32768ull && chunks * 2 <= p.n_tiles) chunks *= 2;
+    chunks = env_flag("VLB_BAKE_CHUNKS", chunks);
+    chunks = std::max(1, std::min(chunks, p.n_tiles));
+    p.tiles_per_chunk = (p.n_tiles + chunks - 1) / chunks;
+    p.chunks = (p.n_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+    if (n_probes * (uint64_t)p.chunks >= (1ull << 32)) return ctx->fail(VLB_ERR_UNSUPPORTED, "bake: too many work items");
+    p.n_items = (uint32_t)(n_probes * (uint64_t)p.chunks);
+    p.pixel_area = (2.0f * kPi / (float)W) * (kPi / (float)H);            // sh.comp:32
+    p.work_counter = ctx->d_work_counter.as<unsigned int>();
+    p.stats = ctx->d_stats.as<unsigned long long>();
+    p.ref_order = (s->flags & VLB_BAKE_REFERENCE_PROBE_ORDER) ? 1 : 0;
+    p.world_frame = (s->flags & VLB_BAKE_SH_WORLD_FRAME) ? 1 : 0;
+    if (p.chunks > 1) {
+        VLB_CUDA(ctx, ctx->d_partials.reserve((size_t)p.n_items * VLB_SH_STRIDE * sizeof(float)));
+        p.out = ctx->d_partials.as<float>();
+    } else {
+        p.out = d_out;
+    }
+
+    const bool count = env_flag("VLB_BAKE_COUNTERS", 0) != 0;
+    const int K = s->sh_order == 2 ? 9 : 16;
+    void (*kern)(const BakeParams) = nullptr;
+    if (K == 9) kern = count ? k_bake<9, true> : k_bake<9, false>;
+    else        kern = count ? k_bake<16, true> : k_bake<16, false>;
+    int per_sm = 0;
+    VLB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBakeBlock, 0));
+    per_sm = std::max(per_sm, 1);
+    const uint32_t warps_needed = p.n_items;
+    uint32_t grid = (uint32_t)(ctx->sm_count * per_sm);
+    grid = std::max(1u, std::min(grid, (warps_needed + (kBakeBlock / 32) - 1) / (kBakeBlock / 32)));
+
+    VLB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    VLB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    kern<<<grid, kBakeBlock, 0, st>>>(p);
+    VLB_LAUNCH_CHECK(ctx);
+    VLB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    if (p.chunks > 1) {
+        const uint32_t n = (uint32_t)n_probes * VLB_SH_STRIDE;
+        k_sum_partials<<<(n + 255) / 256, 256, 0, st>>>(p, ctx->d_partials.as<float>(), (uint32_t)n_probes, d_out);
+        VLB_LAUNCH_CHECK(ctx);
+    }
+    if (s->flags & VLB_BAKE_ACCUMULATE_ACROSS_PROBES) {
+        k_running_total<<<1, 64, 0, st>>>(d_out, (uint32_t)n_probes);
+        VLB_LAUNCH_CHECK(ctx);
+    }
+    VLB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    // the axis staging vector dies at scope exit and stats are read back: synchronise
+    unsigned long long h[4] = {0, 0, 0, 0};
+    VLB_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_stats.p, sizeof h, cudaMemcpyDeviceToHost, st));
+    VLB_CUDA(ctx, cudaStreamSynchronize(st));
+    vlb_bake_stats& b = ctx->last_bake;
+    b.n_probes = n_probes; b.n_primary_rays = n_probes * (uint64_t)W * H; b.n_shadow_rays = h[0];
+    b.n_nodes_visited = h[1]; b.n_tris_tested = h[2];
+    VLB_CUDA(ctx, cudaEventElapsedTime(&b.kernel_ms, ctx->ev[2], ctx->ev[3]));
+    VLB_CUDA(ctx, cudaEventElapsedTime(&b.total_ms, ctx->ev[0], ctx->ev[1]));
+    return VLB_OK;
+}
+
+// =========================================================================================
+// Validation: ray casts through the BVH and through a brute-force intersector that shares
+// intersect_tri(), so hit ids must agree bit for bit (BASELINE.json north_star).
+// =========================================================================================
+__global__ void k_trace_bvh(BvhView b, const float* __restrict__ o, const float* __restrict__ d, uint32_t n, float tmin,
+                            float tmax, int kind, int* __restrict__ ids, float* __restrict__ tuv) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Vec3 ro = mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), rd = mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+    HitRec h; h.id = -1; h.t = tmax; h.u = 0.f; h.v = 0.f;
+    if (kind == VLB_TRACE_ANY) {
+        HitRec a;
+        if (trace_any<false>(b, ro, rd, tmin, tmax, nullptr, &a)) h = a;
+    } else {
+        h = trace_closest<false>(b, ro, rd, tmin, tmax, nullptr);
+    }
+    ids[i] = h.id;
+    if (tuv) { tuv[3 * i] = h.t; tuv[3 * i + 1] = h.u; tuv[3 * i + 2] = h.v; }
+}
+
+constexpr int kBruteSeg = 2048;   // triangles per thread block column
+
+__global__ void k_brute_init(unsigned long long* keys, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = ~0ull;
+}
+
+// grid = (ray blocks, triangle segments): every thread tests its ray against one segment and
+// publishes (t bits, flat id) with a 64-bit atomicMin: smallest t, then smallest id.
+__global__ void k_brute(const float4* __restrict__ tri_flat, uint32_t n_tris, const float* __restrict__ o,
+                        const float* __restrict__ d, uint32_t n, float tmin, float tmax, unsigned long long* keys) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Vec3 ro = mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), rd = mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+    const uint32_t s0 = blockIdx.y * kBruteSeg, s1 = min(s0 + kBruteSeg, n_tris);
+    unsigned long long best = ~0ull;
+    for (uint32_t k = s0; k < s1; ++k) {
+        float t, u, v;
+        if (intersect_tri(ld4(tri_flat + 3ull * k), ld4(tri_flat + 3ull * k + 1), ld4(tri_flat + 3ull * k + 2), ro, rd, t, u, v) &&
+            t > tmin && t < tmax) {
+            const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | k;
+            best = key < best ? key : best;
+        }
+    }
+    if (best != ~0ull) atomicMin(keys + i, best);
+}
+
+__global__ void k_brute_finish(const float4* __restrict__ tri_flat, const float* __restrict__ o, const float* __restrict__ d,
+                               uint32_t n, float tmax, const unsigned long long* __restrict__ keys, int* ids, float* tuv) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long key = keys[i];
+    int id = -1; float t = tmax, u = 0.f, v = 0.f;
+    if (key != ~0ull) {
+        id = (int)(key & 0xffffffffu);
+        const Vec3 ro = mk3(o[3 * i], o[3 * i + 1], o[3 * i + 2]), rd = mk3(d[3 * i], d[3 * i + 1], d[3 * i + 2]);
+        intersect_tri(tri_flat[3ull * id], tri_flat[3ull * id + 1], tri_flat[3ull * id + 2], ro, rd, t, u, v);
+    }
+    ids[i] = id;
+    if (tuv) { tuv[3 * i] = t; tuv[3 * i + 1] = u; tuv[3 * i + 2] = v; }
+}
+
+int trace_rays(vlb_ctx* ctx, const float* o, const float* d, uint64_t n64, float tmin, float tmax, int accel, int kind,
+               int32_t* ids, float* tuv) {
+    if (n64 >= (1ull << 31)) return ctx->fail(VLB_ERR_UNSUPPORTED, "vlb_trace_rays: too many rays in one call");
+    if (tmin < 0.f) return ctx->fail(VLB_ERR_INVALID, "vlb_trace_rays: tmin must be >= 0");
+    const uint32_t n = (uint32_t)n64;
+    cudaStream_t st = ctx->stream;
+    VLB_CUDA(ctx, ctx->d_ray_o.reserve(3ull * n * sizeof(float)));
+    VLB_CUDA(ctx, ctx->d_ray_d.reserve(3ull * n * sizeof(float)));
+    VLB_CUDA(ctx, ctx->d_hit_id.reserve(n * sizeof(int)));
+    VLB_CUDA(ctx, ctx->d_hit_tuv.reserve(3ull * n * sizeof(float)));
+    VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_ray_o.p, o, 3ull * n * sizeof(float), cudaMemcpyHostToDevice, st));
+    VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_ray_d.p, d, 3ull * n * sizeof(float), cudaMemcpyHostToDevice, st));
+    const unsigned grid = (n + 127) / 128;
+    if (accel == VLB_TRACE_BVH) {
+        BvhView b; b.nodes = ctx->d_nodes.as<float4>(); b.tris = ctx->d_tris.as<float4>(); b.n_tris = (uint32_t)ctx->n_tris;
+        k_trace_bvh<<<grid, 128, 0, st>>>(b, ctx->d_ray_o.as<float>(), ctx->d_ray_d.as<float>(), n, tmin, tmax, kind,
+                                          ctx->d_hit_id.as<int>(), ctx->d_hit_tuv.as<float>());
+        VLB_LAUNCH_CHECK(ctx);
+    } else if (accel == VLB_TRACE_BRUTE_FORCE) {
+        VLB_CUDA(ctx, ctx->d_hit_key.reserve(n * sizeof(unsigned long long)));
+        k_brute_init<<<(n + 255) / 256, 256, 0, st>>>(ctx->d_hit_key.as<unsigned long long>(), n);
+        VLB_LAUNCH_CHECK(ctx);
+        const uint32_t nt = (uint32_t)ctx->n_tris;
+        if (nt) {
+            const dim3 g(grid, (nt + kBruteSeg - 1) / kBruteSeg);
+            if (g.y > 65535) return ctx->fail(VLB_ERR_UNSUPPORTED, "brute force: scene too large");
+            k_brute<<<g, 128, 0, st>>>(ctx->d_tri_flat.as<float4>(), nt, ctx->d_ray_o.as<float>(), ctx->d_ray_d.as<float>(), n,
+                                       tmin, tmax, ctx->d_hit_key.as<unsigned long long>());
+            VLB_LAUNCH_CHECK(ctx);
+        }
+        k_brute_finish<<<(n + 255) / 256, 256, 0, st>>>(ctx->d_tri_flat.as<float4>(), ctx->d_ray_o.as<float>(), ctx->d_ray_d.as<float>(),
+                                                        n, tmax, ctx->d_hit_key.as<unsigned long long>(), ctx->d_hit_id.as<int>(),
+                                                        ctx->d_hit_tuv.as<float>());
+        VLB_LAUNCH_CHECK(ctx);
+    } else {
+        return ctx->fail(VLB_ERR_INVALID, "vlb_trace_rays: unknown accel");
+    }
+    VLB_CUDA(ctx, cudaMemcpyAsync(ids, ctx->d_hit_id.p, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (tuv) VLB_CUDA(ctx, cudaMemcpyAsync(tuv, ctx->d_hit_tuv.p, 3ull * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    VLB_CUDA(ctx, cudaStreamSynchronize(st));
+    return VLB_OK;
+}
+
+}  // namespace vlb

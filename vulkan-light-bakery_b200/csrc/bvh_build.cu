@@ -1,0 +1,219 @@
+// bvh_build.cu — software LBVH build on the GPU; replaces the driver acceleration-structure
+// build of the reference (Scene_t::buildAccelerationStructures, src/scene_manager.cpp:385-443).
+//
+//   k_scene_bounds   tight AABB + centroid AABB of the flattened triangles   (reads 48 B/tri)
+//   k_morton         63-bit Morton key of each centroid                       (reads 48 B/tri)
+//   cub radix sort   (key, flat id) pairs, 8 passes over 12 B/tri
+//   k_gather         triangles into Morton order + leaf AABBs                 (48 B in, 80 B out)
+//   k_karras         Karras-2012 hierarchy, one thread per internal node
+//   k_refit          bottom-up AABB refit, atomic arrival flags
+//   k_emit           64-byte traversal nodes (vlb_bvh.cuh), small subtrees collapsed to leaves
+#include <cub/device/device_radix_sort.cuh>
+
+#include "vlb_bvh.cuh"
+#include "vlb_context.h"
+
+namespace vlb {
+
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+    if (v >= 0.f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
+
+// scratch[0..2] tight lo, [3..5] tight hi, [6..8] centroid lo, [9..11] centroid hi
+__global__ void k_init_bounds(float* scratch) {
+    const int i = threadIdx.x;
+    if (i < 12) scratch[i] = ((i / 3) & 1) ? -INFINITY : INFINITY;
+}
+
+__global__ void k_scene_bounds(const float4* __restrict__ tri_flat, uint32_t n, float* scratch) {
+    float v[12];
+    for (int k = 0; k < 12; ++k) v[k] = ((k / 3) & 1) ? -INFINITY : INFINITY;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        float4 lo, hi;
+        tri_aabb(tri_flat[3ull * t], tri_flat[3ull * t + 1], tri_flat[3ull * t + 2], &lo, &hi);
+        const float c[3] = {0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z)};
+        v[0] = fminf(v[0], lo.x); v[1] = fminf(v[1], lo.y); v[2] = fminf(v[2], lo.z);
+        v[3] = fmaxf(v[3], hi.x); v[4] = fmaxf(v[4], hi.y); v[5] = fmaxf(v[5], hi.z);
+        for (int k = 0; k < 3; ++k) { v[6 + k] = fminf(v[6 + k], c[k]); v[9 + k] = fmaxf(v[9 + k], c[k]); }
+    }
+    for (int k = 0; k < 12; ++k) {
+        const bool is_max = (k / 3) & 1;
+        for (int off = 16; off > 0; off >>= 1) {
+            const float o = __shfl_xor_sync(0xffffffffu, v[k], off);
+            v[k] = is_max ? fmaxf(v[k], o) : fminf(v[k], o);
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        for (int k = 0; k < 12; ++k) {
+            if ((k / 3) & 1) atomic_max_float(scratch + k, v[k]);
+            else atomic_min_float(scratch + k, v[k]);
+        }
+    }
+}
+
+__global__ void k_morton(const float4* __restrict__ tri_flat, uint32_t n, const float* __restrict__ scratch,
+                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    float4 lo, hi;
+    tri_aabb(tri_flat[3ull * t], tri_flat[3ull * t + 1], tri_flat[3ull * t + 2], &lo, &hi);
+    const float c[3] = {0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z)};
+    float nrm[3];
+    for (int k = 0; k < 3; ++k) {
+        const float ext = scratch[9 + k] - scratch[6 + k];
+        nrm[k] = ext > 0.f ? (c[k] - scratch[6 + k]) / ext : 0.f;
+    }
+    keys[t] = morton63(nrm[0], nrm[1], nrm[2]);
+    vals[t] = t;
+}
+
+__global__ void k_gather(const float4* __restrict__ tri_flat, const uint32_t* __restrict__ order, uint32_t n,
+                         float4* __restrict__ tris, float4* __restrict__ lbox) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint32_t t = order[j];
+    const float4 v0 = tri_flat[3ull * t], e1 = tri_flat[3ull * t + 1], e2 = tri_flat[3ull * t + 2];
+    tris[3ull * j] = v0; tris[3ull * j + 1] = e1; tris[3ull * j + 2] = e2;
+    float4 lo, hi;
+    tri_aabb(v0, e1, e2, &lo, &hi);
+    lbox[2ull * j] = lo; lbox[2ull * j + 1] = hi;
+}
+
+__global__ void k_karras(const uint64_t* __restrict__ keys, int n, int* left, int* right, int* first, int* last,
+                         int* parent_i, int* parent_l) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    if (i == 0) parent_i[0] = -1;
+    karras_node(keys, n, i, left, right, first, last, parent_i, parent_l);
+}
+
+__global__ void k_refit(int n, const int* __restrict__ left, const int* __restrict__ right,
+                        const int* __restrict__ parent_i, const int* __restrict__ parent_l,
+                        const float4* __restrict__ lbox, float4* ibox, int* flags) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    int cur = parent_l[j];
+    while (cur >= 0) {
+        if (atomicAdd(&flags[cur], 1) == 0) return;   // first arrival: the sibling subtree is not done yet
+        __threadfence();
+        float4 lo[2], hi[2];
+        const int ch[2] = {left[cur], right[cur]};
+        for (int c = 0; c < 2; ++c) {
+            if (ch[c] < 0) { lo[c] = lbox[2 * (~ch[c])]; hi[c] = lbox[2 * (~ch[c]) + 1]; }
+            else { lo[c] = __ldcg(&ibox[2 * ch[c]]); hi[c] = __ldcg(&ibox[2 * ch[c] + 1]); }
+        }
+        ibox[2 * cur] = make_float4(fminf(lo[0].x, lo[1].x), fminf(lo[0].y, lo[1].y), fminf(lo[0].z, lo[1].z), 0.f);
+        ibox[2 * cur + 1] = make_float4(fmaxf(hi[0].x, hi[1].x), fmaxf(hi[0].y, hi[1].y), fmaxf(hi[0].z, hi[1].z), 0.f);
+        __threadfence();
+        cur = parent_i[cur];
+    }
+}
+
+__global__ void k_emit(int n, const int* __restrict__ left, const int* __restrict__ right,
+                       const int* __restrict__ first, const int* __restrict__ last,
+                       const float4* __restrict__ ibox, const float4* __restrict__ lbox, int max_leaf,
+                       const float* __restrict__ scratch, float4* __restrict__ nodes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const float ext = fmaxf(scratch[3] - scratch[0], fmaxf(scratch[4] - scratch[1], scratch[5] - scratch[2]));
+    emit_node(i, left, right, first, last, ibox, lbox, max_leaf, ext * 1e-6f, nodes);
+}
+
+// n == 1: a single node whose two children are the same one-triangle leaf.
+__global__ void k_emit_single(const float4* __restrict__ lbox, const float* __restrict__ scratch, float4* nodes) {
+    float4 lo = lbox[0], hi = lbox[1];
+    const float ext = fmaxf(scratch[3] - scratch[0], fmaxf(scratch[4] - scratch[1], scratch[5] - scratch[2]));
+    pad_box(&lo, &hi, ext * 1e-6f);
+    nodes[0] = make_float4(lo.x, hi.x, lo.y, hi.y);
+    nodes[1] = nodes[0];
+    nodes[2] = make_float4(lo.z, hi.z, lo.z, hi.z);
+    const int r = leaf_ref(0, 1);
+    nodes[3] = make_float4(i2f(r), i2f(r), i2f(0), i2f(0));
+}
+
+int bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats) {
+    const uint32_t n = (uint32_t)ctx->n_tris;
+    cudaStream_t st = ctx->stream;
+    float sort_ms = 0.f, build_ms = 0.f;
+    VLB_CUDA(ctx, ctx->d_scratch.reserve(64 * sizeof(float)));
+    VLB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    k_init_bounds<<<1, 32, 0, st>>>(ctx->d_scratch.as<float>());
+    VLB_LAUNCH_CHECK(ctx);
+    ctx->n_nodes = 0;
+    if (n > 0) {
+        const int B = 256;
+        const unsigned grid_n = (n + B - 1) / B;
+        VLB_CUDA(ctx, ctx->d_tris.reserve(3ull * n * sizeof(float4)));
+        VLB_CUDA(ctx, ctx->d_nodes.reserve(4ull * std::max<uint32_t>(n - 1, 1) * sizeof(float4)));
+        VLB_CUDA(ctx, ctx->d_keys.reserve(n * sizeof(uint64_t)));
+        VLB_CUDA(ctx, ctx->d_keys_sorted.reserve(n * sizeof(uint64_t)));
+        VLB_CUDA(ctx, ctx->d_vals.reserve(n * sizeof(uint32_t)));
+        VLB_CUDA(ctx, ctx->d_vals_sorted.reserve(n * sizeof(uint32_t)));
+        VLB_CUDA(ctx, ctx->d_lbox.reserve(2ull * n * sizeof(float4)));
+        for (DevBuf* b : {&ctx->d_left, &ctx->d_right, &ctx->d_first, &ctx->d_last, &ctx->d_parent_i, &ctx->d_parent_l, &ctx->d_flags})
+            VLB_CUDA(ctx, b->reserve(n * sizeof(int)));
+        VLB_CUDA(ctx, ctx->d_ibox.reserve(2ull * n * sizeof(float4)));
+
+        const unsigned red_grid = std::min<unsigned>(grid_n, (unsigned)ctx->sm_count * 8u);
+        k_scene_bounds<<<red_grid, B, 0, st>>>(ctx->d_tri_flat.as<float4>(), n, ctx->d_scratch.as<float>());
+        VLB_LAUNCH_CHECK(ctx);
+        k_morton<<<grid_n, B, 0, st>>>(ctx->d_tri_flat.as<float4>(), n, ctx->d_scratch.as<float>(),
+                                      ctx->d_keys.as<uint64_t>(), ctx->d_vals.as<uint32_t>());
+        VLB_LAUNCH_CHECK(ctx);
+
+        size_t tmp_bytes = 0;
+        VLB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->d_keys.as<uint64_t>(), ctx->d_keys_sorted.as<uint64_t>(),
+                                                      ctx->d_vals.as<uint32_t>(), ctx->d_vals_sorted.as<uint32_t>(), (int)n, 0, 63, st));
+        VLB_CUDA(ctx, ctx->d_sort_tmp.reserve(tmp_bytes));
+        VLB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+        VLB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_sort_tmp.p, tmp_bytes, ctx->d_keys.as<uint64_t>(), ctx->d_keys_sorted.as<uint64_t>(),
+                                                      ctx->d_vals.as<uint32_t>(), ctx->d_vals_sorted.as<uint32_t>(), (int)n, 0, 63, st));
+        ctx->launches += 8;   // cub onesweep: histogram + 7 passes for 63 key bits (library kernels)
+        VLB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+
+        k_gather<<<grid_n, B, 0, st>>>(ctx->d_tri_flat.as<float4>(), ctx->d_vals_sorted.as<uint32_t>(), n,
+                                      ctx->d_tris.as<float4>(), ctx->d_lbox.as<float4>());
+        VLB_LAUNCH_CHECK(ctx);
+        if (n == 1) {
+            k_emit_single<<<1, 1, 0, st>>>(ctx->d_lbox.as<float4>(), ctx->d_scratch.as<float>(), ctx->d_nodes.as<float4>());
+            VLB_LAUNCH_CHECK(ctx);
+            ctx->n_nodes = 1;
+        } else {
+            VLB_CUDA(ctx, cudaMemsetAsync(ctx->d_flags.p, 0, n * sizeof(int), st));
+            k_karras<<<grid_n, B, 0, st>>>(ctx->d_keys_sorted.as<uint64_t>(), (int)n, ctx->d_left.as<int>(), ctx->d_right.as<int>(),
+                                          ctx->d_first.as<int>(), ctx->d_last.as<int>(), ctx->d_parent_i.as<int>(), ctx->d_parent_l.as<int>());
+            VLB_LAUNCH_CHECK(ctx);
+            k_refit<<<grid_n, B, 0, st>>>((int)n, ctx->d_left.as<int>(), ctx->d_right.as<int>(), ctx->d_parent_i.as<int>(),
+                                         ctx->d_parent_l.as<int>(), ctx->d_lbox.as<float4>(), ctx->d_ibox.as<float4>(), ctx->d_flags.as<int>());
+            VLB_LAUNCH_CHECK(ctx);
+            k_emit<<<grid_n, B, 0, st>>>((int)n, ctx->d_left.as<int>(), ctx->d_right.as<int>(), ctx->d_first.as<int>(), ctx->d_last.as<int>(),
+                                        ctx->d_ibox.as<float4>(), ctx->d_lbox.as<float4>(), ctx->max_leaf, ctx->d_scratch.as<float>(),
+                                        ctx->d_nodes.as<float4>());
+            VLB_LAUNCH_CHECK(ctx);
+            ctx->n_nodes = n - 1;
+        }
+    }
+    VLB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    float h[12];
+    VLB_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_scratch.p, sizeof h, cudaMemcpyDeviceToHost, st));
+    VLB_CUDA(ctx, cudaStreamSynchronize(st));
+    VLB_CUDA(ctx, cudaEventElapsedTime(&build_ms, ctx->ev[0], ctx->ev[1]));
+    if (n > 0) VLB_CUDA(ctx, cudaEventElapsedTime(&sort_ms, ctx->ev[2], ctx->ev[3]));
+    for (int k = 0; k < 6; ++k) ctx->tight_bounds[k] = n ? h[k] : 0.f;
+    ctx->have_tight_bounds = true;
+    ctx->have_bvh = true;
+    if (stats) {
+        stats->n_triangles = n; stats->n_nodes = ctx->n_nodes; stats->max_leaf_size = (uint32_t)ctx->max_leaf;
+        stats->reserved = 0;
+        for (int k = 0; k < 6; ++k) stats->bounds[k] = ctx->tight_bounds[k];
+        stats->build_ms = build_ms; stats->sort_ms = sort_ms;
+    }
+    return VLB_OK;
+}
+
+}  // namespace vlb

@@ -1,0 +1,429 @@
+// context.cu — C ABI glue of libvlb_bake.so (include/vlb_bake.h): context life cycle, scene and
+// skybox upload, host-pointer wrappers around the device paths. No compute happens on the host.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+
+#include "vlb_context.h"
+#include "vlb_math.cuh"
+
+namespace vlb {
+
+static thread_local std::string g_thread_error;
+void set_thread_error(const char* msg) { g_thread_error = msg ? msg : ""; }
+
+// ---- flatten: instances x primitives -> world-space triangle soup -------------
+// One thread per flat triangle. Positions are read at the reference's 44-byte vertex stride
+// (shader::Vertex, structures.h:20-26) and moved to world space by the instance transform
+// (Node_t::getMatrix, src/scene_manager.cpp:445-461); normals stay in object space as
+// env_map.rchit:59-64 reads them.
+__global__ void k_flatten(const float* __restrict__ verts, const uint32_t* __restrict__ indices,
+                          const InstanceDev* __restrict__ insts, const uint32_t* __restrict__ tri_offsets,
+                          uint32_t n_insts, uint32_t n_tris, float4* __restrict__ tri_flat,
+                          float4* __restrict__ tri_shade) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tris) return;
+    // binary search: last instance with tri_offset <= t
+    uint32_t lo = 0, hi = n_insts;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (tri_offsets[mid] <= t) lo = mid; else hi = mid;
+    }
+    const InstanceDev& in = insts[lo];
+    const uint32_t local = t - tri_offsets[lo];
+    const uint32_t* ix = indices + in.first_index + 3ull * local;
+    Vec3 p[3], n[3];
+    for (int k = 0; k < 3; ++k) {
+        const float* v = verts + 11ull * (in.first_vertex + ix[k]);
+        p[k] = xform_point(in.m, mk3(v[0], v[1], v[2]));
+        n[k] = mk3(v[4], v[5], v[6]);
+    }
+    tri_flat[3ull * t + 0] = make_float4(p[0].x, p[0].y, p[0].z, __int_as_float((int)t));
+    tri_flat[3ull * t + 1] = make_float4(f_sub(p[1].x, p[0].x), f_sub(p[1].y, p[0].y), f_sub(p[1].z, p[0].z), 0.f);
+    tri_flat[3ull * t + 2] = make_float4(f_sub(p[2].x, p[0].x), f_sub(p[2].y, p[0].y), f_sub(p[2].z, p[0].z), 0.f);
+    tri_shade[3ull * t + 0] = make_float4(n[0].x, n[0].y, n[0].z, __int_as_float((int)lo));
+    tri_shade[3ull * t + 1] = make_float4(n[1].x, n[1].y, n[1].z, 0.f);
+    tri_shade[3ull * t + 2] = make_float4(n[2].x, n[2].y, n[2].z, 0.f);
+}
+
+__global__ void k_rgba8_to_f32(const uchar4* __restrict__ in, float4* __restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uchar4 c = in[i];
+    out[i] = make_float4((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f, (float)c.w / 255.0f);
+}
+
+static int check_device(vlb_ctx* ctx) {
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return ctx->fail(VLB_ERR_NO_DEVICE, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
+    return VLB_OK;
+}
+
+}  // namespace vlb
+
+using namespace vlb;
+
+extern "C" {
+
+int vlb_abi_version(void) { return VLB_ABI_VERSION; }
+
+const char* vlb_last_error(const vlb_ctx* ctx) {
+    if (ctx) return ctx->err.c_str();
+    return g_thread_error.c_str();
+}
+
+int vlb_ctx_create(int device_id, vlb_ctx** out) {
+    if (!out) { set_thread_error("vlb_ctx_create: out is NULL"); return VLB_ERR_INVALID; }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "vlb_ctx_create: no CUDA device (%s); this library has no CPU path",
+                 e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        set_thread_error(buf);
+        cudaGetLastError();
+        return VLB_ERR_NO_DEVICE;
+    }
+    if (device_id < 0 || device_id >= count) { set_thread_error("vlb_ctx_create: device id out of range"); return VLB_ERR_INVALID; }
+    vlb_ctx* ctx = new (std::nothrow) vlb_ctx();
+    if (!ctx) { set_thread_error("vlb_ctx_create: out of host memory"); return VLB_ERR_NOMEM; }
+    ctx->device = device_id;
+    e = cudaSetDevice(device_id);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device_id);
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    if (e != cudaSuccess) {
+        set_thread_error(cudaGetErrorString(e));
+        delete ctx;
+        return VLB_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return VLB_OK;
+}
+
+void vlb_ctx_destroy(vlb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* bufs[] = {&ctx->d_verts, &ctx->d_indices, &ctx->d_insts_in, &ctx->d_tri_offsets, &ctx->d_tri_flat,
+                      &ctx->d_tri_shade, &ctx->d_inst, &ctx->d_base_color, &ctx->d_tris, &ctx->d_nodes, &ctx->d_keys,
+                      &ctx->d_keys_sorted, &ctx->d_vals, &ctx->d_vals_sorted, &ctx->d_sort_tmp, &ctx->d_left,
+                      &ctx->d_right, &ctx->d_first, &ctx->d_last, &ctx->d_parent_i, &ctx->d_parent_l, &ctx->d_flags,
+                      &ctx->d_ibox, &ctx->d_lbox, &ctx->d_scratch, &ctx->d_sky, &ctx->d_proj_in, &ctx->d_proj_out,
+                      &ctx->d_proj_partials, &ctx->d_proj_counters, &ctx->d_row_tab, &ctx->d_col_tab, &ctx->d_bake_out,
+                      &ctx->d_partials, &ctx->d_work_counter, &ctx->d_axis, &ctx->d_row_sc, &ctx->d_col_sc,
+                      &ctx->d_stats, &ctx->d_ray_o, &ctx->d_ray_d, &ctx->d_hit_id, &ctx->d_hit_tuv, &ctx->d_hit_key};
+    for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int vlb_ctx_set_stream(vlb_ctx* ctx, uint64_t handle) {
+    if (!ctx) return VLB_ERR_INVALID;
+    ctx->stream = handle ? reinterpret_cast<cudaStream_t>(handle) : ctx->own_stream;
+    return VLB_OK;
+}
+
+int vlb_ctx_synchronize(vlb_ctx* ctx) {
+    if (!ctx) return VLB_ERR_INVALID;
+    if (int r = check_device(ctx)) return r;
+    VLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VLB_OK;
+}
+
+uint64_t vlb_ctx_launch_count(const vlb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int vlb_scene_set_triangles(vlb_ctx* ctx, const vlb_vertex* vertices, uint64_t n_vertices,
+                            const uint32_t* indices, uint64_t n_indices, const vlb_instance* instances,
+                            uint32_t n_instances, const vlb_material* materials, uint32_t n_materials) {
+    if (!ctx) return VLB_ERR_INVALID;
+    if (int r = check_device(ctx)) return r;
+    static_assert(sizeof(vlb_vertex) == 44, "shader::Vertex is 44 bytes (structures.h:20-26)");
+    static_assert(sizeof(vlb_material) == 144, "shader::Material is 144 bytes (structures.h:28-71)");
+    if ((n_vertices && !vertices) || (n_indices && !indices) || (n_instances && !instances) ||
+        (n_materials && !materials))
+        return ctx->fail(VLB_ERR_INVALID, "vlb_scene_set_triangles: NULL array with non-zero count");
+    ctx->have_scene = false; ctx->have_bvh = false; ctx->have_tight_bounds = false;
+
+    // per-instance records + reference bounds (Scene_t::loadNode, src/scene_manager.cpp:497-507:
+    // bounds start at the origin and take the two transformed corners of the local AABB)
+    std::vector<InstanceDev> insts(n_instances);
+    std::vector<uint32_t> offsets(n_instances + 1, 0);
+    std::vector<float4> inst_rec(3 * (size_t)n_instances);
+    for (int k = 0; k < 6; ++k) ctx->ref_bounds[k] = 0.f;
+    uint64_t tri_total = 0;
+    for (uint32_t i = 0; i < n_instances; ++i) {
+        const vlb_instance& vi = instances[i];
+        if ((uint64_t)vi.first_index + vi.index_count > n_indices || (uint64_t)vi.first_vertex + vi.vertex_count > n_vertices)
+            return ctx->fail(VLB_ERR_INVALID, "vlb_scene_set_triangles: instance %u exceeds the vertex/index arrays", i);
+        InstanceDev& d = insts[i];
+        std::memcpy(d.m, vi.transform, sizeof d.m);
+        host_inverse3x3(d.m, d.minv);
+        d.first_index = vi.first_index; d.first_vertex = vi.first_vertex;
+        // default material = last entry (src/scene_manager.cpp:510, 851)
+        d.material = vi.material_index < n_materials ? vi.material_index : (n_materials ? n_materials - 1 : 0);
+        d.tri_offset = (uint32_t)tri_total;
+        offsets[i] = (uint32_t)tri_total;
+        tri_total += vi.index_count / 3;
+        inst_rec[3 * i + 0] = make_float4(d.minv[0], d.minv[1], d.minv[2], 0.f);
+        std::memcpy(&inst_rec[3 * i + 0].w, &d.material, 4);
+        inst_rec[3 * i + 1] = make_float4(d.minv[3], d.minv[4], d.minv[5], 0.f);
+        inst_rec[3 * i + 2] = make_float4(d.minv[6], d.minv[7], d.minv[8], 0.f);
+        for (uint32_t k = 0; k < vi.index_count; ++k)
+            if (indices[vi.first_index + k] >= vi.vertex_count)
+                return ctx->fail(VLB_ERR_INVALID, "vlb_scene_set_triangles: index out of range in instance %u", i);
+        if (vi.vertex_count) {
+            float lo[3] = {3.4e38f, 3.4e38f, 3.4e38f}, hi[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+            for (uint32_t v = 0; v < vi.vertex_count; ++v) {
+                const float* p = vertices[vi.first_vertex + v].position;
+                for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); }
+            }
+            const float* m = d.m;
+            float a[3], b[3];
+            for (int r = 0; r < 3; ++r) {
+                a[r] = fmaf(m[4 * r + 2], lo[2], fmaf(m[4 * r + 1], lo[1], fmaf(m[4 * r + 0], lo[0], m[4 * r + 3])));
+                b[r] = fmaf(m[4 * r + 2], hi[2], fmaf(m[4 * r + 1], hi[1], fmaf(m[4 * r + 0], hi[0], m[4 * r + 3])));
+            }
+            for (int k = 0; k < 3; ++k) {
+                ctx->ref_bounds[k] = std::min(ctx->ref_bounds[k], a[k]);
+                ctx->ref_bounds[3 + k] = std::max(ctx->ref_bounds[3 + k], b[k]);
+            }
+        }
+    }
+    offsets[n_instances] = (uint32_t)tri_total;
+    if (tri_total >= (1ull << 28)) return ctx->fail(VLB_ERR_UNSUPPORTED, "more than 2^28 triangles");
+
+    // resolved baseColor per material (env_map.rchit:36-49; texture branch: SURVEY §8 f3)
+    std::vector<float4> base(std::max<uint32_t>(n_materials, 1), make_float4(1.f, 1.f, 1.f, 1.f));
+    for (uint32_t m = 0; m < n_materials; ++m) {
+        const float* f = materials[m].base_color_factor;
+        if (f[0] != 0.f || f[1] != 0.f || f[2] != 0.f || f[3] != 0.f) base[m] = make_float4(f[0], f[1], f[2], f[3]);
+    }
+
+    ctx->n_tris = tri_total; ctx->n_verts = n_vertices; ctx->n_indices = n_indices;
+    ctx->n_insts = n_instances; ctx->n_mats = n_materials;
+    VLB_CUDA(ctx, ctx->d_verts.reserve(n_vertices * sizeof(vlb_vertex)));
+    VLB_CUDA(ctx, ctx->d_indices.reserve(n_indices * sizeof(uint32_t)));
+    VLB_CUDA(ctx, ctx->d_insts_in.reserve(insts.size() * sizeof(InstanceDev)));
+    VLB_CUDA(ctx, ctx->d_tri_offsets.reserve(offsets.size() * sizeof(uint32_t)));
+    VLB_CUDA(ctx, ctx->d_inst.reserve(inst_rec.size() * sizeof(float4)));
+    VLB_CUDA(ctx, ctx->d_base_color.reserve(base.size() * sizeof(float4)));
+    VLB_CUDA(ctx, ctx->d_tri_flat.reserve(3 * tri_total * sizeof(float4)));
+    VLB_CUDA(ctx, ctx->d_tri_shade.reserve(3 * tri_total * sizeof(float4)));
+    cudaStream_t st = ctx->stream;
+    if (n_vertices) VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_verts.p, vertices, n_vertices * sizeof(vlb_vertex), cudaMemcpyHostToDevice, st));
+    if (n_indices) VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_indices.p, indices, n_indices * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    if (n_instances) {
+        VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_insts_in.p, insts.data(), insts.size() * sizeof(InstanceDev), cudaMemcpyHostToDevice, st));
+        VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_inst.p, inst_rec.data(), inst_rec.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+    }
+    VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_tri_offsets.p, offsets.data(), offsets.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_base_color.p, base.data(), base.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
+    if (tri_total) {
+        const uint32_t n = (uint32_t)tri_total;
+        k_flatten<<<(n + 255) / 256, 256, 0, st>>>(ctx->d_verts.as<float>(), ctx->d_indices.as<uint32_t>(),
+                                                   ctx->d_insts_in.as<InstanceDev>(), ctx->d_tri_offsets.as<uint32_t>(),
+                                                   n_instances, n, ctx->d_tri_flat.as<float4>(), ctx->d_tri_shade.as<float4>());
+        VLB_LAUNCH_CHECK(ctx);
+    }
+    // host staging vectors die at scope exit: the copies above must have completed
+    VLB_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->have_scene = true;
+    return VLB_OK;
+}
+
+int vlb_scene_bounds(vlb_ctx* ctx, int tight, float out[6]) {
+    if (!ctx || !out) return VLB_ERR_INVALID;
+    if (!ctx->have_scene) return ctx->fail(VLB_ERR_STATE, "vlb_scene_bounds: no scene set");
+    if (!tight) { std::memcpy(out, ctx->ref_bounds, sizeof ctx->ref_bounds); return VLB_OK; }
+    if (!ctx->have_tight_bounds) {
+        int r = vlb_bvh_build(ctx, nullptr);   // the build computes the tight AABB on the device
+        if (r) return r;
+    }
+    std::memcpy(out, ctx->tight_bounds, sizeof ctx->tight_bounds);
+    return VLB_OK;
+}
+
+int vlb_bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats) {
+    if (!ctx) return VLB_ERR_INVALID;
+    if (int r = check_device(ctx)) return r;
+    if (!ctx->have_scene) return ctx->fail(VLB_ERR_STATE, "vlb_bvh_build: no scene set");
+    return bvh_build(ctx, stats);
+}
+
+int vlb_skybox_set(vlb_ctx* ctx, const void* texels, int format, int width, int height) {
+    if (!ctx) return VLB_ERR_INVALID;
+    if (int r = check_device(ctx)) return r;
+    if (!texels || width <= 0 || height <= 0 || (format != VLB_FMT_RGBA8 && format != VLB_FMT_RGBA32F))
+        return ctx->fail(VLB_ERR_INVALID, "vlb_skybox_set: bad arguments");
+    const size_t n = (size_t)width * height;
+    VLB_CUDA(ctx, ctx->d_sky.reserve(n * sizeof(float4)));
+    if (format == VLB_FMT_RGBA32F) {
+        VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_sky.p, texels, n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        VLB_CUDA(ctx, ctx->d_proj_in.reserve(n * 4));
+        VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_proj_in.p, texels, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        k_rgba8_to_f32<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_proj_in.as<uchar4>(), ctx->d_sky.as<float4>(), n);
+        VLB_LAUNCH_CHECK(ctx);
+    }
+    VLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->sky_w = width; ctx->sky_h = height;
+    return VLB_OK;
+}
+
+static int project_host(vlb_ctx* ctx, const void* const* maps, uint32_t n_maps, int format, int W, int H, int order,
+                        int variant, float* out) {
+    if (!ctx) return VLB_ERR_INVALID;
+    if (int r = check_device(ctx)) return r;
+    if (!maps || !out || n_maps == 0 || W <= 0 || H <= 0 || (order != 2 && order != 3) ||
+        (format != VLB_FMT_RGBA8 && format != VLB_FMT_RGBA32F))
+        return ctx->fail(VLB_ERR_INVALID, "project_sh: bad arguments");
+    const size_t bpt = format == VLB_FMT_RGBA32F ? 16 : 4;
+    const size_t map_bytes = (size_t)W * H * bpt;
+    const size_t stride = (map_bytes + 255) & ~size_t(255);
+    VLB_CUDA(ctx, ctx->d_proj_in.reserve(stride * n_maps));
+    VLB_CUDA(ctx, ctx->d_proj_out.reserve((size_t)n_maps * VLB_SH_STRIDE * sizeof(float)));
+    for (uint32_t i = 0; i < n_maps; ++i) {
+        if (!maps[i]) return ctx->fail(VLB_ERR_INVALID, "project_sh: maps[%u] is NULL", i);
+        VLB_CUDA(ctx, cudaMemcpyAsync((char*)ctx->d_proj_in.p + stride * i, maps[i], map_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    int r = project_sh_device(ctx, ctx->d_proj_in.p, stride, n_maps, format, W, H, order, variant, ctx->d_proj_out.as<float>());
+    if (r) return r;
+    VLB_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_proj_out.p, (size_t)n_maps * VLB_SH_STRIDE * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    VLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VLB_OK;
+}
+
+int vlb_skybox_project_sh(vlb_ctx* ctx, const void* texels, int format, int width, int height, int sh_order, float* out48) {
+    const void* maps[1] = {texels};
+    return project_host(ctx, texels ? maps : nullptr, 1, format, width, height, sh_order, 0, out48);
+}
+
+int vlb_skybox_project_sh_batched(vlb_ctx* ctx, const void* const* maps, uint32_t n_maps, int format, int width,
+                                  int height, int sh_order, float* out) {
+    return project_host(ctx, maps, n_maps, format, width, height, sh_order, 0, out);
+}
+
+int vlb_envmap_project_sh(vlb_ctx* ctx, const void* texels, int format, int width, int height, int sh_order, float* out48) {
+    const void* maps[1] = {texels};
+    return project_host(ctx, texels ? maps : nullptr, 1, format, width, height, sh_order, 1, out48);
+}
+
+int vlb_skybox_project_sh_device(vlb_ctx* ctx, const void* d_texels, uint64_t map_stride_bytes, uint32_t n_maps,
+                                 int format, int width, int height, int sh_order, float* d_out) {
+    if (!ctx) return VLB_ERR_INVALID;
+    if (int r = check_device(ctx)) return r;
+    if (!d_texels || !d_out || n_maps == 0 || width <= 0 || height <= 0 || (sh_order != 2 && sh_order != 3) ||
+        (format != VLB_FMT_RGBA8 && format != VLB_FMT_RGBA32F))
+        return ctx->fail(VLB_ERR_INVALID, "vlb_skybox_project_sh_device: bad arguments");
+    return project_sh_device(ctx, d_texels, map_stride_bytes, n_maps, format, width, height, sh_order, 0, d_out);
+}
+
+// ---- bake -------------------------------------------------------------------------------
+void vlb_bake_settings_default(vlb_bake_settings* s) {
+    if (!s) return;
+    std::memset(s, 0, sizeof *s);
+    s->probes[0] = s->probes[1] = s->probes[2] = 7;        // light_baker.cpp:38
+    s->step[0] = s->step[1] = s->step[2] = 1.f;
+    s->dir_w = 3141; s->dir_h = 1000;                       // light_baker.cpp:65, env_map_generator.cpp:24-28
+    s->sh_order = 3;                                        // 16 coefficients, light_baker.cpp:294
+    s->light_pos[0] = 1.f; s->light_pos[1] = 10.f; s->light_pos[2] = 1.f;   // env_map.rchit:25
+    s->shadow_bias = 0.005f; s->c_diffuse = 0.5f; s->c_specular = 0.5f; s->gloss = 16.f; s->ambient = 0.f;
+    s->tmin = 0.001f; s->tmax = 10000.f;                    // env_map.rgen:22-23
+    s->flags = VLB_BAKE_SHADOW_RAYS | VLB_BAKE_SKYBOX_ON_MISS | VLB_BAKE_SRGB_ENCODE | VLB_BAKE_QUANTIZE_RGBA8;
+    s->slab_k0 = 0; s->slab_k1 = -1;
+}
+
+int vlb_bake_settings_from_bounds(vlb_bake_settings* s, const float b[6]) {
+    if (!s || !b) return VLB_ERR_INVALID;
+    for (int d = 0; d < 3; ++d) {
+        if (s->probes[d] < 1) return VLB_ERR_INVALID;
+        s->origin[d] = b[d];
+        // gridStep = (max - min) / (count - 1) (light_baker.cpp:85); a single probe divides by zero
+        // in the reference, here the step is 0.
+        s->step[d] = s->probes[d] > 1 ? (b[3 + d] - b[d]) / ((float)s->probes[d] - 1.f) : 0.f;
+    }
+    return VLB_OK;
+}
+
+int vlb_probe_positions(const vlb_bake_settings* s, float* out) {
+    if (!s || !out || s->probes[0] < 1 || s->probes[1] < 1 || s->probes[2] < 1) return VLB_ERR_INVALID;
+    const int Nx = s->probes[0], Ny = s->probes[1], Nz = s->probes[2];
+    std::vector<float> px(Nx), py(Ny), pz(Nz);
+    host_axis_coords(s->origin[0], s->step[0], Nx, px.data());
+    host_axis_coords(s->origin[1], s->step[1], Ny, py.data());
+    host_axis_coords(s->origin[2], s->step[2], Nz, pz.data());
+    for (int k = 0; k < Nz; ++k) for (int j = 0; j < Ny; ++j) for (int i = 0; i < Nx; ++i) {
+        const size_t idx = (s->flags & VLB_BAKE_REFERENCE_PROBE_ORDER) ? ref_order_index(i, j, k, Nx, Ny, Nz)
+                                                                     : (size_t)i + (size_t)j * Nx + (size_t)k * Nx * Ny;
+        out[3 * idx] = px[i]; out[3 * idx + 1] = py[j]; out[3 * idx + 2] = pz[k];
+    }
+    return VLB_OK;
+}
+
+static int slab_range(vlb_ctx* ctx, const vlb_bake_settings* s, int* k0, int* k1) {
+    if (!s) return ctx->fail(VLB_ERR_INVALID, "bake: settings is NULL");
+    if (s->probes[0] < 1 || s->probes[1] < 1 || s->probes[2] < 1 || s->dir_w < 1 || s->dir_h < 1 ||
+        (s->sh_order != 2 && s->sh_order != 3))
+        return ctx->fail(VLB_ERR_INVALID, "bake: bad probe grid / direction grid / sh_order");
+    *k0 = s->slab_k1 < 0 ? 0 : s->slab_k0;
+    *k1 = s->slab_k1 < 0 ? s->probes[2] : s->slab_k1;
+    if (*k0 < 0 || *k1 > s->probes[2] || *k0 > *k1) return ctx->fail(VLB_ERR_INVALID, "bake: bad slab range");
+    if ((s->flags & (VLB_BAKE_REFERENCE_PROBE_ORDER | VLB_BAKE_ACCUMULATE_ACROSS_PROBES)) &&
+        (*k0 != 0 || *k1 != s->probes[2]))
+        return ctx->fail(VLB_ERR_INVALID, "bake: reference probe order / accumulation need the whole grid");
+    return VLB_OK;
+}
+
+int vlb_bake_probes_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out) {
+    if (!ctx) return VLB_ERR_INVALID;
+    if (int r = check_device(ctx)) return r;
+    int k0, k1;
+    if (int r = slab_range(ctx, s, &k0, &k1)) return r;
+    if (!d_out) return ctx->fail(VLB_ERR_INVALID, "bake: output is NULL");
+    if (!ctx->have_scene) return ctx->fail(VLB_ERR_STATE, "bake: no scene set (vlb_scene_set_triangles)");
+    if (!ctx->have_bvh) { if (int r = bvh_build(ctx, nullptr)) return r; }
+    if ((s->flags & VLB_BAKE_SKYBOX_ON_MISS) && ctx->sky_w == 0)
+        return ctx->fail(VLB_ERR_STATE, "bake: VLB_BAKE_SKYBOX_ON_MISS without a skybox (vlb_skybox_set)");
+    return bake_device(ctx, s, d_out);
+}
+
+int vlb_bake_probes(vlb_ctx* ctx, const vlb_bake_settings* s, float* out) {
+    if (!ctx) return VLB_ERR_INVALID;
+    if (int r = check_device(ctx)) return r;
+    int k0, k1;
+    if (int r = slab_range(ctx, s, &k0, &k1)) return r;
+    if (!out) return ctx->fail(VLB_ERR_INVALID, "bake: output is NULL");
+    const size_t n = (size_t)s->probes[0] * s->probes[1] * (size_t)(k1 - k0);
+    if (n == 0) return VLB_OK;
+    VLB_CUDA(ctx, ctx->d_bake_out.reserve(n * VLB_SH_STRIDE * sizeof(float)));
+    if (int r = vlb_bake_probes_device(ctx, s, ctx->d_bake_out.as<float>())) return r;
+    VLB_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_bake_out.p, n * VLB_SH_STRIDE * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    VLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VLB_OK;
+}
+
+int vlb_bake_last_stats(vlb_ctx* ctx, vlb_bake_stats* out) {
+    if (!ctx || !out) return VLB_ERR_INVALID;
+    *out = ctx->last_bake;
+    return VLB_OK;
+}
+
+int vlb_trace_rays(vlb_ctx* ctx, const float* origins, const float* dirs, uint64_t n, float tmin, float tmax,
+                   int accel, int kind, int32_t* hit_ids, float* hit_tuv) {
+    if (!ctx) return VLB_ERR_INVALID;
+    if (int r = check_device(ctx)) return r;
+    if (!origins || !dirs || !hit_ids) return ctx->fail(VLB_ERR_INVALID, "vlb_trace_rays: NULL argument");
+    if (!ctx->have_scene) return ctx->fail(VLB_ERR_STATE, "vlb_trace_rays: no scene set");
+    if (accel == VLB_TRACE_BVH && !ctx->have_bvh) { if (int r = bvh_build(ctx, nullptr)) return r; }
+    if (n == 0) return VLB_OK;
+    return trace_rays(ctx, origins, dirs, n, tmin, tmax, accel, kind, hit_ids, hit_tuv);
+}
+
+}  // extern "C"

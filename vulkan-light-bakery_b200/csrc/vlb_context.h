@@ -1,0 +1,127 @@
+// vlb_context.h — internal C++ side of libvlb_bake.so: the context object behind the C ABI
+// (include/vlb_bake.h), device buffers, error plumbing and launch accounting.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/vlb_bake.h"
+
+namespace vlb {
+
+void set_thread_error(const char* msg);
+
+// Owning device allocation. Grows on demand, never shrinks (buffers are reused across calls).
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+        if (e == cudaSuccess) cap = bytes ? bytes : 16;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct InstanceDev {       // device-side instance record used by the flatten kernel
+    float m[12];
+    float minv[9];
+    uint32_t first_index, first_vertex, material, tri_offset;
+};
+
+}  // namespace vlb
+
+struct vlb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+
+    // ---- scene ----
+    bool have_scene = false, have_bvh = false;
+    uint64_t n_tris = 0, n_verts = 0, n_indices = 0;
+    uint32_t n_insts = 0, n_mats = 0;
+    float ref_bounds[6] = {0, 0, 0, 0, 0, 0};
+    float tight_bounds[6] = {0, 0, 0, 0, 0, 0};
+    bool have_tight_bounds = false;
+    vlb::DevBuf d_verts, d_indices, d_insts_in, d_tri_offsets;
+    vlb::DevBuf d_tri_flat;   // 3 float4 per triangle, flat order (before Morton sort)
+    vlb::DevBuf d_tri_shade;  // 3 float4 per triangle, flat order
+    vlb::DevBuf d_inst;       // 3 float4 per instance
+    vlb::DevBuf d_base_color; // float4 per material
+    // ---- BVH ----
+    vlb::DevBuf d_tris;       // 3 float4 per triangle, Morton order
+    vlb::DevBuf d_nodes;      // 4 float4 per node
+    vlb::DevBuf d_keys, d_keys_sorted, d_vals, d_vals_sorted, d_sort_tmp;
+    vlb::DevBuf d_left, d_right, d_first, d_last, d_parent_i, d_parent_l, d_flags, d_ibox, d_lbox, d_scratch;
+    uint64_t n_nodes = 0;
+    int max_leaf = 4;
+    // ---- skybox ----
+    vlb::DevBuf d_sky;        // RGBA32F
+    int sky_w = 0, sky_h = 0;
+    // ---- projection (skybox / envmap) ----
+    vlb::DevBuf d_proj_in, d_proj_out, d_proj_partials, d_proj_counters, d_row_tab, d_col_tab;
+    int tab_w = 0, tab_h = 0, tab_variant = -1;
+    // ---- bake ----
+    vlb::DevBuf d_bake_out, d_partials, d_work_counter, d_axis, d_row_sc, d_col_sc, d_stats;
+    int dir_w = 0, dir_h = 0;
+    vlb_bake_stats last_bake{};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // ---- trace ----
+    vlb::DevBuf d_ray_o, d_ray_d, d_hit_id, d_hit_tuv, d_hit_key;
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+        err = buf;
+        vlb::set_thread_error(buf);
+        return code;
+    }
+};
+
+#define VLB_CUDA(ctx, expr)                                                                      \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess)                                                                   \
+            return (ctx)->fail(VLB_ERR_CUDA, "%s:%d: %s -> %s", __FILE__, __LINE__, #expr,        \
+                               cudaGetErrorString(_e));                                          \
+    } while (0)
+
+#define VLB_LAUNCH_CHECK(ctx)                                                                    \
+    do {                                                                                         \
+        (ctx)->launches++;                                                                       \
+        cudaError_t _e = cudaGetLastError();                                                     \
+        if (_e != cudaSuccess)                                                                   \
+            return (ctx)->fail(VLB_ERR_CUDA, "%s:%d: kernel launch -> %s", __FILE__, __LINE__,   \
+                               cudaGetErrorString(_e));                                          \
+    } while (0)
+
+namespace vlb {
+// host_tables.cpp
+void host_axis_coords(float origin, float step, int n, float* out);
+void host_dir_tables(int W, int H, float phi_shift, float* row_sc /*H x 2: sin,cos theta*/,
+                     float* col_cs /*W x 2: cos,sin phi*/);
+void host_proj_row_table(int W, int H, float* row_tab /*H x 8*/);
+void host_inverse3x3(const float* m12, float* out9);
+size_t ref_order_index(int i, int j, int k, int Nx, int Ny, int Nz);
+
+// implemented in the .cu files
+int scene_flatten(vlb_ctx* ctx);
+int bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats);
+int project_sh_device(vlb_ctx* ctx, const void* d_texels, uint64_t map_stride, uint32_t n_maps, int fmt,
+                      int W, int H, int order, int variant, float* d_out);
+int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out);
+int trace_rays(vlb_ctx* ctx, const float* o, const float* d, uint64_t n, float tmin, float tmax, int accel,
+               int kind, int32_t* ids, float* tuv);
+}  // namespace vlb

@@ -1,0 +1,143 @@
+// vlb_shade.cuh — radiance of one probe ray: the CUDA restatement of what the reference does in
+// shaders/env_map.rgen:18-28 (ray), env_map.rchit:51-102 (hit shading + shadow ray),
+// main.rmiss:18-41 (sky lookup) and shadow.rmiss:6-9 (visibility).
+#pragma once
+
+#include "vlb_bvh.cuh"
+
+namespace vlb {
+
+// Device-resident shading inputs (all 16-byte records):
+//   tri_shade[3*id+0..2]  id = flat triangle id: (n0.xyz, bits(instance)), (n1.xyz, 0), (n2.xyz, 0)
+//                         OBJECT-space vertex normals, as env_map.rchit:59-64 fetches them
+//   inst[3*k+0..2]        (Minv row0.xyz, bits(material)), (Minv row1.xyz, 0), (Minv row2.xyz, 0)
+//   base_color[m]         resolved baseColor of material m (env_map.rchit:36-49, factor path)
+struct ShadeView {
+    const float4* tri_shade;
+    const float4* inst;
+    const float4* base_color;
+    const float4* sky;       // RGBA32F texels, NULL if no skybox set
+    int sky_w, sky_h;
+};
+
+struct BakeConsts {
+    float light[3];
+    float shadow_bias, c_diffuse, c_specular, gloss, ambient;
+    float tmin, tmax;
+    uint32_t flags;
+};
+
+VLB_HD float glsl_mod(float x, float y) { return x - y * floorf(x / y); }
+VLB_HD float clampf(float x, float a, float b) { return fminf(fmaxf(x, a), b); }
+VLB_HD int wrapi(int i, int n) { int r = i % n; return r < 0 ? r + n : r; }
+
+// main.rmiss:18-35 + bilinear / repeat lookup at LOD 0 (sampler: src/application.hpp:45-52)
+VLB_HD void sky_lookup(const ShadeView& s, Vec3 dir, float rgb[3]) {
+    float theta = acosf(clampf(dir.y, -1.0f, 1.0f));
+    float phi = atan2f(dir.x, dir.z);
+    theta = glsl_mod(theta, 2.0f * kPi);
+    theta = clampf(theta, 0.0f, 2.0f * kPi);
+    if (theta > kPi) { theta = 2.0f * kPi - theta; phi += kPi; }
+    phi = glsl_mod(phi, 2.0f * kPi);
+    phi = clampf(phi, 0.0f, 2.0f * kPi);
+    const float u = phi / (2.0f * kPi), v = theta / kPi;
+    const int W = s.sky_w, H = s.sky_h;
+    const float fx = u * (float)W - 0.5f, fy = v * (float)H - 0.5f;
+    const float flx = floorf(fx), fly = floorf(fy);
+    const float ax = fx - flx, ay = fy - fly;
+    const int x0 = wrapi((int)flx, W), x1 = wrapi((int)flx + 1, W);
+    const int y0 = wrapi((int)fly, H), y1 = wrapi((int)fly + 1, H);
+    const float4 p00 = ld4(s.sky + (size_t)y0 * W + x0);
+    const float4 p10 = ld4(s.sky + (size_t)y0 * W + x1);
+    const float4 p01 = ld4(s.sky + (size_t)y1 * W + x0);
+    const float4 p11 = ld4(s.sky + (size_t)y1 * W + x1);
+    const float t0 = p00.x + (p10.x - p00.x) * ax, b0 = p01.x + (p11.x - p01.x) * ax;
+    const float t1 = p00.y + (p10.y - p00.y) * ax, b1 = p01.y + (p11.y - p01.y) * ax;
+    const float t2 = p00.z + (p10.z - p00.z) * ax, b2 = p01.z + (p11.z - p01.z) * ax;
+    rgb[0] = t0 + (b0 - t0) * ay;
+    rgb[1] = t1 + (b1 - t1) * ay;
+    rgb[2] = t2 + (b2 - t2) * ay;
+}
+
+VLB_HD float quant8(float c) {
+    // imageStore to rgba8 (src/baker/env_map_generator.hpp:39): clamp, round-half-even to n/255
+    return rintf(clampf(c, 0.0f, 1.0f) * 255.0f) / 255.0f;
+}
+
+// Hit shading up to the point where the shadow ray is needed. Returns false when no light
+// reaches the point regardless of occlusion (sDotN == 0), i.e. no shadow ray is traced.
+struct ShadePrelude {
+    Vec3 N, Ln, so;     // shading normal, unit light vector, biased shadow-ray origin
+    float llen, sDotN;
+    float bc[3];
+};
+
+VLB_HD bool shade_prelude(const ShadeView& s, const BakeConsts& c, const HitRec& h, Vec3 o, Vec3 r,
+                          ShadePrelude& p) {
+    const float4 a0 = ld4(s.tri_shade + 3 * (size_t)h.id + 0);
+    const float4 a1 = ld4(s.tri_shade + 3 * (size_t)h.id + 1);
+    const float4 a2 = ld4(s.tri_shade + 3 * (size_t)h.id + 2);
+    const int inst = f2i(a0.w);
+    const float4 m0 = ld4(s.inst + 3 * (size_t)inst + 0);
+    const float4 m1 = ld4(s.inst + 3 * (size_t)inst + 1);
+    const float4 m2 = ld4(s.inst + 3 * (size_t)inst + 2);
+    const float4 bc = ld4(s.base_color + f2i(m0.w));
+    p.bc[0] = bc.x; p.bc[1] = bc.y; p.bc[2] = bc.z;
+    const float b0 = 1.0f - h.u - h.v, b1 = h.u, b2 = h.v;              // env_map.rchit:63
+    const Vec3 nrm = mk3(a0.x * b0 + a1.x * b1 + a2.x * b2, a0.y * b0 + a1.y * b1 + a2.y * b2,
+                         a0.z * b0 + a1.z * b1 + a2.z * b2);            // :64
+    const float nm[9] = {m0.x, m0.y, m0.z, m1.x, m1.y, m1.z, m2.x, m2.y, m2.z};
+    p.N = normalize_exact(xform_normal(nm, nrm));                       // :68
+    const Vec3 P = mk3(f_fma(r.x, h.t, o.x), f_fma(r.y, h.t, o.y), f_fma(r.z, h.t, o.z));  // :67
+    const Vec3 L = mk3(c.light[0] - P.x, c.light[1] - P.y, c.light[2] - P.z);             // :73
+    p.llen = f_sqrt(dot_exact(L, L));
+    p.Ln = mk3(f_div(L.x, p.llen), f_div(L.y, p.llen), f_div(L.z, p.llen));
+    p.sDotN = fmaxf(dot_exact(p.Ln, p.N), 0.0f);                        // :79
+    p.so = mk3(f_fma(c.shadow_bias, p.N.x, P.x), f_fma(c.shadow_bias, p.N.y, P.y),
+               f_fma(c.shadow_bias, p.N.z, P.z));                       // :82
+    return p.sDotN != 0.0f;                                             // :84
+}
+
+VLB_HD void shade_finish(const BakeConsts& c, const ShadePrelude& p, Vec3 r, bool in_shadow, float rgb[3]) {
+    float diffuse = 0.f, specular = 0.f;
+    if (!in_shadow) {                                                   // env_map.rchit:90-99
+        diffuse = c.c_diffuse * p.sDotN;
+        const float dn = dot_exact(p.N, p.Ln);
+        const Vec3 R = mk3(p.Ln.x - 2.0f * dn * p.N.x, p.Ln.y - 2.0f * dn * p.N.y, p.Ln.z - 2.0f * dn * p.N.z);
+        const float rd = fmaxf(dot_exact(R, r), 0.0f);
+        specular = c.c_specular * powf(rd, c.gloss);
+    }
+    const float k = c.ambient + diffuse + specular;
+    for (int ch = 0; ch < 3; ++ch) {
+        const float v = p.bc[ch] * k;
+        rgb[ch] = (c.flags & 4u) ? srgb_encode(v) : v;                  // :101 (VLB_BAKE_SRGB_ENCODE)
+    }
+}
+
+// Full radiance of one ray (primary + shadow), used by the bake kernel and by tests/emu.
+template <bool COUNT>
+VLB_HD void probe_ray_radiance(const BvhView& b, const ShadeView& s, const BakeConsts& c, Vec3 o, Vec3 r,
+                               float rgb[3], TraceCounters* cnt, uint32_t* shadow_rays) {
+    rgb[0] = rgb[1] = rgb[2] = 0.0f;                                    // env_map.rgen:25
+    const HitRec h = trace_closest<COUNT>(b, o, r, c.tmin, c.tmax, cnt);
+    if (h.id >= 0) {
+        ShadePrelude p;
+        bool lit = shade_prelude(s, c, h, o, r, p);
+        bool in_shadow = true;                                          // env_map.rchit:83
+        if (lit) {
+            if (c.flags & 1u) {                                         // VLB_BAKE_SHADOW_RAYS
+                if (shadow_rays) ++*shadow_rays;
+                in_shadow = trace_any<COUNT>(b, p.so, p.Ln, 0.0f, p.llen, cnt, nullptr);  // :87
+            } else {
+                in_shadow = false;
+            }
+        }
+        shade_finish(c, p, r, in_shadow, rgb);
+    } else if ((c.flags & 2u) && s.sky) {                               // VLB_BAKE_SKYBOX_ON_MISS
+        sky_lookup(s, r, rgb);
+        if (c.flags & 4u) { rgb[0] = srgb_encode(rgb[0]); rgb[1] = srgb_encode(rgb[1]); rgb[2] = srgb_encode(rgb[2]); }
+    }
+    if (c.flags & 8u) { rgb[0] = quant8(rgb[0]); rgb[1] = quant8(rgb[1]); rgb[2] = quant8(rgb[2]); }  // QUANTIZE_RGBA8
+}
+
+}  // namespace vlb

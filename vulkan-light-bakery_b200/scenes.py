@@ -1,0 +1,268 @@
+"""Synthetic inputs of the named BASELINE.json shapes (there is no network for assets): the
+procedural "atrium" scene, HDR equirect skyboxes, small KAT scenes, and the reference's own
+default cube fixture (src/vendor/default_blender_cube.gltf geometry restated as arrays).
+
+Everything is produced in the layouts the C ABI takes (include/vlb_bake.h): shader::Vertex (44 B),
+u32 indices, instances (primitive + world transform) and shader::Material (144 B).
+"""
+import math
+
+import numpy as np
+
+from . import INSTANCE_DTYPE, MATERIAL_DTYPE, VERTEX_DTYPE
+
+PALETTE = np.array([
+    [0.80, 0.80, 0.80], [0.75, 0.25, 0.20], [0.20, 0.55, 0.30], [0.25, 0.35, 0.75],
+    [0.85, 0.75, 0.35], [0.60, 0.40, 0.25], [0.90, 0.90, 0.85], [0.35, 0.35, 0.40],
+    [0.70, 0.55, 0.65], [0.45, 0.65, 0.70], [0.95, 0.60, 0.30], [0.30, 0.30, 0.30],
+    [0.65, 0.70, 0.45], [0.55, 0.25, 0.45], [0.85, 0.85, 0.95], [0.50, 0.50, 0.50]], np.float32)
+
+
+def make_materials(colors=PALETTE):
+    m = np.zeros(len(colors), MATERIAL_DTYPE)
+    m["textures"][:, :, 0] = -1                     # Texture::index = -1 (structures.h:48)
+    m["base_color_factor"][:, :3] = colors
+    m["base_color_factor"][:, 3] = 1.0
+    m["metallic"] = 1.0
+    m["roughness"] = 1.0
+    return m
+
+
+def identity12():
+    return np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32)
+
+
+def trs12(translate=(0, 0, 0), scale=(1, 1, 1), rot_y=0.0):
+    c, s = math.cos(rot_y), math.sin(rot_y)
+    r = np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]], np.float64) * np.asarray(scale, np.float64)[None, :]
+    m = np.zeros((3, 4), np.float64)
+    m[:, :3] = r
+    m[:, 3] = translate
+    return m.astype(np.float32).reshape(12)
+
+
+class _Builder:
+    def __init__(self):
+        self.v, self.i, self.inst = [], [], []
+        self.nv = 0
+        self.ni = 0
+
+    def add_mesh(self, pos, nrm, idx):
+        """Appends a mesh, returns its (first_index, index_count, first_vertex, vertex_count)."""
+        v = np.zeros(len(pos), VERTEX_DTYPE)
+        v["position"][:, :3] = pos
+        v["position"][:, 3] = 1.0
+        n = np.asarray(nrm, np.float32)
+        ln = np.linalg.norm(n, axis=1, keepdims=True)
+        v["normal"] = n / np.maximum(ln, 1e-20)
+        idx = np.asarray(idx, np.uint32).reshape(-1)
+        rec = (self.ni, idx.size, self.nv, len(pos))
+        self.v.append(v)
+        self.i.append(idx)
+        self.nv += len(pos)
+        self.ni += idx.size
+        return rec
+
+    def add_instance(self, mesh, transform, material):
+        r = np.zeros(1, INSTANCE_DTYPE)
+        r["first_index"], r["index_count"], r["first_vertex"], r["vertex_count"] = mesh
+        r["material_index"] = material
+        r["transform"] = transform
+        self.inst.append(r)
+
+    def n_tris(self):
+        return sum(int(r["index_count"][0]) // 3 for r in self.inst)
+
+    def finish(self, materials):
+        return {"vertices": np.concatenate(self.v) if self.v else np.zeros(0, VERTEX_DTYPE),
+                "indices": np.concatenate(self.i) if self.i else np.zeros(0, np.uint32),
+                "instances": np.concatenate(self.inst) if self.inst else np.zeros(0, INSTANCE_DTYPE),
+                "materials": materials}
+
+
+def _grid(nu, nv):
+    """(nu+1)x(nv+1) vertex lattice -> 2*nu*nv triangles (indices into the lattice)."""
+    a = (np.arange(nv)[:, None] * (nu + 1) + np.arange(nu)[None, :]).reshape(-1)
+    b, c, d = a + 1, a + nu + 1, a + nu + 2
+    return np.stack([a, b, d, a, d, c], 1).reshape(-1, 3)
+
+
+def _plane(origin, du, dv, nu, nv, normal, height=None):
+    u = np.linspace(0, 1, nu + 1)
+    v = np.linspace(0, 1, nv + 1)
+    uu, vv = np.meshgrid(u, v)
+    o, du, dv, normal = (np.asarray(a, np.float64) for a in (origin, du, dv, normal))
+    p = o[None, None, :] + uu[..., None] * du + vv[..., None] * dv
+    n = np.broadcast_to(normal, p.shape).copy()
+    if height is not None:
+        p = p + height[..., None] * normal
+        # finite-difference normals of the displaced sheet
+        gu = np.gradient(height, axis=1) * nu / max(np.linalg.norm(du), 1e-9)
+        gv = np.gradient(height, axis=0) * nv / max(np.linalg.norm(dv), 1e-9)
+        n = normal[None, None, :] - gu[..., None] * du / np.linalg.norm(du) - gv[..., None] * dv / np.linalg.norm(dv)
+    idx = _grid(nu, nv)
+    # orient the triangles so that the geometric normal agrees with `normal`
+    if np.dot(np.cross(du, dv), normal) < 0:
+        idx = idx[:, ::-1]
+    return p.reshape(-1, 3).astype(np.float32), n.reshape(-1, 3).astype(np.float32), idx
+
+
+def _cylinder(seg, rings):
+    """Unit cylinder: radius 1 around +y, y in [0,1], open ends, smooth normals."""
+    th = np.linspace(0, 2 * np.pi, seg + 1)
+    y = np.linspace(0, 1, rings + 1)
+    tt, yy = np.meshgrid(th, y)
+    p = np.stack([np.cos(tt), yy, np.sin(tt)], -1)
+    n = np.stack([np.cos(tt), np.zeros_like(tt), np.sin(tt)], -1)
+    return p.reshape(-1, 3).astype(np.float32), n.reshape(-1, 3).astype(np.float32), _grid(seg, rings)[:, ::-1]
+
+
+def _arch(arc_seg, tube_seg, radius, tube):
+    """Half torus in the xy plane (arch spanning x in [-radius, radius], apex at +y)."""
+    a = np.linspace(0, np.pi, arc_seg + 1)
+    b = np.linspace(0, 2 * np.pi, tube_seg + 1)
+    aa, bb = np.meshgrid(a, b)
+    cx, cy = np.cos(aa), np.sin(aa)
+    p = np.stack([(radius + tube * np.cos(bb)) * cx, (radius + tube * np.cos(bb)) * cy, tube * np.sin(bb)], -1)
+    n = np.stack([np.cos(bb) * cx, np.cos(bb) * cy, np.sin(bb)], -1)
+    return p.reshape(-1, 3).astype(np.float32), n.reshape(-1, 3).astype(np.float32), _grid(arc_seg, tube_seg)
+
+
+HALL = (30.0, 12.0, 18.0)
+ATRIUM_LIGHT = (10.0, 10.0, 6.4)     # the reference's (1,10,1) point light moved into the hall
+
+
+def atrium(n_tris=262144, seed=7):
+    """Procedural atrium with EXACTLY n_tris triangles (BASELINE.json configs 2-4):
+    open-top box hall 30x12x18 m, two tiers of tessellated columns joined by arches, gallery
+    slabs, a displaced-grid floor, factor-only materials from a 16-entry palette. Columns and
+    arches are instanced (shared meshes + per-instance transforms with non-uniform scale)."""
+    rng = np.random.default_rng(seed)
+    t = math.sqrt(n_tris / 262144.0)
+    q = lambda x: max(2, int(round(x * t)))
+    b = _Builder()
+    X, Y, Z = HALL
+    # walls (inward normals), each its own mesh with slight relief
+    walls = [((0, 0, 0), (X, 0, 0), (0, Y, 0), (0, 0, 1), q(96), q(40)),
+             ((0, 0, Z), (X, 0, 0), (0, Y, 0), (0, 0, -1), q(96), q(40)),
+             ((0, 0, 0), (0, 0, Z), (0, Y, 0), (1, 0, 0), q(56), q(40)),
+             ((X, 0, 0), (0, 0, Z), (0, Y, 0), (-1, 0, 0), q(56), q(40))]
+    for w, (o, du, dv, nrm, nu, nv) in enumerate(walls):
+        h = 0.03 * rng.standard_normal((nv + 1, nu + 1))
+        h[0, :] = h[-1, :] = 0.0
+        h[:, 0] = h[:, -1] = 0.0
+        p, n, idx = _plane(o, du, dv, nu, nv, nrm, h)
+        b.add_instance(b.add_mesh(p, n, idx), identity12(), 6 + (w & 1) * 8)
+    # columns: two rows x 8, two tiers (instanced unit cylinder)
+    cyl = b.add_mesh(*_cylinder(q(32), q(48)))
+    xs = np.linspace(3.0, X - 3.0, 8)
+    for tier, (y0, hgt, rad) in enumerate([(0.0, 5.5, 0.42), (6.0, 5.0, 0.30)]):
+        for row, z in enumerate((4.0, Z - 4.0)):
+            for c, x in enumerate(xs):
+                b.add_instance(cyl, trs12((x, y0, z), (rad, hgt, rad * (1.0 + 0.15 * ((c + row) & 1))),
+                                          rot_y=0.37 * c + row), 1 + ((c + tier + row) % 5))
+    # arches between neighbouring columns (instanced half torus)
+    gap = float(xs[1] - xs[0])
+    arch = b.add_mesh(*_arch(q(32), q(16), 0.5, 0.12))
+    for tier, y in enumerate((5.5 - 0.5 * gap * 0.0, 11.0)):
+        for z in (4.0, Z - 4.0):
+            for c in range(7):
+                b.add_instance(arch, trs12((0.5 * (xs[c] + xs[c + 1]), y - 0.0, z), (gap, 1.2, 1.0)), 8 + (c % 4))
+    # gallery slabs between the long walls and the column rows (top and bottom sheets)
+    for z0, z1 in ((0.0, 4.0), (Z - 4.0, Z)):
+        for y, nrm in ((5.75, (0, 1, 0)), (5.55, (0, -1, 0))):
+            p, n, idx = _plane((0, y, z0), (X, 0, 0), (0, 0, z1 - z0), q(60), q(8), nrm)
+            b.add_instance(b.add_mesh(p, n, idx), identity12(), 12)
+    # floor: displaced grid sized to land on the exact triangle budget
+    rest = n_tris - b.n_tris()
+    if rest < 8:
+        raise ValueError("triangle budget too small for the atrium (%d)" % n_tris)
+    nu = max(2, int(round(math.sqrt(rest / 2.0 * X / Z))))
+    nv = max(1, rest // (2 * nu))
+    fx, fz = np.meshgrid(np.linspace(0, 1, nu + 1), np.linspace(0, 1, nv + 1))
+    h = 0.05 * np.sin(17 * fx) * np.cos(11 * fz) + 0.02 * rng.standard_normal(fx.shape)
+    p, n, idx = _plane((0, 0, 0), (X, 0, 0), (0, 0, Z), nu, nv, (0, 1, 0), h)
+    b.add_instance(b.add_mesh(p, n, idx), identity12(), 5)
+    # remainder: small rubble triangles resting on the floor
+    rest = n_tris - b.n_tris()
+    if rest > 0:
+        c = np.stack([rng.uniform(1, X - 1, rest), np.full(rest, 0.12), rng.uniform(1, Z - 1, rest)], 1)
+        d = rng.normal(size=(rest, 3, 3)) * 0.08
+        p = (c[:, None, :] + d).reshape(-1, 3).astype(np.float32)
+        fn = np.cross(d[:, 1] - d[:, 0], d[:, 2] - d[:, 0])
+        n = np.repeat(fn, 3, axis=0).astype(np.float32)
+        b.add_instance(b.add_mesh(p, n, np.arange(rest * 3).reshape(-1, 3)), identity12(), 11)
+    scene = b.finish(make_materials())
+    assert b.n_tris() == n_tris, (b.n_tris(), n_tris)
+    return scene
+
+
+def default_cube():
+    """Geometry of the reference's only in-repo scene, src/vendor/default_blender_cube.gltf:
+    24 vertices / 12 triangles, POSITION min/max +-1, one material with baseColorFactor 0.8
+    (SURVEY §4). Vertex order follows the fixture's accessors (4 vertices per face)."""
+    faces = [((1, 0, 0), (0, 1, 0), (0, 0, 1)), ((-1, 0, 0), (0, 0, 1), (0, 1, 0)),
+             ((0, 1, 0), (0, 0, 1), (1, 0, 0)), ((0, -1, 0), (1, 0, 0), (0, 0, 1)),
+             ((0, 0, 1), (1, 0, 0), (0, 1, 0)), ((0, 0, -1), (0, 1, 0), (1, 0, 0))]
+    pos, nrm, idx = [], [], []
+    for f, (n, u, v) in enumerate(faces):
+        n, u, v = (np.array(a, np.float32) for a in (n, u, v))
+        for su, sv in ((-1, -1), (1, -1), (1, 1), (-1, 1)):
+            pos.append(n + su * u + sv * v)
+            nrm.append(n)
+        idx += [[4 * f, 4 * f + 1, 4 * f + 2], [4 * f, 4 * f + 2, 4 * f + 3]]
+    b = _Builder()
+    b.add_instance(b.add_mesh(np.array(pos), np.array(nrm), np.array(idx)), identity12(), 0)
+    return b.finish(make_materials(np.array([[0.8, 0.8, 0.8]], np.float32)))
+
+
+def small_room(n_side=6, seed=3):
+    """A few-hundred-triangle closed room with two boxes: small enough for brute-force oracles."""
+    rng = np.random.default_rng(seed)
+    b = _Builder()
+    S = 4.0
+    planes = [((0, 0, 0), (S, 0, 0), (0, 0, S), (0, 1, 0)), ((0, S, 0), (S, 0, 0), (0, 0, S), (0, -1, 0)),
+              ((0, 0, 0), (S, 0, 0), (0, S, 0), (0, 0, 1)), ((0, 0, S), (S, 0, 0), (0, S, 0), (0, 0, -1)),
+              ((0, 0, 0), (0, 0, S), (0, S, 0), (1, 0, 0))]            # x = S side left open: sky visible
+    for k, (o, du, dv, n) in enumerate(planes):
+        h = 0.02 * rng.standard_normal((n_side + 1, n_side + 1))
+        b.add_instance(b.add_mesh(*_plane(o, du, dv, n_side, n_side, n, h)), identity12(), k % 5)
+    cube = default_cube()
+    m = b.add_mesh(cube["vertices"]["position"][:, :3], cube["vertices"]["normal"], cube["indices"].reshape(-1, 3))
+    b.add_instance(m, trs12((1.2, 0.5, 1.5), (0.5, 0.5, 0.5), rot_y=0.5), 7)
+    b.add_instance(m, trs12((2.8, 0.9, 2.6), (0.4, 0.9, 0.3), rot_y=-0.8), 9)
+    return b.finish(make_materials())
+
+
+def hdr_sky(width, height, seed=1):
+    """BASELINE C1 input: smooth HDR sky rgb = a + b*max(0, d.s)^p plus U[0,0.1) per-texel noise,
+    alpha 1, RGBA32F."""
+    rng = np.random.default_rng(seed)
+    y = (np.arange(height) + 0.5) / height * np.pi
+    x = (np.arange(width) + 0.5) / width * 2 * np.pi
+    st, ct = np.sin(y)[:, None], np.cos(y)[:, None]
+    d = np.stack([st * np.sin(x)[None, :], np.broadcast_to(ct, (height, width)), st * np.cos(x)[None, :]], -1)
+    sun = np.array([0.35, 0.8, 0.48])
+    sun /= np.linalg.norm(sun)
+    lobe = np.maximum(0.0, d @ sun) ** 24
+    a = np.array([0.25, 0.35, 0.55])[None, None, :] * (0.6 + 0.4 * np.clip(d[..., 1:2], -1, 1))
+    img = np.empty((height, width, 4), np.float32)
+    img[..., :3] = a + np.array([6.0, 5.0, 3.5])[None, None, :] * lobe[..., None] + rng.uniform(0, 0.1, (height, width, 3))
+    img[..., 3] = 1.0
+    return img
+
+
+def atrium_settings(probes=(16, 8, 16), dirs=(32, 32), order=2, bounds=None):
+    """BakeSettings of BASELINE configs 2/3: grid spanning the bounds, equirect direction grid,
+    flags SHADOW_RAYS | SKYBOX_ON_MISS | SRGB_ENCODE, sun moved into the hall."""
+    from . import SHADOW_RAYS, SKYBOX_ON_MISS, SRGB_ENCODE, default_settings, settings_from_bounds
+    s = default_settings()
+    s.probes[:] = probes
+    s.dir_w, s.dir_h = dirs
+    s.sh_order = order
+    s.light_pos[:] = ATRIUM_LIGHT
+    s.flags = SHADOW_RAYS | SKYBOX_ON_MISS | SRGB_ENCODE
+    if bounds is None:
+        bounds = (0.0, 0.0, 0.0) + HALL
+    settings_from_bounds(s, bounds)
+    return s
