@@ -1,0 +1,413 @@
+#!/usr/bin/env python
+"""bench.py — the reference's headline path measured on B200.
+
+  python bench.py --gpus N --steps K --warmup W            our arm  (CUDA path through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  CPU arm  (the oracle port on host cores)
+
+A "step" is one pass of the bake over one batch of synthetic input: BASELINE.json configs[1]
+(C2: procedural atrium, 262,144 triangles, 16x8x16 probes x 1,024 rays, L2 SH, shadow rays, skybox
+on miss). For N > 1 every rank bakes a C2-sized z-slab of a grid that is N times deeper
+(16 x 8 x 16N probes; weak scaling: per-GPU work fixed) and the slabs are all-gathered over NCCL
+inside the timed region. One JSON line is printed by rank 0.
+
+  value  probe (primary) rays per second, inputs resident in HBM (scene, BVH, skybox uploaded and
+         built before the timed region); max over ranks of the summed per-step CUDA-event times.
+  e2e    same metric through the reference-facing calls with HOST buffers: scene upload + LBVH
+         build + skybox upload + bake + read-back of the coefficients, every step.
+  roofline / skybox  see DESIGN.md §Measurement.
+"""
+import argparse
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "probe_rays_per_s"
+UNIT = "Grays/s"
+N_TRIS = 262144
+PROBES_C2 = (16, 8, 16)
+DIRS_C2 = (32, 32)
+SKY_WH = (2048, 1024)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.sm_max = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake": 0x80, "sync_boost": 0x10, "applications_clocks": 0x2, "display_clocks": 0x100}
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def pinned_like(torch, a):
+    """Copy of a numpy array living in pinned host memory (so H2D copies are direct DMA)."""
+    t = torch.empty(a.nbytes, dtype=torch.uint8, pin_memory=True)
+    v = t.numpy().view(a.dtype).reshape(a.shape)
+    v[...] = a
+    return v, t
+
+
+def workload(vlb, scenes, world):
+    scene = scenes.atrium(N_TRIS, seed=7)
+    sky = scenes.hdr_sky(SKY_WH[0], SKY_WH[1], seed=1)
+    probes = (PROBES_C2[0], PROBES_C2[1], PROBES_C2[2] * world)
+    bounds = (0.0, 0.0, 0.0, scenes.HALL[0], scenes.HALL[1], scenes.HALL[2])
+    s = scenes.atrium_settings(probes=probes, dirs=DIRS_C2, order=2, bounds=bounds)
+    return scene, sky, s
+
+
+def config_dict(world, s):
+    return {"workload": "C2 (BASELINE configs[1]): procedural atrium seed 7, %d triangles; %dx%dx%d probes "
+                        "(16x8x16 per GPU z-slab) x %d rays (%dx%d equirect); L2 SH (9 coeffs); direct sun + "
+                        "shadow rays + 2048x1024 RGBA32F skybox on miss; sRGB encode" %
+                        (N_TRIS, s.probes[0], s.probes[1], s.probes[2], s.dir_w * s.dir_h, s.dir_w, s.dir_h),
+            "triangles": N_TRIS, "probes": list(s.probes), "rays_per_probe": s.dir_w * s.dir_h, "sh_order": s.sh_order,
+            "parallelism": "probe z-slabs x%d, scene+BVH replicated, 1 NCCL all-gather" % world,
+            "l2_policy": "bake: 256 MiB L2 flush written between timed steps (BVH+skybox working set is L2-resident "
+                         "by design); skybox roofline: 8 distinct 32 MiB maps rotated (268 MB > 126 MB L2)"}
+
+
+# =============================================================================================
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    vlb = importlib.import_module("vulkan-light-bakery_b200")
+    scenes = importlib.import_module("vulkan-light-bakery_b200.scenes")
+    par = importlib.import_module("vulkan-light-bakery_b200.parallel")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the bake path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = args.steps, max(args.warmup, 3)
+
+    scene, sky, s = workload(vlb, scenes, world)
+    ctx = vlb.Context(local)
+    stream = torch.cuda.Stream(device=dev)     # one stream for torch, NCCL and the library
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    ctx.set_scene(scene)
+    bvh = ctx.build_bvh()
+    ctx.set_skybox(sky)
+    mine = par.shard_settings(s, rank, world)
+    n_local = s.probes[0] * s.probes[1] * (mine.slab_k1 - mine.slab_k0)
+    rays_local = n_local * s.dir_w * s.dir_h
+    rays_total = s.n_probes * s.dir_w * s.dir_h
+    out = torch.zeros((n_local, 48), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        ctx.bake_probes_device(mine, out.data_ptr())
+        return par.gather_slabs(out, s, rank, world)
+
+    # ---- value: inputs resident in HBM ------------------------------------------------------
+    for _ in range(W):
+        flush.zero_()
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = ctx.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    kernel_ms = []
+    shadow = 0
+    for i in range(K):
+        flush.zero_()                      # L2 flush, outside the per-step event pair
+        ev[i][0].record(stream)
+        full = step_resident()
+        ev[i][1].record(stream)
+        st = ctx.last_bake_stats()
+        kernel_ms.append(st.kernel_ms)
+        shadow = st.n_shadow_rays
+    barrier()
+    launches = ctx.launch_count - launches0
+    t_ms = sum(a.elapsed_time(b) for a, b in ev)
+    kern_ms = float(np.mean(kernel_ms))
+
+    # ---- e2e: host buffers in, host buffer out, every step -----------------------------------
+    pins = {k: pinned_like(torch, np.ascontiguousarray(scene[k])) for k in ("vertices", "indices", "instances", "materials")}
+    pscene = {k: v[0] for k, v in pins.items()}
+    psky, _keep_sky = pinned_like(torch, sky)
+    h2d = sum(v[0].nbytes for v in pins.values()) + psky.nbytes
+    full_host = torch.empty((s.n_probes, 48), dtype=torch.float32, pin_memory=True)
+    e2e_steps = max(3, min(K, 50))
+
+    def step_e2e():
+        ctx.set_scene(pscene)
+        ctx.build_bvh()
+        ctx.set_skybox(psky)
+        ctx.bake_probes_device(mine, out.data_ptr())
+        g = par.gather_slabs(out, s, rank, world)
+        full_host.copy_(g, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        step_e2e()
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    clocks = sampler.finish()
+
+    # max over ranks
+    if world > 1:
+        tt = torch.tensor([t_ms, e2e_ms, kern_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_ms, e2e_ms, kern_ms = (float(x) for x in tt.tolist())
+        sh = torch.tensor([shadow], dtype=torch.int64, device=dev)
+        dist.all_reduce(sh)
+        shadow_total = int(sh.item())
+    else:
+        shadow_total = int(shadow)
+    ms_per_step = t_ms / K
+    value = rays_total / (ms_per_step * 1e-3) / 1e9
+
+    extra = {}
+    if rank == 0:
+        # instrumented pass (outside any timed region): nodes visited / triangles tested per ray
+        os.environ["VLB_BAKE_COUNTERS"] = "1"
+        ctx.bake_probes_device(mine, out.data_ptr())
+        ctx.synchronize()
+        os.environ["VLB_BAKE_COUNTERS"] = "0"
+        st = ctx.last_bake_stats()
+        nrays = st.n_primary_rays + st.n_shadow_rays
+        alg_bytes = st.n_nodes_visited * 64 + st.n_tris_tested * 48      # per launch (this rank's slab)
+        peak, peak_src = measured_peaks()
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "vlb::k_bake<9,false>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": int(alg_bytes),
+                    "nodes_per_ray": st.n_nodes_visited / max(nrays, 1), "tris_per_ray": st.n_tris_tested / max(nrays, 1),
+                    "kernel_ms": kern_ms,
+                    "note": "traversal reads 64 B nodes + 48 B triangles that are L2-resident (BVH 29 MB); algorithmic "
+                            "bytes = nodes visited x 64 + triangles tested x 48 from the instrumented build of the same "
+                            "kernel; the kernel is latency/issue bound, not HBM bound (see profiles/)"}
+        extra["roofline"] = roofline
+        extra["skybox"] = bench_skybox(torch, ctx, scenes, dev, stream, peak, peak_src)
+        extra["cpu_baseline"] = cpu_baseline(scene, sky, s if world == 1 else workload(vlb, scenes, 1)[2])
+        extra["bvh"] = {"build_ms": bvh.build_ms, "sort_ms": bvh.sort_ms, "nodes": int(bvh.n_nodes),
+                        "mtris_per_s": N_TRIS / (bvh.build_ms * 1e-3) / 1e6}
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config_dict(world, s), "clocks": clocks,
+                "e2e": {"value": rays_total / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(full_host.numel() * 4), "ms_per_step": e2e_ms, "steps": e2e_steps,
+                        "includes": "scene upload + LBVH build + skybox upload + bake + all-gather + coefficient read-back"},
+                "gpu_launches": int(launches),
+                "probes_per_s": s.n_probes / (ms_per_step * 1e-3),
+                "rays_incl_shadow_per_s_G": (rays_total + shadow_total) / (ms_per_step * 1e-3) / 1e9,
+                "shadow_rays_per_step": shadow_total}
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_skybox(torch, ctx, scenes, dev, stream, peak, peak_src, n_buf=8, reps=10):
+    """BASELINE configs[0] (C1): one 2048x1024 RGBA32F equirect -> L2 SH. 8 distinct maps are
+    rotated so every launch reads from HBM, not L2."""
+    Wd, Hd = SKY_WH
+    maps = torch.empty((n_buf, Hd, Wd, 4), dtype=torch.float32, device=dev)
+    for i in range(n_buf):
+        maps[i].copy_(torch.from_numpy(scenes.hdr_sky(Wd, Hd, seed=1 + i)))
+    outs = torch.zeros((n_buf, 48), dtype=torch.float32, device=dev)
+    stride = Hd * Wd * 16
+    vlbm = importlib.import_module("vulkan-light-bakery_b200")
+
+    def one(i):
+        ctx.skybox_project_sh_device(maps[i].data_ptr(), stride, 1, vlbm.FMT_RGBA32F, Wd, Hd, 2, outs[i].data_ptr())
+
+    for i in range(n_buf):
+        one(i)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(stream)
+    for _ in range(reps):
+        for i in range(n_buf):
+            one(i)
+    b.record(stream)
+    torch.cuda.synchronize()
+    us = a.elapsed_time(b) * 1e3 / (reps * n_buf)
+    gbs = stride / (us * 1e-6) / 1e9
+    # batched launch: all 8 maps in one kernel
+    ctx.skybox_project_sh_device(maps.data_ptr(), stride, n_buf, vlbm.FMT_RGBA32F, Wd, Hd, 2, outs.data_ptr())
+    torch.cuda.synchronize()
+    a.record(stream)
+    for _ in range(reps):
+        ctx.skybox_project_sh_device(maps.data_ptr(), stride, n_buf, vlbm.FMT_RGBA32F, Wd, Hd, 2, outs.data_ptr())
+    b.record(stream)
+    torch.cuda.synchronize()
+    us_b = a.elapsed_time(b) * 1e3 / reps
+    gbs_b = stride * n_buf / (us_b * 1e-6) / 1e9
+    return {"workload": "C1 (BASELINE configs[0]): 2048x1024 RGBA32F equirect -> L2 SH, 8 distinct maps rotated",
+            "kernel": "vlb::k_project<9,RGBA32F>", "bound": "hbm", "algorithmic_bytes_per_launch": stride,
+            "us_per_launch": us, "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+            "frac_of_8TBs_nominal": gbs / 8000.0, "peak_source": peak_src,
+            "batched8": {"us_per_launch": us_b, "achieved": gbs_b, "frac": gbs_b / peak}}
+
+
+def cpu_baseline(scene, sky, s, budget_s=12.0):
+    """The oracle port (oracle/vlb_oracle.cpp, OpenMP) on this box's host cores: bake of a bounded
+    sample of C2's probes with its CPU BVH. Reported baseline, not the target."""
+    from oracle import oracle_api as oa
+    osc = oa.Scene(scene)
+    osc.set_skybox(sky)
+    n = s.n_probes
+    ids = np.linspace(0, n - 1, 64).astype(np.int64)
+    t0 = time.perf_counter()
+    osc.bake_probes(s, probe_ids=ids)
+    dt = time.perf_counter() - t0
+    m = int(min(n, max(64, 64 * budget_s / max(dt, 1e-6))))
+    ids = np.linspace(0, n - 1, m).astype(np.int64)
+    t0 = time.perf_counter()
+    osc.bake_probes(s, probe_ids=ids)
+    dt = time.perf_counter() - t0
+    rays = m * s.dir_w * s.dir_h
+    return {"value": rays / dt / 1e9, "unit": UNIT, "cores": oa.num_threads(), "kind": "port",
+            "sample": "%d of %d C2 probes (evenly strided) x %d rays, CPU BVH already built, %.2f s" % (m, n, s.dir_w * s.dir_h, dt)}
+
+
+# =============================================================================================
+def run_reference(args):
+    """Reference arm: the reference's path on the host CPU. The reference itself cannot be built
+    here (needs Vulkan + an RT-capable driver / lavapipe + glslang, none in the image), so this is
+    the oracle port — the CPU restatement of its shaders — with all host threads. Each step = scene
+    flatten + CPU BVH build + bake of a bounded sample of C2's probes (same boundaries as our e2e)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    vlb = importlib.import_module("vulkan-light-bakery_b200")
+    scenes = importlib.import_module("vulkan-light-bakery_b200.scenes")
+    from oracle import oracle_api as oa
+    scene, sky, s = workload(vlb, scenes, world)
+    K, W = args.steps, args.warmup
+    n = s.n_probes
+    # calibrate: as many of the grid's probes per step as fit in ~2 s of CPU time (all of C2 if possible)
+    osc = oa.Scene(scene)
+    osc.set_skybox(sky)
+    t0 = time.perf_counter()
+    osc.bake_probes(s, probe_ids=np.linspace(0, n - 1, 64).astype(np.int64))
+    per_probe = (time.perf_counter() - t0) / 64
+    osc.close()
+    m = int(min(n, max(64, 2.0 / max(per_probe, 1e-9))))
+    ids = np.linspace(0, n - 1, m).astype(np.int64)
+
+    def step():
+        osc = oa.Scene(scene)
+        osc.set_skybox(sky)
+        osc.bake_probes(s, probe_ids=ids)
+        osc.close()
+
+    # bound the whole run to a few minutes
+    t0 = time.perf_counter()
+    step()
+    one = time.perf_counter() - t0
+    K = max(1, min(K, int(150.0 / max(one, 1e-3))))
+    W = max(0, min(W, int(30.0 / max(one, 1e-3))))
+    for _ in range(W):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step()
+    dt = (time.perf_counter() - t0) / K
+    rays = m * s.dir_w * s.dir_h
+    v = rays / dt / 1e9
+    sample = "each step: flatten + CPU BVH build of %d triangles + bake of %d of %d probes x %d rays" % (N_TRIS, m, n, s.dir_w * s.dir_h)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_dict(world, s),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": oa.num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "oracle port of the reference shaders on host cores; the Vulkan reference cannot run in this image"}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

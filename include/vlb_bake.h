@@ -156,8 +156,9 @@ typedef struct vlb_bake_stats {
 /* Replaces vlb::Application's device bring-up (src/application.cpp:540-556). */
 int  vlb_ctx_create(int device_id, vlb_ctx** out);
 void vlb_ctx_destroy(vlb_ctx* ctx);
-/* Use an existing CUDA stream (a cudaStream_t passed as an integer handle); 0 restores the
- * ctx's own stream. */
+/* Use an existing CUDA stream (a cudaStream_t passed as an integer handle; 0 is CUDA's legacy
+ * default stream, as everywhere in CUDA); VLB_STREAM_OWN restores the ctx's own stream. */
+#define VLB_STREAM_OWN (~(uint64_t)0)
 int  vlb_ctx_set_stream(vlb_ctx* ctx, uint64_t cuda_stream_handle);
 int  vlb_ctx_synchronize(vlb_ctx* ctx);
 /* Last error text of this ctx (or of the calling thread when ctx == NULL). Never NULL. */

@@ -1,0 +1,69 @@
+"""The C-ABI library loads and exports every symbol include/vlb_bake.h declares; host-only helpers
+behave; and without a GPU every compute entry point fails loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "vlb_bake.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(vlb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(vlb):
+    lib = ctypes.CDLL(vlb.LIB_PATH)
+    declared = _header_functions()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), "libvlb_bake.so does not export %s" % name
+    assert sorted(vlb.ABI_SYMBOLS) == declared
+    assert vlb.load_library().vlb_abi_version() == 1
+
+
+def test_struct_layouts_match_reference(vlb):
+    # shaders/structures.h:13-71 scalar layout
+    assert vlb.VERTEX_DTYPE.itemsize == 44 and vlb.MATERIAL_DTYPE.itemsize == 144
+    assert vlb.VERTEX_DTYPE.fields["normal"][1] == 16 and vlb.VERTEX_DTYPE.fields["uv0"][1] == 28
+    assert vlb.MATERIAL_DTYPE.fields["base_color_factor"][1] == 64
+    assert ctypes.sizeof(vlb.BakeSettings) == 4 * (3 + 3 + 3 + 3 + 3 + 5 + 2 + 1 + 2 + 4)
+
+
+def test_default_settings_are_the_reference_constants(vlb):
+    s = vlb.default_settings()
+    assert list(s.probes) == [7, 7, 7]                      # light_baker.cpp:38
+    assert (s.dir_w, s.dir_h) == (3141, 1000)               # light_baker.cpp:65 / env_map_generator.cpp:24-28
+    assert int(np.float32(3.1415926538) * np.float32(500) * np.float32(2)) == 3141
+    assert s.sh_order == 3
+    assert list(s.light_pos) == [1.0, 10.0, 1.0]            # env_map.rchit:25
+    assert (s.shadow_bias, s.c_diffuse, s.c_specular, s.gloss, s.ambient) == (np.float32(0.005), 0.5, 0.5, 16.0, 0.0)
+    assert (s.tmin, s.tmax) == (np.float32(0.001), 10000.0)  # env_map.rgen:22-23
+    assert s.flags == vlb.SHADOW_RAYS | vlb.SKYBOX_ON_MISS | vlb.SRGB_ENCODE | vlb.QUANTIZE_RGBA8
+    assert s.slab == (0, 7)
+
+
+def test_no_gpu_means_loud_failure(vlb):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(vlb.VlbError) as e:
+        vlb.Context(0)
+    assert e.value.code == vlb.ERR_NO_DEVICE
+    assert "no CPU path" in str(e.value)
+
+
+def test_slab_partition(vlb):
+    import importlib
+    par = importlib.import_module("vulkan-light-bakery_b200.parallel")
+    for nz in (1, 7, 16, 64, 65):
+        for world in (1, 2, 3, 4, 8):
+            ranges = [par.slab_range(nz, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == nz
+            assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+            sizes = [b - a for a, b in ranges]
+            assert max(sizes) - min(sizes) <= 1

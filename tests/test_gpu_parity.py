@@ -22,7 +22,7 @@ def _rays(n, lo, hi, seed=0):
 
 # ---------------------------------------------------------------- skybox projection ----------
 @pytest.mark.parametrize("order", [2, 3])
-@pytest.mark.parametrize("shape", [(32, 64), (256, 512), (100, 314), (7, 13), (1, 1)])
+@pytest.mark.parametrize("shape", [(32, 64), (256, 512), (100, 314), (7, 13), (1, 1), (33, 130), (130, 66), (1000, 3141)])
 def test_skybox_rgba32f_vs_oracle(ctx, oa, scenes, order, shape):
     img = scenes.hdr_sky(shape[1], shape[0], seed=5)
     got = ctx.skybox_project_sh(img, order)
@@ -37,6 +37,23 @@ def test_skybox_rgba8_vs_oracle(ctx, oa, order):
     rng = np.random.default_rng(11)
     img = rng.integers(0, 256, (96, 200, 4), dtype=np.uint8)
     assert rel_l2(ctx.skybox_project_sh(img, order), oa.skybox_project(img, order)) <= SKY_TOL
+
+
+@pytest.mark.parametrize("order", [2, 3])
+@pytest.mark.parametrize("shape", [(50, 97), (64, 1), (37, 258)])
+def test_skybox_rgba8_unaligned_rows_fallback_kernel(ctx, oa, order, shape):
+    # W*4 is not a multiple of 16: the TMA bulk-copy path cannot be used, the LDG kernel runs
+    rng = np.random.default_rng(12)
+    img = rng.integers(0, 256, (shape[0], shape[1], 4), dtype=np.uint8)
+    assert rel_l2(ctx.skybox_project_sh(img, order), oa.skybox_project(img, order)) <= SKY_TOL
+
+
+def test_skybox_many_maps_more_tiles_than_sms(ctx, oa, scenes):
+    # 40 maps x 8 strips = 320 whole-column tiles > 148 persistent CTAs: several tiles per CTA
+    maps = [scenes.hdr_sky(512, 64, seed=200 + i) for i in range(40)]
+    got = ctx.skybox_project_sh_batched(maps, 2)
+    for i in (0, 7, 39):
+        assert rel_l2(got[i], oa.skybox_project(maps[i], 2)) <= SKY_TOL
 
 
 @pytest.mark.parametrize("order", [2, 3])

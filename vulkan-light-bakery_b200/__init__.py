@@ -39,6 +39,7 @@ REFERENCE_PROBE_ORDER = 1 << 4
 ACCUMULATE_ACROSS_PROBES = 1 << 5
 SH_WORLD_FRAME = 1 << 6
 
+STREAM_OWN = (1 << 64) - 1
 TRACE_BVH, TRACE_BRUTE_FORCE = 0, 1
 TRACE_CLOSEST, TRACE_ANY = 0, 1
 
@@ -208,7 +209,8 @@ class Context:
 
     # -- plumbing
     def set_stream(self, handle):
-        self._check(self._lib.vlb_ctx_set_stream(self._h, int(handle)))
+        """handle: cudaStream_t as int (0 = CUDA's legacy default stream); None = the ctx's own stream."""
+        self._check(self._lib.vlb_ctx_set_stream(self._h, STREAM_OWN if handle is None else int(handle)))
 
     def synchronize(self):
         self._check(self._lib.vlb_ctx_synchronize(self._h))

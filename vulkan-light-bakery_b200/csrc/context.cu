@@ -126,7 +126,7 @@ void vlb_ctx_destroy(vlb_ctx* ctx) {
 
 int vlb_ctx_set_stream(vlb_ctx* ctx, uint64_t handle) {
     if (!ctx) return VLB_ERR_INVALID;
-    ctx->stream = handle ? reinterpret_cast<cudaStream_t>(handle) : ctx->own_stream;
+    ctx->stream = handle == VLB_STREAM_OWN ? ctx->own_stream : reinterpret_cast<cudaStream_t>(handle);
     return VLB_OK;
 }
 
