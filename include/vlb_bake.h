@@ -197,6 +197,13 @@ int vlb_skybox_project_sh_batched(vlb_ctx* ctx, const void* const* maps, uint32_
 int vlb_skybox_project_sh_device(vlb_ctx* ctx, const void* d_texels, uint64_t map_stride_bytes,
                                  uint32_t n_maps, int format, int width, int height,
                                  int sh_order, float* d_out);
+/* n independent maps of identical size at n DEVICE addresses (host array of device pointers),
+ * d_out = n x 48 floats. One launch per map; the launches alternate over internal streams forked
+ * from and joined to the ctx stream, so that one map streams from HBM while another is being
+ * reduced; for the caller the call is ordered on the ctx stream like any other. Replaces a loop of Skybox_t::computeSH over pushed skyboxes
+ * (src/skybox_manager.cpp:284-298 -> 107-130). */
+int vlb_skybox_project_sh_device_ptrs(vlb_ctx* ctx, const void* const* d_maps, uint32_t n_maps,
+                                      int format, int width, int height, int sh_order, float* d_out);
 /* shaders/sh.comp applied to a caller-supplied environment image (the reference's image-input
  * debug path, src/baker/light_baker.cpp:68-73): SH argument is the un-swizzled toVector. */
 int vlb_envmap_project_sh(vlb_ctx* ctx, const void* texels, int format, int width, int height,

@@ -90,6 +90,41 @@ def test_skybox_deterministic(ctx, scenes):
         assert np.array_equal(a, ctx.skybox_project_sh(img, 3))
 
 
+@pytest.mark.parametrize("order,fmt", [(2, "f32"), (3, "f32"), (3, "u8")])
+def test_skybox_device_ptrs_lanes_vs_oracle(ctx, vlb, oa, scenes, order, fmt):
+    # 11 independent device-resident maps (more than the auxiliary lanes) through the multi-pointer
+    # entry point: every map must match the oracle and the single-launch path bit for bit
+    import torch
+    n, W, H = 11, 320, 96
+    if fmt == "f32":
+        host = [scenes.hdr_sky(W, H, seed=300 + i) for i in range(n)]
+        code = vlb.FMT_RGBA32F
+    else:
+        rng = np.random.default_rng(7)
+        host = [rng.integers(0, 256, (H, W, 4), dtype=np.uint8) for _ in range(n)]
+        code = vlb.FMT_RGBA8
+    dev = [torch.from_numpy(m).cuda() for m in host]
+    out = torch.full((n, 48), -1.0, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    ctx.skybox_project_sh_device_ptrs([d.data_ptr() for d in dev], code, W, H, order, out.data_ptr())
+    ctx.synchronize()
+    got = out.cpu().numpy().reshape(n, 16, 3)
+    for i in range(n):
+        assert rel_l2(got[i], oa.skybox_project(host[i], order)) <= SKY_TOL
+        assert np.array_equal(got[i], ctx.skybox_project_sh(host[i], order))
+    if order == 2:
+        assert np.all(got[:, 9:] == 0)
+
+
+def test_skybox_device_ptrs_errors(ctx, vlb):
+    import torch
+    out = torch.zeros((2, 48), device="cuda")
+    with pytest.raises(vlb.VlbError):
+        ctx.skybox_project_sh_device_ptrs([0, 0], vlb.FMT_RGBA32F, 64, 32, 2, out.data_ptr())
+    with pytest.raises(vlb.VlbError):
+        ctx.skybox_project_sh_device_ptrs([out.data_ptr()], vlb.FMT_RGBA32F, 64, 32, 5, out.data_ptr())
+
+
 # ---------------------------------------------------------------- BVH hit ids ----------------
 @pytest.fixture(scope="module")
 def room(ctx, oa, scenes):

@@ -94,7 +94,7 @@ ABI_SYMBOLS = [
     "vlb_abi_version", "vlb_ctx_create", "vlb_ctx_destroy", "vlb_ctx_set_stream", "vlb_ctx_synchronize",
     "vlb_last_error", "vlb_ctx_launch_count", "vlb_scene_set_triangles", "vlb_scene_bounds", "vlb_bvh_build",
     "vlb_skybox_set", "vlb_skybox_project_sh", "vlb_skybox_project_sh_batched", "vlb_skybox_project_sh_device",
-    "vlb_envmap_project_sh", "vlb_bake_settings_default", "vlb_bake_settings_from_bounds", "vlb_probe_positions",
+    "vlb_skybox_project_sh_device_ptrs", "vlb_envmap_project_sh", "vlb_bake_settings_default", "vlb_bake_settings_from_bounds", "vlb_probe_positions",
     "vlb_bake_probes", "vlb_bake_probes_device", "vlb_bake_last_stats", "vlb_trace_rays",
     "vlb_bake_serialize_gltf", "vlb_bake_deserialize_gltf",
 ]
@@ -128,6 +128,7 @@ def load_library():
         "vlb_skybox_project_sh": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "vlb_skybox_project_sh_batched": (i32, [vp, vp, u32, i32, i32, i32, i32, vp]),
         "vlb_skybox_project_sh_device": (i32, [vp, vp, u64, u32, i32, i32, i32, i32, vp]),
+        "vlb_skybox_project_sh_device_ptrs": (i32, [vp, vp, u32, i32, i32, i32, i32, vp]),
         "vlb_envmap_project_sh": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "vlb_bake_settings_default": (None, [S]),
         "vlb_bake_settings_from_bounds": (i32, [S, vp]),
@@ -275,6 +276,11 @@ class Context:
     def skybox_project_sh_device(self, d_texels, map_stride, n_maps, fmt, width, height, order, d_out):
         self._check(self._lib.vlb_skybox_project_sh_device(self._h, int(d_texels), int(map_stride), int(n_maps), fmt,
                                                            width, height, order, int(d_out)))
+
+    def skybox_project_sh_device_ptrs(self, d_maps, fmt, width, height, order, d_out):
+        """d_maps: device addresses of n independent maps; d_out: device address of n x 48 floats."""
+        arr = d_maps if isinstance(d_maps, ctypes.Array) else (ctypes.c_void_p * len(d_maps))(*[int(x) for x in d_maps])
+        self._check(self._lib.vlb_skybox_project_sh_device_ptrs(self._h, arr, len(arr), fmt, width, height, order, int(d_out)))
 
     # -- bake (LightBaker::bake)
     def bake_probes(self, s):

@@ -54,6 +54,11 @@ __global__ void k_rgba8_to_f32(const uchar4* __restrict__ in, float4* __restrict
     out[i] = make_float4((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f, (float)c.w / 255.0f);
 }
 
+static int env_lanes() {
+    const char* v = getenv("VLB_PROJ_LANES");
+    return v && *v ? atoi(v) : VLB_MAX_LANES;
+}
+
 static int check_device(vlb_ctx* ctx) {
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return ctx->fail(VLB_ERR_NO_DEVICE, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
@@ -63,6 +68,9 @@ static int check_device(vlb_ctx* ctx) {
 }  // namespace vlb
 
 using namespace vlb;
+#ifdef VLB_PROJ_TIMING
+namespace vlb { int proj_timing_dump(vlb_ctx* ctx, int n_launches); }
+#endif
 
 extern "C" {
 
@@ -120,6 +128,11 @@ void vlb_ctx_destroy(vlb_ctx* ctx) {
                       &ctx->d_stats, &ctx->d_ray_o, &ctx->d_ray_d, &ctx->d_hit_id, &ctx->d_hit_tuv, &ctx->d_hit_key};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    for (int l = 0; l < VLB_MAX_LANES; ++l) {
+        if (ctx->lane_stream[l]) { cudaStreamSynchronize(ctx->lane_stream[l]); cudaStreamDestroy(ctx->lane_stream[l]); }
+        if (ctx->lane_join[l]) cudaEventDestroy(ctx->lane_join[l]);
+    }
+    if (ctx->lane_fork) cudaEventDestroy(ctx->lane_fork);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -323,6 +336,39 @@ int vlb_skybox_project_sh_device(vlb_ctx* ctx, const void* d_texels, uint64_t ma
         (format != VLB_FMT_RGBA8 && format != VLB_FMT_RGBA32F))
         return ctx->fail(VLB_ERR_INVALID, "vlb_skybox_project_sh_device: bad arguments");
     return project_sh_device(ctx, d_texels, map_stride_bytes, n_maps, format, width, height, sh_order, 0, d_out);
+}
+
+int vlb_skybox_project_sh_device_ptrs(vlb_ctx* ctx, const void* const* d_maps, uint32_t n_maps, int format, int width,
+                                      int height, int sh_order, float* d_out) {
+    if (!ctx) return VLB_ERR_INVALID;
+    if (int r = check_device(ctx)) return r;
+    if (!d_maps || !d_out || n_maps == 0 || width <= 0 || height <= 0 || (sh_order != 2 && sh_order != 3) ||
+        (format != VLB_FMT_RGBA8 && format != VLB_FMT_RGBA32F))
+        return ctx->fail(VLB_ERR_INVALID, "vlb_skybox_project_sh_device_ptrs: bad arguments");
+    for (uint32_t i = 0; i < n_maps; ++i)
+        if (!d_maps[i]) return ctx->fail(VLB_ERR_INVALID, "vlb_skybox_project_sh_device_ptrs: d_maps[%u] is NULL", i);
+    // one launch per map, alternating over auxiliary streams forked from / joined to the ctx stream
+    const int lanes = std::max(1, std::min<int>({env_lanes(), VLB_MAX_LANES, (int)n_maps}));
+    cudaStream_t st = ctx->stream;
+    if (!ctx->lane_fork) VLB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_fork, cudaEventDisableTiming));
+    for (int l = 0; l < lanes; ++l) {
+        if (!ctx->lane_stream[l]) VLB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking));
+        if (!ctx->lane_join[l]) VLB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_join[l], cudaEventDisableTiming));
+    }
+    VLB_CUDA(ctx, cudaEventRecord(ctx->lane_fork, st));
+    for (int l = 0; l < lanes; ++l) VLB_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_stream[l], ctx->lane_fork, 0));
+    int rc = VLB_OK;
+    for (uint32_t i = 0; i < n_maps && rc == VLB_OK; ++i)
+        rc = project_sh_device(ctx, d_maps[i], 0, 1, format, width, height, sh_order, 0,
+                               d_out + (size_t)i * VLB_SH_STRIDE, (int)(i % lanes));
+    for (int l = 0; l < lanes; ++l) {      // always join, also after an error, so the streams stay ordered
+        VLB_CUDA(ctx, cudaEventRecord(ctx->lane_join[l], ctx->lane_stream[l]));
+        VLB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->lane_join[l], 0));
+    }
+#ifdef VLB_PROJ_TIMING
+    if (rc == VLB_OK) return proj_timing_dump(ctx, (int)n_maps);
+#endif
+    return rc;
 }
 
 // ---- bake -------------------------------------------------------------------------------

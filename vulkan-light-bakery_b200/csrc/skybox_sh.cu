@@ -26,6 +26,8 @@
 // a fixed order. No float atomics: results are bitwise reproducible for a given launch geometry.
 //
 // Algorithmic bytes per texel: 16 (RGBA32F) or 4 (RGBA8) read; 192 bytes written per map.
+#include <cuda.h>   // CUtensorMap types only; the encoder is fetched with cudaGetDriverEntryPoint
+
 #include <algorithm>
 
 #include "vlb_context.h"
@@ -50,10 +52,21 @@ struct ProjParams {
     unsigned int* counters;   // [map], self-resetting
     float* out;               // [map][48]
     int variant;              // 0: skybox_sh.comp (SH argument d.xzy), 1: sh.comp (SH argument d)
-    // k_project_tma only
-    uint32_t n_units;
-    int n_stages, bpt;
+    // k_project_tiles only
+    uint32_t n_tiles, tiles_per_map, row_tiles;
+    uint32_t split_q, split_r;   // CTA b owns q + (b < r) consecutive tiles
+    int n_stages;
+#ifdef VLB_PROJ_TIMING
+    unsigned long long* timing;  // [grid][8] %globaltimer stamps (debug builds only)
+#endif
 };
+
+#ifdef VLB_PROJ_TIMING
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define VLB_STAMP(k) do { if ((threadIdx.x & 255) == 0 && (k) < 8) p.timing[blockIdx.x * 8 + (k)] = gtime(); } while (0)
+#else
+#define VLB_STAMP(k) do {} while (0)
+#endif
 
 // Moment of dx^a dy^b dz^c for one channel from the column sums G and the column's phi factors.
 // G index: (p,q) -> {(0,0):0,(1,0):1,(2,0):2,(0,1):3,(1,1):4,(3,0):5,(2,1):6}
@@ -119,10 +132,10 @@ struct FinishSmem {
 // arrives last for `map`, sums all P partials of the map in a fixed order and writes the result.
 // SYNC() must be a barrier over exactly the threads that call this function.
 template <class SYNC>
-__device__ __forceinline__ void publish_and_finish(const ProjParams& p, uint32_t map, uint32_t slot, uint32_t P,
-                                                   float my_value, int tid, FinishSmem& fs, SYNC sync) {
+__device__ __forceinline__ void publish_and_finish(const ProjParams& p, uint32_t map, size_t base_slot, uint32_t slot,
+                                                   uint32_t P, float my_value, int tid, FinishSmem& fs, SYNC sync) {
     if (tid < VLB_SH_STRIDE) {
-        p.partials[((size_t)map * P + slot) * VLB_SH_STRIDE + tid] = my_value;
+        p.partials[(base_slot + slot) * VLB_SH_STRIDE + tid] = my_value;
         __threadfence();
     }
     sync();
@@ -134,14 +147,20 @@ __device__ __forceinline__ void publish_and_finish(const ProjParams& p, uint32_t
     sync();
     if (fs.last) {
         __threadfence();
-        const float4* base = reinterpret_cast<const float4*>(p.partials + (size_t)map * P * VLB_SH_STRIDE);
+        const float4* base = reinterpret_cast<const float4*>(p.partials + base_slot * VLB_SH_STRIDE);
         if (tid < kFinGroups * 12) {
             const int g = tid / 12, c4 = tid % 12;
             float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-            for (uint32_t k = g; k < P; k += kFinGroups) {
-                const float4 v = __ldcg(base + (size_t)k * 12 + c4);
-                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            // batches of 8 independent loads (one L2 round trip covers P <= 168 partials)
+            for (uint32_t k0 = g; k0 < P; k0 += 8 * kFinGroups) {
+                float4 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t k = k0 + j * kFinGroups;
+                    v[j] = k < P ? __ldcg(base + (size_t)k * 12 + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s.x += v[j].x; s.y += v[j].y; s.z += v[j].z; s.w += v[j].w; }
             }
             fs.grp[g][c4] = s;
         }
@@ -246,18 +265,32 @@ __global__ void __launch_bounds__(kProjBlock) k_project_ldg(const ProjParams p) 
 #pragma unroll
         for (int w = 0; w < kProjBlock / 32; ++w) mine += s_red[w][tid];
     }
-    publish_and_finish(p, map, bid % P, P, mine, tid, s_fin, [] { __syncthreads(); });
+    publish_and_finish(p, map, (size_t)map * P, bid % P, P, mine, tid, s_fin, [] { __syncthreads(); });
 }
 
 // =========================================================================================
-// Main kernel: persistent CTAs, TMA bulk copies into a shared-memory ring.
+// Main kernel: persistent CTAs (one per SM), TMA tensor-map tiles into a shared-memory ring.
+//
+// Tiles of 64 columns x 32 rows are linearised as ((map * strips + strip) * row_tiles + row_tile)
+// and split evenly over the CTAs (tile counts differ by at most one). One elected producer thread
+// issues, per tile, ONE cp.async.bulk.tensor.3d (SASS UTMALDG; out-of-range rows / columns are
+// zero-filled by the TMA unit, so there are no edge predicates in the consumers) plus one 1 KB
+// cp.async.bulk (UBLKCP) of the tile's 32 row-weight records; both complete on the stage's
+// mbarrier. 8 consumer warps read the stage with conflict-free LDS.128 (texels) and broadcast
+// LDS.128 (weights). Per-column sums live in registers across the row tiles of one strip; at a
+// strip boundary they are folded into the SH polynomials, at a map boundary the CTA's 48-float
+// partial is published; the last CTA of a map sums that map's partials in CTA order.
 // =========================================================================================
 constexpr int kTCols = 64;                 // columns per tile
-constexpr int kTRows = 32;                 // rows per pipeline stage
 constexpr int kTPhases = 4;                // row phases: 64 columns x 4 phases = 256 consumer threads
 constexpr int kTConsumers = kTCols * kTPhases;
 constexpr int kTThreads = kTConsumers + 32;
 constexpr int kTMaxStages = 8;
+constexpr int kTCtasPerSm = 2;             // two CTAs share an SM: one streams while the other starts up or flushes
+// rows per tile (= pipeline stage): 16 KB of texels per TMA instruction in either format
+__host__ __device__ constexpr int tile_rows(int fmt) { return fmt == VLB_FMT_RGBA32F ? 16 : 64; }
+constexpr int kTRowsMax = 64;
+constexpr int kScratchSets = 1 + VLB_MAX_LANES;   // the ctx stream's set + one per auxiliary lane
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -285,37 +318,40 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void tma_tile_g2s(void* dst, const CUtensorMap* tmap, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kTConsumers) : "memory"); }
 
-struct TmaUnit {
-    uint32_t map;
-    int strip, r0, r1, c0, ncols;
-};
-__device__ __forceinline__ TmaUnit decode_unit(const ProjParams& p, uint32_t u) {
-    TmaUnit t;
-    const int rb = u % p.row_blocks;
-    t.strip = (u / p.row_blocks) % p.strips;
-    t.map = u / (p.row_blocks * p.strips);
-    t.r0 = rb * p.rows_per_block;
-    t.r1 = min(p.H, t.r0 + p.rows_per_block);
-    t.c0 = t.strip * kTCols;
-    t.ncols = min(kTCols, p.W - t.c0);
-    return t;
+// CTA that owns tile t under the even split (first r CTAs own q + 1 tiles, the rest q).
+__device__ __forceinline__ uint32_t cta_of_tile(const ProjParams& p, uint32_t t) {
+    const uint32_t big = p.split_r * (p.split_q + 1);
+    return t < big ? t / (p.split_q + 1) : p.split_r + (t - big) / p.split_q;
 }
 
 template <int K, int FMT>
-__global__ void __launch_bounds__(kTThreads, 1) k_project_tma(const ProjParams p) {
+__global__ void __launch_bounds__(kTThreads, kTCtasPerSm) k_project_tiles(const __grid_constant__ CUtensorMap tmap, const ProjParams p) {
     constexpr int NG = K > 9 ? 7 : 5;
     constexpr int BPT = FMT == VLB_FMT_RGBA32F ? 16 : 4;
-    constexpr int STAGE_BYTES = kTRows * kTCols * BPT;
-    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int TR = tile_rows(FMT);
+    constexpr int TILE_BYTES = TR * kTCols * BPT;
+    constexpr int WEIGHT_BYTES = TR * 32;            // 8 floats per row
+    constexpr int STAGE_BYTES = TILE_BYTES + WEIGHT_BYTES;
+    extern __shared__ unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full[kTMaxStages], empty[kTMaxStages];
     __shared__ float s_red[6][32];
     __shared__ FinishSmem s_fin;
+    // TMA tile destinations must be 128-byte aligned
+    unsigned char* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     float* s_g = reinterpret_cast<float*>(smem + (size_t)p.n_stages * STAGE_BYTES);   // [4][64][NG*3]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = p.n_stages;
+    const uint32_t b = blockIdx.x;
+    const uint32_t t0 = b * p.split_q + min(b, p.split_r);
+    const uint32_t nt = p.split_q + (b < p.split_r ? 1u : 0u);
+    VLB_STAMP(0);
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kTConsumers / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -323,22 +359,19 @@ __global__ void __launch_bounds__(kTThreads, 1) k_project_tma(const ProjParams p
     __syncthreads();
 
     if (warp == kTConsumers / 32) {
-        // ===== producer warp: one bulk copy per tile row, 32 rows per stage =====
-        uint32_t it = 0;
-        for (uint32_t u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-            const TmaUnit t = decode_unit(p, u);
-            const uint32_t row_bytes = (uint32_t)t.ncols * BPT;
-            const char* gbase = reinterpret_cast<const char*>(p.texels) + (size_t)t.map * p.map_stride +
-                                ((size_t)t.r0 * p.W + t.c0) * BPT;
-            for (int r = t.r0; r < t.r1; r += kTRows, ++it) {
-                const int s = it % S;
-                mbar_wait(&empty[s], ((it / S) & 1) ^ 1);
-                const int nr = min(kTRows, t.r1 - r);
-                if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)nr * row_bytes);
-                __syncwarp();
-                if (lane < nr)
-                    bulk_g2s(smem + (size_t)s * STAGE_BYTES + (size_t)lane * kTCols * BPT,
-                             gbase + (size_t)(r - t.r0 + lane) * p.W * BPT, row_bytes, &full[s]);
+        // ===== producer: one elected thread, two copies per tile =====
+        if (lane == 0) {
+            for (uint32_t i = 0; i < nt; ++i) {
+                const uint32_t t = t0 + i;
+                const uint32_t rt = t % p.row_tiles, ms = t / p.row_tiles;
+                const uint32_t strip = ms % p.strips, map = ms / p.strips;
+                const int s = i % S;
+                mbar_wait(&empty[s], ((i / S) & 1) ^ 1);
+                unsigned char* stage = smem + (size_t)s * STAGE_BYTES;
+                mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+                tma_tile_g2s(stage, &tmap, (int)(strip * kTCols * 4), (int)(rt * TR), (int)map, &full[s]);
+                bulk_g2s(stage + TILE_BYTES, reinterpret_cast<const char*>(p.row_tab) + (size_t)rt * WEIGHT_BYTES,
+                         WEIGHT_BYTES, &full[s]);
             }
         }
         return;
@@ -346,79 +379,99 @@ __global__ void __launch_bounds__(kTThreads, 1) k_project_tma(const ProjParams p
 
     // ===== consumer warps =====
     const int col = tid & (kTCols - 1), ph = tid / kTCols;
-    uint32_t it = 0;
-    for (uint32_t u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-        const TmaUnit t = decode_unit(p, u);
-        float g[NG][3];
+    float g[NG][3];
 #pragma unroll
-        for (int i = 0; i < NG; ++i) g[i][0] = g[i][1] = g[i][2] = 0.f;
-        for (int r = t.r0; r < t.r1; r += kTRows, ++it) {
-            const int s = it % S;
-            mbar_wait(&full[s], (it / S) & 1);
-            const int nr = min(kTRows, t.r1 - r);
-            const unsigned char* stage = smem + (size_t)s * STAGE_BYTES;
-            if (col < t.ncols) {
+    for (int i = 0; i < NG; ++i) g[i][0] = g[i][1] = g[i][2] = 0.f;
+    float macc = 0.f;   // threads tid < K*3: this CTA's running partial of coefficient tid of the current map
+    for (uint32_t i = 0; i < nt; ++i) {
+        const uint32_t t = t0 + i;
+        const int s = i % S;
+        mbar_wait(&full[s], (i / S) & 1);
+        if (i == 0) VLB_STAMP(1);
+        const unsigned char* stage = smem + (size_t)s * STAGE_BYTES;
+        const float4* wts = reinterpret_cast<const float4*>(stage + TILE_BYTES);
 #pragma unroll
-                for (int j = 0; j < kTRows / kTPhases; ++j) {
-                    const int rr = ph + j * kTPhases;
-                    if (rr < nr) {
-                        float4 tx;
-                        if (FMT == VLB_FMT_RGBA32F) {
-                            tx = reinterpret_cast<const float4*>(stage)[rr * kTCols + col];
-                        } else {
-                            const uchar4 c = reinterpret_cast<const uchar4*>(stage)[rr * kTCols + col];
-                            tx = make_float4((float)c.x, (float)c.y, (float)c.z, 0.f);
-                        }
-                        const float4 ra = __ldg(p.row_tab + 2 * (r + rr));
-                        const float4 rb4 = __ldg(p.row_tab + 2 * (r + rr) + 1);
-                        const float tw[7] = {ra.x, ra.y, ra.z, ra.w, rb4.x, rb4.y, rb4.z};
+        for (int j = 0; j < TR / kTPhases; ++j) {
+            const int rr = j * kTPhases + ph;
+            float4 tx;
+            if (FMT == VLB_FMT_RGBA32F) {
+                tx = reinterpret_cast<const float4*>(stage)[rr * kTCols + col];
+            } else {
+                const uchar4 c = reinterpret_cast<const uchar4*>(stage)[rr * kTCols + col];
+                tx = make_float4((float)c.x, (float)c.y, (float)c.z, 0.f);
+            }
+            const float4 ra = wts[2 * rr], rb4 = wts[2 * rr + 1];
+            const float tw[7] = {ra.x, ra.y, ra.z, ra.w, rb4.x, rb4.y, rb4.z};
 #pragma unroll
-                        for (int i = 0; i < NG; ++i) {
-                            g[i][0] = fmaf(tw[i], tx.x, g[i][0]);
-                            g[i][1] = fmaf(tw[i], tx.y, g[i][1]);
-                            g[i][2] = fmaf(tw[i], tx.z, g[i][2]);
-                        }
-                    }
+            for (int k = 0; k < NG; ++k) {
+                g[k][0] = fmaf(tw[k], tx.x, g[k][0]);
+                g[k][1] = fmaf(tw[k], tx.y, g[k][1]);
+                g[k][2] = fmaf(tw[k], tx.z, g[k][2]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+
+        const bool last = i + 1 == nt;
+        if (i == 1) VLB_STAMP(6);
+        if (i == 3) VLB_STAMP(7);
+        if (last) VLB_STAMP(2);
+        if (last || (t + 1) % p.row_tiles == 0) {
+            // ---- strip boundary: merge the 4 row phases, apply the phi factors, reduce over columns ----
+            const uint32_t ms = t / p.row_tiles, strip = ms % p.strips;
+            float* mine_g = s_g + ((size_t)ph * kTCols + col) * (NG * 3);
+#pragma unroll
+            for (int k = 0; k < NG; ++k) {
+                mine_g[3 * k] = g[k][0]; mine_g[3 * k + 1] = g[k][1]; mine_g[3 * k + 2] = g[k][2];
+                g[k][0] = g[k][1] = g[k][2] = 0.f;
+            }
+            consumer_sync();
+            if (tid < 3 * kTCols) {
+                const int c = tid & (kTCols - 1), ch = tid / kTCols;
+                ColumnMoments<NG> m;
+                const float scale = FMT == VLB_FMT_RGBA8 ? (1.0f / 255.0f) : 1.0f;
+#pragma unroll
+                for (int k = 0; k < NG; ++k) {
+                    float v = 0.f;
+#pragma unroll
+                    for (int q = 0; q < kTPhases; ++q) v += s_g[((size_t)q * kTCols + c) * (NG * 3) + 3 * k + ch];
+                    m.g[k] = v * scale;
                 }
+                float o[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) o[k] = 0.f;
+                const int x = (int)strip * kTCols + c;
+                if (x < p.W) {
+                    m.set_phi(__ldg(p.col_cs + x));
+                    sh_from_moments<K, NG>(m, p.variant, o);
+                }
+                warp_transpose_reduce<32>(o, lane);        // lane l: sum over this warp's 32 columns of coefficient l
+                s_red[warp][lane] = o[0];
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-        }
-        // ---- flush this unit: merge the 4 row phases, apply the phi factors, reduce over columns ----
-        float* mine_g = s_g + ((size_t)ph * kTCols + col) * (NG * 3);
-#pragma unroll
-        for (int i = 0; i < NG; ++i) { mine_g[3 * i] = g[i][0]; mine_g[3 * i + 1] = g[i][1]; mine_g[3 * i + 2] = g[i][2]; }
-        consumer_sync();
-        if (tid < 3 * kTCols) {
-            const int c = tid & (kTCols - 1), ch = tid / kTCols;
-            ColumnMoments<NG> m;
-            const float scale = FMT == VLB_FMT_RGBA8 ? (1.0f / 255.0f) : 1.0f;
-#pragma unroll
-            for (int i = 0; i < NG; ++i) {
-                float v = 0.f;
-#pragma unroll
-                for (int q = 0; q < kTPhases; ++q) v += s_g[((size_t)q * kTCols + c) * (NG * 3) + 3 * i + ch];
-                m.g[i] = v * scale;
+            consumer_sync();
+            if (tid < K * 3) {
+                const int k = tid / 3, ch = tid % 3;
+                macc += s_red[2 * ch][k] + s_red[2 * ch + 1][k];
             }
-            float o[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = 0.f;
-            if (c < t.ncols) {
-                m.set_phi(__ldg(p.col_cs + t.c0 + c));
-                sh_from_moments<K, NG>(m, p.variant, o);
+            if (last) VLB_STAMP(3);
+            if (last || (t + 1) % p.tiles_per_map == 0) {
+                // ---- map boundary: publish this CTA's partial of the map ----
+                const uint32_t map = t / p.tiles_per_map;
+                const uint32_t b_first = cta_of_tile(p, map * p.tiles_per_map);
+                const uint32_t b_last = cta_of_tile(p, (map + 1) * p.tiles_per_map - 1);
+                const uint32_t P = b_last - b_first + 1;
+                if (P == 1) {
+                    if (tid < VLB_SH_STRIDE) p.out[(size_t)map * VLB_SH_STRIDE + tid] = macc;
+                } else {
+                    // (CTA, map) pairs form a monotone staircase, so slot b + map is unique
+                    publish_and_finish(p, map, (size_t)b_first + map, b - b_first, P, macc, tid, s_fin, [] { consumer_sync(); });
+                }
+                macc = 0.f;
+                if (last) VLB_STAMP(4);
             }
-            warp_transpose_reduce<32>(o, lane);        // lane l: sum over this warp's 32 columns of coefficient l
-            s_red[warp][lane] = o[0];
         }
-        consumer_sync();
-        float mine = 0.f;
-        if (tid < K * 3) {
-            const int i = tid / 3, ch = tid % 3;
-            mine = s_red[2 * ch][i] + s_red[2 * ch + 1][i];
-        }
-        const uint32_t P = p.strips * p.row_blocks;
-        publish_and_finish(p, t.map, u % P, P, mine, tid, s_fin, [] { consumer_sync(); });
     }
+    VLB_STAMP(5);
 }
 
 static int env_int(const char* name, int dflt) {
@@ -426,20 +479,89 @@ static int env_int(const char* name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
+#ifdef VLB_PROJ_TIMING
+static DevBuf g_tbuf;
+static unsigned g_tgrid = 0;
+int proj_timing_dump(vlb_ctx* ctx, int n_launches) {
+    if (!env_int("VLB_PROJ_TIMING", 0) || !g_tbuf.p) return VLB_OK;
+    std::vector<unsigned long long> h((size_t)kScratchSets * 512 * 8);
+    VLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    VLB_CUDA(ctx, cudaMemcpy(h.data(), g_tbuf.p, h.size() * 8, cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull;
+    for (unsigned b = 0; b < g_tgrid; ++b) t0 = std::min(t0, h[b * 8]);
+    static const char* names[8] = {"start", "first", "last", "flushed", "published", "exit", "tile1", "tile3"};
+    for (int l = 0; l < n_launches && l < kScratchSets; ++l) {
+        fprintf(stderr, "[launch %d us]", l);
+        for (int k = 0; k < 8; ++k) {
+            double mn = 1e30, mx = 0, av = 0;
+            for (unsigned b = 0; b < g_tgrid; ++b) {
+                const double d = (double)(long long)(h[((size_t)l * 512 + b) * 8 + k] - t0) * 1e-3;
+                mn = std::min(mn, d); mx = std::max(mx, d); av += d / g_tgrid;
+            }
+            fprintf(stderr, " %s %.1f/%.1f/%.1f |", names[k], mn, av, mx);
+        }
+        fprintf(stderr, "\n");
+    }
+    return VLB_OK;
+}
+#endif
+
 template <int K, int FMT>
-static cudaError_t launch_tma(const ProjParams& p, unsigned grid, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(k_project_tma<K, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    k_project_tma<K, FMT><<<grid, kTThreads, smem, st>>>(p);
+static cudaError_t launch_tiles(const CUtensorMap& tmap, const ProjParams& p, unsigned grid, size_t smem, cudaStream_t st) {
+    static size_t allowed = 0;   // per instantiation; raising the limit is idempotent, so a race is harmless
+    if (smem > allowed) {
+        cudaError_t e = cudaFuncSetAttribute(k_project_tiles<K, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        allowed = smem;
+    }
+    k_project_tiles<K, FMT><<<grid, kTThreads, smem, st>>>(tmap, p);
     return cudaSuccess;
 }
 
+// Partials + arrival counters of scratch set `set` (0: ctx stream, 1 + lane: auxiliary lanes). Growing a
+// buffer frees the old one, which synchronises the device, so it is safe while other lanes run; the
+// counters are self-resetting and only need zeroing when (re)allocated.
+static int scratch_set(vlb_ctx* ctx, int set, size_t n_slots, size_t n_maps, float** partials, unsigned** counters) {
+    if (ctx->d_proj_partials.cap < kScratchSets * n_slots * VLB_SH_STRIDE * sizeof(float) ||
+        ctx->d_proj_counters.cap < kScratchSets * n_maps * sizeof(unsigned)) {
+        VLB_CUDA(ctx, cudaDeviceSynchronize());
+        VLB_CUDA(ctx, ctx->d_proj_partials.reserve(kScratchSets * n_slots * VLB_SH_STRIDE * sizeof(float)));
+        VLB_CUDA(ctx, ctx->d_proj_counters.reserve(kScratchSets * n_maps * sizeof(unsigned)));
+        VLB_CUDA(ctx, cudaMemset(ctx->d_proj_counters.p, 0, ctx->d_proj_counters.cap));
+    }
+    // sets are laid out by the CURRENT call's sizes; a set is only ever used by one stream at a time
+    *partials = ctx->d_proj_partials.as<float>() + (size_t)set * n_slots * VLB_SH_STRIDE;
+    *counters = ctx->d_proj_counters.as<unsigned>() + (size_t)set * n_maps;
+    return VLB_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point query: libvlb_bake.so links only libcudart.
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+// lane < 0: an ordinary launch on the ctx stream. lane >= 0: a launch on the ctx's auxiliary stream
+// `lane` with that lane's scratch set (vlb_skybox_project_sh_device_ptrs: independent maps alternate
+// over the lanes, so one map streams from HBM while another flushes, reduces and retires).
 int project_sh_device(vlb_ctx* ctx, const void* d_texels, uint64_t map_stride, uint32_t n_maps, int fmt, int W, int H,
-                      int order, int variant, float* d_out) {
-    cudaStream_t st = ctx->stream;
-    // tables (cached per size/variant): per-row quadrature factors, per-column cos/sin(phi)
+                      int order, int variant, float* d_out, int lane) {
+    cudaStream_t st = lane < 0 ? ctx->stream : ctx->lane_stream[lane];
+    // tables (cached per size/variant): per-row quadrature factors (zero-padded to whole tiles), per-column cos/sin(phi)
     if (ctx->tab_w != W || ctx->tab_h != H || ctx->tab_variant != variant) {
-        std::vector<float> row_tab(8 * (size_t)H), row_sc(2 * (size_t)H), col(2 * (size_t)W);
+        const size_t h_pad = ((size_t)H + kTRowsMax - 1) / kTRowsMax * kTRowsMax;
+        std::vector<float> row_tab(8 * h_pad, 0.f), row_sc(2 * (size_t)H), col(2 * (size_t)W);
         host_proj_row_table(W, H, row_tab.data());
         host_dir_tables(W, H, variant == 0 ? kPi / 2.0f : 0.f, row_sc.data(), col.data());   // skybox_sh.comp:28
         VLB_CUDA(ctx, ctx->d_row_tab.reserve(row_tab.size() * sizeof(float)));
@@ -454,45 +576,57 @@ int project_sh_device(vlb_ctx* ctx, const void* d_texels, uint64_t map_stride, u
     p.row_tab = ctx->d_row_tab.as<float4>(); p.col_cs = ctx->d_col_tab.as<float2>();
     p.out = d_out; p.variant = variant;
     const int bpt = fmt == VLB_FMT_RGBA32F ? 16 : 4;
-    p.bpt = bpt;
-    const bool aligned = ((size_t)W * bpt) % 16 == 0 && map_stride % 16 == 0 && (reinterpret_cast<uintptr_t>(d_texels) % 16) == 0;
-    const bool use_tma = aligned && env_int("VLB_PROJ_TMA", 1) != 0;
+    // TMA needs a 16-byte aligned base and 16-byte multiples for the row and map pitches
+    const bool aligned = ((size_t)W * bpt) % 16 == 0 && (n_maps == 1 || map_stride % 16 == 0) &&
+                         (reinterpret_cast<uintptr_t>(d_texels) % 16) == 0 && (uint64_t)W * 4 < (1ull << 32);
+    const bool use_tma = aligned && env_int("VLB_PROJ_TMA", 1) != 0 && encode_tiled_fn() != nullptr;
 
     if (use_tma) {
         p.strips = (W + kTCols - 1) / kTCols;
-        const long long n_ms = (long long)n_maps * p.strips;
-        const int sms = ctx->sm_count;
-        int rows = H;
-        if (n_ms < sms) {
-            const int rbk = std::max<long long>(1, sms / n_ms);
-            rows = (H + rbk - 1) / rbk;
-            rows = std::max(kTPhases, (rows + kTPhases - 1) / kTPhases * kTPhases);
-        }
-        rows = env_int("VLB_PROJ_ROWS", rows);
-        rows = std::max(1, std::min(rows, H));
-        p.rows_per_block = rows;
-        p.row_blocks = (H + rows - 1) / rows;
-        const uint64_t P = (uint64_t)p.strips * p.row_blocks;
-        const uint64_t n_units = P * n_maps;
-        if (n_units >= (1ull << 31)) return ctx->fail(VLB_ERR_UNSUPPORTED, "project_sh: too many tiles");
-        p.n_units = (uint32_t)n_units;
-        const int stage_bytes = kTRows * kTCols * bpt;
+        const int TR = tile_rows(fmt);
+        p.row_tiles = (uint32_t)((H + TR - 1) / TR);
+        const uint64_t tiles_per_map = (uint64_t)p.strips * p.row_tiles;
+        const uint64_t n_tiles = tiles_per_map * n_maps;
+        if (n_tiles >= (1ull << 31)) return ctx->fail(VLB_ERR_UNSUPPORTED, "project_sh: too many tiles");
+        p.tiles_per_map = (uint32_t)tiles_per_map; p.n_tiles = (uint32_t)n_tiles;
+        // Long launches (many maps) fill both CTA slots of every SM. Short ones (a single map) take one
+        // slot per SM, so that a launch on another lane / stream runs in the other slot and streams
+        // while this one flushes, publishes and sums.
+        const bool long_launch = n_tiles >= (uint64_t)ctx->sm_count * kTCtasPerSm * 16;
+        const int per_sm = env_int("VLB_PROJ_CTAS_PER_SM", long_launch ? kTCtasPerSm : 1);
+        const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * std::max(1, std::min(per_sm, kTCtasPerSm)));
+        p.split_q = p.n_tiles / grid; p.split_r = p.n_tiles % grid;
+
+        CUtensorMap tmap;
+        const cuuint64_t gdim[3] = {(cuuint64_t)W * 4, (cuuint64_t)H, (cuuint64_t)n_maps};
+        const cuuint64_t gstride[2] = {(cuuint64_t)W * bpt, n_maps == 1 ? (cuuint64_t)W * bpt * H : (cuuint64_t)map_stride};
+        const cuuint32_t box[3] = {(cuuint32_t)kTCols * 4, (cuuint32_t)TR, 1};
+        const cuuint32_t estride[3] = {1, 1, 1};
+        const CUresult cr = encode_tiled_fn()(&tmap, bpt == 16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
+                                              const_cast<void*>(d_texels), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) return ctx->fail(VLB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+
+        const int stage_bytes = TR * kTCols * bpt + TR * 32;
         const int ng3 = (order == 2 ? 5 : 7) * 3;
         const size_t merge_bytes = (size_t)kTPhases * kTCols * ng3 * sizeof(float);
-        int stages = env_int("VLB_PROJ_STAGES", bpt == 16 ? 6 : kTMaxStages);
+        // lanes: 3 stages (52 KB in flight per CTA) so that three launches fit on an SM side by side
+        int stages = env_int("VLB_PROJ_STAGES", lane < 0 ? 5 : 3);
         stages = std::max(2, std::min(stages, kTMaxStages));
         p.n_stages = stages;
-        const size_t smem = (size_t)stages * stage_bytes + merge_bytes;
-        const unsigned grid = (unsigned)std::min<uint64_t>(n_units, (uint64_t)sms);
-        VLB_CUDA(ctx, ctx->d_proj_partials.reserve(n_units * VLB_SH_STRIDE * sizeof(float)));
-        if (ctx->d_proj_counters.cap < n_maps * sizeof(unsigned)) {
-            VLB_CUDA(ctx, ctx->d_proj_counters.reserve(n_maps * sizeof(unsigned)));
-            VLB_CUDA(ctx, cudaMemsetAsync(ctx->d_proj_counters.p, 0, ctx->d_proj_counters.cap, st));
-        }
-        p.partials = ctx->d_proj_partials.as<float>(); p.counters = ctx->d_proj_counters.as<unsigned>();
+        const size_t smem = (size_t)stages * stage_bytes + merge_bytes + 128;
+        const size_t n_slots = (size_t)grid + n_maps;
+        const int set = lane < 0 ? 0 : 1 + lane;
+        if (int r = scratch_set(ctx, set, n_slots, n_maps, &p.partials, &p.counters)) return r;
+#ifdef VLB_PROJ_TIMING
+        VLB_CUDA(ctx, g_tbuf.reserve((size_t)kScratchSets * 512 * 8 * sizeof(unsigned long long)));
+        p.timing = g_tbuf.as<unsigned long long>() + (size_t)set * 512 * 8;
+        g_tgrid = grid;
+#endif
         cudaError_t e;
-        if (order == 2) e = fmt == VLB_FMT_RGBA32F ? launch_tma<9, VLB_FMT_RGBA32F>(p, grid, smem, st) : launch_tma<9, VLB_FMT_RGBA8>(p, grid, smem, st);
-        else            e = fmt == VLB_FMT_RGBA32F ? launch_tma<16, VLB_FMT_RGBA32F>(p, grid, smem, st) : launch_tma<16, VLB_FMT_RGBA8>(p, grid, smem, st);
+        if (order == 2) e = fmt == VLB_FMT_RGBA32F ? launch_tiles<9, VLB_FMT_RGBA32F>(tmap, p, grid, smem, st) : launch_tiles<9, VLB_FMT_RGBA8>(tmap, p, grid, smem, st);
+        else            e = fmt == VLB_FMT_RGBA32F ? launch_tiles<16, VLB_FMT_RGBA32F>(tmap, p, grid, smem, st) : launch_tiles<16, VLB_FMT_RGBA8>(tmap, p, grid, smem, st);
         VLB_CUDA(ctx, e);
         VLB_LAUNCH_CHECK(ctx);
         return VLB_OK;
@@ -511,12 +645,7 @@ int project_sh_device(vlb_ctx* ctx, const void* d_texels, uint64_t map_stride, u
     const uint64_t P = (uint64_t)p.strips * p.row_blocks;
     const uint64_t n_blocks = P * n_maps;
     if (n_blocks >= (1ull << 31)) return ctx->fail(VLB_ERR_UNSUPPORTED, "project_sh: launch too large");
-    VLB_CUDA(ctx, ctx->d_proj_partials.reserve(n_blocks * VLB_SH_STRIDE * sizeof(float)));
-    if (ctx->d_proj_counters.cap < n_maps * sizeof(unsigned)) {
-        VLB_CUDA(ctx, ctx->d_proj_counters.reserve(n_maps * sizeof(unsigned)));
-        VLB_CUDA(ctx, cudaMemsetAsync(ctx->d_proj_counters.p, 0, ctx->d_proj_counters.cap, st));
-    }
-    p.partials = ctx->d_proj_partials.as<float>(); p.counters = ctx->d_proj_counters.as<unsigned>();
+    if (int r = scratch_set(ctx, lane < 0 ? 0 : 1 + lane, n_blocks, n_maps, &p.partials, &p.counters)) return r;
     const unsigned grid = (unsigned)n_blocks;
     if (order == 2) {
         if (fmt == VLB_FMT_RGBA32F) k_project_ldg<9, VLB_FMT_RGBA32F><<<grid, kProjBlock, 0, st>>>(p);

@@ -12,6 +12,8 @@
 
 #include "../../include/vlb_bake.h"
 
+#define VLB_MAX_LANES 4
+
 namespace vlb {
 
 void set_thread_error(const char* msg);
@@ -78,6 +80,9 @@ struct vlb_ctx {
     int dir_w = 0, dir_h = 0;
     vlb_bake_stats last_bake{};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // ---- auxiliary lanes (independent skybox maps in flight side by side) ----
+    cudaStream_t lane_stream[VLB_MAX_LANES] = {};
+    cudaEvent_t lane_fork = nullptr, lane_join[VLB_MAX_LANES] = {};
     // ---- trace ----
     vlb::DevBuf d_ray_o, d_ray_d, d_hit_id, d_hit_tuv, d_hit_key;
 
@@ -120,7 +125,7 @@ size_t ref_order_index(int i, int j, int k, int Nx, int Ny, int Nz);
 int scene_flatten(vlb_ctx* ctx);
 int bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats);
 int project_sh_device(vlb_ctx* ctx, const void* d_texels, uint64_t map_stride, uint32_t n_maps, int fmt,
-                      int W, int H, int order, int variant, float* d_out);
+                      int W, int H, int order, int variant, float* d_out, int lane = -1);
 int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out);
 int trace_rays(vlb_ctx* ctx, const float* o, const float* d, uint64_t n, float tmin, float tmax, int accel,
                int kind, int32_t* ids, float* tuv);
