@@ -100,13 +100,9 @@ void* emu_scene_create(const vlb_vertex* verts, const uint32_t* indices, const v
         tri_aabb(s->tris[3 * j], s->tris[3 * j + 1], s->tris[3 * j + 2], &lbox[2 * j], &lbox[2 * j + 1]);
     }
     const float ext = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
-    s->nodes.resize(4 * (size_t)std::max(n - 1, 1u));
+    s->nodes.resize((size_t)kNodeQuads * std::max(n - 1, 1u));
     if (n == 1) {
-        float4 a = lbox[0], b = lbox[1];
-        pad_box(&a, &b, ext * 1e-6f);
-        s->nodes[0] = mk4(a.x, b.x, a.y, b.y); s->nodes[1] = s->nodes[0]; s->nodes[2] = mk4(a.z, b.z, a.z, b.z);
-        int r = leaf_ref(0, 1);
-        s->nodes[3] = mk4(i2f(r), i2f(r), 0, 0);
+        emit_single4(lbox.data(), ext * 1e-6f, s->nodes.data());
         return s;
     }
     s->left.assign(n, 0); s->right.assign(n, 0); s->first.assign(n, 0); s->last.assign(n, 0);
@@ -131,18 +127,19 @@ void* emu_scene_create(const vlb_vertex* verts, const uint32_t* indices, const v
             cur = s->parent_i[cur];
         }
     }
-    for (int i = 0; i < (int)n - 1; ++i)   // k_emit
-        emit_node(i, s->left.data(), s->right.data(), s->first.data(), s->last.data(), ibox.data(), lbox.data(), max_leaf,
-                  ext * 1e-6f, s->nodes.data());
-    // tree depth (stack bound) by DFS over the emitted nodes
+    for (int i = 0; i < (int)n - 1; ++i) {   // k_emit
+        if (i != 0 && (s->last[i] - s->first[i] + 1 <= max_leaf || (node_depth(s->parent_i.data(), i) & 1))) continue;
+        emit_node4(i, s->left.data(), s->right.data(), s->first.data(), s->last.data(), ibox.data(), lbox.data(), max_leaf,
+                   ext * 1e-6f, s->nodes.data());
+    }
+    // worst-case number of pending stack entries, by DFS over the emitted nodes (3 pushes per level)
     std::vector<std::pair<int, int>> st; st.push_back({0, 1});
     while (!st.empty()) {
         auto [nd, dp] = st.back(); st.pop_back();
         s->max_depth = std::max(s->max_depth, dp);
-        const float4 meta = s->nodes[4 * nd + 3];
-        const int r0 = f2i(meta.x), r1 = f2i(meta.y);
-        if (r0 >= 0) st.push_back({r0, dp + 1});
-        if (r1 >= 0) st.push_back({r1, dp + 1});
+        const float4 refs = s->nodes[(size_t)kNodeQuads * nd + 6];
+        const int r[4] = {f2i(refs.x), f2i(refs.y), f2i(refs.z), f2i(refs.w)};
+        for (int k = 0; k < 4; ++k) if (r[k] >= 0) st.push_back({r[k], dp + 1});
     }
     return s;
 }
@@ -156,7 +153,7 @@ void emu_scene_set_skybox(void* h, const float* rgba32f, int W, int H) {
     s->sky_w = W; s->sky_h = H;
 }
 
-static BvhView view(EmuScene* s) { BvhView b; b.nodes = s->nodes.data(); b.tris = s->tris.data(); b.n_tris = s->n; return b; }
+static BvhView view(EmuScene* s) { BvhView b; b.nodes = s->nodes.data(); b.tris = s->tris.data(); b.n_tris = s->n; b.overflow = nullptr; return b; }
 
 void emu_trace_rays(void* h, const float* o, const float* d, uint64_t n, float tmin, float tmax, int kind, int32_t* ids,
                     float* tuv, uint64_t* counters) {

@@ -16,6 +16,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvlb_bake.so")
+LIB_PATH = os.environ.get("VLB_LIB", LIB_PATH)   # A/B runs of instrumented / variant builds
 
 # ---- layouts shared with shaders/structures.h (scalar layout) ------------------------------
 VERTEX_DTYPE = np.dtype([("position", "<f4", (4,)), ("normal", "<f4", (3,)), ("uv0", "<f4", (2,)),

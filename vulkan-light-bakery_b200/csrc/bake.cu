@@ -17,6 +17,7 @@ namespace vlb {
 constexpr int kBakeBlock = 128;
 constexpr int kTileW = 8, kTileH = 4;   // one warp = an 8x4 tile of adjacent direction texels
 
+struct WarpQueues;
 struct BakeParams {
     BvhView bvh;
     ShadeView shade;
@@ -33,6 +34,8 @@ struct BakeParams {
     unsigned int* work_counter;
     unsigned long long* stats;   // [0] shadow rays, [1] nodes visited, [2] triangles tested
     int ref_order, world_frame;
+    WarpQueues* stream_scratch;  // k_bake_stream: per-warp radiance tile + ray queues, [grid * warps per block]
+    int node_min;                // k_bake_stream: the node loop yields to the leaf phase below this many lanes
 };
 
 __device__ __forceinline__ size_t out_slot(const BakeParams& p, uint32_t q) {
@@ -109,6 +112,267 @@ __global__ void __launch_bounds__(kBakeBlock) k_bake(const BakeParams p) {
     }
 }
 
+// =========================================================================================
+// k_bake_stream — the production bake kernel: a warp is a small wavefront path tracer.
+//
+// A warp owns a work item = (probe, run of 256-direction chunks). Inside a chunk every LANE is a ray
+// slot: an idle lane first takes a queued shadow ray, otherwise the next direction of the chunk
+// (ballot + popc ranks; directions in 8x4-texel tile order so the rays in flight stay angularly
+// adjacent), and traverses the LBVH. Primary (closest-hit) and shadow (any-hit) rays share one
+// "while-while" loop: all lanes step through internal nodes until most of them hold a leaf, then
+// the leaves are intersected. A finished primary ray only pushes its hit record into a per-warp
+// queue and frees its lane; once 32 records are queued the whole warp shades them
+// together (env_map.rchit / main.rmiss arithmetic at full SIMD width) and pushes the shadow rays
+// that are needed into a second queue. A finished shadow ray selects the lit or dark radiance
+// computed at shading time. Radiance goes to a shared-memory tile indexed by direction; when the
+// chunk is drained the warp projects its 256 radiances onto SH cooperatively (lane l takes
+// directions l, l+32, ... in a fixed order, so the result is bitwise reproducible whatever the
+// run-time ray scheduling was), reduces with shuffles and keeps one or two running coefficients per
+// lane. Radiance never leaves the SM; HBM sees 192 bytes per item.
+// The per-ray arithmetic is exactly that of probe_ray_radiance (vlb_shade.cuh).
+// =========================================================================================
+constexpr int kChunkTiles = 8;
+constexpr int kChunkDirs = kChunkTiles * 32;
+constexpr int kRayDone = kNoChild;          // traversal finished
+constexpr int kHitCap = 64;                 // queued hit records per warp (<= 31 waiting + 32 arriving)
+constexpr int kShadowCap = 64;              // queued shadow rays per warp (shading needs 32 free slots)
+constexpr int kStreamWarps = kBakeBlock / 32;
+
+struct WarpQueues {
+    float rad[3][kChunkDirs];      // radiance of the current chunk, by direction
+    // hit queue (SoA): flat triangle id (-1: miss), t, u, v, direction index
+    int hq_id[kHitCap]; float hq_t[kHitCap], hq_u[kHitCap], hq_v[kHitCap]; int hq_dir[kHitCap];
+    // shadow-ray queue: origin, unit direction, length, direction index, radiance if lit / if occluded
+    float sq_o[3][kShadowCap], sq_d[3][kShadowCap], sq_len[kShadowCap]; int sq_dir[kShadowCap];
+    float sq_rgb[6][kShadowCap];
+    float lane_rgb[6][32];         // the same two radiances for the shadow ray a lane is tracing
+};
+
+template <int K, bool COUNT>
+__global__ void __launch_bounds__(kBakeBlock, 8) k_bake_stream(const BakeParams p) {
+    constexpr int V = (K * 3 <= 32) ? 32 : 64;
+    // The per-warp queues live in a global scratch buffer (L1/L2 resident, ~9 KB per resident warp),
+    // not in shared memory: measured on B200, leaving the SM's 228 KB to the L1 cache (BVH nodes)
+    // and fitting 8 blocks per SM is worth more than shared-memory latency for the queue traffic
+    // (about 100 bytes per ray against ~1.5 KB of node and triangle reads).
+    WarpQueues* s_all = p.stream_scratch + (size_t)blockIdx.x * kStreamWarps;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    WarpQueues& S = s_all[warp];
+    const BvhView& bvh = p.bvh;
+    const bool want_shadow = (p.c.flags & 1u) != 0;
+    TraceCounters cnt; cnt.nodes = 0; cnt.tris = 0;
+    uint32_t shadow = 0;
+    int stack[kStackSize];
+
+    for (;;) {
+        unsigned item = 0;
+        if (lane == 0) item = atomicAdd(p.work_counter, 1u);
+        item = __shfl_sync(full, item, 0);
+        if (item >= p.n_items) break;
+        const uint32_t q = item / (uint32_t)p.chunks, part = item % (uint32_t)p.chunks;
+        const uint32_t g = q + (uint32_t)p.k0 * (uint32_t)(p.Nx * p.Ny);
+        const Vec3 po = mk3(p.px[g % p.Nx], p.py[(g / p.Nx) % p.Ny], p.pz[g / (p.Nx * p.Ny)]);
+        const int tile_begin = part * p.tiles_per_chunk;
+        const int tile_end = min(tile_begin + p.tiles_per_chunk, p.n_tiles);
+        float coef0 = 0.f, coef1 = 0.f;   // running sums of coefficient `lane` (V=32) / 2*lane, 2*lane+1 (V=64)
+
+        for (int base_tile = tile_begin; base_tile < tile_end; base_tile += kChunkTiles) {
+            const int n_dirs = min(kChunkTiles, tile_end - base_tile) * 32;
+            // ------------------------------ trace the chunk ------------------------------
+            int next = 0, n_hit = 0, n_sh = 0;   // warp-uniform: directions handed out, queue fills
+            bool busy = false;
+            int kind = 0;                        // 0 primary (closest hit), 1 shadow (any hit)
+            int my_dir = 0, cur = kRayDone, sp = 0;
+            Vec3 ro = po, rd = po, idir = po, ood = po;
+            float tmin = 0.f, tcull = 0.f;
+            HitRec best; best.id = -1; best.t = 0.f; best.u = 0.f; best.v = 0.f;
+            for (;;) {
+                // ---- 1. refill idle lanes: queued shadow rays first, then new directions ----
+                const unsigned idle = __ballot_sync(full, !busy);
+                if (idle != 0u && (n_sh > 0 || next < n_dirs)) {
+                    const int n_idle = __popc(idle), rank = __popc(idle & lt_mask);
+                    const int take_sh = min(n_idle, n_sh);
+                    const int take_new = min(n_idle - take_sh, n_dirs - next);
+                    if (!busy && rank < take_sh) {
+                        const int e = n_sh - 1 - rank;
+                        ro = mk3(S.sq_o[0][e], S.sq_o[1][e], S.sq_o[2][e]);
+                        rd = mk3(S.sq_d[0][e], S.sq_d[1][e], S.sq_d[2][e]);
+                        tmin = 0.0f; tcull = S.sq_len[e];                               // env_map.rchit:87
+                        my_dir = S.sq_dir[e];
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) S.lane_rgb[k][lane] = S.sq_rgb[k][e];
+                        kind = 1; busy = true;
+                    } else if (!busy && rank - take_sh < take_new) {
+                        const int cand = next + rank - take_sh;
+                        const int tile = base_tile + (cand >> 5), w = cand & 31;
+                        const int x = (tile % p.tiles_x) * kTileW + (w & (kTileW - 1));
+                        const int y = (tile / p.tiles_x) * kTileH + (w / kTileW);
+                        if (x < p.W && y < p.H) {
+                            const float2 row = __ldg(p.row_sc + y), col = __ldg(p.col_cs + x);
+                            const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);   // sh_common.h:8-12
+                            rd = mk3(t.x, t.z, t.y);                                   // env_map.rgen:21 .xzy
+                            ro = po;
+                            tmin = p.c.tmin; tcull = p.c.tmax;
+                            my_dir = cand; kind = 0; busy = true;
+                        } else {
+                            S.rad[0][cand] = 0.f; S.rad[1][cand] = 0.f; S.rad[2][cand] = 0.f;   // outside the direction grid
+                        }
+                    }
+                    if (busy && cur == kRayDone) {     // freshly started ray
+                        idir = mk3(safe_inv(rd.x), safe_inv(rd.y), safe_inv(rd.z));
+                        ood = mk3(ro.x * idir.x, ro.y * idir.y, ro.z * idir.z);
+                        best.id = -1; best.t = tcull; best.u = 0.f; best.v = 0.f;
+                        sp = 0;
+                        cur = bvh.n_tris ? 0 : kRayDone;
+                    }
+                    n_sh -= take_sh;
+                    next += take_new;
+                    __syncwarp();
+                }
+                const unsigned running = __ballot_sync(full, busy);
+                // ---- 2. shade queued hits: a full warp of them, or whatever is left when nothing runs ----
+                if ((n_hit >= 32 && n_sh <= kShadowCap - 32) || (running == 0u && n_hit > 0)) {
+                    const int take = min(n_hit, 32);
+                    const int e = n_hit - take + lane;
+                    bool push = false;
+                    float lit_rgb[3] = {0.f, 0.f, 0.f}, dark_rgb[3] = {0.f, 0.f, 0.f};
+                    ShadePrelude pre;
+                    int dir = 0;
+                    if (lane < take) {
+                        HitRec h; h.id = S.hq_id[e]; h.t = S.hq_t[e]; h.u = S.hq_u[e]; h.v = S.hq_v[e];
+                        dir = S.hq_dir[e];
+                        const int tile = base_tile + (dir >> 5), w = dir & 31;
+                        const int x = (tile % p.tiles_x) * kTileW + (w & (kTileW - 1));
+                        const int y = (tile / p.tiles_x) * kTileH + (w / kTileW);
+                        const float2 row = __ldg(p.row_sc + y), col = __ldg(p.col_cs + x);
+                        const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);
+                        const Vec3 r = mk3(t.x, t.z, t.y);
+                        float rgb[3] = {0.f, 0.f, 0.f};                                 // env_map.rgen:25
+                        if (h.id >= 0) {
+                            const bool lit = shade_prelude(p.shade, p.c, h, po, r, pre);
+                            if (lit && want_shadow) {
+                                // radiance for both outcomes now, the shadow ray decides (env_map.rchit:83-99)
+                                shade_finish(p.c, pre, r, false, lit_rgb);
+                                shade_finish(p.c, pre, r, true, dark_rgb);
+                                push = true;
+                            } else {
+                                shade_finish(p.c, pre, r, !lit, rgb);
+                            }
+                        } else if ((p.c.flags & 2u) && p.shade.sky) {                   // VLB_BAKE_SKYBOX_ON_MISS
+                            sky_lookup(p.shade, r, rgb);
+                            if (p.c.flags & 4u) { rgb[0] = srgb_encode(rgb[0]); rgb[1] = srgb_encode(rgb[1]); rgb[2] = srgb_encode(rgb[2]); }
+                        }
+                        if (!push) {
+                            if (p.c.flags & 8u) { rgb[0] = quant8(rgb[0]); rgb[1] = quant8(rgb[1]); rgb[2] = quant8(rgb[2]); }
+                            S.rad[0][dir] = rgb[0]; S.rad[1][dir] = rgb[1]; S.rad[2][dir] = rgb[2];
+                        }
+                    }
+                    const unsigned pm = __ballot_sync(full, push);
+                    if (push) {
+                        const int d = n_sh + __popc(pm & lt_mask);
+                        S.sq_o[0][d] = pre.so.x; S.sq_o[1][d] = pre.so.y; S.sq_o[2][d] = pre.so.z;   // env_map.rchit:82
+                        S.sq_d[0][d] = pre.Ln.x; S.sq_d[1][d] = pre.Ln.y; S.sq_d[2][d] = pre.Ln.z;
+                        S.sq_len[d] = pre.llen; S.sq_dir[d] = dir;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) { S.sq_rgb[k][d] = lit_rgb[k]; S.sq_rgb[3 + k][d] = dark_rgb[k]; }
+                        ++shadow;
+                    }
+                    n_sh += __popc(pm);
+                    n_hit -= take;
+                    __syncwarp();
+                    continue;
+                }
+                if (running == 0u) {
+                    if (n_sh == 0 && next >= n_dirs) break;
+                    continue;
+                }
+                // ---- 3. internal nodes: lanes step until most of them hold a leaf ----
+                for (;;) {
+                    const bool at_node = busy && cur >= 0;
+                    const unsigned nm = __ballot_sync(full, at_node);
+                    if (nm == 0u || (__popc(nm) < p.node_min && __popc(running) - __popc(nm) >= p.node_min)) break;
+                    if (at_node) {
+                        if (COUNT) cnt.nodes++;
+                        cur = bvh4_step<true>(bvh, cur, idir, ood, tmin, tcull, stack, sp);   // one code path for both ray kinds
+                    }
+                }
+                // ---- 4. leaves ----
+                if (busy && cur < 0 && cur != kRayDone) {
+                    const bool terminated = kind ? leaf_step<true, COUNT>(bvh, cur, ro, rd, tmin, tcull, best, &cnt)
+                                                 : leaf_step<false, COUNT>(bvh, cur, ro, rd, tmin, tcull, best, &cnt);
+                    cur = (terminated || sp == 0) ? kRayDone : stack[--sp];
+                }
+                // ---- 5. finished rays free their lane ----
+                const bool fin = busy && cur == kRayDone;
+                const unsigned fp = __ballot_sync(full, fin && kind == 0);
+                if (fin) {
+                    if (kind == 0) {
+                        const int e = n_hit + __popc(fp & lt_mask);
+                        S.hq_id[e] = best.id; S.hq_t[e] = best.t; S.hq_u[e] = best.u; S.hq_v[e] = best.v; S.hq_dir[e] = my_dir;
+                    } else {
+                        const int o3 = best.id >= 0 ? 3 : 0;                            // occluded -> dark
+                        float rgb[3] = {S.lane_rgb[o3 + 0][lane], S.lane_rgb[o3 + 1][lane], S.lane_rgb[o3 + 2][lane]};
+                        if (p.c.flags & 8u) { rgb[0] = quant8(rgb[0]); rgb[1] = quant8(rgb[1]); rgb[2] = quant8(rgb[2]); }  // QUANTIZE_RGBA8
+                        S.rad[0][my_dir] = rgb[0]; S.rad[1][my_dir] = rgb[1]; S.rad[2][my_dir] = rgb[2];
+                    }
+                    busy = false;
+                }
+                n_hit += __popc(fp);
+                if (n_hit > kHitCap) __trap();     // invariant: <= 31 waiting + 32 arriving
+                __syncwarp();
+            }
+            __syncwarp();
+            // ------------------------------ project the chunk ------------------------------
+            float acc[V];
+#pragma unroll
+            for (int i = 0; i < V; ++i) acc[i] = 0.f;
+            for (int tt = 0; tt * 32 < n_dirs; ++tt) {
+                const int tile = base_tile + tt;
+                const int x = (tile % p.tiles_x) * kTileW + (lane & (kTileW - 1));
+                const int y = (tile / p.tiles_x) * kTileH + (lane / kTileW);
+                if (x < p.W && y < p.H) {
+                    const float2 row = __ldg(p.row_sc + y), col = __ldg(p.col_cs + x);
+                    const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);
+                    const float w = p.pixel_area * row.x;                               // sh.comp:32-33
+                    float b[K];
+                    sh_basis<K>(p.world_frame ? mk3(t.x, t.z, t.y) : t, b);             // sh.comp:30,39
+                    const float r0 = S.rad[0][tt * 32 + lane], r1 = S.rad[1][tt * 32 + lane], r2 = S.rad[2][tt * 32 + lane];
+#pragma unroll
+                    for (int i = 0; i < K; ++i) {
+                        const float bw = b[i] * w;
+                        acc[3 * i + 0] = fmaf(bw, r0, acc[3 * i + 0]);
+                        acc[3 * i + 1] = fmaf(bw, r1, acc[3 * i + 1]);
+                        acc[3 * i + 2] = fmaf(bw, r2, acc[3 * i + 2]);
+                    }
+                }
+            }
+            warp_transpose_reduce<V>(acc, lane);
+            coef0 += acc[0];
+            if (V == 64) coef1 += acc[1];
+            __syncwarp();
+        }
+        float* dst = p.out + (p.chunks == 1 ? out_slot(p, q) : (size_t)item) * VLB_SH_STRIDE;
+        if (V == 32) {
+            dst[lane] = lane < K * 3 ? coef0 : 0.f;
+            if (lane + 32 < VLB_SH_STRIDE) dst[lane + 32] = 0.f;
+        } else {
+            if (2 * lane < VLB_SH_STRIDE) { dst[2 * lane] = coef0; dst[2 * lane + 1] = coef1; }
+        }
+    }
+    // statistics: one atomic per warp
+    unsigned long long s = shadow, nn = cnt.nodes, nt = cnt.tris;
+    for (int off = 16; off > 0; off >>= 1) {
+        s += __shfl_xor_sync(full, s, off);
+        if (COUNT) { nn += __shfl_xor_sync(full, nn, off); nt += __shfl_xor_sync(full, nt, off); }
+    }
+    if (lane == 0) {
+        atomicAdd(p.stats + 0, s);
+        if (COUNT) { atomicAdd(p.stats + 1, nn); atomicAdd(p.stats + 2, nt); }
+    }
+}
+
 // chunks > 1: per-probe sum of the chunk partials in chunk order (fixed order => deterministic).
 __global__ void k_sum_partials(const BakeParams p, const float* __restrict__ partials, uint32_t n_probes, float* out) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -165,6 +429,7 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out) {
 
     BakeParams p{};
     p.bvh.nodes = ctx->d_nodes.as<float4>(); p.bvh.tris = ctx->d_tris.as<float4>(); p.bvh.n_tris = (uint32_t)ctx->n_tris;
+    p.bvh.overflow = reinterpret_cast<unsigned int*>(ctx->d_scratch.as<float>() + 13);
     p.shade.tri_shade = ctx->d_tri_shade.as<float4>(); p.shade.inst = ctx->d_inst.as<float4>();
     p.shade.base_color = ctx->d_base_color.as<float4>();
     p.shade.sky = ctx->sky_w ? ctx->d_sky.as<float4>() : nullptr; p.shade.sky_w = ctx->sky_w; p.shade.sky_h = ctx->sky_h;
@@ -193,6 +458,7 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out) {
     p.stats = ctx->d_stats.as<unsigned long long>();
     p.ref_order = (s->flags & VLB_BAKE_REFERENCE_PROBE_ORDER) ? 1 : 0;
     p.world_frame = (s->flags & VLB_BAKE_SH_WORLD_FRAME) ? 1 : 0;
+    p.node_min = std::max(1, std::min(32, env_flag("VLB_BAKE_NODE_MIN", 8)));
     if (p.chunks > 1) {
         VLB_CUDA(ctx, ctx->d_partials.reserve((size_t)p.n_items * VLB_SH_STRIDE * sizeof(float)));
         p.out = ctx->d_partials.as<float>();
@@ -203,8 +469,13 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out) {
     const bool count = env_flag("VLB_BAKE_COUNTERS", 0) != 0;
     const int K = s->sh_order == 2 ? 9 : 16;
     void (*kern)(const BakeParams) = nullptr;
-    if (K == 9) kern = count ? k_bake<9, true> : k_bake<9, false>;
-    else        kern = count ? k_bake<16, true> : k_bake<16, false>;
+    if (env_flag("VLB_BAKE_KERNEL", 2) == 1) {      // the round-1 tile-per-warp kernel, kept for A/B runs
+        if (K == 9) kern = count ? k_bake<9, true> : k_bake<9, false>;
+        else        kern = count ? k_bake<16, true> : k_bake<16, false>;
+    } else {
+        if (K == 9) kern = count ? k_bake_stream<9, true> : k_bake_stream<9, false>;
+        else        kern = count ? k_bake_stream<16, true> : k_bake_stream<16, false>;
+    }
     int per_sm = 0;
     VLB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBakeBlock, 0));
     per_sm = std::max(per_sm, 1);
@@ -212,6 +483,8 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out) {
     uint32_t grid = (uint32_t)(ctx->sm_count * per_sm);
     grid = std::max(1u, std::min(grid, (warps_needed + (kBakeBlock / 32) - 1) / (kBakeBlock / 32)));
 
+    VLB_CUDA(ctx, ctx->d_stream_scratch.reserve((size_t)grid * kStreamWarps * sizeof(WarpQueues)));
+    p.stream_scratch = ctx->d_stream_scratch.as<WarpQueues>();
     VLB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
     VLB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     kern<<<grid, kBakeBlock, 0, st>>>(p);
@@ -229,8 +502,11 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out) {
     VLB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     // the axis staging vector dies at scope exit and stats are read back: synchronise
     unsigned long long h[4] = {0, 0, 0, 0};
+    unsigned int overflow = 0;
     VLB_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_stats.p, sizeof h, cudaMemcpyDeviceToHost, st));
+    VLB_CUDA(ctx, cudaMemcpyAsync(&overflow, ctx->d_scratch.as<float>() + 13, 4, cudaMemcpyDeviceToHost, st));
     VLB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (overflow) return ctx->fail(VLB_ERR_UNSUPPORTED, "bake: BVH traversal stack overflow (tree deeper than %d pending nodes)", kStackSize);
     vlb_bake_stats& b = ctx->last_bake;
     b.n_probes = n_probes; b.n_primary_rays = n_probes * (uint64_t)W * H; b.n_shadow_rays = h[0];
     b.n_nodes_visited = h[1]; b.n_tris_tested = h[2];
@@ -316,6 +592,7 @@ int trace_rays(vlb_ctx* ctx, const float* o, const float* d, uint64_t n64, float
     const unsigned grid = (n + 127) / 128;
     if (accel == VLB_TRACE_BVH) {
         BvhView b; b.nodes = ctx->d_nodes.as<float4>(); b.tris = ctx->d_tris.as<float4>(); b.n_tris = (uint32_t)ctx->n_tris;
+        b.overflow = reinterpret_cast<unsigned int*>(ctx->d_scratch.as<float>() + 13);
         k_trace_bvh<<<grid, 128, 0, st>>>(b, ctx->d_ray_o.as<float>(), ctx->d_ray_d.as<float>(), n, tmin, tmax, kind,
                                           ctx->d_hit_id.as<int>(), ctx->d_hit_tuv.as<float>());
         VLB_LAUNCH_CHECK(ctx);
@@ -340,7 +617,10 @@ int trace_rays(vlb_ctx* ctx, const float* o, const float* d, uint64_t n64, float
     }
     VLB_CUDA(ctx, cudaMemcpyAsync(ids, ctx->d_hit_id.p, n * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (tuv) VLB_CUDA(ctx, cudaMemcpyAsync(tuv, ctx->d_hit_tuv.p, 3ull * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    unsigned int overflow = 0;
+    if (accel == VLB_TRACE_BVH) VLB_CUDA(ctx, cudaMemcpyAsync(&overflow, ctx->d_scratch.as<float>() + 13, 4, cudaMemcpyDeviceToHost, st));
     VLB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (overflow) return ctx->fail(VLB_ERR_UNSUPPORTED, "vlb_trace_rays: BVH traversal stack overflow");
     return VLB_OK;
 }
 

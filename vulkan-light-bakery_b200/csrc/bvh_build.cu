@@ -7,7 +7,7 @@
 //   k_gather         triangles into Morton order + leaf AABBs                 (48 B in, 80 B out)
 //   k_karras         Karras-2012 hierarchy, one thread per internal node
 //   k_refit          bottom-up AABB refit, atomic arrival flags
-//   k_emit           64-byte traversal nodes (vlb_bvh.cuh), small subtrees collapsed to leaves
+//   k_emit           128-byte 4-wide traversal nodes (vlb_bvh.cuh): every second level collapsed, small subtrees -> leaves
 #include <cub/device/device_radix_sort.cuh>
 
 #include "vlb_bvh.cuh"
@@ -24,10 +24,12 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
     else atomicMin(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
 }
 
-// scratch[0..2] tight lo, [3..5] tight hi, [6..8] centroid lo, [9..11] centroid hi
+// scratch[0..2] tight lo, [3..5] tight hi, [6..8] centroid lo, [9..11] centroid hi, [12] nodes emitted (u32),
+// [13] traversal stack overflow flag (u32, set by any traversal of this BVH)
 __global__ void k_init_bounds(float* scratch) {
     const int i = threadIdx.x;
     if (i < 12) scratch[i] = ((i / 3) & 1) ? -INFINITY : INFINITY;
+    if (i >= 12 && i < 16) scratch[i] = 0.f;   // [12] emitted-node counter, [13] traversal stack overflow flag
 }
 
 __global__ void k_scene_bounds(const float4* __restrict__ tri_flat, uint32_t n, float* scratch) {
@@ -114,32 +116,31 @@ __global__ void k_refit(int n, const int* __restrict__ left, const int* __restri
     }
 }
 
+// One thread per binary internal node: nodes at even depth that span more than max_leaf triangles
+// (and the root) emit a 4-wide traversal node; the others are absorbed by their parents.
 __global__ void k_emit(int n, const int* __restrict__ left, const int* __restrict__ right,
-                       const int* __restrict__ first, const int* __restrict__ last,
+                       const int* __restrict__ first, const int* __restrict__ last, const int* __restrict__ parent_i,
                        const float4* __restrict__ ibox, const float4* __restrict__ lbox, int max_leaf,
-                       const float* __restrict__ scratch, float4* __restrict__ nodes) {
+                       const float* __restrict__ scratch, float4* __restrict__ nodes, unsigned int* n_emitted) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
+    if (i != 0 && (last[i] - first[i] + 1 <= max_leaf || (node_depth(parent_i, i) & 1))) return;
     const float ext = fmaxf(scratch[3] - scratch[0], fmaxf(scratch[4] - scratch[1], scratch[5] - scratch[2]));
-    emit_node(i, left, right, first, last, ibox, lbox, max_leaf, ext * 1e-6f, nodes);
+    emit_node4(i, left, right, first, last, ibox, lbox, max_leaf, ext * 1e-6f, nodes);
+    atomicAdd(n_emitted, 1u);
 }
 
-// n == 1: a single node whose two children are the same one-triangle leaf.
+// n == 1: a single node whose only child is the one-triangle leaf.
 __global__ void k_emit_single(const float4* __restrict__ lbox, const float* __restrict__ scratch, float4* nodes) {
-    float4 lo = lbox[0], hi = lbox[1];
     const float ext = fmaxf(scratch[3] - scratch[0], fmaxf(scratch[4] - scratch[1], scratch[5] - scratch[2]));
-    pad_box(&lo, &hi, ext * 1e-6f);
-    nodes[0] = make_float4(lo.x, hi.x, lo.y, hi.y);
-    nodes[1] = nodes[0];
-    nodes[2] = make_float4(lo.z, hi.z, lo.z, hi.z);
-    const int r = leaf_ref(0, 1);
-    nodes[3] = make_float4(i2f(r), i2f(r), i2f(0), i2f(0));
+    emit_single4(lbox, ext * 1e-6f, nodes);
 }
 
 int bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats) {
     const uint32_t n = (uint32_t)ctx->n_tris;
     cudaStream_t st = ctx->stream;
     float sort_ms = 0.f, build_ms = 0.f;
+    if (const char* v = getenv("VLB_BVH_MAX_LEAF")) ctx->max_leaf = std::max(1, std::min(kMaxLeaf, atoi(v)));
     VLB_CUDA(ctx, ctx->d_scratch.reserve(64 * sizeof(float)));
     VLB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
     k_init_bounds<<<1, 32, 0, st>>>(ctx->d_scratch.as<float>());
@@ -149,7 +150,7 @@ int bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats) {
         const int B = 256;
         const unsigned grid_n = (n + B - 1) / B;
         VLB_CUDA(ctx, ctx->d_tris.reserve(3ull * n * sizeof(float4)));
-        VLB_CUDA(ctx, ctx->d_nodes.reserve(4ull * std::max<uint32_t>(n - 1, 1) * sizeof(float4)));
+        VLB_CUDA(ctx, ctx->d_nodes.reserve((size_t)kNodeQuads * std::max<uint32_t>(n - 1, 1) * sizeof(float4)));
         VLB_CUDA(ctx, ctx->d_keys.reserve(n * sizeof(uint64_t)));
         VLB_CUDA(ctx, ctx->d_keys_sorted.reserve(n * sizeof(uint64_t)));
         VLB_CUDA(ctx, ctx->d_vals.reserve(n * sizeof(uint32_t)));
@@ -192,16 +193,17 @@ int bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats) {
                                          ctx->d_parent_l.as<int>(), ctx->d_lbox.as<float4>(), ctx->d_ibox.as<float4>(), ctx->d_flags.as<int>());
             VLB_LAUNCH_CHECK(ctx);
             k_emit<<<grid_n, B, 0, st>>>((int)n, ctx->d_left.as<int>(), ctx->d_right.as<int>(), ctx->d_first.as<int>(), ctx->d_last.as<int>(),
-                                        ctx->d_ibox.as<float4>(), ctx->d_lbox.as<float4>(), ctx->max_leaf, ctx->d_scratch.as<float>(),
-                                        ctx->d_nodes.as<float4>());
+                                        ctx->d_parent_i.as<int>(), ctx->d_ibox.as<float4>(), ctx->d_lbox.as<float4>(), ctx->max_leaf,
+                                        ctx->d_scratch.as<float>(), ctx->d_nodes.as<float4>(),
+                                        reinterpret_cast<unsigned int*>(ctx->d_scratch.as<float>() + 12));
             VLB_LAUNCH_CHECK(ctx);
-            ctx->n_nodes = n - 1;
         }
     }
     VLB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
-    float h[12];
+    float h[13];
     VLB_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_scratch.p, sizeof h, cudaMemcpyDeviceToHost, st));
     VLB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (n > 1) { unsigned int ne; memcpy(&ne, &h[12], 4); ctx->n_nodes = ne; }
     VLB_CUDA(ctx, cudaEventElapsedTime(&build_ms, ctx->ev[0], ctx->ev[1]));
     if (n > 0) VLB_CUDA(ctx, cudaEventElapsedTime(&sort_ms, ctx->ev[2], ctx->ev[3]));
     for (int k = 0; k < 6; ++k) ctx->tight_bounds[k] = n ? h[k] : 0.f;

@@ -125,7 +125,7 @@ void vlb_ctx_destroy(vlb_ctx* ctx) {
                       &ctx->d_ibox, &ctx->d_lbox, &ctx->d_scratch, &ctx->d_sky, &ctx->d_proj_in, &ctx->d_proj_out,
                       &ctx->d_proj_partials, &ctx->d_proj_counters, &ctx->d_row_tab, &ctx->d_col_tab, &ctx->d_bake_out,
                       &ctx->d_partials, &ctx->d_work_counter, &ctx->d_axis, &ctx->d_row_sc, &ctx->d_col_sc,
-                      &ctx->d_stats, &ctx->d_ray_o, &ctx->d_ray_d, &ctx->d_hit_id, &ctx->d_hit_tuv, &ctx->d_hit_key};
+                      &ctx->d_stats, &ctx->d_stream_scratch, &ctx->d_ray_o, &ctx->d_ray_d, &ctx->d_hit_id, &ctx->d_hit_tuv, &ctx->d_hit_key};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     for (int l = 0; l < VLB_MAX_LANES; ++l) {

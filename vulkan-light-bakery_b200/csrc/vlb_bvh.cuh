@@ -1,16 +1,19 @@
 // vlb_bvh.cuh — software LBVH: data layout in HBM, per-thread build steps and traversal.
 //
 // Replaces the driver-built BLAS/TLAS of the reference (src/scene_manager.cpp:339-443) on a GPU
-// without RT cores: Morton codes -> radix sort -> Karras-2012 hierarchy -> bottom-up AABB refit ->
-// emission of 64-byte two-child traversal nodes read as four 16-byte loads.
+// without RT cores: Morton codes -> radix sort -> Karras-2012 binary hierarchy -> bottom-up AABB
+// refit -> collapse of every second level into 4-wide traversal nodes of 128 bytes, read as seven
+// 16-byte loads. Four children per step halve the number of dependent memory round trips per ray,
+// which is what bounds traversal on L2-resident data.
 //
 // HBM layout (all float4 arrays, 16-byte aligned):
 //   tri[3*j+0..2]   j = position in Morton order:  (v0.xyz, bits(flat id)), (e1.xyz, 0), (e2.xyz, 0)
-//   node[4*i+0..3]  i = Karras internal node id:   (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)
-//                                                  (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
-//                                                  (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
-//                                                  bits(ref0, ref1, first, last)
-//   ref >= 0 : internal node index.  ref < 0 : leaf, ~ref = (first_tri << 3) | (count - 1).
+//   node[8*i+0..7]  i = Karras id of a binary node at EVEN depth (odd-depth nodes are absorbed by
+//                   their parent; their slots stay unused):
+//                   [0] lo.x of children 0..3   [1] hi.x   [2] lo.y   [3] hi.y   [4] lo.z   [5] hi.z
+//                   [6] bits(ref of children 0..3)         [7] unused (pads the node to one 128-byte line)
+//   ref >= 0 : node index.  ref < 0 : leaf, ~ref = (first_tri << 3) | (count - 1).
+//   kNoChild (0x80000000) marks an empty slot; its box is (+inf, -inf) and can never be hit.
 //
 // Per-thread bodies are `__host__ __device__` (see vlb_math.cuh) so tests/emu can execute them
 // serially on the CPU; the kernels in bvh_build.cu / bake.cu are thin wrappers.
@@ -23,7 +26,9 @@
 namespace vlb {
 
 constexpr int kMaxLeaf = 8;
-constexpr int kStackSize = 64;
+constexpr int kStackSize = 96;              // up to three pushes per 4-wide node
+constexpr int kNodeQuads = 8;               // float4s per traversal node (128 bytes)
+constexpr int kNoChild = (int)0x80000000;   // empty child slot / "no node": never a valid leaf ref (n_tris < 2^28)
 // Culling slack: a node is skipped only if its entry distance exceeds best_t * kCullSlack, so
 // that two triangles whose computed t differ by rounding are both reached and the
 // (t, flat id) tie-break decides exactly as in the brute-force intersector.
@@ -33,6 +38,7 @@ struct BvhView {
     const float4* nodes;
     const float4* tris;
     uint32_t n_tris;
+    unsigned int* overflow;   // set to 1 if a traversal stack overflowed (device pointer, may be NULL)
 };
 
 VLB_HD float i2f(int v) {
@@ -137,38 +143,80 @@ VLB_HD void pad_box(float4* lo, float4* hi, float abs_pad) {
 
 VLB_HD int leaf_ref(int first_tri, int count) { return ~((first_tri << 3) | (count - 1)); }
 
-// Emit traversal node i from the Karras arrays and the refitted boxes. Subtrees of at most
-// `max_leaf` triangles become one leaf (their triangles are contiguous in Morton order).
-VLB_HD void emit_node(int i, const int* left, const int* right, const int* first, const int* last,
-                      const float4* ibox, const float4* lbox, int max_leaf, float abs_pad,
-                      float4* nodes) {
-    int refs[2];
-    float4 lo[2], hi[2];
-    const int ch[2] = {left[i], right[i]};
-    for (int c = 0; c < 2; ++c) {
-        if (ch[c] < 0) {
-            const int leaf = ~ch[c];
-            refs[c] = leaf_ref(leaf, 1);
-            lo[c] = lbox[2 * leaf]; hi[c] = lbox[2 * leaf + 1];
-        } else {
-            const int k = ch[c];
-            const int cnt = last[k] - first[k] + 1;
-            refs[c] = cnt <= max_leaf ? leaf_ref(first[k], cnt) : k;
-            lo[c] = ibox[2 * k]; hi[c] = ibox[2 * k + 1];
-        }
-        pad_box(&lo[c], &hi[c], abs_pad);
-    }
-    nodes[4 * i + 0] = make_float4(lo[0].x, hi[0].x, lo[0].y, hi[0].y);
-    nodes[4 * i + 1] = make_float4(lo[1].x, hi[1].x, lo[1].y, hi[1].y);
-    nodes[4 * i + 2] = make_float4(lo[0].z, hi[0].z, lo[1].z, hi[1].z);
-    float4 meta;
-    meta.x = i2f(refs[0]);
-    meta.y = i2f(refs[1]);
-    meta.z = i2f(first[i]);
-    meta.w = i2f(last[i]);
-    nodes[4 * i + 3] = meta;
+// Depth of binary internal node i (root = 0), by walking the parent chain.
+VLB_HD int node_depth(const int* parent_internal, int i) {
+    int d = 0;
+    for (int k = parent_internal[i]; k >= 0; k = parent_internal[k]) ++d;
+    return d;
 }
 
+// One child slot of a 4-wide node from a binary child reference `c` (>= 0 internal Karras id,
+// < 0 : ~leaf index). Subtrees of at most `max_leaf` triangles become one leaf (their triangles are
+// contiguous in Morton order). Returns true if `c` is a large internal node (to be expanded or
+// referenced).
+VLB_HD bool classify_child(int c, const int* first, const int* last, const float4* ibox, const float4* lbox,
+                           int max_leaf, int* ref, float4* lo, float4* hi) {
+    if (c < 0) {
+        const int leaf = ~c;
+        *ref = leaf_ref(leaf, 1);
+        *lo = lbox[2 * leaf]; *hi = lbox[2 * leaf + 1];
+        return false;
+    }
+    const int cnt = last[c] - first[c] + 1;
+    *lo = ibox[2 * c]; *hi = ibox[2 * c + 1];
+    if (cnt <= max_leaf) { *ref = leaf_ref(first[c], cnt); return false; }
+    *ref = c;
+    return true;
+}
+
+// Emit the 4-wide traversal node of binary node i (which must sit at even depth and span more than
+// max_leaf triangles, or be the root): its children are i's grandchildren, or i's children where
+// those are leaves.
+VLB_HD void emit_node4(int i, const int* left, const int* right, const int* first, const int* last,
+                       const float4* ibox, const float4* lbox, int max_leaf, float abs_pad, float4* nodes) {
+    int refs[4] = {kNoChild, kNoChild, kNoChild, kNoChild};
+    float4 lo[4], hi[4];
+    int n = 0;
+    const int ch[2] = {left[i], right[i]};
+    for (int c = 0; c < 2; ++c) {
+        int r; float4 l, h;
+        if (classify_child(ch[c], first, last, ibox, lbox, max_leaf, &r, &l, &h)) {
+            const int gc[2] = {left[ch[c]], right[ch[c]]};
+            for (int g = 0; g < 2; ++g) {
+                classify_child(gc[g], first, last, ibox, lbox, max_leaf, &refs[n], &lo[n], &hi[n]);
+                pad_box(&lo[n], &hi[n], abs_pad);
+                ++n;
+            }
+        } else {
+            refs[n] = r; lo[n] = l; hi[n] = h;
+            pad_box(&lo[n], &hi[n], abs_pad);
+            ++n;
+        }
+    }
+    const float inf = INFINITY;
+    for (; n < 4; ++n) { lo[n] = make_float4(inf, inf, inf, 0.f); hi[n] = make_float4(-inf, -inf, -inf, 0.f); }
+    float4* q = nodes + (size_t)kNodeQuads * i;
+    q[0] = make_float4(lo[0].x, lo[1].x, lo[2].x, lo[3].x);
+    q[1] = make_float4(hi[0].x, hi[1].x, hi[2].x, hi[3].x);
+    q[2] = make_float4(lo[0].y, lo[1].y, lo[2].y, lo[3].y);
+    q[3] = make_float4(hi[0].y, hi[1].y, hi[2].y, hi[3].y);
+    q[4] = make_float4(lo[0].z, lo[1].z, lo[2].z, lo[3].z);
+    q[5] = make_float4(hi[0].z, hi[1].z, hi[2].z, hi[3].z);
+    q[6] = make_float4(i2f(refs[0]), i2f(refs[1]), i2f(refs[2]), i2f(refs[3]));
+    q[7] = make_float4(i2f(first[i]), i2f(last[i]), 0.f, 0.f);
+}
+
+// Single-triangle scene: one node with one leaf child.
+VLB_HD void emit_single4(const float4* lbox, float abs_pad, float4* nodes) {
+    float4 lo = lbox[0], hi = lbox[1];
+    pad_box(&lo, &hi, abs_pad);
+    const float inf = INFINITY;
+    nodes[0] = make_float4(lo.x, inf, inf, inf); nodes[1] = make_float4(hi.x, -inf, -inf, -inf);
+    nodes[2] = make_float4(lo.y, inf, inf, inf); nodes[3] = make_float4(hi.y, -inf, -inf, -inf);
+    nodes[4] = make_float4(lo.z, inf, inf, inf); nodes[5] = make_float4(hi.z, -inf, -inf, -inf);
+    nodes[6] = make_float4(i2f(leaf_ref(0, 1)), i2f(kNoChild), i2f(kNoChild), i2f(kNoChild));
+    nodes[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
 
 struct HitRec {
     int id;       // flat triangle id, -1 = miss
@@ -187,21 +235,110 @@ VLB_HD float4 ld4(const float4* p) {
 #endif
 }
 
-// Two-child slab test. Returns entry distances (tn0, tn1) and hit flags.
-VLB_HD void test_children(const float4 n0xy, const float4 n1xy, const float4 nz, Vec3 idir, Vec3 ood,
-                          float tmin, float tcull, float& tn0, float& tn1, bool& h0, bool& h1) {
-    const float c0lox = f_fma(n0xy.x, idir.x, -ood.x), c0hix = f_fma(n0xy.y, idir.x, -ood.x);
-    const float c0loy = f_fma(n0xy.z, idir.y, -ood.y), c0hiy = f_fma(n0xy.w, idir.y, -ood.y);
-    const float c0loz = f_fma(nz.x, idir.z, -ood.z), c0hiz = f_fma(nz.y, idir.z, -ood.z);
-    const float c1lox = f_fma(n1xy.x, idir.x, -ood.x), c1hix = f_fma(n1xy.y, idir.x, -ood.x);
-    const float c1loy = f_fma(n1xy.z, idir.y, -ood.y), c1hiy = f_fma(n1xy.w, idir.y, -ood.y);
-    const float c1loz = f_fma(nz.z, idir.z, -ood.z), c1hiz = f_fma(nz.w, idir.z, -ood.z);
-    tn0 = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tmin));
-    const float tf0 = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tcull));
-    tn1 = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tmin));
-    const float tf1 = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tcull));
-    h0 = tn0 <= tf0;
-    h1 = tn1 <= tf1;
+VLB_HD void order2(float& ta, int& ra, float& tb, int& rb) {
+    const bool sw = tb < ta;
+    const float t0 = sw ? tb : ta, t1 = sw ? ta : tb;
+    const int r0 = sw ? rb : ra, r1 = sw ? ra : rb;
+    ta = t0; tb = t1; ra = r0; rb = r1;
+}
+
+// three-input min / max: one FMNMX3 on sm_100
+VLB_HD float max3(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+    float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
+#else
+    return fmaxf(fmaxf(a, b), c);
+#endif
+}
+VLB_HD float min3(float a, float b, float c) {
+#ifdef __CUDA_ARCH__
+    float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r;
+#else
+    return fminf(fminf(a, b), c);
+#endif
+}
+
+// One step through 4-wide node `cur`: slab-tests the four children against (tmin, tcull). ORDERED
+// (closest-hit rays): returns the nearest hit child and pushes the others so that they pop in
+// near-to-far order. Unordered (any-hit rays): returns the first hit child, pushes the rest. With
+// no hit child it pops. Returns kNoChild when the traversal is finished. THE node step of every
+// traversal in the library (closest hit, any hit, the bake kernel).
+template <bool ORDERED>
+VLB_HD int bvh4_step(const BvhView& b, int cur, Vec3 idir, Vec3 ood, float tmin, float tcull, int* stack, int& sp) {
+    const float4* q = b.nodes + (size_t)kNodeQuads * cur;
+    // near / far planes by the sign of the direction: no per-child min/max pairs
+    const int sx = idir.x < 0.0f, sy = idir.y < 0.0f, sz = idir.z < 0.0f;
+    const float4 nx = ld4(q + sx), fx = ld4(q + 1 - sx);
+    const float4 ny = ld4(q + 2 + sy), fy = ld4(q + 3 - sy);
+    const float4 nz = ld4(q + 4 + sz), fz = ld4(q + 5 - sz);
+    const float4 rf = ld4(q + 6);
+    float tn[4]; int r[4];
+    const float inf = INFINITY;
+#define VLB_SLAB(k, c)                                                                                           \
+    {                                                                                                            \
+        const float a = fmaxf(max3(f_fma(nx.c, idir.x, -ood.x), f_fma(ny.c, idir.y, -ood.y),                      \
+                                   f_fma(nz.c, idir.z, -ood.z)), tmin);                                          \
+        const float e = fminf(min3(f_fma(fx.c, idir.x, -ood.x), f_fma(fy.c, idir.y, -ood.y),                      \
+                                   f_fma(fz.c, idir.z, -ood.z)), tcull);                                         \
+        const bool hit = a <= e;                                                                                 \
+        tn[k] = hit ? a : inf;                                                                                   \
+        r[k] = hit ? f2i(rf.c) : kNoChild;                                                                       \
+    }
+    VLB_SLAB(0, x) VLB_SLAB(1, y) VLB_SLAB(2, z) VLB_SLAB(3, w)
+#undef VLB_SLAB
+    if (ORDERED) {
+        // sort the (entry distance, ref) pairs ascending; misses carry +inf and sink to the end
+        order2(tn[0], r[0], tn[1], r[1]);
+        order2(tn[2], r[2], tn[3], r[3]);
+        order2(tn[0], r[0], tn[2], r[2]);
+        order2(tn[1], r[1], tn[3], r[3]);
+        order2(tn[1], r[1], tn[2], r[2]);
+        if (r[0] == kNoChild) return sp ? stack[--sp] : kNoChild;
+        if (r[1] != kNoChild) {
+            if (sp + 3 > kStackSize) {      // never silently drop subtrees: flag it
+                if (b.overflow) *b.overflow = 1u;
+            } else {
+                if (r[3] != kNoChild) stack[sp++] = r[3];
+                if (r[2] != kNoChild) stack[sp++] = r[2];
+                stack[sp++] = r[1];
+            }
+        }
+        return r[0];
+    }
+    if (sp + 4 > kStackSize) {
+        if (b.overflow) *b.overflow = 1u;
+    } else {
+        if (r[3] != kNoChild) stack[sp++] = r[3];
+        if (r[2] != kNoChild) stack[sp++] = r[2];
+        if (r[1] != kNoChild) stack[sp++] = r[1];
+        if (r[0] != kNoChild) stack[sp++] = r[0];
+    }
+    return sp ? stack[--sp] : kNoChild;
+}
+
+// Intersects the triangles of leaf `ref` (< 0). Closest-hit rays update `best` and the culling
+// distance; any-hit rays return true at the first triangle inside (tmin, tcull).
+template <bool ANY, bool COUNT>
+VLB_HD bool leaf_step(const BvhView& b, int ref, Vec3 o, Vec3 d, float tmin, float& tcull, HitRec& best, TraceCounters* cnt) {
+    const int x = ~ref;
+    const int first = x >> 3, count = (x & 7) + 1;
+    for (int k = 0; k < count; ++k) {
+        const float4 v0 = ld4(b.tris + 3 * (first + k) + 0);
+        const float4 e1 = ld4(b.tris + 3 * (first + k) + 1);
+        const float4 e2 = ld4(b.tris + 3 * (first + k) + 2);
+        if (COUNT) cnt->tris++;
+        float t, u, v;
+        if (intersect_tri(v0, e1, e2, o, d, t, u, v) && t > tmin) {
+            const int id = f2i(v0.w);
+            if (ANY) {
+                if (t < tcull) { best.id = id; best.t = t; best.u = u; best.v = v; return true; }
+            } else if (t < best.t || (t == best.t && best.id >= 0 && id < best.id)) {
+                best.id = id; best.t = t; best.u = u; best.v = v;
+                tcull = t * kCullSlack;
+            }
+        }
+    }
+    return false;
 }
 
 // Closest hit with tmin < t < tmax; ties: smaller t, then smaller flat id.
@@ -216,43 +353,14 @@ VLB_HD HitRec trace_closest(const BvhView& b, Vec3 o, Vec3 d, float tmin, float 
     int sp = 0;
     int cur = 0;
     float tcull = tmax;
-    for (;;) {
+    while (cur != kNoChild) {
         if (cur >= 0) {
-            const float4 n0xy = ld4(b.nodes + 4 * cur + 0);
-            const float4 n1xy = ld4(b.nodes + 4 * cur + 1);
-            const float4 nz = ld4(b.nodes + 4 * cur + 2);
-            const float4 meta = ld4(b.nodes + 4 * cur + 3);
             if (COUNT) cnt->nodes++;
-            float tn0, tn1; bool h0, h1;
-            test_children(n0xy, n1xy, nz, idir, ood, tmin, tcull, tn0, tn1, h0, h1);
-            const int r0 = f2i(meta.x), r1 = f2i(meta.y);
-            if (h0 && h1) {
-                const bool swap = tn1 < tn0;
-                cur = swap ? r1 : r0;
-                if (sp < kStackSize) stack[sp++] = swap ? r0 : r1;
-                continue;
-            } else if (h0) { cur = r0; continue; }
-            else if (h1) { cur = r1; continue; }
+            cur = bvh4_step<true>(b, cur, idir, ood, tmin, tcull, stack, sp);
         } else {
-            const int x = ~cur;
-            const int first = x >> 3, count = (x & 7) + 1;
-            for (int k = 0; k < count; ++k) {
-                const float4 v0 = ld4(b.tris + 3 * (first + k) + 0);
-                const float4 e1 = ld4(b.tris + 3 * (first + k) + 1);
-                const float4 e2 = ld4(b.tris + 3 * (first + k) + 2);
-                if (COUNT) cnt->tris++;
-                float t, u, v;
-                if (intersect_tri(v0, e1, e2, o, d, t, u, v) && t > tmin) {
-                    const int id = f2i(v0.w);
-                    if (t < best.t || (t == best.t && best.id >= 0 && id < best.id)) {
-                        best.id = id; best.t = t; best.u = u; best.v = v;
-                        tcull = t * kCullSlack;
-                    }
-                }
-            }
+            leaf_step<false, COUNT>(b, cur, o, d, tmin, tcull, best, cnt);
+            cur = sp ? stack[--sp] : kNoChild;
         }
-        if (sp == 0) break;
-        cur = stack[--sp];
     }
     return best;
 }
@@ -266,39 +374,19 @@ VLB_HD bool trace_any(const BvhView& b, Vec3 o, Vec3 d, float tmin, float tmax, 
     int stack[kStackSize];
     int sp = 0;
     int cur = 0;
-    for (;;) {
+    float tcull = tmax;
+    HitRec h; h.id = -1; h.t = tmax; h.u = 0.f; h.v = 0.f;
+    while (cur != kNoChild) {
         if (cur >= 0) {
-            const float4 n0xy = ld4(b.nodes + 4 * cur + 0);
-            const float4 n1xy = ld4(b.nodes + 4 * cur + 1);
-            const float4 nz = ld4(b.nodes + 4 * cur + 2);
-            const float4 meta = ld4(b.nodes + 4 * cur + 3);
             if (COUNT) cnt->nodes++;
-            float tn0, tn1; bool h0, h1;
-            test_children(n0xy, n1xy, nz, idir, ood, tmin, tmax, tn0, tn1, h0, h1);
-            const int r0 = f2i(meta.x), r1 = f2i(meta.y);
-            if (h0 && h1) {
-                cur = r0;
-                if (sp < kStackSize) stack[sp++] = r1;
-                continue;
-            } else if (h0) { cur = r0; continue; }
-            else if (h1) { cur = r1; continue; }
+            cur = bvh4_step<false>(b, cur, idir, ood, tmin, tcull, stack, sp);
         } else {
-            const int x = ~cur;
-            const int first = x >> 3, count = (x & 7) + 1;
-            for (int k = 0; k < count; ++k) {
-                const float4 v0 = ld4(b.tris + 3 * (first + k) + 0);
-                const float4 e1 = ld4(b.tris + 3 * (first + k) + 1);
-                const float4 e2 = ld4(b.tris + 3 * (first + k) + 2);
-                if (COUNT) cnt->tris++;
-                float t, u, v;
-                if (intersect_tri(v0, e1, e2, o, d, t, u, v) && t > tmin && t < tmax) {
-                    if (out) { out->id = f2i(v0.w); out->t = t; out->u = u; out->v = v; }
-                    return true;
-                }
+            if (leaf_step<true, COUNT>(b, cur, o, d, tmin, tcull, h, cnt)) {
+                if (out) *out = h;
+                return true;
             }
+            cur = sp ? stack[--sp] : kNoChild;
         }
-        if (sp == 0) break;
-        cur = stack[--sp];
     }
     return false;
 }

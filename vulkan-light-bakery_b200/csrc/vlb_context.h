@@ -76,7 +76,7 @@ struct vlb_ctx {
     vlb::DevBuf d_proj_in, d_proj_out, d_proj_partials, d_proj_counters, d_row_tab, d_col_tab;
     int tab_w = 0, tab_h = 0, tab_variant = -1;
     // ---- bake ----
-    vlb::DevBuf d_bake_out, d_partials, d_work_counter, d_axis, d_row_sc, d_col_sc, d_stats;
+    vlb::DevBuf d_bake_out, d_partials, d_work_counter, d_axis, d_row_sc, d_col_sc, d_stats, d_stream_scratch;
     int dir_w = 0, dir_h = 0;
     vlb_bake_stats last_bake{};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
