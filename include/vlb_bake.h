@@ -127,7 +127,10 @@ typedef struct vlb_bake_settings {
     float    tmin, tmax;
     uint32_t flags;
     int32_t  slab_k0, slab_k1;   /* bake only z-slices k0 <= k < k1; k1 < 0 = whole grid      */
-    int32_t  reserved[4];
+    int32_t  slab_stride;        /* > 1: only every slab_stride-th slice of [k0, k1), i.e.
+                                    k = k0, k0 + stride, ... (cyclic sharding over GPUs: rank r of
+                                    N bakes k0 = r, k1 = Nz, stride = N); 0 or 1 = contiguous     */
+    int32_t  reserved[3];
 } vlb_bake_settings;
 
 #define VLB_SH_STRIDE 48         /* floats per probe: vec3 coeffs[16] (shaders/sh.comp:21)     */
@@ -175,6 +178,15 @@ int vlb_scene_set_triangles(vlb_ctx* ctx,
                             const uint32_t* indices, uint64_t n_indices,
                             const vlb_instance* instances, uint32_t n_instances,
                             const vlb_material* materials, uint32_t n_materials);
+/* SceneManager::pushScene(std::string&) (src/scene_manager.cpp:1013-1034): tinygltf load of a .gltf /
+ * .glb file (:32-67), materials (+ trailing default, :837-857), node hierarchy in loadNode's
+ * pre-order with world matrices (:445-538), vertices as shader::Vertex and u32 indices
+ * (:257-337); then the same upload as vlb_scene_set_triangles. vlb_scene_bounds(tight=0) afterwards
+ * returns the reference's bounds including its local-matrix quirk (:497-507). */
+int vlb_scene_load_gltf(vlb_ctx* ctx, const char* gltf_path);
+/* Host-only: parse a glTF and report counts = {vertices, indices, instances (node x primitive),
+ * materials incl. the default, triangles} and the reference-mode bounds. No CUDA device needed. */
+int vlb_gltf_probe(const char* gltf_path, uint64_t counts[5], float ref_bounds_min_max[6]);
 /* Scene_t::getBounds (src/scene_manager.cpp:214-217). mode 0: the reference's semantics
  * (bounds start at the origin, only the two local AABB corners are transformed,
  * scene_manager.cpp:497-507); mode 1: tight world-space AABB of all triangles. */
@@ -220,7 +232,10 @@ int vlb_probe_positions(const vlb_bake_settings* s, float* out_xyz);
 /* LightBaker::bake (src/baker/light_baker.cpp:287-328). out = n_slab_probes x 48 floats
  * (float[probe][16][3], light_baker.cpp:294-322). */
 int vlb_bake_probes(vlb_ctx* ctx, const vlb_bake_settings* s, float* out);
+/* Device-resident output; enqueues on the ctx stream and returns WITHOUT synchronising. */
 int vlb_bake_probes_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out);
+/* Statistics of the last bake call. Synchronises with that call; returns VLB_ERR_UNSUPPORTED if
+ * its traversal overflowed the per-ray stack (vlb_bake_probes reports that itself). */
 int vlb_bake_last_stats(vlb_ctx* ctx, vlb_bake_stats* out);
 
 /* --- validation entry points (BVH hit IDs bit-exact vs brute force) --------------------- */

@@ -189,9 +189,7 @@ class Scene:
     def bake_probes(self, settings, probe_ids=None, brute=False):
         """Whole slab (probe_ids None) or the listed x-fastest grid indices. Returns (coeffs, n_shadow_rays)."""
         if probe_ids is None:
-            k1 = settings.probes[2] if settings.slab_k1 < 0 else settings.slab_k1
-            k0 = 0 if settings.slab_k1 < 0 else settings.slab_k0
-            n = settings.probes[0] * settings.probes[1] * (k1 - k0)
+            n = settings.n_slab_probes
             ids = None
         else:
             ids = np.ascontiguousarray(probe_ids, np.int64)

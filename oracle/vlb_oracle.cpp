@@ -813,7 +813,7 @@ void vo_trace_rays(void* h, const float* origins, const float* dirs, uint64_t n,
 }
 
 // Bakes the probes listed in probe_ids (indices in x-fastest grid order, i + j*Nx + k*Nx*Ny) or,
-// when probe_ids == NULL, the whole slab [slab_k0, slab_k1). out = n x 48 floats in list order
+// when probe_ids == NULL, the slices slab_k0, slab_k0 + slab_stride, ... < slab_k1. out = n x 48 floats in list order
 // (slab mode: output order as the settings' flags say, relative to the slab start).
 // Returns the number of shadow rays traced.
 uint64_t vo_bake_probes(void* h, const vlb_bake_settings* st, const int64_t* probe_ids,
@@ -826,13 +826,15 @@ uint64_t vo_bake_probes(void* h, const vlb_bake_settings* st, const int64_t* pro
     axis_coords(st->origin[2], st->step[2], Nz, pz);
     const DirTable dt = make_dirs(st->dir_w, st->dir_h);
     const int k0 = st->slab_k1 < 0 ? 0 : st->slab_k0, k1 = st->slab_k1 < 0 ? Nz : st->slab_k1;
-    const uint64_t n = probe_ids ? n_ids : (uint64_t)Nx * Ny * (k1 - k0);
+    const int kstride = st->slab_stride > 1 ? st->slab_stride : 1;      // slices k0, k0 + stride, ... < k1
+    const uint64_t n = probe_ids ? n_ids : (uint64_t)Nx * Ny * ((k1 - k0 + kstride - 1) / kstride);
     const bool ref_order = !probe_ids && (st->flags & VLB_BAKE_REFERENCE_PROBE_ORDER);
     uint64_t shadow_total = 0;
     std::vector<double> all((size_t)n * 48, 0.0);
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : shadow_total)
     for (int64_t q = 0; q < (int64_t)n; ++q) {
-        const int64_t g = probe_ids ? probe_ids[q] : (int64_t)q + (int64_t)k0 * Nx * Ny;
+        const int64_t nxy = (int64_t)Nx * Ny;
+        const int64_t g = probe_ids ? probe_ids[q] : q % nxy + (k0 + (q / nxy) * kstride) * nxy;
         const int i = (int)(g % Nx), j = (int)((g / Nx) % Ny), k = (int)(g / ((int64_t)Nx * Ny));
         uint64_t sr = 0;
         size_t slot = (size_t)q;

@@ -205,6 +205,37 @@ def test_bake_slab_union_is_bitwise_full(ctx, vlb, scenes, room):
     assert np.array_equal(full, np.concatenate(parts))
 
 
+def test_bake_cyclic_slices_union_is_bitwise_full(ctx, vlb, scenes, room):
+    # cyclic sharding (rank r of N bakes k = r, r + N, ...): interleaving the shares reproduces the full bake
+    sc, _ = room
+    ctx.set_scene(sc)
+    ctx.set_skybox(scenes.hdr_sky(64, 32, seed=4))
+    s = _room_settings(vlb, ctx, vlb.SHADOW_RAYS | vlb.SKYBOX_ON_MISS | vlb.SRGB_ENCODE, probes=(3, 2, 5))
+    full = ctx.bake_probes(s).reshape(5, 6, 16, 3)
+    world = 3
+    for r in range(world):
+        p = s.copy()
+        p.slab_k0, p.slab_k1, p.slab_stride = r, 5, world
+        assert p.slab_slices == list(range(r, 5, world))
+        part = ctx.bake_probes(p).reshape(len(p.slab_slices), 6, 16, 3)
+        assert np.array_equal(part, full[r::world])
+
+
+def test_bake_device_is_asynchronous_and_stats_collect(ctx, vlb, scenes, room):
+    import torch
+    sc, _ = room
+    ctx.set_scene(sc)
+    s = _room_settings(vlb, ctx, vlb.SHADOW_RAYS | vlb.SRGB_ENCODE, probes=(3, 2, 3))
+    ref = ctx.bake_probes(s)
+    out = torch.zeros((s.n_probes, 48), device="cuda")
+    ctx.bake_probes_device(s, out.data_ptr())
+    ctx.bake_probes_device(s, out.data_ptr())          # a second enqueue first collects the pending statistics
+    st = ctx.last_bake_stats()
+    assert st.n_probes == s.n_probes and st.n_primary_rays == s.n_probes * s.dir_w * s.dir_h
+    assert 0 < st.n_shadow_rays <= st.n_primary_rays and st.kernel_ms > 0
+    assert np.array_equal(out.cpu().numpy().reshape(ref.shape), ref)
+
+
 def test_bake_reference_probe_order_and_accumulate(ctx, vlb, oa, scenes, room):
     sc, osc = room
     ctx.set_scene(sc)

@@ -54,7 +54,8 @@ class BakeSettings(ctypes.Structure):
                 ("light_pos", ctypes.c_float * 3), ("shadow_bias", ctypes.c_float), ("c_diffuse", ctypes.c_float),
                 ("c_specular", ctypes.c_float), ("gloss", ctypes.c_float), ("ambient", ctypes.c_float),
                 ("tmin", ctypes.c_float), ("tmax", ctypes.c_float), ("flags", ctypes.c_uint32),
-                ("slab_k0", ctypes.c_int32), ("slab_k1", ctypes.c_int32), ("reserved", ctypes.c_int32 * 4)]
+                ("slab_k0", ctypes.c_int32), ("slab_k1", ctypes.c_int32), ("slab_stride", ctypes.c_int32),
+                ("reserved", ctypes.c_int32 * 3)]
 
     def copy(self):
         c = BakeSettings()
@@ -70,6 +71,16 @@ class BakeSettings(ctypes.Structure):
         k1 = self.probes[2] if self.slab_k1 < 0 else self.slab_k1
         k0 = 0 if self.slab_k1 < 0 else self.slab_k0
         return k0, k1
+
+    @property
+    def slab_slices(self):
+        """The z-slices this settings object bakes, in output order."""
+        k0, k1 = self.slab
+        return list(range(k0, k1, max(1, self.slab_stride)))
+
+    @property
+    def n_slab_probes(self):
+        return self.probes[0] * self.probes[1] * len(self.slab_slices)
 
 
 class BvhStats(ctypes.Structure):
@@ -93,7 +104,7 @@ class VlbError(RuntimeError):
 # every symbol include/vlb_bake.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "vlb_abi_version", "vlb_ctx_create", "vlb_ctx_destroy", "vlb_ctx_set_stream", "vlb_ctx_synchronize",
-    "vlb_last_error", "vlb_ctx_launch_count", "vlb_scene_set_triangles", "vlb_scene_bounds", "vlb_bvh_build",
+    "vlb_last_error", "vlb_ctx_launch_count", "vlb_scene_set_triangles", "vlb_scene_load_gltf", "vlb_gltf_probe", "vlb_scene_bounds", "vlb_bvh_build",
     "vlb_skybox_set", "vlb_skybox_project_sh", "vlb_skybox_project_sh_batched", "vlb_skybox_project_sh_device",
     "vlb_skybox_project_sh_device_ptrs", "vlb_envmap_project_sh", "vlb_bake_settings_default", "vlb_bake_settings_from_bounds", "vlb_probe_positions",
     "vlb_bake_probes", "vlb_bake_probes_device", "vlb_bake_last_stats", "vlb_trace_rays",
@@ -123,6 +134,8 @@ def load_library():
         "vlb_last_error": (ctypes.c_char_p, [vp]),
         "vlb_ctx_launch_count": (u64, [vp]),
         "vlb_scene_set_triangles": (i32, [vp, vp, u64, vp, u64, vp, u32, vp, u32]),
+        "vlb_scene_load_gltf": (i32, [vp, ctypes.c_char_p]),
+        "vlb_gltf_probe": (i32, [ctypes.c_char_p, vp, vp]),
         "vlb_scene_bounds": (i32, [vp, i32, vp]),
         "vlb_bvh_build": (i32, [vp, ctypes.POINTER(BvhStats)]),
         "vlb_skybox_set": (i32, [vp, vp, i32, i32, i32]),
@@ -230,6 +243,10 @@ class Context:
         self._check(self._lib.vlb_scene_set_triangles(self._h, _ptr(v), v.size, _ptr(i), i.size, _ptr(inst), inst.size,
                                                       _ptr(m), m.size))
 
+    def load_gltf(self, path):
+        """SceneManager::pushScene: ingest a .gltf / .glb file."""
+        self._check(self._lib.vlb_scene_load_gltf(self._h, os.fsencode(path)))
+
     def scene_bounds(self, tight=False):
         out = np.zeros(6, np.float32)
         self._check(self._lib.vlb_scene_bounds(self._h, int(bool(tight)), _ptr(out)))
@@ -285,8 +302,7 @@ class Context:
 
     # -- bake (LightBaker::bake)
     def bake_probes(self, s):
-        k0, k1 = s.slab
-        n = s.probes[0] * s.probes[1] * (k1 - k0)
+        n = s.n_slab_probes
         out = np.zeros((n, 16, 3), np.float32)
         self._check(self._lib.vlb_bake_probes(self._h, ctypes.byref(s), _ptr(out)))
         return out
@@ -308,6 +324,18 @@ class Context:
         self._check(self._lib.vlb_trace_rays(self._h, _ptr(o), _ptr(d), o.shape[0], tmin, tmax, accel, kind, _ptr(ids),
                                              _ptr(tuv)))
         return ids, tuv
+
+
+def gltf_probe(path):
+    """Host-only parse: ({vertices, indices, instances, materials, triangles}, reference-mode bounds)."""
+    lib = load_library()
+    counts = (ctypes.c_uint64 * 5)()
+    bounds = np.zeros(6, np.float32)
+    r = lib.vlb_gltf_probe(os.fsencode(path), counts, _ptr(bounds))
+    if r != 0:
+        raise VlbError(r, lib.vlb_last_error(None).decode())
+    keys = ("vertices", "indices", "instances", "materials", "triangles")
+    return dict(zip(keys, (int(c) for c in counts))), bounds
 
 
 def serialize_gltf(in_path, out_path, coeffs, settings):

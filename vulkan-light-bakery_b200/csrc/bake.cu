@@ -25,7 +25,7 @@ struct BakeParams {
     const float* px; const float* py; const float* pz;   // probe axis coordinates
     const float2* row_sc;                                // (sin, cos) theta per direction row
     const float2* col_cs;                                // (cos, sin) phi per direction column
-    int Nx, Ny, Nz, k0;
+    int Nx, Ny, Nz, k0, kstride;   // the call bakes z-slices k0, k0 + kstride, ...
     int W, H, tiles_x, n_tiles;
     int chunks, tiles_per_chunk;
     uint32_t n_items;
@@ -58,8 +58,8 @@ __global__ void __launch_bounds__(kBakeBlock) k_bake(const BakeParams p) {
         item = __shfl_sync(0xffffffffu, item, 0);
         if (item >= p.n_items) break;
         const uint32_t q = item / (uint32_t)p.chunks, chunk = item % (uint32_t)p.chunks;
-        const uint32_t g = q + (uint32_t)p.k0 * (uint32_t)(p.Nx * p.Ny);
-        const Vec3 o = mk3(p.px[g % p.Nx], p.py[(g / p.Nx) % p.Ny], p.pz[g / (p.Nx * p.Ny)]);
+        const uint32_t nxy = (uint32_t)(p.Nx * p.Ny), in_slice = q % nxy;
+        const Vec3 o = mk3(p.px[in_slice % p.Nx], p.py[in_slice / p.Nx], p.pz[p.k0 + (q / nxy) * p.kstride]);
         float acc[V];
 #pragma unroll
         for (int i = 0; i < V; ++i) acc[i] = 0.f;
@@ -172,8 +172,8 @@ __global__ void __launch_bounds__(kBakeBlock, 8) k_bake_stream(const BakeParams 
         item = __shfl_sync(full, item, 0);
         if (item >= p.n_items) break;
         const uint32_t q = item / (uint32_t)p.chunks, part = item % (uint32_t)p.chunks;
-        const uint32_t g = q + (uint32_t)p.k0 * (uint32_t)(p.Nx * p.Ny);
-        const Vec3 po = mk3(p.px[g % p.Nx], p.py[(g / p.Nx) % p.Ny], p.pz[g / (p.Nx * p.Ny)]);
+        const uint32_t nxy = (uint32_t)(p.Nx * p.Ny), in_slice = q % nxy;
+        const Vec3 po = mk3(p.px[in_slice % p.Nx], p.py[in_slice / p.Nx], p.pz[p.k0 + (q / nxy) * p.kstride]);
         const int tile_begin = part * p.tiles_per_chunk;
         const int tile_end = min(tile_begin + p.tiles_per_chunk, p.n_tiles);
         float coef0 = 0.f, coef1 = 0.f;   // running sums of coefficient `lane` (V=32) / 2*lane, 2*lane+1 (V=64)
@@ -401,7 +401,9 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out) {
     cudaStream_t st = ctx->stream;
     const int Nx = s->probes[0], Ny = s->probes[1], Nz = s->probes[2];
     const int k0 = s->slab_k1 < 0 ? 0 : s->slab_k0, k1 = s->slab_k1 < 0 ? Nz : s->slab_k1;
-    const uint64_t n_probes = (uint64_t)Nx * Ny * (uint64_t)(k1 - k0);
+    const int kstride = s->slab_stride > 1 ? s->slab_stride : 1;
+    const uint64_t n_probes = (uint64_t)Nx * Ny * (uint64_t)((k1 - k0 + kstride - 1) / kstride);
+    if (int r = bake_collect_stats(ctx)) return r;     // a previous asynchronous bake still owns the stats buffers
     ctx->last_bake = vlb_bake_stats{};
     if (n_probes == 0) return VLB_OK;
     const int W = s->dir_w, H = s->dir_h;
@@ -438,15 +440,19 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out) {
     p.c.gloss = s->gloss; p.c.ambient = s->ambient; p.c.tmin = s->tmin; p.c.tmax = s->tmax; p.c.flags = s->flags;
     p.px = ctx->d_axis.as<float>(); p.py = p.px + Nx; p.pz = p.py + Ny;
     p.row_sc = ctx->d_row_sc.as<float2>(); p.col_cs = ctx->d_col_sc.as<float2>();
-    p.Nx = Nx; p.Ny = Ny; p.Nz = Nz; p.k0 = k0; p.W = W; p.H = H;
+    p.Nx = Nx; p.Ny = Ny; p.Nz = Nz; p.k0 = k0; p.kstride = kstride; p.W = W; p.H = H;
     p.tiles_x = (W + kTileW - 1) / kTileW;
     p.n_tiles = p.tiles_x * ((H + kTileH - 1) / kTileH);
     // Work decomposition: a function of the WHOLE grid and the direction grid only (never of the
-    // slab), so that a probe's coefficients are bit-identical however the grid is sharded.
-    // Probes are split into direction chunks until there are >= 32768 items in the whole grid.
+    // slab), so that a probe's coefficients are bit-identical however the grid is sharded. An item is
+    // one 256-direction chunk of one probe (8 tiles: measured best on B200 for large grids); for
+    // small grids the chunk is halved down to one tile until the whole grid has >= 2^18 items, i.e.
+    // every GPU of an 8-way shard still sees several waves of warps.
     const uint64_t total_probes = (uint64_t)Nx * Ny * Nz;
-    int chunks = 1;
-    while (total_probes * (uint64_t)chunks < 32768ull && chunks * 2 <= p.n_tiles) chunks *= 2;
+    int tiles_per_item = kChunkTiles;
+    while (tiles_per_item > 1 && total_probes * (uint64_t)((p.n_tiles + tiles_per_item - 1) / tiles_per_item) < (1ull << 18))
+        tiles_per_item >>= 1;
+    int chunks = (p.n_tiles + tiles_per_item - 1) / tiles_per_item;
     chunks = env_flag("VLB_BAKE_CHUNKS", chunks);
     chunks = std::max(1, std::min(chunks, p.n_tiles));
     p.tiles_per_chunk = (p.n_tiles + chunks - 1) / chunks;
@@ -500,18 +506,30 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out) {
         VLB_LAUNCH_CHECK(ctx);
     }
     VLB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
-    // the axis staging vector dies at scope exit and stats are read back: synchronise
-    unsigned long long h[4] = {0, 0, 0, 0};
-    unsigned int overflow = 0;
-    VLB_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_stats.p, sizeof h, cudaMemcpyDeviceToHost, st));
-    VLB_CUDA(ctx, cudaMemcpyAsync(&overflow, ctx->d_scratch.as<float>() + 13, 4, cudaMemcpyDeviceToHost, st));
-    VLB_CUDA(ctx, cudaStreamSynchronize(st));
-    if (overflow) return ctx->fail(VLB_ERR_UNSUPPORTED, "bake: BVH traversal stack overflow (tree deeper than %d pending nodes)", kStackSize);
+    // statistics + overflow flag travel to pinned host memory asynchronously; bake_collect_stats() waits for them.
+    // (The axis table above was copied from pageable memory, which is staged before cudaMemcpyAsync returns.)
+    if (!ctx->h_bake_stats) VLB_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_bake_stats), 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+    ctx->h_bake_stats[3] = 0;
+    VLB_CUDA(ctx, cudaMemcpyAsync(ctx->h_bake_stats, ctx->d_stats.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    VLB_CUDA(ctx, cudaMemcpyAsync(ctx->h_bake_stats + 3, ctx->d_scratch.as<float>() + 13, 4, cudaMemcpyDeviceToHost, st));
+    VLB_CUDA(ctx, cudaEventRecord(ctx->ev_done, st));
+    ctx->last_bake.n_probes = n_probes;
+    ctx->last_bake.n_primary_rays = n_probes * (uint64_t)W * H;
+    ctx->bake_pending = true;
+    return VLB_OK;
+}
+
+// Waits for the last enqueued bake and fills ctx->last_bake; reports a traversal stack overflow.
+int bake_collect_stats(vlb_ctx* ctx) {
+    if (!ctx->bake_pending) return VLB_OK;
+    ctx->bake_pending = false;
+    VLB_CUDA(ctx, cudaEventSynchronize(ctx->ev_done));
     vlb_bake_stats& b = ctx->last_bake;
-    b.n_probes = n_probes; b.n_primary_rays = n_probes * (uint64_t)W * H; b.n_shadow_rays = h[0];
-    b.n_nodes_visited = h[1]; b.n_tris_tested = h[2];
+    b.n_shadow_rays = ctx->h_bake_stats[0]; b.n_nodes_visited = ctx->h_bake_stats[1]; b.n_tris_tested = ctx->h_bake_stats[2];
     VLB_CUDA(ctx, cudaEventElapsedTime(&b.kernel_ms, ctx->ev[2], ctx->ev[3]));
     VLB_CUDA(ctx, cudaEventElapsedTime(&b.total_ms, ctx->ev[0], ctx->ev[1]));
+    if (ctx->h_bake_stats[3])
+        return ctx->fail(VLB_ERR_UNSUPPORTED, "bake: BVH traversal stack overflow (more than %d pending nodes on a ray)", kStackSize);
     return VLB_OK;
 }
 

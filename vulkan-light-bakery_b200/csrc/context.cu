@@ -103,6 +103,7 @@ int vlb_ctx_create(int device_id, vlb_ctx** out) {
     cudaDeviceProp prop;
     if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, device_id);
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_done, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         set_thread_error(cudaGetErrorString(e));
         delete ctx;
@@ -128,11 +129,13 @@ void vlb_ctx_destroy(vlb_ctx* ctx) {
                       &ctx->d_stats, &ctx->d_stream_scratch, &ctx->d_ray_o, &ctx->d_ray_d, &ctx->d_hit_id, &ctx->d_hit_tuv, &ctx->d_hit_key};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
+    if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
     for (int l = 0; l < VLB_MAX_LANES; ++l) {
         if (ctx->lane_stream[l]) { cudaStreamSynchronize(ctx->lane_stream[l]); cudaStreamDestroy(ctx->lane_stream[l]); }
         if (ctx->lane_join[l]) cudaEventDestroy(ctx->lane_join[l]);
     }
     if (ctx->lane_fork) cudaEventDestroy(ctx->lane_fork);
+    if (ctx->h_bake_stats) cudaFreeHost(ctx->h_bake_stats);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -413,16 +416,18 @@ int vlb_probe_positions(const vlb_bake_settings* s, float* out) {
     return VLB_OK;
 }
 
-static int slab_range(vlb_ctx* ctx, const vlb_bake_settings* s, int* k0, int* k1) {
+// Validates the settings and returns the z-slices the call bakes: k0, k0 + stride, ... < k1.
+static int slab_range(vlb_ctx* ctx, const vlb_bake_settings* s, int* k0, int* k1, int* stride) {
     if (!s) return ctx->fail(VLB_ERR_INVALID, "bake: settings is NULL");
     if (s->probes[0] < 1 || s->probes[1] < 1 || s->probes[2] < 1 || s->dir_w < 1 || s->dir_h < 1 ||
         (s->sh_order != 2 && s->sh_order != 3))
         return ctx->fail(VLB_ERR_INVALID, "bake: bad probe grid / direction grid / sh_order");
     *k0 = s->slab_k1 < 0 ? 0 : s->slab_k0;
     *k1 = s->slab_k1 < 0 ? s->probes[2] : s->slab_k1;
+    *stride = s->slab_stride > 1 ? s->slab_stride : 1;
     if (*k0 < 0 || *k1 > s->probes[2] || *k0 > *k1) return ctx->fail(VLB_ERR_INVALID, "bake: bad slab range");
     if ((s->flags & (VLB_BAKE_REFERENCE_PROBE_ORDER | VLB_BAKE_ACCUMULATE_ACROSS_PROBES)) &&
-        (*k0 != 0 || *k1 != s->probes[2]))
+        (*k0 != 0 || *k1 != s->probes[2] || *stride != 1))
         return ctx->fail(VLB_ERR_INVALID, "bake: reference probe order / accumulation need the whole grid");
     return VLB_OK;
 }
@@ -430,8 +435,8 @@ static int slab_range(vlb_ctx* ctx, const vlb_bake_settings* s, int* k0, int* k1
 int vlb_bake_probes_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out) {
     if (!ctx) return VLB_ERR_INVALID;
     if (int r = check_device(ctx)) return r;
-    int k0, k1;
-    if (int r = slab_range(ctx, s, &k0, &k1)) return r;
+    int k0, k1, stride;
+    if (int r = slab_range(ctx, s, &k0, &k1, &stride)) return r;
     if (!d_out) return ctx->fail(VLB_ERR_INVALID, "bake: output is NULL");
     if (!ctx->have_scene) return ctx->fail(VLB_ERR_STATE, "bake: no scene set (vlb_scene_set_triangles)");
     if (!ctx->have_bvh) { if (int r = bvh_build(ctx, nullptr)) return r; }
@@ -443,20 +448,22 @@ int vlb_bake_probes_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_ou
 int vlb_bake_probes(vlb_ctx* ctx, const vlb_bake_settings* s, float* out) {
     if (!ctx) return VLB_ERR_INVALID;
     if (int r = check_device(ctx)) return r;
-    int k0, k1;
-    if (int r = slab_range(ctx, s, &k0, &k1)) return r;
+    int k0, k1, stride;
+    if (int r = slab_range(ctx, s, &k0, &k1, &stride)) return r;
     if (!out) return ctx->fail(VLB_ERR_INVALID, "bake: output is NULL");
-    const size_t n = (size_t)s->probes[0] * s->probes[1] * (size_t)(k1 - k0);
+    const size_t n = (size_t)s->probes[0] * s->probes[1] * (size_t)((k1 - k0 + stride - 1) / stride);
     if (n == 0) return VLB_OK;
     VLB_CUDA(ctx, ctx->d_bake_out.reserve(n * VLB_SH_STRIDE * sizeof(float)));
     if (int r = vlb_bake_probes_device(ctx, s, ctx->d_bake_out.as<float>())) return r;
     VLB_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_bake_out.p, n * VLB_SH_STRIDE * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    VLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return VLB_OK;
+    vlb_bake_stats st;
+    return vlb_bake_last_stats(ctx, &st);      // synchronises and surfaces a traversal stack overflow
 }
 
 int vlb_bake_last_stats(vlb_ctx* ctx, vlb_bake_stats* out) {
     if (!ctx || !out) return VLB_ERR_INVALID;
+    if (int r = check_device(ctx)) return r;
+    if (int r = bake_collect_stats(ctx)) return r;
     *out = ctx->last_bake;
     return VLB_OK;
 }

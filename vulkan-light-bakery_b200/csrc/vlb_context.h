@@ -68,7 +68,7 @@ struct vlb_ctx {
     vlb::DevBuf d_keys, d_keys_sorted, d_vals, d_vals_sorted, d_sort_tmp;
     vlb::DevBuf d_left, d_right, d_first, d_last, d_parent_i, d_parent_l, d_flags, d_ibox, d_lbox, d_scratch;
     uint64_t n_nodes = 0;
-    int max_leaf = 4;
+    int max_leaf = 3;
     // ---- skybox ----
     vlb::DevBuf d_sky;        // RGBA32F
     int sky_w = 0, sky_h = 0;
@@ -79,7 +79,10 @@ struct vlb_ctx {
     vlb::DevBuf d_bake_out, d_partials, d_work_counter, d_axis, d_row_sc, d_col_sc, d_stats, d_stream_scratch;
     int dir_w = 0, dir_h = 0;
     vlb_bake_stats last_bake{};
+    bool bake_pending = false;             // a device bake was enqueued and its statistics not yet collected
+    unsigned long long* h_bake_stats = nullptr;   // pinned: [0] shadow rays, [1] nodes, [2] triangles, [3] stack overflow
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_done = nullptr;         // recorded after the last bake's statistics copies
     // ---- auxiliary lanes (independent skybox maps in flight side by side) ----
     cudaStream_t lane_stream[VLB_MAX_LANES] = {};
     cudaEvent_t lane_fork = nullptr, lane_join[VLB_MAX_LANES] = {};
@@ -127,6 +130,7 @@ int bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats);
 int project_sh_device(vlb_ctx* ctx, const void* d_texels, uint64_t map_stride, uint32_t n_maps, int fmt,
                       int W, int H, int order, int variant, float* d_out, int lane = -1);
 int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out);
+int bake_collect_stats(vlb_ctx* ctx);
 int trace_rays(vlb_ctx* ctx, const float* o, const float* d, uint64_t n, float tmin, float tmax, int accel,
                int kind, int32_t* ids, float* tuv);
 }  // namespace vlb

@@ -1,11 +1,17 @@
-"""Multi-GPU bake: probes shard across the GPUs of one box by contiguous z-slabs of the grid (k is
-the slowest index of i + j*Nx + k*Nx*Ny, so a slab is one contiguous byte range of the output),
-scene + BVH + skybox replicated on every GPU, and the per-GPU SH slabs are gathered with ONE
-all-gather (NCCL over NVLink on GPUs; gloo in the CPU tests). One process per GPU
-(torch.distributed); there is no other data-path collective — probes are independent.
+"""Multi-GPU bake: probes shard across the GPUs of one box by z-slices of the grid (k is the slowest
+index of i + j*Nx + k*Nx*Ny, so a slice is one contiguous byte range of the output), scene + BVH +
+skybox replicated on every GPU, and the per-GPU SH buffers are gathered with ONE all-gather (NCCL
+over NVLink on GPUs; gloo in the CPU tests). One process per GPU (torch.distributed); there is no
+other data-path collective -- probes are independent.
+
+Two partitions of the slices:
+  contiguous  rank r bakes one slab [k0, k1) (sizes differ by at most one, first ranks larger)
+  cyclic      rank r bakes k = r, r + world, r + 2*world, ...  Every rank then samples the whole depth
+              of the scene, which evens out the cost of probes near geometry; the gathered buffer
+              is un-interleaved with one strided device copy. This is what bench.py uses.
 
 The reference is single-device (src/application.cpp:90-136 always picks physical device 0); this
-is the build's only parallel axis.
+is the build's only parallel axis (SURVEY \u00a78e).
 """
 import numpy as np
 
@@ -21,42 +27,55 @@ def slab_sizes(nz, world):
     return [slab_range(nz, r, world)[1] - slab_range(nz, r, world)[0] for r in range(world)]
 
 
-def shard_settings(settings, rank, world):
+def cyclic_slices(nz, rank, world):
+    return list(range(rank, int(nz), int(world)))
+
+
+def shard_settings(settings, rank, world, cyclic=False):
     s = settings.copy()
-    s.slab_k0, s.slab_k1 = slab_range(settings.probes[2], rank, world)
+    if cyclic:
+        s.slab_k0, s.slab_k1, s.slab_stride = rank, settings.probes[2], world
+    else:
+        s.slab_k0, s.slab_k1 = slab_range(settings.probes[2], rank, world)
+        s.slab_stride = 1
     return s
 
 
-def gather_slabs(local, settings, rank, world, group=None):
-    """All-gathers the per-rank slabs ([n_local_probes, 48] torch tensors on the bake device) into
-    the full [Nx*Ny*Nz, 48] buffer, identical on every rank. Slabs are padded to the largest slab
-    so a single equal-size all_gather_into_tensor moves everything."""
+def gather_slabs(local, settings, rank, world, group=None, cyclic=False):
+    """All-gathers the per-rank buffers ([n_local_probes, 48] torch tensors on the bake device) into
+    the full [Nx*Ny*Nz, 48] buffer in x-fastest order, identical on every rank. Buffers are padded to
+    the largest share so a single equal-size all_gather_into_tensor moves everything."""
     import torch
     import torch.distributed as dist
+    if world == 1:
+        return local
+    nz = settings.probes[2]
     nxy = settings.probes[0] * settings.probes[1]
-    sizes = slab_sizes(settings.probes[2], world)
+    sizes = [len(cyclic_slices(nz, r, world)) for r in range(world)] if cyclic else slab_sizes(nz, world)
     pad = max(sizes) * nxy
     send = local
     if local.shape[0] != pad:
         send = torch.zeros((pad, 48), dtype=local.dtype, device=local.device)
         send[: local.shape[0]] = local
-    if world == 1:
-        return local
     recv = torch.empty((world * pad, 48), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
+    if cyclic:
+        # recv[r, i] is slice k = r + i*world: transpose (rank, i) -> (i, rank) and drop the padding slices
+        full = recv.view(world, max(sizes), nxy, 48).transpose(0, 1).reshape(max(sizes) * world * nxy, 48)
+        return full[: nz * nxy] if full.shape[0] != nz * nxy else full
     if all(sz == sizes[0] for sz in sizes):
         return recv
     parts = [recv[r * pad: r * pad + sizes[r] * nxy] for r in range(world)]
     return torch.cat(parts, 0)
 
 
-def bake_sharded(bake_slab, settings, rank, world, device=None, group=None):
+def bake_sharded(bake_slab, settings, rank, world, device=None, group=None, cyclic=False):
     """bake_slab(slab_settings, out_tensor) fills out_tensor ([n_local, 48] float32 on `device`)
-    with this rank's slab; returns the gathered full grid on every rank."""
+    with this rank's share; returns the gathered full grid on every rank."""
     import torch
-    s = shard_settings(settings, rank, world)
-    n_local = settings.probes[0] * settings.probes[1] * (s.slab_k1 - s.slab_k0)
+    s = shard_settings(settings, rank, world, cyclic)
+    n_local = s.n_slab_probes
     out = torch.empty((max(n_local, 1), 48), dtype=torch.float32, device=device)[:n_local]
     if n_local:
         bake_slab(s, out)
-    return gather_slabs(out, settings, rank, world, group)
+    return gather_slabs(out, settings, rank, world, group, cyclic)

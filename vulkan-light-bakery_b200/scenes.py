@@ -266,3 +266,84 @@ def atrium_settings(probes=(16, 8, 16), dirs=(32, 32), order=2, bounds=None):
         bounds = (0.0, 0.0, 0.0) + HALL
     settings_from_bounds(s, bounds)
     return s
+
+
+def write_gltf(scene, path, index_dtype=np.uint16, embed=True):
+    """Writes a scene dict (the arrays the C ABI takes) as a glTF 2.0 file: one mesh + one node per
+    instance, the instance transform as the node's column-major `matrix`, materials as
+    pbrMetallicRoughness.baseColorFactor. Loading the file back with vlb_scene_load_gltf must give
+    the same geometry (tests/test_gltf.py). `embed`: base64 data URI, else a .bin next to the file."""
+    import base64
+    import json
+    import os
+    verts, idx, insts, mats = scene["vertices"], scene["indices"], scene["instances"], scene["materials"]
+    blob = bytearray()
+    views, accessors, meshes, nodes = [], [], [], []
+
+    def add_view(data, target=None):
+        while len(blob) % 4:
+            blob.append(0)
+        v = {"buffer": 0, "byteOffset": len(blob), "byteLength": len(data)}
+        if target:
+            v["target"] = target
+        blob.extend(data)
+        views.append(v)
+        return len(views) - 1
+
+    for inst in insts:
+        fv, nv = int(inst["first_vertex"]), int(inst["vertex_count"])
+        fi, ni = int(inst["first_index"]), int(inst["index_count"])
+        pos = np.ascontiguousarray(verts["position"][fv:fv + nv, :3], np.float32)
+        nrm = np.ascontiguousarray(verts["normal"][fv:fv + nv], np.float32)
+        ii = np.ascontiguousarray(idx[fi:fi + ni])
+        dt = index_dtype if (nv <= np.iinfo(index_dtype).max + 1) else np.uint32
+        comp = {np.uint8: 5121, np.uint16: 5123, np.uint32: 5125}[np.dtype(dt).type]
+        a_pos = len(accessors)
+        accessors.append({"bufferView": add_view(pos.tobytes(), 34962), "componentType": 5126, "count": nv, "type": "VEC3",
+                          "min": [float(x) for x in pos.min(0)] if nv else [0, 0, 0],
+                          "max": [float(x) for x in pos.max(0)] if nv else [0, 0, 0]})
+        accessors.append({"bufferView": add_view(nrm.tobytes(), 34962), "componentType": 5126, "count": nv, "type": "VEC3"})
+        accessors.append({"bufferView": add_view(ii.astype(dt).tobytes(), 34963), "componentType": comp, "count": ni, "type": "SCALAR"})
+        prim = {"attributes": {"POSITION": a_pos, "NORMAL": a_pos + 1}, "indices": a_pos + 2}
+        if int(inst["material_index"]) < len(mats):
+            prim["material"] = int(inst["material_index"])
+        meshes.append({"primitives": [prim]})
+        m = np.asarray(inst["transform"], np.float32).reshape(3, 4)
+        col_major = [float(m[r, c]) for c in range(4) for r in range(3)]
+        matrix = col_major[0:3] + [0.0] + col_major[3:6] + [0.0] + col_major[6:9] + [0.0] + col_major[9:12] + [1.0]
+        nodes.append({"mesh": len(meshes) - 1, "matrix": matrix})
+    doc = {"asset": {"version": "2.0", "generator": "vulkan-light-bakery_b200.scenes.write_gltf"},
+           "scene": 0, "scenes": [{"nodes": list(range(len(nodes)))}], "nodes": nodes, "meshes": meshes,
+           "materials": [{"pbrMetallicRoughness": {"baseColorFactor": [float(x) for x in m["base_color_factor"]]}} for m in mats],
+           "accessors": accessors, "bufferViews": views}
+    if embed:
+        doc["buffers"] = [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(bytes(blob)).decode()}]
+    else:
+        bin_name = os.path.splitext(os.path.basename(path))[0] + ".bin"
+        with open(os.path.join(os.path.dirname(path), bin_name), "wb") as f:
+            f.write(bytes(blob))
+        doc["buffers"] = [{"byteLength": len(blob), "uri": bin_name}]
+    with open(path, "w") as f:
+        json.dump(doc, f)
+    return path
+
+
+def write_glb(scene, path):
+    """Same content as write_gltf in the binary .glb container (JSON chunk + BIN chunk)."""
+    import json
+    import os
+    import struct
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        tmp = write_gltf(scene, os.path.join(d, "x.gltf"), embed=False)
+        doc = json.load(open(tmp))
+        blob = open(os.path.join(d, "x.bin"), "rb").read()
+    del doc["buffers"][0]["uri"]
+    js = json.dumps(doc).encode()
+    js += b" " * (-len(js) % 4)
+    blob += b"\0" * (-len(blob) % 4)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<4sII", b"glTF", 2, 12 + 8 + len(js) + 8 + len(blob)))
+        f.write(struct.pack("<II", len(js), 0x4E4F534A) + js)
+        f.write(struct.pack("<II", len(blob), 0x004E4942) + blob)
+    return path
