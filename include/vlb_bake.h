@@ -130,7 +130,13 @@ typedef struct vlb_bake_settings {
     int32_t  slab_stride;        /* > 1: only every slab_stride-th slice of [k0, k1), i.e.
                                     k = k0, k0 + stride, ... (cyclic sharding over GPUs: rank r of
                                     N bakes k0 = r, k1 = Nz, stride = N); 0 or 1 = contiguous     */
-    int32_t  reserved[3];
+    /* Multi-bounce gather (BASELINE configs[3]). The reference bakes direct light only;
+     * its run-time shader gathers indirect light from the baked probes (shaders/main.rchit:124-167,
+     * shaders/sh.rmiss:27-36). bounces = B > 0 re-bakes the grid B more times, every hit adding
+     * indirect_gain * (that gather operator applied to the previous pass). 0 = the reference bake. */
+    int32_t  bounces;
+    float    indirect_gain;      /* scale of the gathered term (main.rchit:165 uses ambient * 1250) */
+    int32_t  reserved;
 } vlb_bake_settings;
 
 #define VLB_SH_STRIDE 48         /* floats per probe: vec3 coeffs[16] (shaders/sh.comp:21)     */
@@ -230,10 +236,21 @@ int vlb_bake_settings_from_bounds(vlb_bake_settings* s, const float bounds_min_m
  * VLB_BAKE_REFERENCE_PROBE_ORDER); out = Nx*Ny*Nz*3 floats. Host-only helper. */
 int vlb_probe_positions(const vlb_bake_settings* s, float* out_xyz);
 /* LightBaker::bake (src/baker/light_baker.cpp:287-328). out = n_slab_probes x 48 floats
- * (float[probe][16][3], light_baker.cpp:294-322). */
+ * (float[probe][16][3], light_baker.cpp:294-322). With s->bounces > 0 the call must cover the whole
+ * grid (no slab) and runs 1 + bounces passes on the device, returning the last one. */
 int vlb_bake_probes(vlb_ctx* ctx, const vlb_bake_settings* s, float* out);
 /* Device-resident output; enqueues on the ctx stream and returns WITHOUT synchronising. */
 int vlb_bake_probes_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out);
+/* One gather pass with a device-resident source: bakes the slab exactly like
+ * vlb_bake_probes_device, but every hit adds indirect_gain * gather(d_prev_full) where d_prev_full
+ * is the PREVIOUS pass over the WHOLE grid ([Nx*Ny*Nz][48] floats, x-fastest probe order; the
+ * reference's consumer layout, shaders/sh.rmiss:25-28). s->bounces is ignored here: the caller
+ * iterates (and, when the grid is sharded over GPUs, all-gathers the slabs between passes).
+ * d_prev_full == NULL is the direct pass. The gather operator (shaders/main.rchit:124-163): cell
+ * ijk = floor((P - origin) / step) clamped into the grid; for its 8 corners in the reference's order
+ * a visibility ray from P + bias*N to the corner probe, weight = |step| - distance (clamped at 0),
+ * value = sum_i prev[corner][i] * SH_i(N); result = sum(w * value) / sum(w) over visible corners. */
+int vlb_bake_gather_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_full, float* d_out);
 /* Statistics of the last bake call. Synchronises with that call; returns VLB_ERR_UNSUPPORTED if
  * its traversal overflowed the per-ray stack (vlb_bake_probes reports that itself). */
 int vlb_bake_last_stats(vlb_ctx* ctx, vlb_bake_stats* out);

@@ -54,6 +54,8 @@ def lib():
         L.vo_trace_rays.argtypes = [_vp, _vp, _vp, _u64, _f32, _f32, _i32, _i32, _vp, _vp]
         L.vo_bake_probes.restype = _u64
         L.vo_bake_probes.argtypes = [_vp, _vp, _vp, _u64, _i32, _vp]
+        L.vo_bake_gather.restype = _u64
+        L.vo_bake_gather.argtypes = [_vp, _vp, _vp, _vp, _u64, _i32, _vp]
         L.vo_probe_envmap.argtypes = [_vp, _vp, _vp, _i32, _vp, _vp]
         _lib = L
     return _lib
@@ -197,6 +199,25 @@ class Scene:
         out = np.zeros((n, 16, 3), np.float32)
         sr = lib().vo_bake_probes(self._h, ctypes.byref(settings), _p(ids), n, int(bool(brute)), _p(out))
         return out, int(sr)
+
+    def bake_gather(self, settings, prev_full, probe_ids=None, brute=False):
+        """One gather pass over prev_full ([n_probes,16,3], whole grid, x-fastest) -- None = direct pass."""
+        if probe_ids is None:
+            n, ids = settings.n_slab_probes, None
+        else:
+            ids = np.ascontiguousarray(probe_ids, np.int64)
+            n = ids.size
+        prev = None if prev_full is None else np.ascontiguousarray(prev_full, np.float32).reshape(settings.n_probes, 48)
+        out = np.zeros((n, 16, 3), np.float32)
+        sr = lib().vo_bake_gather(self._h, ctypes.byref(settings), _p(prev), _p(ids), n, int(bool(brute)), _p(out))
+        return out, int(sr)
+
+    def bake_multibounce(self, settings, brute=False):
+        """1 + settings.bounces passes over the whole grid (include/vlb_bake.h: vlb_bake_probes with bounces > 0)."""
+        prev = None
+        for _ in range(1 + max(0, settings.bounces)):
+            prev, _sr = self.bake_gather(settings, prev, brute=brute)
+        return prev
 
     def probe_envmap(self, settings, pos, brute=False):
         img = np.zeros((settings.dir_h, settings.dir_w, 3), np.float32)

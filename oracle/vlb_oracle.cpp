@@ -508,9 +508,61 @@ static void base_color(const vlb_material& m, float out[4]) {
     }
 }
 
+// ---- multi-bounce gather: the reference's run-time operator, shaders/main.rchit:124-163 with the
+// probe lookup of shaders/sh.rmiss:20-36, restated for an arbitrary grid. "Parity unpinned": the
+// reference never runs this inside the bake (it bakes direct light only), so this restatement is the
+// specification of BASELINE configs[3]. Deviations from the literal shader, all documented in
+// include/vlb_bake.h: the grid origin is honoured (main.rchit:126 assumes 0); the cell is clamped into
+// the grid (the shader hard-codes 7x7x7, sh.rmiss:22); each corner reads ITS probe (sh.rmiss:25 reads
+// the cell's base probe for all eight -- evident defect); weights are clamped at 0 and an empty
+// weight sum yields 0 (the shader divides 0/0); the SH argument is the normal in the frame the bake
+// stored the coefficients in.
+struct GatherCtx {
+    const float* prev;                 // [Nx*Ny*Nz][48], x-fastest
+    const float* px; const float* py; const float* pz;
+    int Nx, Ny, Nz;
+};
+
+static inline int cell_of(float p, float origin, float step, int n) {
+    if (n < 2) return 0;
+    const float g = std::floor((p - origin) / step);                 // main.rchit:126
+    if (!(g > 0.0f)) return 0;                                       // also NaN (step == 0)
+    return g >= (float)(n - 2) ? n - 2 : (int)g;
+}
+
+static void gather_indirect(const Scene& s, const vlb_bake_settings& st, const GatherCtx& g, V3 P, V3 N,
+                            V3 so, bool brute, float out[3]) {
+    const int K = n_coeffs(st.sh_order);
+    const int ci = cell_of(P.x, st.origin[0], st.step[0], g.Nx);
+    const int cj = cell_of(P.y, st.origin[1], st.step[1], g.Ny);
+    const int ck = cell_of(P.z, st.origin[2], st.step[2], g.Nz);
+    const float weightMax = sqrtf(dot3(v3(st.step[0], st.step[1], st.step[2]), v3(st.step[0], st.step[1], st.step[2])));  // :141
+    float b[25];
+    sh_basis25((st.flags & VLB_BAKE_SH_WORLD_FRAME) ? N : v3(N.x, N.z, N.y), b);
+    float sum[3] = {0.f, 0.f, 0.f}, wsum = 0.f;
+    for (int c = 0; c < 8; ++c) {                                    // gridVertices order, :128-137
+        const int i = std::min(ci + ((c >> 2) & 1), g.Nx - 1), j = std::min(cj + ((c >> 1) & 1), g.Ny - 1),
+                  k = std::min(ck + (c & 1), g.Nz - 1);
+        const V3 d = v3(g.px[i] - P.x, g.py[j] - P.y, g.pz[k] - P.z);    // :145
+        const float tmax = sqrtf(dot3(d, d));                            // :154
+        const float w = std::max(weightMax - tmax, 0.0f);                // :156
+        bool occluded = false;
+        if (tmax > 0.0f) occluded = trace_any(s, so, v3(d.x / tmax, d.y / tmax, d.z / tmax), 0.0f, tmax, brute, nullptr);  // :155
+        if (occluded) continue;
+        const float* sh = g.prev + ((size_t)i + (size_t)g.Nx * ((size_t)j + (size_t)g.Ny * k)) * 48;   // sh.rmiss:25
+        float v[3] = {0.f, 0.f, 0.f};
+        for (int q = 0; q < K; ++q) {                                    // sh.rmiss:27-34
+            v[0] = fmaf(sh[3 * q + 0], b[q], v[0]); v[1] = fmaf(sh[3 * q + 1], b[q], v[1]); v[2] = fmaf(sh[3 * q + 2], b[q], v[2]);
+        }
+        sum[0] = fmaf(w, v[0], sum[0]); sum[1] = fmaf(w, v[1], sum[1]); sum[2] = fmaf(w, v[2], sum[2]);   // :160
+        wsum += w;                                                        // :161
+    }
+    for (int c = 0; c < 3; ++c) out[c] = wsum > 0.0f ? st.indirect_gain * (sum[c] / wsum) : 0.0f;        // :164-165
+}
+
 // env_map.rchit:51-102
 static void shade_hit(const Scene& s, const vlb_bake_settings& st, const Hit& h, V3 o, V3 r,
-                      bool brute, float rgb[3], uint64_t* shadow_rays) {
+                      bool brute, float rgb[3], uint64_t* shadow_rays, const GatherCtx* g = nullptr) {
     const Tri& tr = s.tris[h.id];
     const Inst& in = s.insts[tr.inst];
     const float b0 = 1.0f - h.u - h.v, b1 = h.u, b2 = h.v;
@@ -543,8 +595,13 @@ static void shade_hit(const Scene& s, const vlb_bake_settings& st, const Hit& h,
         specular = st.c_specular * (float)std::pow((double)rd, (double)st.gloss);
     }
     const float k = st.ambient + diffuse + specular;
+    float ind[3] = {0.f, 0.f, 0.f};
+    if (g) {                                                           // main.rchit:102,124-165
+        const V3 so = v3(fmaf(st.shadow_bias, N.x, P.x), fmaf(st.shadow_bias, N.y, P.y), fmaf(st.shadow_bias, N.z, P.z));
+        gather_indirect(s, st, *g, P, N, so, brute, ind);
+    }
     for (int c = 0; c < 3; ++c) {
-        float v = bc[c] * k;
+        float v = bc[c] * (k + ind[c]);
         rgb[c] = (st.flags & VLB_BAKE_SRGB_ENCODE) ? srgb1(v) : v;
     }
 }
@@ -587,7 +644,7 @@ static inline size_t ref_order_index(int i, int j, int k, int Nx, int Ny, int Nz
 }
 
 static void bake_one(const Scene& s, const vlb_bake_settings& st, const DirTable& dt, V3 pos,
-                     bool brute, double* acc48, float* image_rgb, uint64_t* shadow_rays) {
+                     bool brute, double* acc48, float* image_rgb, uint64_t* shadow_rays, const GatherCtx* g = nullptr) {
     const int K = n_coeffs(st.sh_order);
     for (int y = 0; y < dt.H; ++y) {
         for (int x = 0; x < dt.W; ++x) {
@@ -596,7 +653,7 @@ static void bake_one(const Scene& s, const vlb_bake_settings& st, const DirTable
             float rgb[3] = {0.f, 0.f, 0.f};                            // env_map.rgen:25
             const Hit h = trace_closest(s, pos, r, st.tmin, st.tmax, brute);
             if (h.id >= 0) {
-                shade_hit(s, st, h, pos, r, brute, rgb, shadow_rays);
+                shade_hit(s, st, h, pos, r, brute, rgb, shadow_rays, g);
             } else if ((st.flags & VLB_BAKE_SKYBOX_ON_MISS) && s.skyW > 0) {
                 sky_lookup(s, r, rgb);
                 if (st.flags & VLB_BAKE_SRGB_ENCODE) for (int c = 0; c < 3; ++c) rgb[c] = srgb1(rgb[c]);
@@ -816,8 +873,8 @@ void vo_trace_rays(void* h, const float* origins, const float* dirs, uint64_t n,
 // when probe_ids == NULL, the slices slab_k0, slab_k0 + slab_stride, ... < slab_k1. out = n x 48 floats in list order
 // (slab mode: output order as the settings' flags say, relative to the slab start).
 // Returns the number of shadow rays traced.
-uint64_t vo_bake_probes(void* h, const vlb_bake_settings* st, const int64_t* probe_ids,
-                        uint64_t n_ids, int brute, float* out) {
+static uint64_t bake_probes_impl(void* h, const vlb_bake_settings* st, const float* prev_full, const int64_t* probe_ids,
+                                 uint64_t n_ids, int brute, float* out) {
     Scene* s = (Scene*)h;
     const int Nx = st->probes[0], Ny = st->probes[1], Nz = st->probes[2];
     std::vector<float> px, py, pz;
@@ -830,6 +887,7 @@ uint64_t vo_bake_probes(void* h, const vlb_bake_settings* st, const int64_t* pro
     const uint64_t n = probe_ids ? n_ids : (uint64_t)Nx * Ny * ((k1 - k0 + kstride - 1) / kstride);
     const bool ref_order = !probe_ids && (st->flags & VLB_BAKE_REFERENCE_PROBE_ORDER);
     uint64_t shadow_total = 0;
+    GatherCtx gctx{prev_full, px.data(), py.data(), pz.data(), Nx, Ny, Nz};
     std::vector<double> all((size_t)n * 48, 0.0);
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : shadow_total)
     for (int64_t q = 0; q < (int64_t)n; ++q) {
@@ -839,7 +897,7 @@ uint64_t vo_bake_probes(void* h, const vlb_bake_settings* st, const int64_t* pro
         uint64_t sr = 0;
         size_t slot = (size_t)q;
         if (ref_order) slot = ref_order_index(i, j, k, Nx, Ny, Nz);     // whole-grid only
-        bake_one(*s, *st, dt, v3(px[i], py[j], pz[k]), brute != 0, &all[slot * 48], nullptr, &sr);
+        bake_one(*s, *st, dt, v3(px[i], py[j], pz[k]), brute != 0, &all[slot * 48], nullptr, &sr, prev_full ? &gctx : nullptr);
         shadow_total += sr;
     }
     if (st->flags & VLB_BAKE_ACCUMULATE_ACROSS_PROBES) {               // light_baker.cpp:110-121 literal
@@ -847,6 +905,18 @@ uint64_t vo_bake_probes(void* h, const vlb_bake_settings* st, const int64_t* pro
     }
     for (size_t c = 0; c < all.size(); ++c) out[c] = (float)all[c];
     return shadow_total;
+}
+
+uint64_t vo_bake_probes(void* h, const vlb_bake_settings* st, const int64_t* probe_ids,
+                        uint64_t n_ids, int brute, float* out) {
+    return bake_probes_impl(h, st, nullptr, probe_ids, n_ids, brute, out);
+}
+
+// One gather pass (include/vlb_bake.h: vlb_bake_gather_device): as vo_bake_probes, every hit adding the
+// gather of prev_full ([Nx*Ny*Nz][48], x-fastest). prev_full == NULL is the direct pass.
+uint64_t vo_bake_gather(void* h, const vlb_bake_settings* st, const float* prev_full, const int64_t* probe_ids,
+                        uint64_t n_ids, int brute, float* out) {
+    return bake_probes_impl(h, st, prev_full, probe_ids, n_ids, brute, out);
 }
 
 // One probe's environment image (what env_map.rgen writes), W*H*3 floats, plus its SH.

@@ -43,6 +43,7 @@ def lib():
         L.emu_scene_set_skybox.argtypes = [_vp, _vp, _i32, _i32]
         L.emu_trace_rays.argtypes = [_vp, _vp, _vp, _u64, _f32, _f32, _i32, _vp, _vp, _vp]
         L.emu_bake.argtypes = [_vp, _vp, _vp]
+        L.emu_bake_gather.argtypes = [_vp, _vp, _vp, _vp]
         _lib = L
     return _lib
 
@@ -78,10 +79,11 @@ class Scene:
         lib().emu_trace_rays(self._h, _p(o), _p(d), o.shape[0], tmin, tmax, kind, _p(ids), _p(tuv), _p(cnt))
         return ids, tuv, cnt
 
-    def bake(self, settings):
+    def bake(self, settings, prev_full=None):
         k1 = settings.probes[2] if settings.slab_k1 < 0 else settings.slab_k1
         k0 = 0 if settings.slab_k1 < 0 else settings.slab_k0
         n = settings.probes[0] * settings.probes[1] * (k1 - k0)
         out = np.zeros((n, 16, 3), np.float32)
-        lib().emu_bake(self._h, ctypes.byref(settings), _p(out))
+        prev = None if prev_full is None else np.ascontiguousarray(prev_full, np.float32).reshape(-1, 48)
+        lib().emu_bake_gather(self._h, ctypes.byref(settings), _p(prev), _p(out))
         return out

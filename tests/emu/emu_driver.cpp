@@ -174,8 +174,9 @@ void emu_trace_rays(void* h, const float* o, const float* d, uint64_t n, float t
     if (counters) { counters[0] = nn; counters[1] = nt; }
 }
 
-// k_bake, serially: probes of the slab in x-fastest order, out = n x 48 floats
-void emu_bake(void* h, const vlb_bake_settings* st, float* out) {
+// k_bake, serially: probes of the slab in x-fastest order, out = n x 48 floats. prev_full != NULL:
+// a gather pass over the previous pass of the whole grid (vlb_bake_gather_device).
+void emu_bake_gather(void* h, const vlb_bake_settings* st, const float* prev_full, float* out) {
     EmuScene* s = (EmuScene*)h;
     BvhView b = view(s);
     ShadeView sv; sv.tri_shade = s->tri_shade.data(); sv.inst = s->inst.data(); sv.base_color = s->base_color.data();
@@ -193,6 +194,9 @@ void emu_bake(void* h, const vlb_bake_settings* st, float* out) {
     const float pixel_area = (2.0f * kPi / (float)W) * (kPi / (float)H);
     const int k0 = st->slab_k1 < 0 ? 0 : st->slab_k0, k1 = st->slab_k1 < 0 ? Nz : st->slab_k1;
     const int K = st->sh_order == 2 ? 9 : 16;
+    GatherView g; g.prev = prev_full; g.px = px.data(); g.py = py.data(); g.pz = pz.data(); g.Nx = Nx; g.Ny = Ny; g.Nz = Nz;
+    for (int k = 0; k < 3; ++k) { g.origin[k] = st->origin[k]; g.step[k] = st->step[k]; }
+    g.gain = st->indirect_gain; g.world_frame = (st->flags & VLB_BAKE_SH_WORLD_FRAME) ? 1 : 0;
     size_t q = 0;
     for (int k = k0; k < k1; ++k) for (int j = 0; j < Ny; ++j) for (int i = 0; i < Nx; ++i, ++q) {
         double acc[48] = {0};
@@ -201,7 +205,8 @@ void emu_bake(void* h, const vlb_bake_settings* st, float* out) {
             const Vec3 t = to_vector_sc(row[2 * y], row[2 * y + 1], col[2 * x], col[2 * x + 1]);
             const Vec3 r = mk3(t.x, t.z, t.y);
             float rgb[3];
-            probe_ray_radiance<false>(b, sv, c, o, r, rgb, nullptr, nullptr);
+            if (K == 9) probe_ray_radiance<false, 9>(b, sv, c, o, r, rgb, nullptr, nullptr, &g);
+            else        probe_ray_radiance<false, 16>(b, sv, c, o, r, rgb, nullptr, nullptr, &g);
             const float w = pixel_area * row[2 * y];
             float bs[16];
             sh_basis<16>((st->flags & VLB_BAKE_SH_WORLD_FRAME) ? r : t, bs);
@@ -210,5 +215,7 @@ void emu_bake(void* h, const vlb_bake_settings* st, float* out) {
         for (int m = 0; m < 48; ++m) out[q * 48 + m] = (float)acc[m];
     }
 }
+
+void emu_bake(void* h, const vlb_bake_settings* st, float* out) { emu_bake_gather(h, st, nullptr, out); }
 
 }  // extern "C"

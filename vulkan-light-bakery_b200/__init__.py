@@ -55,7 +55,7 @@ class BakeSettings(ctypes.Structure):
                 ("c_specular", ctypes.c_float), ("gloss", ctypes.c_float), ("ambient", ctypes.c_float),
                 ("tmin", ctypes.c_float), ("tmax", ctypes.c_float), ("flags", ctypes.c_uint32),
                 ("slab_k0", ctypes.c_int32), ("slab_k1", ctypes.c_int32), ("slab_stride", ctypes.c_int32),
-                ("reserved", ctypes.c_int32 * 3)]
+                ("bounces", ctypes.c_int32), ("indirect_gain", ctypes.c_float), ("reserved", ctypes.c_int32)]
 
     def copy(self):
         c = BakeSettings()
@@ -107,7 +107,7 @@ ABI_SYMBOLS = [
     "vlb_last_error", "vlb_ctx_launch_count", "vlb_scene_set_triangles", "vlb_scene_load_gltf", "vlb_gltf_probe", "vlb_scene_bounds", "vlb_bvh_build",
     "vlb_skybox_set", "vlb_skybox_project_sh", "vlb_skybox_project_sh_batched", "vlb_skybox_project_sh_device",
     "vlb_skybox_project_sh_device_ptrs", "vlb_envmap_project_sh", "vlb_bake_settings_default", "vlb_bake_settings_from_bounds", "vlb_probe_positions",
-    "vlb_bake_probes", "vlb_bake_probes_device", "vlb_bake_last_stats", "vlb_trace_rays",
+    "vlb_bake_probes", "vlb_bake_probes_device", "vlb_bake_gather_device", "vlb_bake_last_stats", "vlb_trace_rays",
     "vlb_bake_serialize_gltf", "vlb_bake_deserialize_gltf",
 ]
 
@@ -149,6 +149,7 @@ def load_library():
         "vlb_probe_positions": (i32, [S, vp]),
         "vlb_bake_probes": (i32, [vp, S, vp]),
         "vlb_bake_probes_device": (i32, [vp, S, vp]),
+        "vlb_bake_gather_device": (i32, [vp, S, vp, vp]),
         "vlb_bake_last_stats": (i32, [vp, ctypes.POINTER(BakeStats)]),
         "vlb_trace_rays": (i32, [vp, vp, vp, u64, f32, f32, i32, i32, vp, vp]),
         "vlb_bake_serialize_gltf": (i32, [ctypes.c_char_p, ctypes.c_char_p, vp, u64, S]),
@@ -309,6 +310,10 @@ class Context:
 
     def bake_probes_device(self, s, d_out):
         self._check(self._lib.vlb_bake_probes_device(self._h, ctypes.byref(s), int(d_out)))
+
+    def bake_gather_device(self, s, d_prev_full, d_out):
+        """One gather pass: d_prev_full = previous pass over the WHOLE grid ([n_probes, 48] device floats) or 0."""
+        self._check(self._lib.vlb_bake_gather_device(self._h, ctypes.byref(s), int(d_prev_full) if d_prev_full else None, int(d_out)))
 
     def last_bake_stats(self):
         st = BakeStats()

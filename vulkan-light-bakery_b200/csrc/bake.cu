@@ -36,6 +36,7 @@ struct BakeParams {
     int ref_order, world_frame;
     WarpQueues* stream_scratch;  // k_bake_stream: per-warp radiance tile + ray queues, [grid * warps per block]
     int node_min;                // k_bake_stream: the node loop yields to the leaf phase below this many lanes
+    GatherView g;                // gather pass source (g.prev == NULL: direct pass)
 };
 
 __device__ __forceinline__ size_t out_slot(const BakeParams& p, uint32_t q) {
@@ -73,7 +74,7 @@ __global__ void __launch_bounds__(kBakeBlock) k_bake(const BakeParams p) {
                 const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);   // sh_common.h:8-12
                 const Vec3 r = mk3(t.x, t.z, t.y);                         // env_map.rgen:21 .xzy
                 float rgb[3];
-                probe_ray_radiance<COUNT>(p.bvh, p.shade, p.c, o, r, rgb, &cnt, &shadow);
+                probe_ray_radiance<COUNT, K>(p.bvh, p.shade, p.c, o, r, rgb, &cnt, &shadow, &p.g);
                 const float w = p.pixel_area * row.x;                      // sh.comp:32-33
                 float b[K];
                 sh_basis<K>(p.world_frame ? r : t, b);                     // sh.comp:30,39
@@ -148,8 +149,8 @@ struct WarpQueues {
     float lane_rgb[6][32];         // the same two radiances for the shadow ray a lane is tracing
 };
 
-template <int K, bool COUNT>
-__global__ void __launch_bounds__(kBakeBlock, 8) k_bake_stream(const BakeParams p) {
+template <int K, bool COUNT, bool GATHER>
+__global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : 8) k_bake_stream(const BakeParams p) {
     constexpr int V = (K * 3 <= 32) ? 32 : 64;
     // The per-warp queues live in a global scratch buffer (L1/L2 resident, ~9 KB per resident warp),
     // not in shared memory: measured on B200, leaving the SM's 228 KB to the L1 cache (BVH nodes)
@@ -252,13 +253,17 @@ __global__ void __launch_bounds__(kBakeBlock, 8) k_bake_stream(const BakeParams 
                         float rgb[3] = {0.f, 0.f, 0.f};                                 // env_map.rgen:25
                         if (h.id >= 0) {
                             const bool lit = shade_prelude(p.shade, p.c, h, po, r, pre);
+                            float ind[3] = {0.f, 0.f, 0.f};
+                            // gather passes: the 8 short visibility rays to the surrounding probes are traced
+                            // right here, per lane (main.rchit:143-163); only the sun shadow ray is queued
+                            if (GATHER) gather_indirect<K, COUNT>(bvh, p.g, pre, ind, &cnt);
                             if (lit && want_shadow) {
                                 // radiance for both outcomes now, the shadow ray decides (env_map.rchit:83-99)
-                                shade_finish(p.c, pre, r, false, lit_rgb);
-                                shade_finish(p.c, pre, r, true, dark_rgb);
+                                shade_finish(p.c, pre, r, false, ind, lit_rgb);
+                                shade_finish(p.c, pre, r, true, ind, dark_rgb);
                                 push = true;
                             } else {
-                                shade_finish(p.c, pre, r, !lit, rgb);
+                                shade_finish(p.c, pre, r, !lit, ind, rgb);
                             }
                         } else if ((p.c.flags & 2u) && p.shade.sky) {                   // VLB_BAKE_SKYBOX_ON_MISS
                             sky_lookup(p.shade, r, rgb);
@@ -397,7 +402,7 @@ static int env_flag(const char* name, int dflt) {
     return v && *v ? atoi(v) : dflt;
 }
 
-int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out) {
+int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_full, float* d_out) {
     cudaStream_t st = ctx->stream;
     const int Nx = s->probes[0], Ny = s->probes[1], Nz = s->probes[2];
     const int k0 = s->slab_k1 < 0 ? 0 : s->slab_k0, k1 = s->slab_k1 < 0 ? Nz : s->slab_k1;
@@ -465,6 +470,10 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out) {
     p.ref_order = (s->flags & VLB_BAKE_REFERENCE_PROBE_ORDER) ? 1 : 0;
     p.world_frame = (s->flags & VLB_BAKE_SH_WORLD_FRAME) ? 1 : 0;
     p.node_min = std::max(1, std::min(32, env_flag("VLB_BAKE_NODE_MIN", 8)));
+    p.g.prev = d_prev_full; p.g.px = p.px; p.g.py = p.py; p.g.pz = p.pz; p.g.Nx = Nx; p.g.Ny = Ny; p.g.Nz = Nz;
+    for (int k = 0; k < 3; ++k) { p.g.origin[k] = s->origin[k]; p.g.step[k] = s->step[k]; }
+    p.g.gain = s->indirect_gain; p.g.world_frame = p.world_frame;
+    const bool gather = d_prev_full != nullptr;
     if (p.chunks > 1) {
         VLB_CUDA(ctx, ctx->d_partials.reserve((size_t)p.n_items * VLB_SH_STRIDE * sizeof(float)));
         p.out = ctx->d_partials.as<float>();
@@ -478,9 +487,12 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out) {
     if (env_flag("VLB_BAKE_KERNEL", 2) == 1) {      // the round-1 tile-per-warp kernel, kept for A/B runs
         if (K == 9) kern = count ? k_bake<9, true> : k_bake<9, false>;
         else        kern = count ? k_bake<16, true> : k_bake<16, false>;
+    } else if (gather) {
+        if (K == 9) kern = count ? k_bake_stream<9, true, true> : k_bake_stream<9, false, true>;
+        else        kern = count ? k_bake_stream<16, true, true> : k_bake_stream<16, false, true>;
     } else {
-        if (K == 9) kern = count ? k_bake_stream<9, true> : k_bake_stream<9, false>;
-        else        kern = count ? k_bake_stream<16, true> : k_bake_stream<16, false>;
+        if (K == 9) kern = count ? k_bake_stream<9, true, false> : k_bake_stream<9, false, false>;
+        else        kern = count ? k_bake_stream<16, true, false> : k_bake_stream<16, false, false>;
     }
     int per_sm = 0;
     VLB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBakeBlock, 0));

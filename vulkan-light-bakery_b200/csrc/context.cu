@@ -124,7 +124,7 @@ void vlb_ctx_destroy(vlb_ctx* ctx) {
                       &ctx->d_keys_sorted, &ctx->d_vals, &ctx->d_vals_sorted, &ctx->d_sort_tmp, &ctx->d_left,
                       &ctx->d_right, &ctx->d_first, &ctx->d_last, &ctx->d_parent_i, &ctx->d_parent_l, &ctx->d_flags,
                       &ctx->d_ibox, &ctx->d_lbox, &ctx->d_scratch, &ctx->d_sky, &ctx->d_proj_in, &ctx->d_proj_out,
-                      &ctx->d_proj_partials, &ctx->d_proj_counters, &ctx->d_row_tab, &ctx->d_col_tab, &ctx->d_bake_out,
+                      &ctx->d_proj_partials, &ctx->d_proj_counters, &ctx->d_row_tab, &ctx->d_col_tab, &ctx->d_bake_out, &ctx->d_bake_prev,
                       &ctx->d_partials, &ctx->d_work_counter, &ctx->d_axis, &ctx->d_row_sc, &ctx->d_col_sc,
                       &ctx->d_stats, &ctx->d_stream_scratch, &ctx->d_ray_o, &ctx->d_ray_d, &ctx->d_hit_id, &ctx->d_hit_tuv, &ctx->d_hit_key};
     for (DevBuf* b : bufs) b->release();
@@ -387,6 +387,7 @@ void vlb_bake_settings_default(vlb_bake_settings* s) {
     s->tmin = 0.001f; s->tmax = 10000.f;                    // env_map.rgen:22-23
     s->flags = VLB_BAKE_SHADOW_RAYS | VLB_BAKE_SKYBOX_ON_MISS | VLB_BAKE_SRGB_ENCODE | VLB_BAKE_QUANTIZE_RGBA8;
     s->slab_k0 = 0; s->slab_k1 = -1;
+    s->bounces = 0; s->indirect_gain = 1.f;                 // 0 bounces = the reference bake (direct light only)
 }
 
 int vlb_bake_settings_from_bounds(vlb_bake_settings* s, const float b[6]) {
@@ -432,7 +433,7 @@ static int slab_range(vlb_ctx* ctx, const vlb_bake_settings* s, int* k0, int* k1
     return VLB_OK;
 }
 
-int vlb_bake_probes_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out) {
+int vlb_bake_gather_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_full, float* d_out) {
     if (!ctx) return VLB_ERR_INVALID;
     if (int r = check_device(ctx)) return r;
     int k0, k1, stride;
@@ -442,7 +443,14 @@ int vlb_bake_probes_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_ou
     if (!ctx->have_bvh) { if (int r = bvh_build(ctx, nullptr)) return r; }
     if ((s->flags & VLB_BAKE_SKYBOX_ON_MISS) && ctx->sky_w == 0)
         return ctx->fail(VLB_ERR_STATE, "bake: VLB_BAKE_SKYBOX_ON_MISS without a skybox (vlb_skybox_set)");
-    return bake_device(ctx, s, d_out);
+    if (d_prev_full && (s->flags & (VLB_BAKE_REFERENCE_PROBE_ORDER | VLB_BAKE_ACCUMULATE_ACROSS_PROBES)))
+        return ctx->fail(VLB_ERR_INVALID, "bake: a gather pass reads the previous pass in x-fastest order; "
+                                          "REFERENCE_PROBE_ORDER / ACCUMULATE_ACROSS_PROBES cannot be combined with it");
+    return bake_device(ctx, s, d_prev_full, d_out);
+}
+
+int vlb_bake_probes_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out) {
+    return vlb_bake_gather_device(ctx, s, nullptr, d_out);
 }
 
 int vlb_bake_probes(vlb_ctx* ctx, const vlb_bake_settings* s, float* out) {
@@ -454,10 +462,35 @@ int vlb_bake_probes(vlb_ctx* ctx, const vlb_bake_settings* s, float* out) {
     const size_t n = (size_t)s->probes[0] * s->probes[1] * (size_t)((k1 - k0 + stride - 1) / stride);
     if (n == 0) return VLB_OK;
     VLB_CUDA(ctx, ctx->d_bake_out.reserve(n * VLB_SH_STRIDE * sizeof(float)));
-    if (int r = vlb_bake_probes_device(ctx, s, ctx->d_bake_out.as<float>())) return r;
-    VLB_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_bake_out.p, n * VLB_SH_STRIDE * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    vlb_bake_stats st;
-    return vlb_bake_last_stats(ctx, &st);      // synchronises and surfaces a traversal stack overflow
+    if (s->bounces <= 0) {
+        if (int r = vlb_bake_probes_device(ctx, s, ctx->d_bake_out.as<float>())) return r;
+        VLB_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_bake_out.p, n * VLB_SH_STRIDE * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        vlb_bake_stats st;
+        return vlb_bake_last_stats(ctx, &st);      // synchronises and surfaces a traversal stack overflow
+    }
+    // Multi-bounce: pass 0 is the direct bake, pass b gathers from pass b-1 (two device buffers,
+    // ping-pong). Every pass needs the previous one over the WHOLE grid, so a sharded grid has to be
+    // driven by the caller: vlb_bake_gather_device per pass + an all-gather between passes.
+    if (k0 != 0 || k1 != s->probes[2] || stride != 1)
+        return ctx->fail(VLB_ERR_INVALID, "bake: bounces > 0 needs the whole grid in one call; for a sharded grid "
+                                          "iterate vlb_bake_gather_device and all-gather the slabs between passes");
+    VLB_CUDA(ctx, ctx->d_bake_prev.reserve(n * VLB_SH_STRIDE * sizeof(float)));
+    float* buf[2] = {ctx->d_bake_out.as<float>(), ctx->d_bake_prev.as<float>()};
+    vlb_bake_stats total{};
+    int cur = 0;
+    for (int pass = 0; pass <= s->bounces; ++pass) {
+        if (int r = vlb_bake_gather_device(ctx, s, pass ? buf[cur ^ 1] : nullptr, buf[cur])) return r;
+        vlb_bake_stats st;
+        if (int r = vlb_bake_last_stats(ctx, &st)) return r;
+        total.n_probes = st.n_probes; total.n_primary_rays += st.n_primary_rays; total.n_shadow_rays += st.n_shadow_rays;
+        total.n_nodes_visited += st.n_nodes_visited; total.n_tris_tested += st.n_tris_tested;
+        total.kernel_ms += st.kernel_ms; total.total_ms += st.total_ms;
+        cur ^= 1;
+    }
+    ctx->last_bake = total;
+    VLB_CUDA(ctx, cudaMemcpyAsync(out, buf[cur ^ 1], n * VLB_SH_STRIDE * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    VLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VLB_OK;
 }
 
 int vlb_bake_last_stats(vlb_ctx* ctx, vlb_bake_stats* out) {

@@ -76,7 +76,7 @@ struct vlb_ctx {
     vlb::DevBuf d_proj_in, d_proj_out, d_proj_partials, d_proj_counters, d_row_tab, d_col_tab;
     int tab_w = 0, tab_h = 0, tab_variant = -1;
     // ---- bake ----
-    vlb::DevBuf d_bake_out, d_partials, d_work_counter, d_axis, d_row_sc, d_col_sc, d_stats, d_stream_scratch;
+    vlb::DevBuf d_bake_out, d_bake_prev, d_partials, d_work_counter, d_axis, d_row_sc, d_col_sc, d_stats, d_stream_scratch;
     int dir_w = 0, dir_h = 0;
     vlb_bake_stats last_bake{};
     bool bake_pending = false;             // a device bake was enqueued and its statistics not yet collected
@@ -129,7 +129,7 @@ int scene_flatten(vlb_ctx* ctx);
 int bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats);
 int project_sh_device(vlb_ctx* ctx, const void* d_texels, uint64_t map_stride, uint32_t n_maps, int fmt,
                       int W, int H, int order, int variant, float* d_out, int lane = -1);
-int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out);
+int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_full, float* d_out);
 int bake_collect_stats(vlb_ctx* ctx);
 int trace_rays(vlb_ctx* ctx, const float* o, const float* d, uint64_t n, float tmin, float tmax, int accel,
                int kind, int32_t* ids, float* tuv);

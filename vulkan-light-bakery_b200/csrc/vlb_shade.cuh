@@ -30,6 +30,7 @@ struct BakeConsts {
 VLB_HD float glsl_mod(float x, float y) { return x - y * floorf(x / y); }
 VLB_HD float clampf(float x, float a, float b) { return fminf(fmaxf(x, a), b); }
 VLB_HD int wrapi(int i, int n) { int r = i % n; return r < 0 ? r + n : r; }
+VLB_HD int mini(int a, int b) { return a < b ? a : b; }
 
 // main.rmiss:18-35 + bilinear / repeat lookup at LOD 0 (sampler: src/application.hpp:45-52)
 VLB_HD void sky_lookup(const ShadeView& s, Vec3 dir, float rgb[3]) {
@@ -68,8 +69,20 @@ VLB_HD float quant8(float c) {
 // reaches the point regardless of occlusion (sDotN == 0), i.e. no shadow ray is traced.
 struct ShadePrelude {
     Vec3 N, Ln, so;     // shading normal, unit light vector, biased shadow-ray origin
+    Vec3 P;             // hit position (gather passes only)
     float llen, sDotN;
     float bc[3];
+};
+
+// Source of a gather pass (include/vlb_bake.h: vlb_bake_gather_device): the previous pass over the
+// whole grid and the grid itself. prev == NULL: direct pass.
+struct GatherView {
+    const float* prev;                                   // [Nx*Ny*Nz][48], x-fastest
+    const float* px; const float* py; const float* pz;   // probe axis coordinates
+    int Nx, Ny, Nz;
+    float origin[3], step[3];
+    float gain;
+    int world_frame;
 };
 
 VLB_HD bool shade_prelude(const ShadeView& s, const BakeConsts& c, const HitRec& h, Vec3 o, Vec3 r,
@@ -95,10 +108,55 @@ VLB_HD bool shade_prelude(const ShadeView& s, const BakeConsts& c, const HitRec&
     p.sDotN = fmaxf(dot_exact(p.Ln, p.N), 0.0f);                        // :79
     p.so = mk3(f_fma(c.shadow_bias, p.N.x, P.x), f_fma(c.shadow_bias, p.N.y, P.y),
                f_fma(c.shadow_bias, p.N.z, P.z));                       // :82
+    p.P = P;
     return p.sDotN != 0.0f;                                             // :84
 }
 
-VLB_HD void shade_finish(const BakeConsts& c, const ShadePrelude& p, Vec3 r, bool in_shadow, float rgb[3]) {
+// Grid cell of coordinate p along one axis, clamped so that the cell's far corner exists
+// (shaders/main.rchit:126 `floor(hitPosition / gridStep)`, for an arbitrary grid).
+VLB_HD int gather_cell(float p, float origin, float step, int n) {
+    if (n < 2) return 0;
+    const float g = floorf(f_div(f_sub(p, origin), step));
+    if (!(g > 0.0f)) return 0;                                          // also NaN (step == 0)
+    return g >= (float)(n - 2) ? n - 2 : (int)g;
+}
+
+// The reference's run-time gather (shaders/main.rchit:124-163, probe lookup shaders/sh.rmiss:20-36)
+// over the previous pass: visibility-weighted interpolation of the 8 probes around the hit, each
+// probe's SH evaluated on the shading normal. Operation order = oracle gather_indirect.
+template <int K, bool COUNT>
+VLB_HD void gather_indirect(const BvhView& b, const GatherView& g, const ShadePrelude& p, float out[3], TraceCounters* cnt) {
+    const int ci = gather_cell(p.P.x, g.origin[0], g.step[0], g.Nx);
+    const int cj = gather_cell(p.P.y, g.origin[1], g.step[1], g.Ny);
+    const int ck = gather_cell(p.P.z, g.origin[2], g.step[2], g.Nz);
+    const float weight_max = f_sqrt(dot_exact(mk3(g.step[0], g.step[1], g.step[2]), mk3(g.step[0], g.step[1], g.step[2])));  // :141
+    float basis[K];
+    sh_basis<K>(g.world_frame ? p.N : mk3(p.N.x, p.N.z, p.N.y), basis);
+    float sum[3] = {0.f, 0.f, 0.f}, wsum = 0.f;
+    for (int c = 0; c < 8; ++c) {                                       // gridVertices order, :128-137
+        const int i = mini(ci + ((c >> 2) & 1), g.Nx - 1), j = mini(cj + ((c >> 1) & 1), g.Ny - 1), k = mini(ck + (c & 1), g.Nz - 1);
+        const Vec3 d = mk3(f_sub(g.px[i], p.P.x), f_sub(g.py[j], p.P.y), f_sub(g.pz[k], p.P.z));   // :145
+        const float tmax = f_sqrt(dot_exact(d, d));                     // :154
+        const float w = fmaxf(f_sub(weight_max, tmax), 0.0f);           // :156
+        bool occluded = false;
+        if (tmax > 0.0f)
+            occluded = trace_any<COUNT>(b, p.so, mk3(f_div(d.x, tmax), f_div(d.y, tmax), f_div(d.z, tmax)), 0.0f, tmax, cnt, nullptr);  // :155
+        if (occluded) continue;
+        const float* sh = g.prev + ((size_t)i + (size_t)g.Nx * ((size_t)j + (size_t)g.Ny * (size_t)k)) * 48;   // sh.rmiss:25
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < K; ++q) {                                   // sh.rmiss:27-34
+            v0 = f_fma(sh[3 * q + 0], basis[q], v0); v1 = f_fma(sh[3 * q + 1], basis[q], v1); v2 = f_fma(sh[3 * q + 2], basis[q], v2);
+        }
+        sum[0] = f_fma(w, v0, sum[0]); sum[1] = f_fma(w, v1, sum[1]); sum[2] = f_fma(w, v2, sum[2]);   // :160
+        wsum = f_add(wsum, w);                                          // :161
+    }
+    for (int c = 0; c < 3; ++c) out[c] = wsum > 0.0f ? f_mul(g.gain, f_div(sum[c], wsum)) : 0.0f;      // :164-165
+}
+
+// `ind` = gathered indirect term per channel (zeros in the direct pass: k + 0 == k, so the direct
+// pass is bit-identical with or without it).
+VLB_HD void shade_finish(const BakeConsts& c, const ShadePrelude& p, Vec3 r, bool in_shadow, const float ind[3], float rgb[3]) {
     float diffuse = 0.f, specular = 0.f;
     if (!in_shadow) {                                                   // env_map.rchit:90-99
         diffuse = c.c_diffuse * p.sDotN;
@@ -109,15 +167,15 @@ VLB_HD void shade_finish(const BakeConsts& c, const ShadePrelude& p, Vec3 r, boo
     }
     const float k = c.ambient + diffuse + specular;
     for (int ch = 0; ch < 3; ++ch) {
-        const float v = p.bc[ch] * k;
+        const float v = p.bc[ch] * (k + ind[ch]);
         rgb[ch] = (c.flags & 4u) ? srgb_encode(v) : v;                  // :101 (VLB_BAKE_SRGB_ENCODE)
     }
 }
 
 // Full radiance of one ray (primary + shadow), used by the bake kernel and by tests/emu.
-template <bool COUNT>
+template <bool COUNT, int K = 9>
 VLB_HD void probe_ray_radiance(const BvhView& b, const ShadeView& s, const BakeConsts& c, Vec3 o, Vec3 r,
-                               float rgb[3], TraceCounters* cnt, uint32_t* shadow_rays) {
+                               float rgb[3], TraceCounters* cnt, uint32_t* shadow_rays, const GatherView* g = nullptr) {
     rgb[0] = rgb[1] = rgb[2] = 0.0f;                                    // env_map.rgen:25
     const HitRec h = trace_closest<COUNT>(b, o, r, c.tmin, c.tmax, cnt);
     if (h.id >= 0) {
@@ -132,7 +190,9 @@ VLB_HD void probe_ray_radiance(const BvhView& b, const ShadeView& s, const BakeC
                 in_shadow = false;
             }
         }
-        shade_finish(c, p, r, in_shadow, rgb);
+        float ind[3] = {0.f, 0.f, 0.f};
+        if (g && g->prev) gather_indirect<K, COUNT>(b, *g, p, ind, cnt);
+        shade_finish(c, p, r, in_shadow, ind, rgb);
     } else if ((c.flags & 2u) && s.sky) {                               // VLB_BAKE_SKYBOX_ON_MISS
         sky_lookup(s, r, rgb);
         if (c.flags & 4u) { rgb[0] = srgb_encode(rgb[0]); rgb[1] = srgb_encode(rgb[1]); rgb[2] = srgb_encode(rgb[2]); }

@@ -79,3 +79,23 @@ def bake_sharded(bake_slab, settings, rank, world, device=None, group=None, cycl
     if n_local:
         bake_slab(s, out)
     return gather_slabs(out, settings, rank, world, group, cyclic)
+
+
+def bake_multibounce_sharded(bake_pass, settings, rank, world, device=None, group=None, cyclic=False):
+    """Multi-bounce bake of a sharded grid (include/vlb_bake.h: vlb_bake_gather_device). Every pass needs
+    the PREVIOUS pass over the whole grid, so this is the one place on the path with a real exchange
+    step: 1 + settings.bounces passes, each followed by one all-gather of the slabs.
+    bake_pass(slab_settings, prev_full_or_None, out_tensor) fills out_tensor ([n_local, 48]) with this
+    rank's share of the pass; prev_full is the gathered [n_probes, 48] tensor of the pass before.
+    Returns the gathered last pass on every rank."""
+    import torch
+    s = shard_settings(settings, rank, world, cyclic)
+    n_local = s.n_slab_probes
+    prev = None
+    for _ in range(1 + max(0, int(settings.bounces))):
+        out = torch.empty((max(n_local, 1), 48), dtype=torch.float32, device=device)[:n_local]
+        if n_local:
+            bake_pass(s, prev, out)
+        full = gather_slabs(out, settings, rank, world, group, cyclic)
+        prev = full.contiguous()
+    return prev
