@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libvlb_bake.so")
+CLI = os.path.join(HERE, "vlb_baker")          # the reference's `baker` executable on top of the C ABI
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 SOURCES = ["context.cu", "bvh_build.cu", "bake.cu", "skybox_sh.cu", "host_tables.cpp", "gltf_io.cpp", "gltf_scene.cpp"]
@@ -59,6 +60,10 @@ def build(force=False, verbose=False):
     if jobs or _stale(LIB, objs):
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
         subprocess.check_call(cmd)
+    cli_src = os.path.join(CSRC, "vlb_baker_main.cpp")
+    if force or _stale(CLI, [cli_src, LIB] + hdrs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(HERE, "..", "include"), cli_src, "-o", CLI,
+                               "-L", HERE, "-lvlb_bake", "-Wl,-rpath,$ORIGIN"])
     return LIB
 
 
