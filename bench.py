@@ -277,7 +277,7 @@ def run_ours(args):
         alg_bytes = st.n_nodes_visited * 112 + st.n_tris_tested * 48     # per launch (this rank's share)
         peak, peak_src = measured_peaks()
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-        kname = "vlb::k_bake_stream<9,false>"
+        kname = "vlb::k_bake_stream<9,false,false>"
         roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": ncu_traffic(kname + ":" + which), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": int(alg_bytes),
@@ -366,7 +366,7 @@ def bench_skybox(torch, ctx, scenes, dev, stream, peak, peak_src, n_buf=8, reps=
     return {"workload": "C1 (BASELINE configs[0]): 2048x1024 RGBA32F equirect -> L2 SH, 8 distinct maps rotated",
             "kernel": "vlb::k_project_tiles<9,RGBA32F>", "bound": "hbm", "algorithmic_bytes_per_launch": stride,
             "us_per_launch": best["us_per_map"], "achieved": best["achieved"], "peak": peak, "unit": "GB/s",
-            "frac": best["frac"], "frac_of_8TBs_nominal": best["achieved"] / 8000.0, "peak_source": peak_src,
+            "frac": best["frac"], "traffic": ncu_traffic("vlb::k_project_tiles<9,RGBA32F>:c1"), "frac_of_8TBs_nominal": best["achieved"] / 8000.0, "peak_source": peak_src,
             "mode": "pipelined (one launch per map, vlb_skybox_project_sh_device_ptrs)", "modes": res}
 
 

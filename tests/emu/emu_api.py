@@ -14,17 +14,19 @@ _vp, _u64, _i32, _f32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c
 _lib = None
 
 
-def build(force=False):
+def build(force=False, so=None, defines=()):
+    """Builds the emulation library; `defines` (e.g. ["-DVLB_NODE_Q8=1"]) + `so` build a variant beside it."""
+    so = so or SO
     srcs = [os.path.join(_HERE, "emu_driver.cpp"),
             os.path.join(_ROOT, "vulkan-light-bakery_b200", "csrc", "host_tables.cpp")]
     csrc = os.path.join(_ROOT, "vulkan-light-bakery_b200", "csrc")
     deps = srcs + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
-    if not force and os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in deps):
-        return SO
+    if not force and os.path.exists(so) and all(os.path.getmtime(d) <= os.path.getmtime(so) for d in deps):
+        return so
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-I", cuda_inc,
-                           "-o", SO] + srcs)
-    return SO
+                           "-o", so] + list(defines) + srcs)
+    return so
 
 
 def _p(a):

@@ -137,7 +137,7 @@ void* emu_scene_create(const vlb_vertex* verts, const uint32_t* indices, const v
     while (!st.empty()) {
         auto [nd, dp] = st.back(); st.pop_back();
         s->max_depth = std::max(s->max_depth, dp);
-        const float4 refs = s->nodes[(size_t)kNodeQuads * nd + 6];
+        const float4 refs = s->nodes[(size_t)kNodeQuads * nd + (kNodeQ8 ? 3 : 6)];
         const int r[4] = {f2i(refs.x), f2i(refs.y), f2i(refs.z), f2i(refs.w)};
         for (int k = 0; k < 4; ++k) if (r[k] >= 0) st.push_back({r[k], dp + 1});
     }

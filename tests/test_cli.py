@@ -61,6 +61,7 @@ def test_cli_bake_equals_abi_bake(ctx, vlb, scenes, tmp_path):
     s.probes[:] = (3, 2, 3)
     s.dir_w, s.dir_h = 64, 32
     s.light_pos[:] = (2.0, 3.5, 2.0)
+    s.flags &= ~vlb.SKYBOX_ON_MISS                 # the CLI has no skybox input (reference bake: App. B-5)
     vlb.settings_from_bounds(s, ctx.scene_bounds(tight=False))
     want = ctx.bake_probes(s)
     assert np.array_equal(np.asarray(coeffs).reshape(want.shape), want)

@@ -10,8 +10,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libvlb_bake.so")
+# VLB_BUILD_TAG=x builds a variant library libvlb_bake_x.so (objects in build_x/) next to the product
+# one, typically with VLB_NVCC_EXTRA=-D...; python loads it with VLB_LIB=<path> for A/B runs.
+TAG = os.environ.get("VLB_BUILD_TAG", "")
+OBJ = os.path.join(HERE, "build" + ("_" + TAG if TAG else ""))
+LIB = os.path.join(HERE, "libvlb_bake%s.so" % ("_" + TAG if TAG else ""))
 CLI = os.path.join(HERE, "vlb_baker")          # the reference's `baker` executable on top of the C ABI
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
@@ -61,7 +64,7 @@ def build(force=False, verbose=False):
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
         subprocess.check_call(cmd)
     cli_src = os.path.join(CSRC, "vlb_baker_main.cpp")
-    if force or _stale(CLI, [cli_src, LIB] + hdrs):
+    if not TAG and (force or _stale(CLI, [cli_src, LIB] + hdrs)):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-I", os.path.join(HERE, "..", "include"), cli_src, "-o", CLI,
                                "-L", HERE, "-lvlb_bake", "-Wl,-rpath,$ORIGIN"])
     return LIB

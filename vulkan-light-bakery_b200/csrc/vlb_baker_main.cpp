@@ -135,7 +135,9 @@ int main(int argc, char** argv) {
     if (o.dirs[0]) { s.dir_w = o.dirs[0]; s.dir_h = o.dirs[1]; }
     if (o.order) s.sh_order = o.order;
     if (o.have_light) for (int k = 0; k < 3; ++k) s.light_pos[k] = o.light[k];
-    s.flags = (s.flags | o.flags_set) & ~o.flags_clear;
+    // no skybox can be given on this command line (decoding image files is outside the bake path), and the
+    // reference's own bake pipeline has no skybox bound either: misses contribute 0
+    s.flags = (s.flags | o.flags_set) & ~(o.flags_clear | VLB_BAKE_SKYBOX_ON_MISS);
     s.bounces = o.bounces;
     if (o.gain >= 0.f) s.indirect_gain = o.gain;
 

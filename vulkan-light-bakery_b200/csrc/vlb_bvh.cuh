@@ -8,10 +8,15 @@
 //
 // HBM layout (all float4 arrays, 16-byte aligned):
 //   tri[3*j+0..2]   j = position in Morton order:  (v0.xyz, bits(flat id)), (e1.xyz, 0), (e2.xyz, 0)
-//   node[8*i+0..7]  i = Karras id of a binary node at EVEN depth (odd-depth nodes are absorbed by
-//                   their parent; their slots stay unused):
+//   node[Q*i+0..Q-1] i = Karras id of a binary node at EVEN depth (odd-depth nodes are absorbed by
+//                   their parent; their slots stay unused). Q = kNodeQuads.
+//                   fp32 format (Q = 7 or 8):
 //                   [0] lo.x of children 0..3   [1] hi.x   [2] lo.y   [3] hi.y   [4] lo.z   [5] hi.z
-//                   [6] bits(ref of children 0..3)         [7] unused (pads the node to one 128-byte line)
+//                   [6] bits(ref of children 0..3)         [7] (Q = 8 only) pads the node to a 128-byte line
+//                   8-bit format (Q = 4, VLB_NODE_Q8): plane = origin + byte * step, step = 2^k per axis
+//                   [0] origin.x, origin.y, origin.z, step.x * 2^15
+//                   [1] step.y * 2^15, step.z * 2^15, lo.x bytes of children 0..3, hi.x bytes
+//                   [2] lo.y bytes, hi.y bytes, lo.z bytes, hi.z bytes        [3] bits(ref of children 0..3)
 //   ref >= 0 : node index.  ref < 0 : leaf, ~ref = (first_tri << 3) | (count - 1).
 //   kNoChild (0x80000000) marks an empty slot; its box is (+inf, -inf) and can never be hit.
 //
@@ -27,7 +32,25 @@ namespace vlb {
 
 constexpr int kMaxLeaf = 8;
 constexpr int kStackSize = 96;              // up to three pushes per 4-wide node
-constexpr int kNodeQuads = 8;               // float4s per traversal node (128 bytes)
+// Node formats (compile-time):
+//   VLB_NODE_Q8 = 0  (default) fp32 planes, VLB_NODE_QUADS float4s per node. 7 = packed 112-byte nodes: the
+//                    same field of different nodes then falls into different L1 data banks, measured 4 %
+//                    faster on B200 than 8 (one 128-byte line per node).
+//   VLB_NODE_Q8 = 1  64-byte nodes (4 float4): child planes quantised to 8 bits in the node's own frame
+//                    (origin + power-of-two step per axis), always conservatively (the quantised box contains
+//                    the padded fp32 box; hit ids stay bit-exact, +1.6 % node visits). 4 instead of 7
+//                    sixteen-byte loads per node step take the L1 data pipe from 87 % to 53 % busy, but the
+//                    decode moves the bound to the ALU pipe (55 % -> 72 %): 5.7 % slower on C3, so it is a
+//                    build option for scenes whose fp32 nodes do not fit L2
+//                    (profiles/r01_bake_kernel_ab_experiments.log).
+#ifndef VLB_NODE_Q8
+#define VLB_NODE_Q8 0
+#endif
+#ifndef VLB_NODE_QUADS
+#define VLB_NODE_QUADS 7
+#endif
+constexpr bool kNodeQ8 = VLB_NODE_Q8 != 0;
+constexpr int kNodeQuads = kNodeQ8 ? 4 : VLB_NODE_QUADS;  // float4s per traversal node
 constexpr int kNoChild = (int)0x80000000;   // empty child slot / "no node": never a valid leaf ref (n_tris < 2^28)
 // Culling slack: a node is skipped only if its entry distance exceeds best_t * kCullSlack, so
 // that two triangles whose computed t differ by rounding are both reached and the
@@ -169,6 +192,77 @@ VLB_HD bool classify_child(int c, const int* first, const int* last, const float
     return true;
 }
 
+// Smallest power of two >= x (x > 0, finite).
+VLB_HD float pow2_ceil(float x) {
+    int e;
+    const float m = frexpf(x, &e);          // x = m * 2^e, m in [0.5, 1)
+    return ldexpf(1.0f, m == 0.5f ? e - 1 : e);
+}
+
+// 8-bit frame of one axis of a node: origin and power-of-two step such that every valid child's (padded)
+// [lo, hi] maps into bytes 0..255 with room for the rounding margins of quant_lo / quant_hi.
+VLB_HD void quant_frame(const float* lo, const float* hi, int n, float* origin, float* step) {
+    float mn = lo[0], mx = hi[0];
+    for (int k = 1; k < n; ++k) { mn = fminf(mn, lo[k]); mx = fmaxf(mx, hi[k]); }
+    const float mag = fmaxf(fabsf(mn), fabsf(mx));
+    // the step never goes below 4 ulp of the coordinates (finer planes are not representable in fp32 anyway)
+    const float s = pow2_ceil(fmaxf(fmaxf((mx - mn) * (1.0f / 250.0f), mag * 4.8e-7f), 1e-30f));
+    float o = mn - 0.125f * s;
+    while ((double)o > (double)mn - 0.0625 * (double)s) o = nextafterf(o, -INFINITY);
+    *origin = o; *step = s;
+}
+// Largest byte whose plane origin + byte * step lies at least 1/64 step below `v` (exact in double), and the
+// mirror image for upper planes. The 1/64 step covers the traversal's extra rounding (< 1/256 step, bvh4_step).
+VLB_HD uint32_t quant_lo(float v, float o, float s) {
+    const double x = floor(((double)v - (double)o) / (double)s - 1.0 / 64.0);
+    return x < 0.0 ? 0u : (x > 255.0 ? 255u : (uint32_t)x);
+}
+VLB_HD uint32_t quant_hi(float v, float o, float s) {
+    const double x = ceil(((double)v - (double)o) / (double)s + 1.0 / 64.0);
+    return x < 0.0 ? 0u : (x > 255.0 ? 255u : (uint32_t)x);
+}
+
+// Writes one traversal node: `n` valid children (padded boxes lo/hi, refs), the remaining slots empty.
+VLB_HD void store_node4(float4* q, const int* refs, const float4* lo, const float4* hi, int n) {
+    if (kNodeQ8) {
+        float o[3], st[3];
+        uint32_t lob[3] = {0, 0, 0}, hib[3] = {0, 0, 0};
+        for (int a = 0; a < 3; ++a) {
+            float l[4], h[4];
+            for (int k = 0; k < n; ++k) {
+                l[k] = a == 0 ? lo[k].x : (a == 1 ? lo[k].y : lo[k].z);
+                h[k] = a == 0 ? hi[k].x : (a == 1 ? hi[k].y : hi[k].z);
+            }
+            quant_frame(l, h, n, &o[a], &st[a]);
+            for (int k = 0; k < 4; ++k) {
+                // empty slots: inverted (255, 0); bvh4_step also rejects them by their kNoChild ref
+                const uint32_t bl = k < n ? quant_lo(l[k], o[a], st[a]) : 255u;
+                const uint32_t bh = k < n ? quant_hi(h[k], o[a], st[a]) : 0u;
+                lob[a] |= bl << (8 * k); hib[a] |= bh << (8 * k);
+            }
+        }
+        q[0] = make_float4(o[0], o[1], o[2], st[0] * 32768.0f);
+        q[1] = make_float4(st[1] * 32768.0f, st[2] * 32768.0f, i2f((int)lob[0]), i2f((int)hib[0]));
+        q[2] = make_float4(i2f((int)lob[1]), i2f((int)hib[1]), i2f((int)lob[2]), i2f((int)hib[2]));
+        q[3] = make_float4(i2f(refs[0]), i2f(refs[1]), i2f(refs[2]), i2f(refs[3]));
+        return;
+    }
+    const float inf = INFINITY;
+    float4 l[4], h[4];
+    for (int k = 0; k < 4; ++k) {
+        l[k] = k < n ? lo[k] : make_float4(inf, inf, inf, 0.f);
+        h[k] = k < n ? hi[k] : make_float4(-inf, -inf, -inf, 0.f);
+    }
+    q[0] = make_float4(l[0].x, l[1].x, l[2].x, l[3].x);
+    q[1] = make_float4(h[0].x, h[1].x, h[2].x, h[3].x);
+    q[2] = make_float4(l[0].y, l[1].y, l[2].y, l[3].y);
+    q[3] = make_float4(h[0].y, h[1].y, h[2].y, h[3].y);
+    q[4] = make_float4(l[0].z, l[1].z, l[2].z, l[3].z);
+    q[5] = make_float4(h[0].z, h[1].z, h[2].z, h[3].z);
+    q[6] = make_float4(i2f(refs[0]), i2f(refs[1]), i2f(refs[2]), i2f(refs[3]));
+    if (kNodeQuads > 7) q[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 // Emit the 4-wide traversal node of binary node i (which must sit at even depth and span more than
 // max_leaf triangles, or be the root): its children are i's grandchildren, or i's children where
 // those are leaves.
@@ -193,29 +287,16 @@ VLB_HD void emit_node4(int i, const int* left, const int* right, const int* firs
             ++n;
         }
     }
-    const float inf = INFINITY;
-    for (; n < 4; ++n) { lo[n] = make_float4(inf, inf, inf, 0.f); hi[n] = make_float4(-inf, -inf, -inf, 0.f); }
-    float4* q = nodes + (size_t)kNodeQuads * i;
-    q[0] = make_float4(lo[0].x, lo[1].x, lo[2].x, lo[3].x);
-    q[1] = make_float4(hi[0].x, hi[1].x, hi[2].x, hi[3].x);
-    q[2] = make_float4(lo[0].y, lo[1].y, lo[2].y, lo[3].y);
-    q[3] = make_float4(hi[0].y, hi[1].y, hi[2].y, hi[3].y);
-    q[4] = make_float4(lo[0].z, lo[1].z, lo[2].z, lo[3].z);
-    q[5] = make_float4(hi[0].z, hi[1].z, hi[2].z, hi[3].z);
-    q[6] = make_float4(i2f(refs[0]), i2f(refs[1]), i2f(refs[2]), i2f(refs[3]));
-    q[7] = make_float4(i2f(first[i]), i2f(last[i]), 0.f, 0.f);
+    store_node4(nodes + (size_t)kNodeQuads * i, refs, lo, hi, n);
 }
 
 // Single-triangle scene: one node with one leaf child.
 VLB_HD void emit_single4(const float4* lbox, float abs_pad, float4* nodes) {
-    float4 lo = lbox[0], hi = lbox[1];
-    pad_box(&lo, &hi, abs_pad);
-    const float inf = INFINITY;
-    nodes[0] = make_float4(lo.x, inf, inf, inf); nodes[1] = make_float4(hi.x, -inf, -inf, -inf);
-    nodes[2] = make_float4(lo.y, inf, inf, inf); nodes[3] = make_float4(hi.y, -inf, -inf, -inf);
-    nodes[4] = make_float4(lo.z, inf, inf, inf); nodes[5] = make_float4(hi.z, -inf, -inf, -inf);
-    nodes[6] = make_float4(i2f(leaf_ref(0, 1)), i2f(kNoChild), i2f(kNoChild), i2f(kNoChild));
-    nodes[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 lo[4], hi[4];
+    lo[0] = lbox[0]; hi[0] = lbox[1];
+    pad_box(&lo[0], &hi[0], abs_pad);
+    const int refs[4] = {leaf_ref(0, 1), kNoChild, kNoChild, kNoChild};
+    store_node4(nodes, refs, lo, hi, 1);
 }
 
 struct HitRec {
@@ -232,6 +313,15 @@ VLB_HD float4 ld4(const float4* p) {
     return __ldg(p);
 #else
     return *p;
+#endif
+}
+
+// 1 + byte k of `w` * 2^-15: the byte dropped into bits 8..15 of 1.0f (one PRMT on the device).
+VLB_HD float byte_to_unit(uint32_t w, int k) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(__byte_perm(w, 0x3F800000u, 0x7604u | ((uint32_t)k << 4)));
+#else
+    return i2f((int)(0x3F800000u | (((w >> (8 * k)) & 0xffu) << 8)));
 #endif
 }
 
@@ -268,12 +358,35 @@ VLB_HD int bvh4_step(const BvhView& b, int cur, Vec3 idir, Vec3 ood, float tmin,
     const float4* q = b.nodes + (size_t)kNodeQuads * cur;
     // near / far planes by the sign of the direction: no per-child min/max pairs
     const int sx = idir.x < 0.0f, sy = idir.y < 0.0f, sz = idir.z < 0.0f;
+    float tn[4]; int r[4];
+    const float inf = INFINITY;
+#if VLB_NODE_Q8
+    const float4 q0 = ld4(q), q1 = ld4(q + 1), q2 = ld4(q + 2), rf = ld4(q + 3);
+    // t(byte) = (origin + byte * step - o) * idir = v * S + C with v = 1 + byte * 2^-15 (the byte dropped into
+    // the mantissa of 1.0f), S = step * 2^15 * idir (exact: step is a power of two), C = (origin * idir - o * idir) - S.
+    // Extra rounding against the fp32 format: < |S| * 2^-23 in t, i.e. < 1/256 step in space (margin: 1/64 step).
+    const float Sx = f_mul(q0.w, idir.x), Sy = f_mul(q1.x, idir.y), Sz = f_mul(q1.y, idir.z);
+    const float Cx = f_sub(f_fma(q0.x, idir.x, -ood.x), Sx), Cy = f_sub(f_fma(q0.y, idir.y, -ood.y), Sy),
+                Cz = f_sub(f_fma(q0.z, idir.z, -ood.z), Sz);
+    const uint32_t nxw = (uint32_t)f2i(sx ? q1.w : q1.z), fxw = (uint32_t)f2i(sx ? q1.z : q1.w);
+    const uint32_t nyw = (uint32_t)f2i(sy ? q2.y : q2.x), fyw = (uint32_t)f2i(sy ? q2.x : q2.y);
+    const uint32_t nzw = (uint32_t)f2i(sz ? q2.w : q2.z), fzw = (uint32_t)f2i(sz ? q2.z : q2.w);
+#define VLB_SLAB(k, c)                                                                                           \
+    {                                                                                                            \
+        const float a = fmaxf(max3(f_fma(byte_to_unit(nxw, k), Sx, Cx), f_fma(byte_to_unit(nyw, k), Sy, Cy),      \
+                                   f_fma(byte_to_unit(nzw, k), Sz, Cz)), tmin);                                  \
+        const float e = fminf(min3(f_fma(byte_to_unit(fxw, k), Sx, Cx), f_fma(byte_to_unit(fyw, k), Sy, Cy),      \
+                                   f_fma(byte_to_unit(fzw, k), Sz, Cz)), tcull);                                 \
+        const int ref = f2i(rf.c);                                                                               \
+        const bool hit = a <= e && ref != kNoChild;                                                              \
+        tn[k] = hit ? a : inf;                                                                                   \
+        r[k] = hit ? ref : kNoChild;                                                                             \
+    }
+#else
     const float4 nx = ld4(q + sx), fx = ld4(q + 1 - sx);
     const float4 ny = ld4(q + 2 + sy), fy = ld4(q + 3 - sy);
     const float4 nz = ld4(q + 4 + sz), fz = ld4(q + 5 - sz);
     const float4 rf = ld4(q + 6);
-    float tn[4]; int r[4];
-    const float inf = INFINITY;
 #define VLB_SLAB(k, c)                                                                                           \
     {                                                                                                            \
         const float a = fmaxf(max3(f_fma(nx.c, idir.x, -ood.x), f_fma(ny.c, idir.y, -ood.y),                      \
@@ -284,6 +397,7 @@ VLB_HD int bvh4_step(const BvhView& b, int cur, Vec3 idir, Vec3 ood, float tmin,
         tn[k] = hit ? a : inf;                                                                                   \
         r[k] = hit ? f2i(rf.c) : kNoChild;                                                                       \
     }
+#endif
     VLB_SLAB(0, x) VLB_SLAB(1, y) VLB_SLAB(2, z) VLB_SLAB(3, w)
 #undef VLB_SLAB
     if (ORDERED) {
