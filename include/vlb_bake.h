@@ -89,6 +89,22 @@ typedef struct vlb_instance {
     float    transform[12];      /* object->world, 3x4 row-major (VkTransformMatrixKHR)      */
 } vlb_instance;
 
+/* One glTF texture = image + sampler, as Scene_t::loadTextures / loadSamplers create them
+ * (src/scene_manager.cpp:941-973, 650-690): RGBA8 texels (tinygltf always expands to 4 components; unorm,
+ * no sRGB decode: src/application.cpp:779-780), wrap mode per axis, filter. The hit shader samples
+ * `texture(textures[material.textures.baseColor.index], uv0)` (shaders/env_map.rchit:36-49): in a ray-tracing
+ * stage that is the base mip level, so only level 0 is kept here. Bilinear weights are exact fp32 (the
+ * Vulkan driver's fixed-point weights are "parity unpinned"). */
+enum { VLB_WRAP_REPEAT = 0, VLB_WRAP_CLAMP_TO_EDGE = 1, VLB_WRAP_MIRRORED_REPEAT = 2 };
+enum { VLB_FILTER_LINEAR = 0, VLB_FILTER_NEAREST = 1 };
+typedef struct vlb_texture {
+    const void* texels;          /* width * height * 4 bytes, row 0 first                      */
+    int32_t width, height;
+    int32_t wrap_u, wrap_v;      /* VLB_WRAP_*  (default sampler: repeat, application.hpp:45-52) */
+    int32_t filter;              /* VLB_FILTER_* (default sampler: linear)                      */
+    int32_t reserved;
+} vlb_texture;
+
 typedef enum vlb_texel_format {
     VLB_FMT_RGBA8   = 0,         /* reference skyboxes: stb RGBA8, value/255, no sRGB decode
                                     (src/skybox_manager.cpp:18, src/application.cpp:690,779)  */
@@ -184,11 +200,18 @@ int vlb_scene_set_triangles(vlb_ctx* ctx,
                             const uint32_t* indices, uint64_t n_indices,
                             const vlb_instance* instances, uint32_t n_instances,
                             const vlb_material* materials, uint32_t n_materials);
+/* Scene_t::loadTextures (src/scene_manager.cpp:941-973): the textures that vlb_material.base_color.index
+ * refers to (index -1 = none: the factor path of env_map.rchit:43-47). May be called before or after
+ * vlb_scene_set_triangles; replaces any previous set; n = 0 removes them. A bake fails with VLB_ERR_STATE
+ * if a material names a texture that has not been set. */
+int vlb_scene_set_textures(vlb_ctx* ctx, const vlb_texture* textures, uint32_t n_textures);
 /* SceneManager::pushScene(std::string&) (src/scene_manager.cpp:1013-1034): tinygltf load of a .gltf /
  * .glb file (:32-67), materials (+ trailing default, :837-857), node hierarchy in loadNode's
  * pre-order with world matrices (:445-538), vertices as shader::Vertex and u32 indices
  * (:257-337); then the same upload as vlb_scene_set_triangles. vlb_scene_bounds(tight=0) afterwards
- * returns the reference's bounds including its local-matrix quirk (:497-507). */
+ * returns the reference's bounds including its local-matrix quirk (:497-507). Textures referenced by
+ * baseColorTexture are decoded (PNG: 8-bit RGB/RGBA/grey, non-interlaced; anything else is
+ * VLB_ERR_UNSUPPORTED) and set with their samplers (:650-690) as by vlb_scene_set_textures. */
 int vlb_scene_load_gltf(vlb_ctx* ctx, const char* gltf_path);
 /* Host-only: parse a glTF and report counts = {vertices, indices, instances (node x primitive),
  * materials incl. the default, triangles} and the reference-mode bounds. No CUDA device needed. */

@@ -50,6 +50,8 @@ def lib():
         L.vo_scene_num_triangles.argtypes = [_vp]
         L.vo_scene_bounds.argtypes = [_vp, _i32, _vp]
         L.vo_scene_set_skybox.argtypes = [_vp, _vp, _i32, _i32, _i32]
+        L.vo_scene_set_textures.argtypes = [_vp, _vp, ctypes.c_uint32]
+        L.vo_tex_sample.argtypes = [_vp, ctypes.c_uint32, _vp, _u64, _vp]
         L.vo_scene_triangles.argtypes = [_vp, _vp]
         L.vo_trace_rays.argtypes = [_vp, _vp, _vp, _u64, _f32, _f32, _i32, _i32, _vp, _vp]
         L.vo_bake_probes.restype = _u64
@@ -150,6 +152,19 @@ class Scene:
         self._keep = [np.ascontiguousarray(scene[k]) for k in ("vertices", "indices", "instances", "materials")]
         v, i, inst, m = self._keep
         self._h = lib().vo_scene_create(_p(v), v.size, _p(i), i.size, _p(inst), inst.size, _p(m), m.size)
+        if scene.get("textures"):
+            self.set_textures(scene["textures"])
+
+    def set_textures(self, textures):
+        import importlib
+        arr, keep = importlib.import_module("vulkan-light-bakery_b200").pack_textures(textures)
+        lib().vo_scene_set_textures(self._h, ctypes.cast(arr, ctypes.c_void_p), len(textures))
+
+    def tex_sample(self, tex, uv):
+        uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        out = np.zeros((uv.shape[0], 3), np.float32)
+        lib().vo_tex_sample(self._h, int(tex), _p(uv), uv.shape[0], _p(out))
+        return out
 
     def close(self):
         if self._h:

@@ -175,6 +175,7 @@ static void project_image(const void* texels, int fmt, int W, int H, int order, 
 struct Tri {
     V3 v0, e1, e2;     // world space
     V3 n0, n1, n2;     // OBJECT-space vertex normals (env_map.rchit:64 interpolates these)
+    float uv[6];       // Vertex::uv0 of the three corners (env_map.rchit:65)
     uint32_t inst;
 };
 
@@ -201,6 +202,9 @@ struct Scene {
     // sky
     std::vector<float> sky;  // RGBA32F copy (RGBA8 is converted value/255)
     int skyW = 0, skyH = 0;
+    // textures (Scene_t::loadTextures, src/scene_manager.cpp:941-973): RGBA8 level 0 + sampler state
+    struct Tex { std::vector<uint8_t> texels; int W = 0, H = 0, wrap_u = 0, wrap_v = 0, filter = 0; };
+    std::vector<Tex> textures;
 };
 
 static inline V3 xform_point(const float* m, V3 p) {
@@ -498,10 +502,48 @@ static void sky_lookup(const Scene& s, V3 dir, float rgb[3]) {
     }
 }
 
-// env_map.rchit:36-49 (texture branch: SURVEY §8 f3, not implemented -> factor path).
-static void base_color(const vlb_material& m, float out[4]) {
+// VkSamplerAddressMode of one texel index (loadSamplers, src/scene_manager.cpp:654-668).
+static inline int wrap_texel(int i, int n, int mode) {
+    auto wrap = [](int i, int n) { int r = i % n; return r < 0 ? r + n : r; };
+    if (mode == VLB_WRAP_CLAMP_TO_EDGE) return i < 0 ? 0 : (i >= n ? n - 1 : i);
+    if (mode == VLB_WRAP_MIRRORED_REPEAT) { const int m = wrap(i, 2 * n); return m < n ? m : 2 * n - 1 - m; }
+    return wrap(i, n);
+}
+
+// texture(textures[idx], uv).rgb (env_map.rchit:42) at the base level ("parity unpinned": the driver's
+// filter arithmetic is not specified bit for bit; this restatement is): unnormalised coordinate
+// u * W - 0.5, four neighbours under the address modes, fp32 lerps in the order of sky_lookup.
+static void tex_sample(const Scene::Tex& t, float u, float v, float rgb[3]) {
+    auto texel = [&](int x, int y, float c[3]) {
+        const uint8_t* p = &t.texels[((size_t)y * t.W + x) * 4];
+        c[0] = (float)p[0] / 255.0f; c[1] = (float)p[1] / 255.0f; c[2] = (float)p[2] / 255.0f;
+    };
+    if (t.filter == VLB_FILTER_NEAREST) {
+        texel(wrap_texel((int)std::floor(u * (float)t.W), t.W, t.wrap_u), wrap_texel((int)std::floor(v * (float)t.H), t.H, t.wrap_v), rgb);
+        return;
+    }
+    const float fx = u * (float)t.W - 0.5f, fy = v * (float)t.H - 0.5f;
+    const float flx = std::floor(fx), fly = std::floor(fy);
+    const float ax = fx - flx, ay = fy - fly;
+    const int x0 = wrap_texel((int)flx, t.W, t.wrap_u), x1 = wrap_texel((int)flx + 1, t.W, t.wrap_u);
+    const int y0 = wrap_texel((int)fly, t.H, t.wrap_v), y1 = wrap_texel((int)fly + 1, t.H, t.wrap_v);
+    float p00[3], p10[3], p01[3], p11[3];
+    texel(x0, y0, p00); texel(x1, y0, p10); texel(x0, y1, p01); texel(x1, y1, p11);
+    for (int c = 0; c < 3; ++c) {
+        const float top = p00[c] + (p10[c] - p00[c]) * ax;
+        const float bot = p01[c] + (p11[c] - p01[c]) * ax;
+        rgb[c] = top + (bot - top) * ay;
+    }
+}
+
+// getBaseColor, env_map.rchit:36-49: texture if the material names one, else the factor if non-zero, else 1.
+static void base_color(const Scene& s, const vlb_material& m, float u, float v, float out[4]) {
     const float* f = m.base_color_factor;
-    if (f[0] != 0.f || f[1] != 0.f || f[2] != 0.f || f[3] != 0.f) {
+    const int ti = m.base_color.index;
+    if (ti >= 0 && ti < (int)s.textures.size()) {
+        tex_sample(s.textures[ti], u, v, out);
+        out[3] = 1.0f;
+    } else if (f[0] != 0.f || f[1] != 0.f || f[2] != 0.f || f[3] != 0.f) {
         out[0] = f[0]; out[1] = f[1]; out[2] = f[2]; out[3] = f[3];
     } else {
         out[0] = out[1] = out[2] = out[3] = 1.0f;
@@ -570,7 +612,9 @@ static void shade_hit(const Scene& s, const vlb_bake_settings& st, const Hit& h,
     const V3 P = v3(fmaf(r.x, h.t, o.x), fmaf(r.y, h.t, o.y), fmaf(r.z, h.t, o.z));
     const V3 N = normalize3(xform_normal(in.nm, nrm));
     float bc[4];
-    base_color(s.mats[in.material], bc);
+    const float tu = (tr.uv[0] * b0 + tr.uv[2] * b1) + tr.uv[4] * b2;       // env_map.rchit:65
+    const float tv = (tr.uv[1] * b0 + tr.uv[3] * b1) + tr.uv[5] * b2;
+    base_color(s, s.mats[in.material], tu, tv, bc);
     const V3 L = v3(st.light_pos[0] - P.x, st.light_pos[1] - P.y, st.light_pos[2] - P.z);
     const float llen = sqrtf(dot3(L, L));
     const V3 Ln = v3(L.x / llen, L.y / llen, L.z / llen);
@@ -816,6 +860,8 @@ void* vo_scene_create(const vlb_vertex* verts, uint64_t n_verts, const uint32_t*
             tr.n0 = v3(a.normal[0], a.normal[1], a.normal[2]);
             tr.n1 = v3(b.normal[0], b.normal[1], b.normal[2]);
             tr.n2 = v3(c.normal[0], c.normal[1], c.normal[2]);
+            tr.uv[0] = a.uv0[0]; tr.uv[1] = a.uv0[1]; tr.uv[2] = b.uv0[0]; tr.uv[3] = b.uv0[1];
+            tr.uv[4] = c.uv0[0]; tr.uv[5] = c.uv0[1];
             tr.inst = ii;
             s->tris.push_back(tr);
         }
@@ -828,6 +874,20 @@ uint64_t vo_scene_num_triangles(void* h) { return ((Scene*)h)->tris.size(); }
 void vo_scene_bounds(void* h, int tight, float out6[6]) {
     Scene* s = (Scene*)h;
     std::memcpy(out6, tight ? s->tight_bounds : s->ref_bounds, 6 * sizeof(float));
+}
+void vo_scene_set_textures(void* h, const vlb_texture* tex, uint32_t n) {
+    Scene* s = (Scene*)h;
+    s->textures.assign(n, Scene::Tex());
+    for (uint32_t i = 0; i < n; ++i) {
+        Scene::Tex& t = s->textures[i];
+        t.W = tex[i].width; t.H = tex[i].height; t.wrap_u = tex[i].wrap_u; t.wrap_v = tex[i].wrap_v; t.filter = tex[i].filter;
+        const uint8_t* p = static_cast<const uint8_t*>(tex[i].texels);
+        t.texels.assign(p, p + (size_t)t.W * t.H * 4);
+    }
+}
+void vo_tex_sample(void* h, uint32_t tex, const float* uv, uint64_t n, float* rgb_out) {
+    Scene* s = (Scene*)h;
+    for (uint64_t i = 0; i < n; ++i) tex_sample(s->textures[tex], uv[2 * i], uv[2 * i + 1], rgb_out + 3 * i);
 }
 void vo_scene_set_skybox(void* h, const void* texels, int fmt, int W, int H) {
     Scene* s = (Scene*)h;

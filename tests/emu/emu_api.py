@@ -43,6 +43,8 @@ def lib():
         L.emu_scene_max_depth.restype = _i32
         L.emu_scene_max_depth.argtypes = [_vp]
         L.emu_scene_set_skybox.argtypes = [_vp, _vp, _i32, _i32]
+        L.emu_scene_set_textures.argtypes = [_vp, _vp, ctypes.c_uint32]
+        L.emu_tex_sample.argtypes = [_vp, _i32, _vp, _u64, _vp]
         L.emu_trace_rays.argtypes = [_vp, _vp, _vp, _u64, _f32, _f32, _i32, _vp, _vp, _vp]
         L.emu_bake.argtypes = [_vp, _vp, _vp]
         L.emu_bake_gather.argtypes = [_vp, _vp, _vp, _vp]
@@ -55,6 +57,19 @@ class Scene:
         self._keep = [np.ascontiguousarray(scene[k]) for k in ("vertices", "indices", "instances", "materials")]
         v, i, inst, m = self._keep
         self._h = lib().emu_scene_create(_p(v), _p(i), _p(inst), inst.size, _p(m), m.size, max_leaf)
+        if scene.get("textures"):
+            self.set_textures(scene["textures"])
+
+    def set_textures(self, textures):
+        import importlib
+        arr, keep = importlib.import_module("vulkan-light-bakery_b200").pack_textures(textures)
+        lib().emu_scene_set_textures(self._h, ctypes.cast(arr, _vp), len(textures))
+
+    def tex_sample(self, tex, uv):
+        uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        out = np.zeros((uv.shape[0], 3), np.float32)
+        lib().emu_tex_sample(self._h, int(tex), _p(uv), uv.shape[0], _p(out))
+        return out
 
     def __del__(self):
         try:

@@ -17,7 +17,9 @@
 using namespace vlb;
 
 struct EmuScene {
-    std::vector<float4> tri_flat, tri_shade, inst, base_color, tris, nodes, sky;
+    std::vector<float4> tri_flat, tri_shade, tri_uv, inst, base_color, tris, nodes, sky;
+    std::vector<int4> tex_desc;
+    std::vector<uchar4> tex_texels;
     std::vector<int> left, right, first, last, parent_i, parent_l;
     int sky_w = 0, sky_h = 0;
     uint32_t n = 0;
@@ -32,10 +34,11 @@ void* emu_scene_create(const vlb_vertex* verts, const uint32_t* indices, const v
                        const vlb_material* mats, uint32_t n_mats, int max_leaf) {
     EmuScene* s = new EmuScene();
     for (uint32_t m = 0; m < std::max(n_mats, 1u); ++m) {
-        float4 b = mk4(1, 1, 1, 1);
+        float4 b = mk4(1, 1, 1, i2f(-1));
         if (m < n_mats) {
             const float* f = mats[m].base_color_factor;
-            if (f[0] != 0.f || f[1] != 0.f || f[2] != 0.f || f[3] != 0.f) b = mk4(f[0], f[1], f[2], f[3]);
+            if (f[0] != 0.f || f[1] != 0.f || f[2] != 0.f || f[3] != 0.f) b = mk4(f[0], f[1], f[2], i2f(-1));
+            if (mats[m].base_color.index >= 0) b.w = i2f(mats[m].base_color.index);
         }
         s->base_color.push_back(b);
     }
@@ -49,11 +52,15 @@ void* emu_scene_create(const vlb_vertex* verts, const uint32_t* indices, const v
         s->inst.push_back(mk4(minv[6], minv[7], minv[8], 0));
         for (uint32_t t = 0; t < vi.index_count / 3; ++t) {
             Vec3 p[3], nn[3];
+            float uv[6];
             for (int k = 0; k < 3; ++k) {
                 const vlb_vertex& v = verts[vi.first_vertex + indices[vi.first_index + 3 * t + k]];
                 p[k] = xform_point(vi.transform, mk3(v.position[0], v.position[1], v.position[2]));
                 nn[k] = mk3(v.normal[0], v.normal[1], v.normal[2]);
+                uv[2 * k] = v.uv0[0]; uv[2 * k + 1] = v.uv0[1];
             }
+            s->tri_uv.push_back(mk4(uv[0], uv[1], uv[2], uv[3]));
+            s->tri_uv.push_back(mk4(uv[4], uv[5], 0, 0));
             const int id = (int)(s->tri_flat.size() / 3);
             s->tri_flat.push_back(mk4(p[0].x, p[0].y, p[0].z, i2f(id)));
             s->tri_flat.push_back(mk4(f_sub(p[1].x, p[0].x), f_sub(p[1].y, p[0].y), f_sub(p[1].z, p[0].z), 0));
@@ -146,6 +153,23 @@ void* emu_scene_create(const vlb_vertex* verts, const uint32_t* indices, const v
 
 void emu_scene_destroy(void* h) { delete (EmuScene*)h; }
 int emu_scene_max_depth(void* h) { return ((EmuScene*)h)->max_depth; }
+// vlb_scene_set_textures, as context.cu lays the atlas out
+void emu_scene_set_textures(void* h, const vlb_texture* tex, uint32_t n) {
+    EmuScene* s = (EmuScene*)h;
+    s->tex_desc.clear(); s->tex_texels.clear();
+    for (uint32_t i = 0; i < n; ++i) {
+        int4 d; d.x = (int)s->tex_texels.size(); d.y = tex[i].width; d.z = tex[i].height;
+        d.w = tex[i].wrap_u | (tex[i].wrap_v << 2) | (tex[i].filter << 4);
+        s->tex_desc.push_back(d);
+        const uchar4* p = static_cast<const uchar4*>(tex[i].texels);
+        s->tex_texels.insert(s->tex_texels.end(), p, p + (size_t)tex[i].width * tex[i].height);
+    }
+}
+void emu_tex_sample(void* h, int tex, const float* uv, uint64_t n, float* rgb) {
+    EmuScene* s = (EmuScene*)h;
+    ShadeView sv{}; sv.tex_desc = s->tex_desc.data(); sv.tex_texels = s->tex_texels.data();
+    for (uint64_t i = 0; i < n; ++i) tex_sample(sv, tex, uv[2 * i], uv[2 * i + 1], rgb + 3 * i);
+}
 void emu_scene_set_skybox(void* h, const float* rgba32f, int W, int H) {
     EmuScene* s = (EmuScene*)h;
     s->sky.resize((size_t)W * H);
@@ -180,6 +204,7 @@ void emu_bake_gather(void* h, const vlb_bake_settings* st, const float* prev_ful
     EmuScene* s = (EmuScene*)h;
     BvhView b = view(s);
     ShadeView sv; sv.tri_shade = s->tri_shade.data(); sv.inst = s->inst.data(); sv.base_color = s->base_color.data();
+    sv.tri_uv = s->tri_uv.data(); sv.tex_desc = s->tex_desc.data(); sv.tex_texels = s->tex_texels.data();
     sv.sky = s->sky_w ? s->sky.data() : nullptr; sv.sky_w = s->sky_w; sv.sky_h = s->sky_h;
     BakeConsts c;
     for (int k = 0; k < 3; ++k) c.light[k] = st->light_pos[k];

@@ -30,6 +30,8 @@ MATERIAL_DTYPE = np.dtype([("textures", "<i4", (8, 2)), ("base_color_factor", "<
 assert VERTEX_DTYPE.itemsize == 44 and INSTANCE_DTYPE.itemsize == 68 and MATERIAL_DTYPE.itemsize == 144
 
 FMT_RGBA8, FMT_RGBA32F = 0, 1
+WRAP_REPEAT, WRAP_CLAMP_TO_EDGE, WRAP_MIRRORED_REPEAT = 0, 1, 2
+FILTER_LINEAR, FILTER_NEAREST = 0, 1
 SH_STRIDE = 48
 
 SHADOW_RAYS = 1 << 0
@@ -83,6 +85,27 @@ class BakeSettings(ctypes.Structure):
         return self.probes[0] * self.probes[1] * len(self.slab_slices)
 
 
+class Texture(ctypes.Structure):
+    """vlb_texture (include/vlb_bake.h): one glTF texture = RGBA8 image + sampler state."""
+    _fields_ = [("texels", ctypes.c_void_p), ("width", ctypes.c_int32), ("height", ctypes.c_int32),
+                ("wrap_u", ctypes.c_int32), ("wrap_v", ctypes.c_int32), ("filter", ctypes.c_int32),
+                ("reserved", ctypes.c_int32)]
+
+
+def pack_textures(textures):
+    """list of {"texels": uint8 [H, W, 4], "wrap_u", "wrap_v", "filter"} -> (ctypes array of Texture, keep-alive list)."""
+    keep = []
+    arr = (Texture * max(len(textures), 1))()
+    for i, t in enumerate(textures):
+        px = np.ascontiguousarray(t["texels"], np.uint8)
+        if px.ndim != 3 or px.shape[2] != 4:
+            raise ValueError("texture %d: texels must be uint8 [H, W, 4]" % i)
+        keep.append(px)
+        arr[i] = Texture(px.ctypes.data, px.shape[1], px.shape[0], int(t.get("wrap_u", WRAP_REPEAT)),
+                         int(t.get("wrap_v", WRAP_REPEAT)), int(t.get("filter", FILTER_LINEAR)), 0)
+    return arr, keep
+
+
 class BvhStats(ctypes.Structure):
     _fields_ = [("n_triangles", ctypes.c_uint64), ("n_nodes", ctypes.c_uint64), ("max_leaf_size", ctypes.c_uint32),
                 ("reserved", ctypes.c_uint32), ("bounds", ctypes.c_float * 6), ("build_ms", ctypes.c_float),
@@ -105,7 +128,7 @@ class VlbError(RuntimeError):
 ABI_SYMBOLS = [
     "vlb_abi_version", "vlb_ctx_create", "vlb_ctx_destroy", "vlb_ctx_set_stream", "vlb_ctx_synchronize",
     "vlb_last_error", "vlb_ctx_launch_count", "vlb_scene_set_triangles", "vlb_scene_load_gltf", "vlb_gltf_probe", "vlb_scene_bounds", "vlb_bvh_build",
-    "vlb_skybox_set", "vlb_skybox_project_sh", "vlb_skybox_project_sh_batched", "vlb_skybox_project_sh_device",
+    "vlb_scene_set_textures", "vlb_skybox_set", "vlb_skybox_project_sh", "vlb_skybox_project_sh_batched", "vlb_skybox_project_sh_device",
     "vlb_skybox_project_sh_device_ptrs", "vlb_envmap_project_sh", "vlb_bake_settings_default", "vlb_bake_settings_from_bounds", "vlb_probe_positions",
     "vlb_bake_probes", "vlb_bake_probes_device", "vlb_bake_gather_device", "vlb_bake_last_stats", "vlb_trace_rays",
     "vlb_bake_serialize_gltf", "vlb_bake_deserialize_gltf",
@@ -138,6 +161,7 @@ def load_library():
         "vlb_gltf_probe": (i32, [ctypes.c_char_p, vp, vp]),
         "vlb_scene_bounds": (i32, [vp, i32, vp]),
         "vlb_bvh_build": (i32, [vp, ctypes.POINTER(BvhStats)]),
+        "vlb_scene_set_textures": (i32, [vp, vp, u32]),
         "vlb_skybox_set": (i32, [vp, vp, i32, i32, i32]),
         "vlb_skybox_project_sh": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "vlb_skybox_project_sh_batched": (i32, [vp, vp, u32, i32, i32, i32, i32, vp]),
@@ -243,6 +267,12 @@ class Context:
         m = np.ascontiguousarray(scene["materials"], MATERIAL_DTYPE)
         self._check(self._lib.vlb_scene_set_triangles(self._h, _ptr(v), v.size, _ptr(i), i.size, _ptr(inst), inst.size,
                                                       _ptr(m), m.size))
+        self.set_textures(scene.get("textures", []))
+
+    def set_textures(self, textures):
+        """Scene_t::loadTextures: the textures vlb_material.base_color.index refers to (see pack_textures)."""
+        arr, keep = pack_textures(textures)
+        self._check(self._lib.vlb_scene_set_textures(self._h, ctypes.cast(arr, ctypes.c_void_p), len(textures)))
 
     def load_gltf(self, path):
         """SceneManager::pushScene: ingest a .gltf / .glb file."""

@@ -439,6 +439,11 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     p.bvh.overflow = reinterpret_cast<unsigned int*>(ctx->d_scratch.as<float>() + 13);
     p.shade.tri_shade = ctx->d_tri_shade.as<float4>(); p.shade.inst = ctx->d_inst.as<float4>();
     p.shade.base_color = ctx->d_base_color.as<float4>();
+    p.shade.tri_uv = ctx->d_tri_uv.as<float4>(); p.shade.tex_desc = ctx->d_tex_desc.as<int4>();
+    p.shade.tex_texels = ctx->d_tex_texels.as<uchar4>();
+    if (ctx->max_tex_index >= (int)ctx->n_textures)
+        return ctx->fail(VLB_ERR_STATE, "bake: a material names baseColor texture %d but %u textures are set (vlb_scene_set_textures)",
+                         ctx->max_tex_index, ctx->n_textures);
     p.shade.sky = ctx->sky_w ? ctx->d_sky.as<float4>() : nullptr; p.shade.sky_w = ctx->sky_w; p.shade.sky_h = ctx->sky_h;
     for (int k = 0; k < 3; ++k) p.c.light[k] = s->light_pos[k];
     p.c.shadow_bias = s->shadow_bias; p.c.c_diffuse = s->c_diffuse; p.c.c_specular = s->c_specular;

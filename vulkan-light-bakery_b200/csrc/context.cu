@@ -21,7 +21,7 @@ void set_thread_error(const char* msg) { g_thread_error = msg ? msg : ""; }
 __global__ void k_flatten(const float* __restrict__ verts, const uint32_t* __restrict__ indices,
                           const InstanceDev* __restrict__ insts, const uint32_t* __restrict__ tri_offsets,
                           uint32_t n_insts, uint32_t n_tris, float4* __restrict__ tri_flat,
-                          float4* __restrict__ tri_shade) {
+                          float4* __restrict__ tri_shade, float4* __restrict__ tri_uv) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tris) return;
     // binary search: last instance with tri_offset <= t
@@ -34,11 +34,15 @@ __global__ void k_flatten(const float* __restrict__ verts, const uint32_t* __res
     const uint32_t local = t - tri_offsets[lo];
     const uint32_t* ix = indices + in.first_index + 3ull * local;
     Vec3 p[3], n[3];
+    float uv[6];
     for (int k = 0; k < 3; ++k) {
         const float* v = verts + 11ull * (in.first_vertex + ix[k]);
         p[k] = xform_point(in.m, mk3(v[0], v[1], v[2]));
         n[k] = mk3(v[4], v[5], v[6]);
+        uv[2 * k] = v[7]; uv[2 * k + 1] = v[8];                          // Vertex::uv0 (structures.h:24)
     }
+    tri_uv[2ull * t + 0] = make_float4(uv[0], uv[1], uv[2], uv[3]);
+    tri_uv[2ull * t + 1] = make_float4(uv[4], uv[5], 0.f, 0.f);
     tri_flat[3ull * t + 0] = make_float4(p[0].x, p[0].y, p[0].z, __int_as_float((int)t));
     tri_flat[3ull * t + 1] = make_float4(f_sub(p[1].x, p[0].x), f_sub(p[1].y, p[0].y), f_sub(p[1].z, p[0].z), 0.f);
     tri_flat[3ull * t + 2] = make_float4(f_sub(p[2].x, p[0].x), f_sub(p[2].y, p[0].y), f_sub(p[2].z, p[0].z), 0.f);
@@ -120,7 +124,7 @@ void vlb_ctx_destroy(vlb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     DevBuf* bufs[] = {&ctx->d_verts, &ctx->d_indices, &ctx->d_insts_in, &ctx->d_tri_offsets, &ctx->d_tri_flat,
-                      &ctx->d_tri_shade, &ctx->d_inst, &ctx->d_base_color, &ctx->d_tris, &ctx->d_nodes, &ctx->d_keys,
+                      &ctx->d_tri_shade, &ctx->d_tri_uv, &ctx->d_tex_desc, &ctx->d_tex_texels, &ctx->d_inst, &ctx->d_base_color, &ctx->d_tris, &ctx->d_nodes, &ctx->d_keys,
                       &ctx->d_keys_sorted, &ctx->d_vals, &ctx->d_vals_sorted, &ctx->d_sort_tmp, &ctx->d_left,
                       &ctx->d_right, &ctx->d_first, &ctx->d_last, &ctx->d_parent_i, &ctx->d_parent_l, &ctx->d_flags,
                       &ctx->d_ibox, &ctx->d_lbox, &ctx->d_scratch, &ctx->d_sky, &ctx->d_proj_in, &ctx->d_proj_out,
@@ -215,11 +219,17 @@ int vlb_scene_set_triangles(vlb_ctx* ctx, const vlb_vertex* vertices, uint64_t n
     offsets[n_instances] = (uint32_t)tri_total;
     if (tri_total >= (1ull << 28)) return ctx->fail(VLB_ERR_UNSUPPORTED, "more than 2^28 triangles");
 
-    // resolved baseColor per material (env_map.rchit:36-49; texture branch: SURVEY §8 f3)
-    std::vector<float4> base(std::max<uint32_t>(n_materials, 1), make_float4(1.f, 1.f, 1.f, 1.f));
+    // resolved baseColor per material (env_map.rchit:36-49): rgb = factor (or 1), w = bits(texture index or -1)
+    const int no_tex = -1;
+    float no_tex_f; std::memcpy(&no_tex_f, &no_tex, 4);
+    std::vector<float4> base(std::max<uint32_t>(n_materials, 1), make_float4(1.f, 1.f, 1.f, no_tex_f));
+    ctx->max_tex_index = -1;
     for (uint32_t m = 0; m < n_materials; ++m) {
         const float* f = materials[m].base_color_factor;
-        if (f[0] != 0.f || f[1] != 0.f || f[2] != 0.f || f[3] != 0.f) base[m] = make_float4(f[0], f[1], f[2], f[3]);
+        if (f[0] != 0.f || f[1] != 0.f || f[2] != 0.f || f[3] != 0.f) base[m] = make_float4(f[0], f[1], f[2], no_tex_f);
+        const int32_t ti = materials[m].base_color.index;
+        if (ti < -1) return ctx->fail(VLB_ERR_INVALID, "vlb_scene_set_triangles: material %u has baseColor texture index %d", m, ti);
+        if (ti >= 0) { std::memcpy(&base[m].w, &ti, 4); ctx->max_tex_index = std::max(ctx->max_tex_index, (int)ti); }
     }
 
     ctx->n_tris = tri_total; ctx->n_verts = n_vertices; ctx->n_indices = n_indices;
@@ -232,6 +242,7 @@ int vlb_scene_set_triangles(vlb_ctx* ctx, const vlb_vertex* vertices, uint64_t n
     VLB_CUDA(ctx, ctx->d_base_color.reserve(base.size() * sizeof(float4)));
     VLB_CUDA(ctx, ctx->d_tri_flat.reserve(3 * tri_total * sizeof(float4)));
     VLB_CUDA(ctx, ctx->d_tri_shade.reserve(3 * tri_total * sizeof(float4)));
+    VLB_CUDA(ctx, ctx->d_tri_uv.reserve(2 * tri_total * sizeof(float4)));
     cudaStream_t st = ctx->stream;
     if (n_vertices) VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_verts.p, vertices, n_vertices * sizeof(vlb_vertex), cudaMemcpyHostToDevice, st));
     if (n_indices) VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_indices.p, indices, n_indices * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
@@ -245,12 +256,41 @@ int vlb_scene_set_triangles(vlb_ctx* ctx, const vlb_vertex* vertices, uint64_t n
         const uint32_t n = (uint32_t)tri_total;
         k_flatten<<<(n + 255) / 256, 256, 0, st>>>(ctx->d_verts.as<float>(), ctx->d_indices.as<uint32_t>(),
                                                    ctx->d_insts_in.as<InstanceDev>(), ctx->d_tri_offsets.as<uint32_t>(),
-                                                   n_instances, n, ctx->d_tri_flat.as<float4>(), ctx->d_tri_shade.as<float4>());
+                                                   n_instances, n, ctx->d_tri_flat.as<float4>(), ctx->d_tri_shade.as<float4>(),
+                                                   ctx->d_tri_uv.as<float4>());
         VLB_LAUNCH_CHECK(ctx);
     }
     // host staging vectors die at scope exit: the copies above must have completed
     VLB_CUDA(ctx, cudaStreamSynchronize(st));
     ctx->have_scene = true;
+    return VLB_OK;
+}
+
+int vlb_scene_set_textures(vlb_ctx* ctx, const vlb_texture* textures, uint32_t n_textures) {
+    if (!ctx) return VLB_ERR_INVALID;
+    if (n_textures && !textures) return ctx->fail(VLB_ERR_INVALID, "vlb_scene_set_textures: null textures");
+    std::vector<int4> desc(n_textures);
+    size_t total = 0;
+    for (uint32_t i = 0; i < n_textures; ++i) {
+        const vlb_texture& t = textures[i];
+        if (!t.texels || t.width <= 0 || t.height <= 0 || t.width > 32768 || t.height > 32768)
+            return ctx->fail(VLB_ERR_INVALID, "vlb_scene_set_textures: texture %u has no texels or a bad size", i);
+        if (t.wrap_u < 0 || t.wrap_u > 2 || t.wrap_v < 0 || t.wrap_v > 2 || t.filter < 0 || t.filter > 1)
+            return ctx->fail(VLB_ERR_INVALID, "vlb_scene_set_textures: texture %u has an unknown wrap mode or filter", i);
+        if (total + (size_t)t.width * t.height >= (1ull << 31))
+            return ctx->fail(VLB_ERR_UNSUPPORTED, "vlb_scene_set_textures: more than 2^31 texels in total");
+        desc[i] = make_int4((int)total, t.width, t.height, t.wrap_u | (t.wrap_v << 2) | (t.filter << 4));
+        total += (size_t)t.width * t.height;
+    }
+    cudaStream_t st = ctx->stream;
+    VLB_CUDA(ctx, ctx->d_tex_desc.reserve(std::max<size_t>(n_textures, 1) * sizeof(int4)));
+    VLB_CUDA(ctx, ctx->d_tex_texels.reserve(std::max<size_t>(total, 1) * 4));
+    if (n_textures) VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_tex_desc.p, desc.data(), n_textures * sizeof(int4), cudaMemcpyHostToDevice, st));
+    for (uint32_t i = 0; i < n_textures; ++i)
+        VLB_CUDA(ctx, cudaMemcpyAsync(static_cast<unsigned char*>(ctx->d_tex_texels.p) + 4 * (size_t)desc[i].x, textures[i].texels,
+                                      4 * (size_t)textures[i].width * textures[i].height, cudaMemcpyHostToDevice, st));
+    VLB_CUDA(ctx, cudaStreamSynchronize(st));     // caller-owned host buffers may go away after the call
+    ctx->n_textures = n_textures;
     return VLB_OK;
 }
 

@@ -61,7 +61,11 @@ struct vlb_ctx {
     vlb::DevBuf d_tri_flat;   // 3 float4 per triangle, flat order (before Morton sort)
     vlb::DevBuf d_tri_shade;  // 3 float4 per triangle, flat order
     vlb::DevBuf d_inst;       // 3 float4 per instance
-    vlb::DevBuf d_base_color; // float4 per material
+    vlb::DevBuf d_base_color; // float4 per material (w = bits of the baseColor texture index, -1 = none)
+    vlb::DevBuf d_tri_uv;     // 2 float4 per triangle, flat order: Vertex::uv0 of the three corners
+    vlb::DevBuf d_tex_desc, d_tex_texels;   // vlb_scene_set_textures: int4 per texture, RGBA8 atlas
+    uint32_t n_textures = 0;
+    int max_tex_index = -1;   // largest baseColor texture index any material names
     // ---- BVH ----
     vlb::DevBuf d_tris;       // 3 float4 per triangle, Morton order
     vlb::DevBuf d_nodes;      // 4 float4 per node

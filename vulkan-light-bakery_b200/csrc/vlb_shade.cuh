@@ -15,7 +15,10 @@ namespace vlb {
 struct ShadeView {
     const float4* tri_shade;
     const float4* inst;
-    const float4* base_color;
+    const float4* base_color;   // rgb = resolved factor; w = bits(baseColor texture index, -1 = none)
+    const float4* tri_uv;       // 2 float4 per flat triangle: (u0, v0, u1, v1), (u2, v2, 0, 0) = Vertex::uv0
+    const int4* tex_desc;       // per texture: (first texel, width, height, wrap_u | wrap_v << 2 | filter << 4)
+    const uchar4* tex_texels;   // RGBA8 texels of all textures, back to back
     const float4* sky;       // RGBA32F texels, NULL if no skybox set
     int sky_w, sky_h;
 };
@@ -60,6 +63,55 @@ VLB_HD void sky_lookup(const ShadeView& s, Vec3 dir, float rgb[3]) {
     rgb[2] = t2 + (b2 - t2) * ay;
 }
 
+// Texel index along one axis under a Vulkan address mode (VkSamplerAddressMode; loadSamplers,
+// src/scene_manager.cpp:654-668). mode: VLB_WRAP_REPEAT / CLAMP_TO_EDGE / MIRRORED_REPEAT.
+VLB_HD int wrap_texel(int i, int n, int mode) {
+    if (mode == 1) return i < 0 ? 0 : (i >= n ? n - 1 : i);
+    if (mode == 2) {
+        const int m = wrapi(i, 2 * n);
+        return m < n ? m : 2 * n - 1 - m;
+    }
+    return wrapi(i, n);
+}
+
+VLB_HD void texel_rgb(const ShadeView& s, int base, int W, int x, int y, float c[3]) {
+#ifdef __CUDA_ARCH__
+    const uchar4 t = __ldg(s.tex_texels + (size_t)base + (size_t)y * W + x);
+#else
+    const uchar4 t = s.tex_texels[(size_t)base + (size_t)y * W + x];
+#endif
+    c[0] = (float)t.x / 255.0f; c[1] = (float)t.y / 255.0f; c[2] = (float)t.z / 255.0f;   // unorm8
+}
+
+// texture(textures[tex], uv).rgb at the base level (env_map.rchit:42): unnormalised coordinate u * W - 0.5,
+// the four neighbours under the sampler's address modes, fp32 weights (same form as sky_lookup).
+VLB_HD void tex_sample(const ShadeView& s, int tex, float u, float v, float rgb[3]) {
+#ifdef __CUDA_ARCH__
+    const int4 d = __ldg(s.tex_desc + tex);
+#else
+    const int4 d = s.tex_desc[tex];
+#endif
+    const int W = d.y, H = d.z, mu = d.w & 3, mv = (d.w >> 2) & 3;
+    if ((d.w >> 4) & 1) {                                                // nearest
+        const int x = wrap_texel((int)floorf(f_mul(u, (float)W)), W, mu), y = wrap_texel((int)floorf(f_mul(v, (float)H)), H, mv);
+        texel_rgb(s, d.x, W, x, y, rgb);
+        return;
+    }
+    const float fx = f_sub(f_mul(u, (float)W), 0.5f), fy = f_sub(f_mul(v, (float)H), 0.5f);
+    const float flx = floorf(fx), fly = floorf(fy);
+    const float ax = fx - flx, ay = fy - fly;
+    const int x0 = wrap_texel((int)flx, W, mu), x1 = wrap_texel((int)flx + 1, W, mu);
+    const int y0 = wrap_texel((int)fly, H, mv), y1 = wrap_texel((int)fly + 1, H, mv);
+    float p00[3], p10[3], p01[3], p11[3];
+    texel_rgb(s, d.x, W, x0, y0, p00); texel_rgb(s, d.x, W, x1, y0, p10);
+    texel_rgb(s, d.x, W, x0, y1, p01); texel_rgb(s, d.x, W, x1, y1, p11);
+    for (int c = 0; c < 3; ++c) {
+        const float top = p00[c] + (p10[c] - p00[c]) * ax;
+        const float bot = p01[c] + (p11[c] - p01[c]) * ax;
+        rgb[c] = top + (bot - top) * ay;
+    }
+}
+
 VLB_HD float quant8(float c) {
     // imageStore to rgba8 (src/baker/env_map_generator.hpp:39): clamp, round-half-even to n/255
     return rintf(clampf(c, 0.0f, 1.0f) * 255.0f) / 255.0f;
@@ -97,6 +149,13 @@ VLB_HD bool shade_prelude(const ShadeView& s, const BakeConsts& c, const HitRec&
     const float4 bc = ld4(s.base_color + f2i(m0.w));
     p.bc[0] = bc.x; p.bc[1] = bc.y; p.bc[2] = bc.z;
     const float b0 = 1.0f - h.u - h.v, b1 = h.u, b2 = h.v;              // env_map.rchit:63
+    const int tex = f2i(bc.w);
+    if (tex >= 0) {                                                     // getBaseColor, texture branch (:40-43)
+        const float4 ua = ld4(s.tri_uv + 2 * (size_t)h.id), ub = ld4(s.tri_uv + 2 * (size_t)h.id + 1);
+        const float tu = f_add(f_add(f_mul(ua.x, b0), f_mul(ua.z, b1)), f_mul(ub.x, b2));   // :65
+        const float tv = f_add(f_add(f_mul(ua.y, b0), f_mul(ua.w, b1)), f_mul(ub.y, b2));
+        tex_sample(s, tex, tu, tv, p.bc);
+    }
     const Vec3 nrm = mk3(a0.x * b0 + a1.x * b1 + a2.x * b2, a0.y * b0 + a1.y * b1 + a2.y * b2,
                          a0.z * b0 + a1.z * b1 + a2.z * b2);            // :64
     const float nm[9] = {m0.x, m0.y, m0.z, m1.x, m1.y, m1.z, m2.x, m2.y, m2.z};

@@ -234,6 +234,42 @@ def small_room(n_side=6, seed=3):
     return b.finish(make_materials())
 
 
+def pattern_texture(width, height, seed=0):
+    """Procedural RGBA8 texture: coloured checker + gradient + per-texel noise (so neighbouring texels differ)."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:height, 0:width]
+    cell = ((x * 8 // max(width, 1)) + (y * 8 // max(height, 1))) & 1
+    base = np.stack([80 + 120 * cell, 60 + 150 * x / max(width - 1, 1), 200 - 140 * y / max(height - 1, 1)], -1)
+    t = np.zeros((height, width, 4), np.uint8)
+    t[..., :3] = np.clip(base + rng.integers(-25, 26, base.shape), 0, 255).astype(np.uint8)
+    t[..., 3] = 255
+    return t
+
+
+def small_room_textured(n_side=6, seed=3):
+    """small_room with texture coordinates on every vertex and four baseColor textures (one per sampler flavour:
+    linear/repeat, linear/clamp, linear/mirror, nearest/repeat) on materials 0, 1, 2 and 7; uv0 runs past [0, 1]
+    so that the address modes matter. The remaining materials keep the factor path (env_map.rchit:43-47)."""
+    from . import WRAP_REPEAT, WRAP_CLAMP_TO_EDGE, WRAP_MIRRORED_REPEAT, FILTER_LINEAR, FILTER_NEAREST
+    scene = small_room(n_side, seed)
+    rng = np.random.default_rng(seed + 100)
+    v = scene["vertices"]
+    p = v["position"][:, :3]
+    # planar-ish mapping with an irrational scale and an offset: covers about [-0.7, 2.3]
+    v["uv0"][:, 0] = 0.37 * p[:, 0] + 0.29 * p[:, 2] - 0.7 + 0.01 * rng.standard_normal(len(v))
+    v["uv0"][:, 1] = 0.41 * p[:, 1] + 0.23 * p[:, 2] - 0.6 + 0.01 * rng.standard_normal(len(v))
+    m = scene["materials"]
+    for slot, mat in enumerate((0, 1, 2, 7)):
+        m["textures"][mat, 2, 0] = slot                # Textures::baseColor.index (structures.h:52-61)
+    scene["textures"] = [
+        {"texels": pattern_texture(16, 8, 1), "wrap_u": WRAP_REPEAT, "wrap_v": WRAP_REPEAT, "filter": FILTER_LINEAR},
+        {"texels": pattern_texture(5, 7, 2), "wrap_u": WRAP_CLAMP_TO_EDGE, "wrap_v": WRAP_CLAMP_TO_EDGE, "filter": FILTER_LINEAR},
+        {"texels": pattern_texture(32, 32, 3), "wrap_u": WRAP_MIRRORED_REPEAT, "wrap_v": WRAP_REPEAT, "filter": FILTER_LINEAR},
+        {"texels": pattern_texture(4, 4, 4), "wrap_u": WRAP_REPEAT, "wrap_v": WRAP_MIRRORED_REPEAT, "filter": FILTER_NEAREST},
+    ]
+    return scene
+
+
 def hdr_sky(width, height, seed=1):
     """BASELINE C1 input: smooth HDR sky rgb = a + b*max(0, d.s)^p plus U[0,0.1) per-texel noise,
     alpha 1, RGBA32F."""
