@@ -216,6 +216,10 @@ int vlb_scene_load_gltf(vlb_ctx* ctx, const char* gltf_path);
 /* Host-only: parse a glTF and report counts = {vertices, indices, instances (node x primitive),
  * materials incl. the default, triangles} and the reference-mode bounds. No CUDA device needed. */
 int vlb_gltf_probe(const char* gltf_path, uint64_t counts[5], float ref_bounds_min_max[6]);
+/* Host-only: texture `index` of a glTF as vlb_scene_load_gltf would set it. info = {width, height, wrap_u,
+ * wrap_v, filter, 1 if the texture is used as a baseColor texture (else it is a 1x1 white placeholder)};
+ * texels (may be NULL to query the size first) receives width*height*4 RGBA8 bytes if capacity allows. */
+int vlb_gltf_texture(const char* gltf_path, uint32_t index, void* texels, uint64_t capacity_bytes, int32_t info[6]);
 /* Scene_t::getBounds (src/scene_manager.cpp:214-217). mode 0: the reference's semantics
  * (bounds start at the origin, only the two local AABB corners are transformed,
  * scene_manager.cpp:497-507); mode 1: tight world-space AABB of all triangles. */

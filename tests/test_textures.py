@@ -120,3 +120,102 @@ def test_texture_errors(ctx, vlb, scenes):
         ctx.set_textures(bad)
     ctx.set_textures(sc["textures"])                    # the ctx stays usable
     assert np.isfinite(ctx.bake_probes(s)).all()
+
+
+# ---------------------------------------------------------------------- glTF texture ingest -----
+@pytest.mark.parametrize("container,embed", [("gltf", True), ("gltf", False), ("glb", True)])
+def test_gltf_textures_decode_to_the_source_texels(vlb, scenes, tmp_path, container, embed):
+    """Scene_t::loadTextures / loadSamplers through the from-scratch PNG reader (csrc/png_decode.cpp): RGB and
+    RGBA PNGs from data URIs, files and bufferViews come back as the RGBA8 texels and sampler state written."""
+    sc = scenes.small_room_textured()
+    if container == "glb":
+        p = scenes.write_glb(sc, str(tmp_path / "room.glb"))
+    else:
+        p = scenes.write_gltf(sc, str(tmp_path / "room.gltf"), embed=embed)
+    for k, want in enumerate(sc["textures"]):
+        got = vlb.gltf_texture(p, k)
+        assert got["used"]
+        assert np.array_equal(got["texels"], want["texels"]), k
+        assert (got["wrap_u"], got["wrap_v"], got["filter"]) == (want["wrap_u"], want["wrap_v"], want["filter"])
+    with pytest.raises(vlb.VlbError):
+        vlb.gltf_texture(p, len(sc["textures"]))
+
+
+def test_png_reader_filters_palette_grey_and_errors(vlb, scenes, tmp_path):
+    import io
+    import json
+    import base64
+    from PIL import Image
+    rng = np.random.default_rng(9)
+    sc = scenes.small_room()
+    sc["materials"]["textures"][0, 2, 0] = 0
+    sc["vertices"]["uv0"][:] = 0.5
+    base = scenes.write_gltf(sc, str(tmp_path / "base.gltf"))
+    doc = json.load(open(base))
+
+    def with_image(data, name):
+        d = dict(doc)
+        d["images"] = [{"uri": "data:image/png;base64," + base64.b64encode(data).decode()}]
+        d["textures"] = [{"source": 0}]
+        p = str(tmp_path / name)
+        json.dump(d, open(p, "w"))
+        return p
+
+    def png(img, **kw):
+        b = io.BytesIO()
+        img.save(b, format="PNG", **kw)
+        return b.getvalue()
+
+    # smooth + noisy content so that the encoder picks all five row filters
+    y, x = np.mgrid[0:37, 0:53]
+    rgb = np.stack([(x * 5) % 256, (y * 7) % 256, (x * y) % 256], -1).astype(np.uint8)
+    rgb[10:20] = rng.integers(0, 256, (10, 53, 3), dtype=np.uint8)
+    got = vlb.gltf_texture(with_image(png(Image.fromarray(rgb, "RGB"), optimize=True), "rgb.gltf"), 0)
+    assert np.array_equal(got["texels"][..., :3], rgb) and (got["texels"][..., 3] == 255).all()
+    assert (got["wrap_u"], got["wrap_v"], got["filter"]) == (vlb.WRAP_REPEAT, vlb.WRAP_REPEAT, vlb.FILTER_LINEAR)   # no sampler: Application::Sampler{}
+    grey = rgb[..., 0]
+    got = vlb.gltf_texture(with_image(png(Image.fromarray(grey, "L")), "grey.gltf"), 0)
+    assert np.array_equal(got["texels"][..., 0], grey) and np.array_equal(got["texels"][..., 2], grey)
+    pal = Image.fromarray(rgb, "RGB").quantize(colors=16)
+    got = vlb.gltf_texture(with_image(png(pal), "pal.gltf"), 0)
+    assert np.array_equal(got["texels"][..., :3], np.asarray(pal.convert("RGB")))
+    rgba = np.concatenate([rgb, rng.integers(0, 256, (37, 53, 1), dtype=np.uint8)], -1)
+    got = vlb.gltf_texture(with_image(png(Image.fromarray(rgba, "RGBA")), "rgba.gltf"), 0)
+    assert np.array_equal(got["texels"], rgba)
+    # unsupported / broken inputs fail loudly with the right code
+    b = io.BytesIO(); Image.fromarray(rgb, "RGB").save(b, format="JPEG")
+    with pytest.raises(vlb.VlbError) as e:
+        vlb.gltf_texture(with_image(b.getvalue(), "jpeg.gltf"), 0)
+    assert e.value.code == vlb.ERR_UNSUPPORTED
+    wide = Image.fromarray((rgb.astype(np.uint16) * 257)[..., 0], "I;16")
+    with pytest.raises(vlb.VlbError) as e:
+        vlb.gltf_texture(with_image(png(wide), "p16.gltf"), 0)
+    assert e.value.code == vlb.ERR_UNSUPPORTED
+    good = png(Image.fromarray(rgb, "RGB"))
+    with pytest.raises(vlb.VlbError) as e:
+        vlb.gltf_texture(with_image(good[:len(good) // 2], "cut.gltf"), 0)
+    assert e.value.code == vlb.ERR_IO
+    # a texture nobody uses as baseColor is not decoded at all (placeholder, like the reference's dummy texture)
+    d = dict(doc)
+    d["images"] = [{"uri": "missing.png"}]
+    d["textures"] = [{"source": 0}]
+    d["materials"] = [dict(m) for m in doc["materials"]]
+    d["materials"][0] = {"pbrMetallicRoughness": {"baseColorFactor": [1, 1, 1, 1]}, "normalTexture": {"index": 0}}
+    json.dump(d, open(str(tmp_path / "unused.gltf"), "w"))
+    got = vlb.gltf_texture(str(tmp_path / "unused.gltf"), 0)
+    assert not got["used"] and got["texels"].shape == (1, 1, 4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("container", ["gltf", "glb"])
+def test_loaded_textured_scene_bakes_like_the_array_scene(ctx, vlb, scenes, tmp_path, container):
+    sc = scenes.small_room_textured()
+    p = (scenes.write_gltf if container == "gltf" else scenes.write_glb)(sc, str(tmp_path / ("room." + container)))
+    s = _settings(vlb, scenes)
+    ctx.set_scene(sc)
+    ctx.build_bvh()
+    a = ctx.bake_probes(s)
+    ctx.load_gltf(p)
+    ctx.build_bvh()
+    b = ctx.bake_probes(s)
+    assert rel_l2(b, a) <= 1e-5          # normals are re-normalised by the loader: last-ulp differences only

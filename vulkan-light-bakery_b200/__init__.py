@@ -128,7 +128,7 @@ class VlbError(RuntimeError):
 ABI_SYMBOLS = [
     "vlb_abi_version", "vlb_ctx_create", "vlb_ctx_destroy", "vlb_ctx_set_stream", "vlb_ctx_synchronize",
     "vlb_last_error", "vlb_ctx_launch_count", "vlb_scene_set_triangles", "vlb_scene_load_gltf", "vlb_gltf_probe", "vlb_scene_bounds", "vlb_bvh_build",
-    "vlb_scene_set_textures", "vlb_skybox_set", "vlb_skybox_project_sh", "vlb_skybox_project_sh_batched", "vlb_skybox_project_sh_device",
+    "vlb_scene_set_textures", "vlb_gltf_texture", "vlb_skybox_set", "vlb_skybox_project_sh", "vlb_skybox_project_sh_batched", "vlb_skybox_project_sh_device",
     "vlb_skybox_project_sh_device_ptrs", "vlb_envmap_project_sh", "vlb_bake_settings_default", "vlb_bake_settings_from_bounds", "vlb_probe_positions",
     "vlb_bake_probes", "vlb_bake_probes_device", "vlb_bake_gather_device", "vlb_bake_last_stats", "vlb_trace_rays",
     "vlb_bake_serialize_gltf", "vlb_bake_deserialize_gltf",
@@ -162,6 +162,7 @@ def load_library():
         "vlb_scene_bounds": (i32, [vp, i32, vp]),
         "vlb_bvh_build": (i32, [vp, ctypes.POINTER(BvhStats)]),
         "vlb_scene_set_textures": (i32, [vp, vp, u32]),
+        "vlb_gltf_texture": (i32, [ctypes.c_char_p, u32, vp, u64, vp]),
         "vlb_skybox_set": (i32, [vp, vp, i32, i32, i32]),
         "vlb_skybox_project_sh": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "vlb_skybox_project_sh_batched": (i32, [vp, vp, u32, i32, i32, i32, i32, vp]),
@@ -371,6 +372,20 @@ def gltf_probe(path):
         raise VlbError(r, lib.vlb_last_error(None).decode())
     keys = ("vertices", "indices", "instances", "materials", "triangles")
     return dict(zip(keys, (int(c) for c in counts))), bounds
+
+
+def gltf_texture(path, index):
+    """Texture `index` of a glTF as the loader decodes it: dict like pack_textures takes, plus "used"."""
+    lib = load_library()
+    info = np.zeros(6, np.int32)
+    r = lib.vlb_gltf_texture(os.fsencode(path), index, None, 0, _ptr(info))
+    if r != 0:
+        raise VlbError(r, lib.vlb_last_error(None).decode())
+    px = np.zeros((int(info[1]), int(info[0]), 4), np.uint8)
+    r = lib.vlb_gltf_texture(os.fsencode(path), index, _ptr(px), px.nbytes, _ptr(info))
+    if r != 0:
+        raise VlbError(r, lib.vlb_last_error(None).decode())
+    return {"texels": px, "wrap_u": int(info[2]), "wrap_v": int(info[3]), "filter": int(info[4]), "used": bool(info[5])}
 
 
 def serialize_gltf(in_path, out_path, coeffs, settings):

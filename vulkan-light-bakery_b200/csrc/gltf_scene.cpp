@@ -9,8 +9,10 @@
 // the .gltf, or the GLB BIN chunk; node TRS / matrix hierarchies; POSITION / NORMAL / TEXCOORD_0/1
 // float attributes with arbitrary byteStride; u8 / u16 / u32 indices; baseColorFactor and the other
 // factor fields of shader::Factors. Not handled (fail with VLB_ERR_UNSUPPORTED, never silently):
-// sparse accessors, non-triangle primitive modes, Draco / meshopt compression. Textures are
-// recorded in the material table but not sampled by the bake.
+// sparse accessors, non-triangle primitive modes, Draco / meshopt compression. Textures that a material
+// names as baseColorTexture are decoded (PNG, png_decode.cpp) with their samplers (loadTextures /
+// loadSamplers, :941-973, 650-690); the other texture slots are recorded in the material table only, as the
+// bake shader never samples them (env_map.rchit:36-49).
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -25,6 +27,9 @@ namespace vlb {
 namespace {
 
 struct Unsupported : std::runtime_error { using std::runtime_error::runtime_error; };
+}  // namespace
+void png_decode_rgba8(const uint8_t* data, size_t size, std::vector<uint8_t>& rgba, int& width, int& height, bool& unsupported);
+namespace {
 
 bool read_all(const std::string& path, std::string& out) {
     std::ifstream f(path.c_str(), std::ios::binary);
@@ -211,11 +216,14 @@ void load_materials(const Document& doc, std::vector<vlb_material>& out) {
     out.push_back(blank());   // the trailing default material (:851); primitives without a material use it (:510)
 }
 
+struct HostTexture { std::vector<uint8_t> rgba; int width = 1, height = 1, wrap_u = 0, wrap_v = 0, filter = 0; bool used = false; };
+
 struct HostScene {
     std::vector<vlb_vertex> vertices;
     std::vector<uint32_t> indices;
     std::vector<vlb_instance> instances;
     std::vector<vlb_material> materials;
+    std::vector<HostTexture> textures;          // one per glTF texture; only those used as baseColor are decoded
     float ref_bounds[6] = {0, 0, 0, 0, 0, 0};   // Scene_t::bounds starts at the origin (scene_manager.hpp:170)
 };
 
@@ -301,10 +309,90 @@ void load_node(const Document& doc, long long index, const M4& parent_world, Hos
     if (const Json* ch = node.find("children")) for (const Json& c : ch->a) load_node(doc, c.integer_value(), world, hs, depth + 1);
 }
 
+// Bytes of glTF image `index`: data URI, file next to the .gltf, or a bufferView (images in a .glb).
+std::vector<uint8_t> image_bytes(const Document& doc, const std::string& base_dir, long long index) {
+    const Json& images = doc.arr("images");
+    if (index < 0 || (size_t)index >= images.a.size()) throw std::runtime_error("glTF: image index out of range");
+    const Json& img = images.a[(size_t)index];
+    if (const Json* uri = img.find("uri")) {
+        if (uri->s.compare(0, 5, "data:") == 0) {
+            const size_t comma = uri->s.find(',');
+            if (comma == std::string::npos || uri->s.find(";base64") == std::string::npos) throw Unsupported("glTF: image data URI is not base64");
+            return base64_decode(uri->s.substr(comma + 1));
+        }
+        std::string raw;
+        if (!read_all(base_dir + uri->s, raw)) throw std::runtime_error("glTF: cannot read image file " + base_dir + uri->s);
+        return std::vector<uint8_t>(raw.begin(), raw.end());
+    }
+    const Json* bvi = img.find("bufferView");
+    const Json& views = doc.arr("bufferViews");
+    if (!bvi || bvi->integer_value() < 0 || (size_t)bvi->integer_value() >= views.a.size()) throw std::runtime_error("glTF: image without uri or bufferView");
+    const Json& v = views.a[(size_t)bvi->integer_value()];
+    const Json* bi = v.find("buffer");
+    if (!bi || bi->integer_value() < 0 || (size_t)bi->integer_value() >= doc.buffers.size()) throw std::runtime_error("glTF: buffer index out of range");
+    const std::vector<uint8_t>& buf = doc.buffers[(size_t)bi->integer_value()];
+    const size_t off = (size_t)(v.find("byteOffset") ? v.find("byteOffset")->integer_value() : 0);
+    const size_t len = (size_t)(v.find("byteLength") ? v.find("byteLength")->integer_value() : 0);
+    if (off + len > buf.size()) throw std::runtime_error("glTF: image bufferView exceeds its buffer");
+    return std::vector<uint8_t>(buf.begin() + off, buf.begin() + off + len);
+}
+
+// Scene_t::loadSamplers + loadTextures (src/scene_manager.cpp:650-690, 941-973). Texture indices stay those of
+// the glTF `textures` array (material.textures.baseColor.index, matchTextures :785-835); entries that no
+// material uses as baseColor stay 1x1 white placeholders, like the reference's dummy texture (:964-970).
+void load_textures(const Document& doc, const std::string& base_dir, HostScene& hs) {
+    const Json& textures = doc.arr("textures");
+    const Json& samplers = doc.arr("samplers");
+    hs.textures.assign(textures.a.size(), HostTexture());
+    for (HostTexture& t : hs.textures) t.rgba.assign(4, 255);
+    std::vector<char> used(textures.a.size(), 0);
+    for (const vlb_material& m : hs.materials) {
+        if (m.base_color.index < 0) continue;
+        if ((size_t)m.base_color.index >= textures.a.size()) throw std::runtime_error("glTF: baseColorTexture index out of range");
+        used[(size_t)m.base_color.index] = 1;
+    }
+    for (size_t i = 0; i < textures.a.size(); ++i) {
+        if (!used[i]) continue;
+        const Json& jt = textures.a[i];
+        HostTexture& t = hs.textures[i];
+        t.used = true;
+        const Json* si = jt.find("sampler");
+        if (si && si->integer_value() >= 0) {
+            if ((size_t)si->integer_value() >= samplers.a.size()) throw std::runtime_error("glTF: sampler index out of range");
+            const Json& js = samplers.a[(size_t)si->integer_value()];
+            auto wrap = [](const Json* w) {                              // toVkWrapMode (:654-668); glTF default 10497 = repeat
+                const long long g = w ? w->integer_value() : 10497;
+                return g == 33071 ? VLB_WRAP_CLAMP_TO_EDGE : (g == 33648 ? VLB_WRAP_MIRRORED_REPEAT : VLB_WRAP_REPEAT);
+            };
+            auto nearest = [](const Json* f) {                           // toVkFilterMode (:670-680)
+                const long long g = f ? f->integer_value() : -1;
+                return g == 9728 || g == 9984 || g == 9985;
+            };
+            t.wrap_u = wrap(js.find("wrapS")); t.wrap_v = wrap(js.find("wrapT"));
+            // one filter per texture at the base level: the sample is a magnification or a minification depending on
+            // footprint, which a ray-tracing stage does not have; magFilter decides (minFilter only if mag is absent)
+            const Json* mag = js.find("magFilter");
+            t.filter = nearest(mag ? mag : js.find("minFilter")) ? VLB_FILTER_NEAREST : VLB_FILTER_LINEAR;
+        }
+        const Json* src = jt.find("source");
+        if (!src) throw Unsupported("glTF: texture without source (extension-only image) is not supported");
+        const std::vector<uint8_t> bytes = image_bytes(doc, base_dir, src->integer_value());
+        bool unsupported = false;
+        try {
+            png_decode_rgba8(bytes.data(), bytes.size(), t.rgba, t.width, t.height, unsupported);
+        } catch (const std::exception& e) {
+            const std::string msg = "glTF: baseColor texture " + std::to_string(i) + ": " + e.what();
+            if (unsupported) throw Unsupported(msg);
+            throw std::runtime_error(msg);
+        }
+    }
+}
+
 void load_host_scene(const char* path, HostScene& hs) {
     Document doc;
     load_document(path, doc);
     load_materials(doc, hs.materials);
+    load_textures(doc, dir_of(path), hs);
     // Scene_t::loadNodes (:860-871): the roots of scenes[0]
     const Json& scenes = doc.arr("scenes");
     if (scenes.a.empty()) throw std::runtime_error("glTF: no scenes (the reference reads model.scenes[0])");
@@ -339,6 +427,20 @@ int vlb_gltf_probe(const char* path, uint64_t counts[5], float ref_bounds[6]) {
     return VLB_OK;
 }
 
+int vlb_gltf_texture(const char* path, uint32_t index, void* texels, uint64_t capacity, int32_t info[6]) {
+    if (!path || !info) return fail_thread(VLB_ERR_INVALID, "vlb_gltf_texture: NULL argument");
+    try {
+        HostScene hs;
+        load_host_scene(path, hs);
+        if (index >= hs.textures.size()) return fail_thread(VLB_ERR_INVALID, "vlb_gltf_texture: texture index out of range");
+        const HostTexture& t = hs.textures[index];
+        info[0] = t.width; info[1] = t.height; info[2] = t.wrap_u; info[3] = t.wrap_v; info[4] = t.filter; info[5] = t.used ? 1 : 0;
+        if (texels && capacity >= t.rgba.size()) std::memcpy(texels, t.rgba.data(), t.rgba.size());
+    } catch (const Unsupported& e) { return fail_thread(VLB_ERR_UNSUPPORTED, e.what());
+    } catch (const std::exception& e) { return fail_thread(VLB_ERR_IO, e.what()); }
+    return VLB_OK;
+}
+
 int vlb_scene_load_gltf(vlb_ctx* ctx, const char* path) {
     if (!ctx) return VLB_ERR_INVALID;
     if (!path) return ctx->fail(VLB_ERR_INVALID, "vlb_scene_load_gltf: NULL path");
@@ -352,7 +454,13 @@ int vlb_scene_load_gltf(vlb_ctx* ctx, const char* path) {
                                           (uint32_t)hs.materials.size());
     if (r != VLB_OK) return r;
     std::memcpy(ctx->ref_bounds, hs.ref_bounds, sizeof hs.ref_bounds);   // local-matrix quirk, see load_node
-    return VLB_OK;
+    std::vector<vlb_texture> tex(hs.textures.size());
+    for (size_t i = 0; i < tex.size(); ++i) {
+        const HostTexture& t = hs.textures[i];
+        tex[i].texels = t.rgba.data(); tex[i].width = t.width; tex[i].height = t.height;
+        tex[i].wrap_u = t.wrap_u; tex[i].wrap_v = t.wrap_v; tex[i].filter = t.filter; tex[i].reserved = 0;
+    }
+    return vlb_scene_set_textures(ctx, tex.data(), (uint32_t)tex.size());
 }
 
 }  // extern "C"

@@ -304,7 +304,7 @@ def atrium_settings(probes=(16, 8, 16), dirs=(32, 32), order=2, bounds=None):
     return s
 
 
-def write_gltf(scene, path, index_dtype=np.uint16, embed=True):
+def write_gltf(scene, path, index_dtype=np.uint16, embed=True, images_in_views=False):
     """Writes a scene dict (the arrays the C ABI takes) as a glTF 2.0 file: one mesh + one node per
     instance, the instance transform as the node's column-major `matrix`, materials as
     pbrMetallicRoughness.baseColorFactor. Loading the file back with vlb_scene_load_gltf must give
@@ -313,6 +313,7 @@ def write_gltf(scene, path, index_dtype=np.uint16, embed=True):
     import json
     import os
     verts, idx, insts, mats = scene["vertices"], scene["indices"], scene["instances"], scene["materials"]
+    textures = scene.get("textures", [])
     blob = bytearray()
     views, accessors, meshes, nodes = [], [], [], []
 
@@ -341,6 +342,10 @@ def write_gltf(scene, path, index_dtype=np.uint16, embed=True):
         accessors.append({"bufferView": add_view(nrm.tobytes(), 34962), "componentType": 5126, "count": nv, "type": "VEC3"})
         accessors.append({"bufferView": add_view(ii.astype(dt).tobytes(), 34963), "componentType": comp, "count": ni, "type": "SCALAR"})
         prim = {"attributes": {"POSITION": a_pos, "NORMAL": a_pos + 1}, "indices": a_pos + 2}
+        if textures:
+            uv = np.ascontiguousarray(verts["uv0"][fv:fv + nv], np.float32)
+            prim["attributes"]["TEXCOORD_0"] = len(accessors)
+            accessors.append({"bufferView": add_view(uv.tobytes(), 34962), "componentType": 5126, "count": nv, "type": "VEC2"})
         if int(inst["material_index"]) < len(mats):
             prim["material"] = int(inst["material_index"])
         meshes.append({"primitives": [prim]})
@@ -348,10 +353,41 @@ def write_gltf(scene, path, index_dtype=np.uint16, embed=True):
         col_major = [float(m[r, c]) for c in range(4) for r in range(3)]
         matrix = col_major[0:3] + [0.0] + col_major[3:6] + [0.0] + col_major[6:9] + [0.0] + col_major[9:12] + [1.0]
         nodes.append({"mesh": len(meshes) - 1, "matrix": matrix})
+    jmats = []
+    for m in mats:
+        jm = {"pbrMetallicRoughness": {"baseColorFactor": [float(x) for x in m["base_color_factor"]]}}
+        if int(m["textures"][2, 0]) >= 0:
+            jm["pbrMetallicRoughness"]["baseColorTexture"] = {"index": int(m["textures"][2, 0])}
+        jmats.append(jm)
     doc = {"asset": {"version": "2.0", "generator": "vulkan-light-bakery_b200.scenes.write_gltf"},
            "scene": 0, "scenes": [{"nodes": list(range(len(nodes)))}], "nodes": nodes, "meshes": meshes,
-           "materials": [{"pbrMetallicRoughness": {"baseColorFactor": [float(x) for x in m["base_color_factor"]]}} for m in mats],
-           "accessors": accessors, "bufferViews": views}
+           "materials": jmats, "accessors": accessors, "bufferViews": views}
+    if textures:
+        # textures as PNG images (RGB when the alpha is all 255, else RGBA), alternating between data URIs / files and
+        # bufferViews so that both image sources of the loader are exercised; one sampler per texture
+        import io
+        from PIL import Image
+        wrap = {0: 10497, 1: 33071, 2: 33648}
+        doc["images"], doc["samplers"], doc["textures"] = [], [], []
+        for k, t in enumerate(textures):
+            px = np.ascontiguousarray(t["texels"], np.uint8)
+            img = Image.fromarray(px[..., :3], "RGB") if (px[..., 3] == 255).all() and (k & 1) else Image.fromarray(px, "RGBA")
+            buf = io.BytesIO()
+            img.save(buf, format="PNG")
+            png = buf.getvalue()
+            if k % 3 == 0 or images_in_views:
+                doc["images"].append({"bufferView": add_view(png), "mimeType": "image/png"})
+            elif embed:
+                doc["images"].append({"uri": "data:image/png;base64," + base64.b64encode(png).decode()})
+            else:
+                name = "%s_tex%d.png" % (os.path.splitext(os.path.basename(path))[0], k)
+                with open(os.path.join(os.path.dirname(path), name), "wb") as f:
+                    f.write(png)
+                doc["images"].append({"uri": name})
+            nearest = int(t.get("filter", 0)) == 1
+            doc["samplers"].append({"wrapS": wrap[int(t.get("wrap_u", 0))], "wrapT": wrap[int(t.get("wrap_v", 0))],
+                                    "magFilter": 9728 if nearest else 9729, "minFilter": 9728 if nearest else 9987})
+            doc["textures"].append({"source": k, "sampler": k})
     if embed:
         doc["buffers"] = [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(bytes(blob)).decode()}]
     else:
@@ -371,7 +407,7 @@ def write_glb(scene, path):
     import struct
     import tempfile
     with tempfile.TemporaryDirectory() as d:
-        tmp = write_gltf(scene, os.path.join(d, "x.gltf"), embed=False)
+        tmp = write_gltf(scene, os.path.join(d, "x.gltf"), embed=False, images_in_views=True)
         doc = json.load(open(tmp))
         blob = open(os.path.join(d, "x.bin"), "rb").read()
     del doc["buffers"][0]["uri"]
