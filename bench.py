@@ -278,7 +278,7 @@ def run_ours(args):
         alg_bytes = st.n_nodes_visited * 112 + st.n_tris_tested * 48     # per launch (this rank's share)
         peak, peak_src = measured_peaks()
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-        kname = "vlb::k_bake_stream<9,false,false>"
+        kname = "vlb::k_bake_stream<9,false,false,false>"
         roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": ncu_traffic(kname + ":" + which), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": int(alg_bytes),

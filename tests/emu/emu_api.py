@@ -43,6 +43,7 @@ def lib():
         L.emu_scene_max_depth.restype = _i32
         L.emu_scene_max_depth.argtypes = [_vp]
         L.emu_scene_set_skybox.argtypes = [_vp, _vp, _i32, _i32]
+        L.emu_scene_node_stats.argtypes = [_vp, _vp]
         L.emu_scene_set_textures.argtypes = [_vp, _vp, ctypes.c_uint32]
         L.emu_tex_sample.argtypes = [_vp, _i32, _vp, _u64, _vp]
         L.emu_trace_rays.argtypes = [_vp, _vp, _vp, _u64, _f32, _f32, _i32, _vp, _vp, _vp]
@@ -82,6 +83,12 @@ class Scene:
     @property
     def max_depth(self):
         return int(lib().emu_scene_max_depth(self._h))
+
+    def node_stats(self):
+        """(wide nodes, child slots in use, leaf children) of the emitted 4-wide tree."""
+        out = np.zeros(3, np.uint64)
+        lib().emu_scene_node_stats(self._h, _p(out))
+        return tuple(int(x) for x in out)
 
     def set_skybox(self, rgba32f):
         t = np.ascontiguousarray(rgba32f, np.float32)

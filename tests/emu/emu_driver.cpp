@@ -134,10 +134,15 @@ void* emu_scene_create(const vlb_vertex* verts, const uint32_t* indices, const v
             cur = s->parent_i[cur];
         }
     }
-    for (int i = 0; i < (int)n - 1; ++i) {   // k_emit
-        if (i != 0 && (s->last[i] - s->first[i] + 1 <= max_leaf || (node_depth(s->parent_i.data(), i) & 1))) continue;
-        emit_node4(i, s->left.data(), s->right.data(), s->first.data(), s->last.data(), ibox.data(), lbox.data(), max_leaf,
-                   ext * 1e-6f, s->nodes.data());
+    {   // k_emit_level, level by level as bvh_build.cu does
+        std::vector<int> frontier{0}, next(n);
+        while (!frontier.empty()) {
+            unsigned int n_next = 0;
+            for (int root : frontier)
+                emit_node4(root, s->left.data(), s->right.data(), s->first.data(), s->last.data(), ibox.data(), lbox.data(), max_leaf,
+                           ext * 1e-6f, s->nodes.data(), next.data(), &n_next);
+            frontier.assign(next.begin(), next.begin() + n_next);
+        }
     }
     // worst-case number of pending stack entries, by DFS over the emitted nodes (3 pushes per level)
     std::vector<std::pair<int, int>> st; st.push_back({0, 1});
@@ -151,6 +156,24 @@ void* emu_scene_create(const vlb_vertex* verts, const uint32_t* indices, const v
     return s;
 }
 
+// {wide nodes reachable from the root, child slots in use, leaf children} of the emitted tree
+void emu_scene_node_stats(void* h, uint64_t out[3]) {
+    EmuScene* s = (EmuScene*)h;
+    out[0] = out[1] = out[2] = 0;
+    if (s->n == 0) return;
+    std::vector<int> st{0};
+    while (!st.empty()) {
+        const int nd = st.back(); st.pop_back();
+        ++out[0];
+        const float4 refs = s->nodes[(size_t)kNodeQuads * nd + (kNodeQ8 ? 3 : 6)];
+        const int r[4] = {f2i(refs.x), f2i(refs.y), f2i(refs.z), f2i(refs.w)};
+        for (int k = 0; k < 4; ++k) {
+            if (r[k] == kNoChild) continue;
+            ++out[1];
+            if (r[k] < 0) ++out[2]; else st.push_back(r[k]);
+        }
+    }
+}
 void emu_scene_destroy(void* h) { delete (EmuScene*)h; }
 int emu_scene_max_depth(void* h) { return ((EmuScene*)h)->max_depth; }
 // vlb_scene_set_textures, as context.cu lays the atlas out

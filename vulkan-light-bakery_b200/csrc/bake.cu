@@ -149,7 +149,7 @@ struct WarpQueues {
     float lane_rgb[6][32];         // the same two radiances for the shadow ray a lane is tracing
 };
 
-template <int K, bool COUNT, bool GATHER>
+template <int K, bool COUNT, bool GATHER, bool TEX>
 __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : 8) k_bake_stream(const BakeParams p) {
     constexpr int V = (K * 3 <= 32) ? 32 : 64;
     // The per-warp queues live in a global scratch buffer (L1/L2 resident, ~9 KB per resident warp),
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : 8) k_bake_stream(cons
                         const Vec3 r = mk3(t.x, t.z, t.y);
                         float rgb[3] = {0.f, 0.f, 0.f};                                 // env_map.rgen:25
                         if (h.id >= 0) {
-                            const bool lit = shade_prelude(p.shade, p.c, h, po, r, pre);
+                            const bool lit = shade_prelude<TEX>(p.shade, p.c, h, po, r, pre);
                             float ind[3] = {0.f, 0.f, 0.f};
                             // gather passes: the 8 short visibility rays to the surrounding probes are traced
                             // right here, per lane (main.rchit:143-163); only the sun shadow ray is queued
@@ -492,12 +492,15 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     if (env_flag("VLB_BAKE_KERNEL", 2) == 1) {      // the round-1 tile-per-warp kernel, kept for A/B runs
         if (K == 9) kern = count ? k_bake<9, true> : k_bake<9, false>;
         else        kern = count ? k_bake<16, true> : k_bake<16, false>;
-    } else if (gather) {
-        if (K == 9) kern = count ? k_bake_stream<9, true, true> : k_bake_stream<9, false, true>;
-        else        kern = count ? k_bake_stream<16, true, true> : k_bake_stream<16, false, true>;
     } else {
-        if (K == 9) kern = count ? k_bake_stream<9, true, false> : k_bake_stream<9, false, false>;
-        else        kern = count ? k_bake_stream<16, true, false> : k_bake_stream<16, false, false>;
+        // TEX: only scenes with a textured material pay for the texture branch of the hit shading
+        const bool tex = ctx->max_tex_index >= 0;
+#define VLB_PICK(KK) (gather ? (tex ? (count ? k_bake_stream<KK, true, true, true> : k_bake_stream<KK, false, true, true>)     \
+                                    : (count ? k_bake_stream<KK, true, true, false> : k_bake_stream<KK, false, true, false>))   \
+                             : (tex ? (count ? k_bake_stream<KK, true, false, true> : k_bake_stream<KK, false, false, true>)   \
+                                    : (count ? k_bake_stream<KK, true, false, false> : k_bake_stream<KK, false, false, false>)))
+        kern = K == 9 ? VLB_PICK(9) : VLB_PICK(16);
+#undef VLB_PICK
     }
     int per_sm = 0;
     VLB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBakeBlock, 0));

@@ -116,18 +116,17 @@ __global__ void k_refit(int n, const int* __restrict__ left, const int* __restri
     }
 }
 
-// One thread per binary internal node: nodes at even depth that span more than max_leaf triangles
-// (and the root) emit a 4-wide traversal node; the others are absorbed by their parents.
-__global__ void k_emit(int n, const int* __restrict__ left, const int* __restrict__ right,
-                       const int* __restrict__ first, const int* __restrict__ last, const int* __restrict__ parent_i,
-                       const float4* __restrict__ ibox, const float4* __restrict__ lbox, int max_leaf,
-                       const float* __restrict__ scratch, float4* __restrict__ nodes, unsigned int* n_emitted) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    if (i != 0 && (last[i] - first[i] + 1 <= max_leaf || (node_depth(parent_i, i) & 1))) return;
+// One level of the top-down collapse: one thread per wide-node root of the current frontier emits its 4-wide
+// node (emit_node4) and appends the roots of the next level.
+__global__ void k_emit_level(const int* __restrict__ frontier, unsigned int n_frontier, const int* __restrict__ left,
+                             const int* __restrict__ right, const int* __restrict__ first, const int* __restrict__ last,
+                             const float4* __restrict__ ibox, const float4* __restrict__ lbox, int max_leaf,
+                             const float* __restrict__ scratch, float4* __restrict__ nodes, int* __restrict__ next,
+                             unsigned int* n_next) {
+    const unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_frontier) return;
     const float ext = fmaxf(scratch[3] - scratch[0], fmaxf(scratch[4] - scratch[1], scratch[5] - scratch[2]));
-    emit_node4(i, left, right, first, last, ibox, lbox, max_leaf, ext * 1e-6f, nodes);
-    atomicAdd(n_emitted, 1u);
+    emit_node4(frontier[t], left, right, first, last, ibox, lbox, max_leaf, ext * 1e-6f, nodes, next, n_next);
 }
 
 // n == 1: a single node whose only child is the one-triangle leaf.
@@ -192,18 +191,35 @@ int bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats) {
             k_refit<<<grid_n, B, 0, st>>>((int)n, ctx->d_left.as<int>(), ctx->d_right.as<int>(), ctx->d_parent_i.as<int>(),
                                          ctx->d_parent_l.as<int>(), ctx->d_lbox.as<float4>(), ctx->d_ibox.as<float4>(), ctx->d_flags.as<int>());
             VLB_LAUNCH_CHECK(ctx);
-            k_emit<<<grid_n, B, 0, st>>>((int)n, ctx->d_left.as<int>(), ctx->d_right.as<int>(), ctx->d_first.as<int>(), ctx->d_last.as<int>(),
-                                        ctx->d_parent_i.as<int>(), ctx->d_ibox.as<float4>(), ctx->d_lbox.as<float4>(), ctx->max_leaf,
-                                        ctx->d_scratch.as<float>(), ctx->d_nodes.as<float4>(),
-                                        reinterpret_cast<unsigned int*>(ctx->d_scratch.as<float>() + 12));
-            VLB_LAUNCH_CHECK(ctx);
+            // top-down collapse into 4-wide nodes, one launch per level of the wide tree (a few dozen levels; the
+            // frontier size comes back through pinned memory, 4 bytes per level)
+            VLB_CUDA(ctx, ctx->d_frontier[0].reserve(n * sizeof(int)));
+            VLB_CUDA(ctx, ctx->d_frontier[1].reserve(n * sizeof(int)));
+            VLB_CUDA(ctx, ctx->d_frontier_n.reserve(2 * sizeof(unsigned int)));
+            if (!ctx->h_frontier_n) VLB_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_frontier_n), sizeof(unsigned int), cudaHostAllocDefault));
+            VLB_CUDA(ctx, cudaMemsetAsync(ctx->d_frontier[0].p, 0, sizeof(int), st));       // frontier 0 = {root}
+            unsigned int n_front = 1, n_emitted = 0;
+            for (int level = 0; n_front > 0; ++level) {
+                if (level > 4096) return ctx->fail(VLB_ERR_CUDA, "bvh: collapse did not terminate");
+                unsigned int* d_n = ctx->d_frontier_n.as<unsigned int>() + (level & 1);
+                VLB_CUDA(ctx, cudaMemsetAsync(d_n, 0, sizeof(unsigned int), st));
+                k_emit_level<<<(n_front + B - 1) / B, B, 0, st>>>(ctx->d_frontier[level & 1].as<int>(), n_front, ctx->d_left.as<int>(),
+                    ctx->d_right.as<int>(), ctx->d_first.as<int>(), ctx->d_last.as<int>(), ctx->d_ibox.as<float4>(),
+                    ctx->d_lbox.as<float4>(), ctx->max_leaf, ctx->d_scratch.as<float>(), ctx->d_nodes.as<float4>(),
+                    ctx->d_frontier[(level + 1) & 1].as<int>(), d_n);
+                VLB_LAUNCH_CHECK(ctx);
+                n_emitted += n_front;
+                VLB_CUDA(ctx, cudaMemcpyAsync(ctx->h_frontier_n, d_n, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+                VLB_CUDA(ctx, cudaStreamSynchronize(st));
+                n_front = *ctx->h_frontier_n;
+            }
+            ctx->n_nodes = n_emitted;
         }
     }
     VLB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     float h[13];
     VLB_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_scratch.p, sizeof h, cudaMemcpyDeviceToHost, st));
     VLB_CUDA(ctx, cudaStreamSynchronize(st));
-    if (n > 1) { unsigned int ne; memcpy(&ne, &h[12], 4); ctx->n_nodes = ne; }
     VLB_CUDA(ctx, cudaEventElapsedTime(&build_ms, ctx->ev[0], ctx->ev[1]));
     if (n > 0) VLB_CUDA(ctx, cudaEventElapsedTime(&sort_ms, ctx->ev[2], ctx->ev[3]));
     for (int k = 0; k < 6; ++k) ctx->tight_bounds[k] = n ? h[k] : 0.f;

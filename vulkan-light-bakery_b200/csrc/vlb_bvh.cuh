@@ -263,29 +263,48 @@ VLB_HD void store_node4(float4* q, const int* refs, const float4* lo, const floa
     if (kNodeQuads > 7) q[7] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-// Emit the 4-wide traversal node of binary node i (which must sit at even depth and span more than
-// max_leaf triangles, or be the root): its children are i's grandchildren, or i's children where
-// those are leaves.
+// Half surface area of an AABB (the SAH weight of a node).
+VLB_HD float box_half_area(const float4 lo, const float4 hi) {
+    const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+// Emit the 4-wide traversal node rooted at binary node i (i spans more than max_leaf triangles, or is the
+// root). Its children are chosen greedily by surface area, as wide-BVH builders collapse a binary BVH: start
+// from i's two children and keep opening the largest child that is still a big internal node until there are
+// four. An LBVH is unbalanced, so taking the grandchildren level by level leaves many slots empty (2.6 children
+// per node on the atrium); the greedy collapse fills them and opens the boxes a ray is most likely to enter.
+// Children that are big internal nodes become roots of the next wide nodes: they are appended to `next`
+// (atomic counter `n_next`; both may be NULL when the caller walks the tree itself and reads the refs back).
 VLB_HD void emit_node4(int i, const int* left, const int* right, const int* first, const int* last,
-                       const float4* ibox, const float4* lbox, int max_leaf, float abs_pad, float4* nodes) {
+                       const float4* ibox, const float4* lbox, int max_leaf, float abs_pad, float4* nodes,
+                       int* next, unsigned int* n_next) {
+    int c[4] = {left[i], right[i], 0, 0};
+    int n = 2;
+    while (n < 4) {
+        int best = -1;
+        float best_area = -1.0f;
+        for (int k = 0; k < n; ++k) {
+            if (c[k] < 0 || last[c[k]] - first[c[k]] + 1 <= max_leaf) continue;       // a leaf stays closed
+            const float area = box_half_area(ibox[2 * c[k]], ibox[2 * c[k] + 1]);
+            if (area > best_area) { best_area = area; best = k; }
+        }
+        if (best < 0) break;
+        const int open = c[best];
+        c[best] = left[open];
+        c[n++] = right[open];
+    }
     int refs[4] = {kNoChild, kNoChild, kNoChild, kNoChild};
     float4 lo[4], hi[4];
-    int n = 0;
-    const int ch[2] = {left[i], right[i]};
-    for (int c = 0; c < 2; ++c) {
-        int r; float4 l, h;
-        if (classify_child(ch[c], first, last, ibox, lbox, max_leaf, &r, &l, &h)) {
-            const int gc[2] = {left[ch[c]], right[ch[c]]};
-            for (int g = 0; g < 2; ++g) {
-                classify_child(gc[g], first, last, ibox, lbox, max_leaf, &refs[n], &lo[n], &hi[n]);
-                pad_box(&lo[n], &hi[n], abs_pad);
-                ++n;
-            }
-        } else {
-            refs[n] = r; lo[n] = l; hi[n] = h;
-            pad_box(&lo[n], &hi[n], abs_pad);
-            ++n;
+    for (int k = 0; k < n; ++k) {
+        if (classify_child(c[k], first, last, ibox, lbox, max_leaf, &refs[k], &lo[k], &hi[k]) && next) {
+#ifdef __CUDA_ARCH__
+            next[atomicAdd(n_next, 1u)] = c[k];
+#else
+            next[(*n_next)++] = c[k];
+#endif
         }
+        pad_box(&lo[k], &hi[k], abs_pad);
     }
     store_node4(nodes + (size_t)kNodeQuads * i, refs, lo, hi, n);
 }
