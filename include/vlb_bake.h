@@ -273,7 +273,7 @@ int vlb_bake_probes_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_ou
  * is the PREVIOUS pass over the WHOLE grid ([Nx*Ny*Nz][48] floats, x-fastest probe order; the
  * reference's consumer layout, shaders/sh.rmiss:25-28). s->bounces is ignored here: the caller
  * iterates (and, when the grid is sharded over GPUs, all-gathers the slabs between passes).
- * d_prev_full == NULL is the direct pass. The gather operator (shaders/main.rchit:124-163): cell
+ * d_prev_full == NULL is the direct pass; otherwise it must be 16-byte aligned. The gather operator (shaders/main.rchit:124-163): cell
  * ijk = floor((P - origin) / step) clamped into the grid; for its 8 corners in the reference's order
  * a visibility ray from P + bias*N to the corner probe, weight = |step| - distance (clamped at 0),
  * value = sum_i prev[corner][i] * SH_i(N); result = sum(w * value) / sum(w) over visible corners. */

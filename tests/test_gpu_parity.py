@@ -146,6 +146,42 @@ def test_hit_ids_room_bvh_vs_brute_vs_oracle(ctx, vlb, room):
     assert 0.02 < (ib < 0).mean() < 0.9
 
 
+def _soup(vlb, scenes, n_tris, seed, duplicates=False):
+    """n_tris random small triangles in the unit cube as one instance (ragged sizes for the LBVH build: the
+    hand-written radix sort works on tiles of 2,048 pairs, the collapse on levels)."""
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(0.05, 0.95, (n_tris, 1, 3))
+    if duplicates:                                   # many identical centroids -> identical Morton keys (ties by index)
+        c[: n_tris // 2] = c[0]
+    p = (c + rng.normal(size=(n_tris, 3, 3)) * 0.03).reshape(-1, 3).astype(np.float32)
+    v = np.zeros(3 * n_tris, vlb.VERTEX_DTYPE)
+    v["position"][:, :3] = p
+    v["position"][:, 3] = 1.0
+    v["normal"][:, 1] = 1.0
+    inst = np.zeros(1, vlb.INSTANCE_DTYPE)
+    inst["index_count"], inst["vertex_count"] = 3 * n_tris, 3 * n_tris
+    inst["transform"] = scenes.identity12()
+    return {"vertices": v, "indices": np.arange(3 * n_tris, dtype=np.uint32), "instances": inst, "materials": scenes.make_materials()}
+
+
+@pytest.mark.parametrize("n_tris,dup", [(1, False), (2, False), (33, False), (2047, False), (2048, False), (2049, False),
+                                         (4096, True), (50000, False), (300000, True)])
+def test_lbvh_any_size_hit_ids_equal_brute_force(ctx, vlb, scenes, n_tris, dup):
+    ctx.set_scene(_soup(vlb, scenes, n_tris, seed=n_tris, duplicates=dup))
+    st = ctx.build_bvh()
+    assert st.n_triangles == n_tris and st.n_nodes >= 1
+    o, d = _rays(4000 if n_tris > 10000 else 20000, 0.0, 1.0, seed=3)
+    ib, tb = ctx.trace_rays(o, d, accel=vlb.TRACE_BRUTE_FORCE)
+    iv, tv = ctx.trace_rays(o, d, accel=vlb.TRACE_BVH)
+    assert np.array_equal(ib, iv) and np.array_equal(tb, tv)
+    if n_tris >= 33:
+        assert (ib >= 0).any()
+    st2 = ctx.build_bvh()                              # deterministic: same tree again
+    assert st2.n_nodes == st.n_nodes
+    iv2, tv2 = ctx.trace_rays(o, d, accel=vlb.TRACE_BVH)
+    assert np.array_equal(iv, iv2) and np.array_equal(tv, tv2)
+
+
 def test_any_hit_room(ctx, vlb, room):
     sc, osc = room
     ctx.set_scene(sc)

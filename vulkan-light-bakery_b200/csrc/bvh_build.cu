@@ -3,14 +3,15 @@
 //
 //   k_scene_bounds   tight AABB + centroid AABB of the flattened triangles   (reads 48 B/tri)
 //   k_morton         63-bit Morton key of each centroid                       (reads 48 B/tri)
-//   cub radix sort   (key, flat id) pairs, 8 passes over 12 B/tri
+//   radix sort       (key, flat id) pairs, 8 passes of 8 bits (radix_sort.cuh, hand-written)
 //   k_gather         triangles into Morton order + leaf AABBs                 (48 B in, 80 B out)
 //   k_karras         Karras-2012 hierarchy, one thread per internal node
 //   k_refit          bottom-up AABB refit, atomic arrival flags
-//   k_emit           128-byte 4-wide traversal nodes (vlb_bvh.cuh): every second level collapsed, small subtrees -> leaves
-#include <cub/device/device_radix_sort.cuh>
+//   k_emit_level     4-wide traversal nodes (vlb_bvh.cuh), top-down, one launch per level: children chosen greedily by
+//                    surface area, small subtrees -> leaves
 
 #include "vlb_bvh.cuh"
+#include "radix_sort.cuh"
 #include "vlb_context.h"
 
 namespace vlb {
@@ -166,17 +167,17 @@ int bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats) {
                                       ctx->d_keys.as<uint64_t>(), ctx->d_vals.as<uint32_t>());
         VLB_LAUNCH_CHECK(ctx);
 
-        size_t tmp_bytes = 0;
-        VLB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->d_keys.as<uint64_t>(), ctx->d_keys_sorted.as<uint64_t>(),
-                                                      ctx->d_vals.as<uint32_t>(), ctx->d_vals_sorted.as<uint32_t>(), (int)n, 0, 63, st));
-        VLB_CUDA(ctx, ctx->d_sort_tmp.reserve(tmp_bytes));
+        VLB_CUDA(ctx, ctx->d_sort_tmp.reserve(radix_sort_scratch_bytes(n)));
         VLB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
-        VLB_CUDA(ctx, cub::DeviceRadixSort::SortPairs(ctx->d_sort_tmp.p, tmp_bytes, ctx->d_keys.as<uint64_t>(), ctx->d_keys_sorted.as<uint64_t>(),
-                                                      ctx->d_vals.as<uint32_t>(), ctx->d_vals_sorted.as<uint32_t>(), (int)n, 0, 63, st));
-        ctx->launches += 8;   // cub onesweep: histogram + 7 passes for 63 key bits (library kernels)
+        const int where = radix_sort_pairs(ctx->d_keys.as<uint64_t>(), ctx->d_vals.as<uint32_t>(), ctx->d_keys_sorted.as<uint64_t>(),
+                                           ctx->d_vals_sorted.as<uint32_t>(), n, 8, ctx->d_sort_tmp.p, st, nullptr);
+        ctx->launches += 3 * 8 - 1;   // three kernels per pass; the check below counts the last one
+        VLB_LAUNCH_CHECK(ctx);
+        const uint64_t* keys_sorted = where ? ctx->d_keys_sorted.as<uint64_t>() : ctx->d_keys.as<uint64_t>();
+        const uint32_t* vals_sorted = where ? ctx->d_vals_sorted.as<uint32_t>() : ctx->d_vals.as<uint32_t>();
         VLB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
 
-        k_gather<<<grid_n, B, 0, st>>>(ctx->d_tri_flat.as<float4>(), ctx->d_vals_sorted.as<uint32_t>(), n,
+        k_gather<<<grid_n, B, 0, st>>>(ctx->d_tri_flat.as<float4>(), vals_sorted, n,
                                       ctx->d_tris.as<float4>(), ctx->d_lbox.as<float4>());
         VLB_LAUNCH_CHECK(ctx);
         if (n == 1) {
@@ -185,7 +186,7 @@ int bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats) {
             ctx->n_nodes = 1;
         } else {
             VLB_CUDA(ctx, cudaMemsetAsync(ctx->d_flags.p, 0, n * sizeof(int), st));
-            k_karras<<<grid_n, B, 0, st>>>(ctx->d_keys_sorted.as<uint64_t>(), (int)n, ctx->d_left.as<int>(), ctx->d_right.as<int>(),
+            k_karras<<<grid_n, B, 0, st>>>(keys_sorted, (int)n, ctx->d_left.as<int>(), ctx->d_right.as<int>(),
                                           ctx->d_first.as<int>(), ctx->d_last.as<int>(), ctx->d_parent_i.as<int>(), ctx->d_parent_l.as<int>());
             VLB_LAUNCH_CHECK(ctx);
             k_refit<<<grid_n, B, 0, st>>>((int)n, ctx->d_left.as<int>(), ctx->d_right.as<int>(), ctx->d_parent_i.as<int>(),

@@ -487,6 +487,8 @@ int vlb_bake_gather_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float
     if (d_prev_full && (s->flags & (VLB_BAKE_REFERENCE_PROBE_ORDER | VLB_BAKE_ACCUMULATE_ACROSS_PROBES)))
         return ctx->fail(VLB_ERR_INVALID, "bake: a gather pass reads the previous pass in x-fastest order; "
                                           "REFERENCE_PROBE_ORDER / ACCUMULATE_ACROSS_PROBES cannot be combined with it");
+    if (d_prev_full && (reinterpret_cast<uintptr_t>(d_prev_full) & 15u))
+        return ctx->fail(VLB_ERR_INVALID, "vlb_bake_gather_device: d_prev_full must be 16-byte aligned (probe records are read as float4)");
     return bake_device(ctx, s, d_prev_full, d_out);
 }
 

@@ -222,7 +222,15 @@ VLB_HD void gather_indirect(const BvhView& b, const GatherView& g, const ShadePr
         if (tmax > 0.0f)
             occluded = trace_any<COUNT>(b, p.so, mk3(f_div(d.x, tmax), f_div(d.y, tmax), f_div(d.z, tmax)), 0.0f, tmax, cnt, nullptr);  // :155
         if (occluded) continue;
-        const float* sh = g.prev + ((size_t)i + (size_t)g.Nx * ((size_t)j + (size_t)g.Ny * (size_t)k)) * 48;   // sh.rmiss:25
+        const float* shp = g.prev + ((size_t)i + (size_t)g.Nx * ((size_t)j + (size_t)g.Ny * (size_t)k)) * 48;   // sh.rmiss:25
+        // the probe's K x 3 coefficients as 16-byte loads (a probe record is 192 bytes, 16-byte aligned)
+        constexpr int NQ = (K * 3 + 3) / 4;
+        float sh[NQ * 4];
+#pragma unroll
+        for (int q4 = 0; q4 < NQ; ++q4) {
+            const float4 t = ld4(reinterpret_cast<const float4*>(shp) + q4);
+            sh[4 * q4] = t.x; sh[4 * q4 + 1] = t.y; sh[4 * q4 + 2] = t.z; sh[4 * q4 + 3] = t.w;
+        }
         float v0 = 0.f, v1 = 0.f, v2 = 0.f;
 #pragma unroll
         for (int q = 0; q < K; ++q) {                                   // sh.rmiss:27-34

@@ -371,7 +371,7 @@ def write_gltf(scene, path, index_dtype=np.uint16, embed=True, images_in_views=F
         doc["images"], doc["samplers"], doc["textures"] = [], [], []
         for k, t in enumerate(textures):
             px = np.ascontiguousarray(t["texels"], np.uint8)
-            img = Image.fromarray(px[..., :3], "RGB") if (px[..., 3] == 255).all() and (k & 1) else Image.fromarray(px, "RGBA")
+            img = Image.fromarray(np.ascontiguousarray(px[..., :3])) if (px[..., 3] == 255).all() and (k & 1) else Image.fromarray(px)
             buf = io.BytesIO()
             img.save(buf, format="PNG")
             png = buf.getvalue()
