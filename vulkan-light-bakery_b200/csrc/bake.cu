@@ -149,8 +149,11 @@ struct WarpQueues {
     float lane_rgb[6][32];         // the same two radiances for the shadow ray a lane is tracing
 };
 
+#ifndef VLB_BAKE_MIN_BLOCKS
+#define VLB_BAKE_MIN_BLOCKS 8      // resident 128-thread blocks per SM the register allocation is held to (8 -> 64 registers)
+#endif
 template <int K, bool COUNT, bool GATHER, bool TEX>
-__global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : 8) k_bake_stream(const BakeParams p) {
+__global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) k_bake_stream(const BakeParams p) {
     constexpr int V = (K * 3 <= 32) ? 32 : 64;
     // The per-warp queues live in a global scratch buffer (L1/L2 resident, ~9 KB per resident warp),
     // not in shared memory: measured on B200, leaving the SM's 228 KB to the L1 cache (BVH nodes)
