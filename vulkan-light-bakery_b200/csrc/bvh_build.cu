@@ -7,12 +7,16 @@
 //   k_gather         triangles into Morton order + leaf AABBs                 (48 B in, 80 B out)
 //   k_karras         Karras-2012 hierarchy, one thread per internal node
 //   k_refit          bottom-up AABB refit, atomic arrival flags
-//   k_emit_level     4-wide traversal nodes (vlb_bvh.cuh), top-down, one launch per level: children chosen greedily by
+//   k_emit_levels    4-wide traversal nodes (vlb_bvh.cuh), top-down in one cooperative launch: children chosen greedily by
 //                    surface area, small subtrees -> leaves
 
 #include "vlb_bvh.cuh"
+#include <cooperative_groups.h>
+
 #include "radix_sort.cuh"
 #include "vlb_context.h"
+
+namespace cg = cooperative_groups;
 
 namespace vlb {
 
@@ -117,17 +121,33 @@ __global__ void k_refit(int n, const int* __restrict__ left, const int* __restri
     }
 }
 
-// One level of the top-down collapse: one thread per wide-node root of the current frontier emits its 4-wide
-// node (emit_node4) and appends the roots of the next level.
-__global__ void k_emit_level(const int* __restrict__ frontier, unsigned int n_frontier, const int* __restrict__ left,
-                             const int* __restrict__ right, const int* __restrict__ first, const int* __restrict__ last,
-                             const float4* __restrict__ ibox, const float4* __restrict__ lbox, int max_leaf,
-                             const float* __restrict__ scratch, float4* __restrict__ nodes, int* __restrict__ next,
-                             unsigned int* n_next) {
-    const unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_frontier) return;
+// Top-down collapse into 4-wide nodes in ONE cooperative launch: the grid walks the wide tree level by level
+// (grid.sync between levels, no host round trips). Every thread takes wide-node roots of the current frontier,
+// emits their nodes (emit_node4) and appends the roots of the next level. Three rotating counters: the level
+// being read, the one being filled, and the one being cleared for the level after.
+__global__ void __launch_bounds__(256) k_emit_levels(int* __restrict__ frontier_a, int* __restrict__ frontier_b, unsigned int* cnt /*[3]*/,
+                                                     const int* __restrict__ left, const int* __restrict__ right,
+                                                     const int* __restrict__ first, const int* __restrict__ last,
+                                                     const float4* __restrict__ ibox, const float4* __restrict__ lbox, int max_leaf,
+                                                     const float* __restrict__ scratch, float4* __restrict__ nodes,
+                                                     unsigned int* n_emitted) {
+    cg::grid_group grid = cg::this_grid();
     const float ext = fmaxf(scratch[3] - scratch[0], fmaxf(scratch[4] - scratch[1], scratch[5] - scratch[2]));
-    emit_node4(frontier[t], left, right, first, last, ibox, lbox, max_leaf, ext * 1e-6f, nodes, next, n_next);
+    const unsigned int gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+    unsigned int total = 0;
+    for (int level = 0;; ++level) {
+        const unsigned int n_front = *reinterpret_cast<volatile unsigned int*>(cnt + level % 3);
+        if (n_front == 0) break;
+        total += n_front;
+        const int* cur = (level & 1) ? frontier_b : frontier_a;
+        int* next = (level & 1) ? frontier_a : frontier_b;
+        if (gtid == 0) cnt[(level + 2) % 3] = 0;
+        for (unsigned int t = gtid; t < n_front; t += gsize)
+            emit_node4(__ldcg(cur + t), left, right, first, last, ibox, lbox, max_leaf, ext * 1e-6f, nodes, next, cnt + (level + 1) % 3);
+        __threadfence();
+        grid.sync();
+    }
+    if (gtid == 0) *n_emitted = total;
 }
 
 // n == 1: a single node whose only child is the one-triangle leaf.
@@ -192,35 +212,34 @@ int bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats) {
             k_refit<<<grid_n, B, 0, st>>>((int)n, ctx->d_left.as<int>(), ctx->d_right.as<int>(), ctx->d_parent_i.as<int>(),
                                          ctx->d_parent_l.as<int>(), ctx->d_lbox.as<float4>(), ctx->d_ibox.as<float4>(), ctx->d_flags.as<int>());
             VLB_LAUNCH_CHECK(ctx);
-            // top-down collapse into 4-wide nodes, one launch per level of the wide tree (a few dozen levels; the
-            // frontier size comes back through pinned memory, 4 bytes per level)
+            // top-down collapse into 4-wide nodes: one cooperative launch (grid.sync per level of the wide tree)
             VLB_CUDA(ctx, ctx->d_frontier[0].reserve(n * sizeof(int)));
             VLB_CUDA(ctx, ctx->d_frontier[1].reserve(n * sizeof(int)));
-            VLB_CUDA(ctx, ctx->d_frontier_n.reserve(2 * sizeof(unsigned int)));
-            if (!ctx->h_frontier_n) VLB_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_frontier_n), sizeof(unsigned int), cudaHostAllocDefault));
+            VLB_CUDA(ctx, ctx->d_frontier_n.reserve(4 * sizeof(unsigned int)));
+            const unsigned int cnt_init[4] = {1u, 0u, 0u, 0u};
+            VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_frontier_n.p, cnt_init, sizeof cnt_init, cudaMemcpyHostToDevice, st));   // pageable: staged at once
             VLB_CUDA(ctx, cudaMemsetAsync(ctx->d_frontier[0].p, 0, sizeof(int), st));       // frontier 0 = {root}
-            unsigned int n_front = 1, n_emitted = 0;
-            for (int level = 0; n_front > 0; ++level) {
-                if (level > 4096) return ctx->fail(VLB_ERR_CUDA, "bvh: collapse did not terminate");
-                unsigned int* d_n = ctx->d_frontier_n.as<unsigned int>() + (level & 1);
-                VLB_CUDA(ctx, cudaMemsetAsync(d_n, 0, sizeof(unsigned int), st));
-                k_emit_level<<<(n_front + B - 1) / B, B, 0, st>>>(ctx->d_frontier[level & 1].as<int>(), n_front, ctx->d_left.as<int>(),
-                    ctx->d_right.as<int>(), ctx->d_first.as<int>(), ctx->d_last.as<int>(), ctx->d_ibox.as<float4>(),
-                    ctx->d_lbox.as<float4>(), ctx->max_leaf, ctx->d_scratch.as<float>(), ctx->d_nodes.as<float4>(),
-                    ctx->d_frontier[(level + 1) & 1].as<int>(), d_n);
-                VLB_LAUNCH_CHECK(ctx);
-                n_emitted += n_front;
-                VLB_CUDA(ctx, cudaMemcpyAsync(ctx->h_frontier_n, d_n, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
-                VLB_CUDA(ctx, cudaStreamSynchronize(st));
-                n_front = *ctx->h_frontier_n;
-            }
-            ctx->n_nodes = n_emitted;
+            int per_sm = 0;
+            VLB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_emit_levels, 256, 0));
+            const unsigned int grid_c = (unsigned int)std::max(1, std::min(per_sm, 4) * ctx->sm_count);
+            int* fa = ctx->d_frontier[0].as<int>(); int* fb = ctx->d_frontier[1].as<int>();
+            unsigned int* cnt = ctx->d_frontier_n.as<unsigned int>();
+            const int* a_left = ctx->d_left.as<int>(); const int* a_right = ctx->d_right.as<int>();
+            const int* a_first = ctx->d_first.as<int>(); const int* a_last = ctx->d_last.as<int>();
+            const float4* a_ibox = ctx->d_ibox.as<float4>(); const float4* a_lbox = ctx->d_lbox.as<float4>();
+            int a_max_leaf = ctx->max_leaf;
+            const float* a_scratch = ctx->d_scratch.as<float>(); float4* a_nodes = ctx->d_nodes.as<float4>();
+            unsigned int* a_emitted = reinterpret_cast<unsigned int*>(ctx->d_scratch.as<float>() + 12);
+            void* args[] = {&fa, &fb, &cnt, &a_left, &a_right, &a_first, &a_last, &a_ibox, &a_lbox, &a_max_leaf, &a_scratch, &a_nodes, &a_emitted};
+            VLB_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_emit_levels), dim3(grid_c), dim3(256), args, 0, st));
+            VLB_LAUNCH_CHECK(ctx);
         }
     }
     VLB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     float h[13];
     VLB_CUDA(ctx, cudaMemcpyAsync(h, ctx->d_scratch.p, sizeof h, cudaMemcpyDeviceToHost, st));
     VLB_CUDA(ctx, cudaStreamSynchronize(st));
+    if (n > 1) { unsigned int ne; memcpy(&ne, &h[12], 4); ctx->n_nodes = ne; }
     VLB_CUDA(ctx, cudaEventElapsedTime(&build_ms, ctx->ev[0], ctx->ev[1]));
     if (n > 0) VLB_CUDA(ctx, cudaEventElapsedTime(&sort_ms, ctx->ev[2], ctx->ev[3]));
     for (int k = 0; k < 6; ++k) ctx->tight_bounds[k] = n ? h[k] : 0.f;

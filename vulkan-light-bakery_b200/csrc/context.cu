@@ -140,7 +140,6 @@ void vlb_ctx_destroy(vlb_ctx* ctx) {
     }
     if (ctx->lane_fork) cudaEventDestroy(ctx->lane_fork);
     if (ctx->h_bake_stats) cudaFreeHost(ctx->h_bake_stats);
-    if (ctx->h_frontier_n) cudaFreeHost(ctx->h_frontier_n);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }

@@ -70,8 +70,7 @@ struct vlb_ctx {
     vlb::DevBuf d_tris;       // 3 float4 per triangle, Morton order
     vlb::DevBuf d_nodes;      // 4 float4 per node
     vlb::DevBuf d_keys, d_keys_sorted, d_vals, d_vals_sorted, d_sort_tmp;
-    vlb::DevBuf d_frontier[2], d_frontier_n;   // wide-node roots of the current / next level of the collapse
-    unsigned int* h_frontier_n = nullptr;     // pinned
+    vlb::DevBuf d_frontier[2], d_frontier_n;   // wide-node roots of the current / next level of the collapse + level counters
     vlb::DevBuf d_left, d_right, d_first, d_last, d_parent_i, d_parent_l, d_flags, d_ibox, d_lbox, d_scratch;
     uint64_t n_nodes = 0;
     int max_leaf = 3;
