@@ -230,6 +230,11 @@ int vlb_bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats_or_null);
 /* --- skybox (replaces Skybox_t) ---------------------------------------------------------- */
 /* Skybox_t::createTexture (src/skybox_manager.cpp:49-63): the map sampled on ray miss. */
 int vlb_skybox_set(vlb_ctx* ctx, const void* texels, int format, int width, int height);
+/* Same, without blocking: the upload is enqueued on a copy stream of the ctx and the call returns at once; the
+ * next bake (or vlb_ctx_synchronize / vlb_skybox_set) waits for it on the device. `texels` must stay valid and
+ * unchanged until then, and should be pinned host memory for the copy to overlap the calls in between
+ * (scene upload, LBVH build). */
+int vlb_skybox_set_async(vlb_ctx* ctx, const void* texels, int format, int width, int height);
 /* Skybox_t::createSHBuffer + computeSH (src/skybox_manager.cpp:65-76,107-130), i.e. one
  * dispatch of shaders/skybox_sh.comp. out = vec3 coeffs[16] (48 floats); order 2 fills
  * entries 0..8 and zero-fills 9..15. */

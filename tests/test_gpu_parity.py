@@ -295,6 +295,33 @@ def test_bake_reference_probe_order_and_accumulate(ctx, vlb, oa, scenes, room):
     assert rel_l2(acc, osc.bake_probes(a)[0]) <= PROBE_TOL
 
 
+def test_skybox_set_async_equals_blocking_upload(ctx, vlb, scenes, room):
+    """vlb_skybox_set_async: the upload overlaps scene upload + LBVH build; the bake waits for it on the device."""
+    sc, _ = room
+    s = vlb.default_settings()
+    s.probes[:] = (3, 2, 3); s.dir_w, s.dir_h = 32, 16; s.sh_order = 2; s.light_pos[:] = (2.0, 3.5, 2.0)
+    s.flags = vlb.SHADOW_RAYS | vlb.SKYBOX_ON_MISS | vlb.SRGB_ENCODE
+    vlb.settings_from_bounds(s, (0.3, 0.3, 0.3, 3.7, 3.7, 3.7))
+    sky_a, sky_b = scenes.hdr_sky(128, 64, seed=4), scenes.hdr_sky(64, 32, seed=5)
+    sky_u8 = (np.clip(sky_b, 0, 1) * 255).astype(np.uint8)
+    want = {}
+    for name, sky in (("a", sky_a), ("b", sky_b), ("u8", sky_u8)):
+        ctx.set_scene(sc); ctx.build_bvh(); ctx.set_skybox(sky)
+        want[name] = ctx.bake_probes(s)
+    assert not np.array_equal(want["a"], want["b"])
+    for name, sky in (("a", sky_a), ("u8", sky_u8), ("b", sky_b), ("a", sky_a)):
+        ctx.set_skybox_async(sky)            # first, then the calls it overlaps
+        ctx.set_scene(sc)
+        ctx.build_bvh()
+        assert np.array_equal(ctx.bake_probes(s), want[name]), name
+    ctx.set_skybox_async(sky_b)
+    ctx.set_skybox(sky_a)                    # a blocking upload right behind an asynchronous one wins
+    assert np.array_equal(ctx.bake_probes(s), want["a"])
+    ctx.set_skybox_async(sky_b)
+    ctx.synchronize()
+    assert np.array_equal(ctx.bake_probes(s), want["b"])
+
+
 def test_bake_errors(vlb, scenes):
     with vlb.Context(0) as c:
         s = vlb.default_settings()

@@ -128,7 +128,7 @@ class VlbError(RuntimeError):
 ABI_SYMBOLS = [
     "vlb_abi_version", "vlb_ctx_create", "vlb_ctx_destroy", "vlb_ctx_set_stream", "vlb_ctx_synchronize",
     "vlb_last_error", "vlb_ctx_launch_count", "vlb_scene_set_triangles", "vlb_scene_load_gltf", "vlb_gltf_probe", "vlb_scene_bounds", "vlb_bvh_build",
-    "vlb_scene_set_textures", "vlb_gltf_texture", "vlb_skybox_set", "vlb_skybox_project_sh", "vlb_skybox_project_sh_batched", "vlb_skybox_project_sh_device",
+    "vlb_scene_set_textures", "vlb_gltf_texture", "vlb_skybox_set", "vlb_skybox_set_async", "vlb_skybox_project_sh", "vlb_skybox_project_sh_batched", "vlb_skybox_project_sh_device",
     "vlb_skybox_project_sh_device_ptrs", "vlb_envmap_project_sh", "vlb_bake_settings_default", "vlb_bake_settings_from_bounds", "vlb_probe_positions",
     "vlb_bake_probes", "vlb_bake_probes_device", "vlb_bake_gather_device", "vlb_bake_last_stats", "vlb_trace_rays",
     "vlb_bake_serialize_gltf", "vlb_bake_deserialize_gltf",
@@ -164,6 +164,7 @@ def load_library():
         "vlb_scene_set_textures": (i32, [vp, vp, u32]),
         "vlb_gltf_texture": (i32, [ctypes.c_char_p, u32, vp, u64, vp]),
         "vlb_skybox_set": (i32, [vp, vp, i32, i32, i32]),
+        "vlb_skybox_set_async": (i32, [vp, vp, i32, i32, i32]),
         "vlb_skybox_project_sh": (i32, [vp, vp, i32, i32, i32, i32, vp]),
         "vlb_skybox_project_sh_batched": (i32, [vp, vp, u32, i32, i32, i32, i32, vp]),
         "vlb_skybox_project_sh_device": (i32, [vp, vp, u64, u32, i32, i32, i32, i32, vp]),
@@ -300,6 +301,13 @@ class Context:
     def set_skybox(self, texels):
         t, fmt = self._texels(texels)
         self._check(self._lib.vlb_skybox_set(self._h, _ptr(t), fmt, t.shape[1], t.shape[0]))
+
+    def set_skybox_async(self, texels):
+        """vlb_skybox_set_async: returns at once; `texels` (ideally pinned) must stay alive until the next bake /
+        synchronize. The array is kept referenced by the Context until then."""
+        t, fmt = self._texels(texels)
+        self._sky_keep = t
+        self._check(self._lib.vlb_skybox_set_async(self._h, _ptr(t), fmt, t.shape[1], t.shape[0]))
 
     def skybox_project_sh(self, texels, order=3):
         t, fmt = self._texels(texels)

@@ -412,6 +412,7 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     const int kstride = s->slab_stride > 1 ? s->slab_stride : 1;
     const uint64_t n_probes = (uint64_t)Nx * Ny * (uint64_t)((k1 - k0 + kstride - 1) / kstride);
     if (int r = bake_collect_stats(ctx)) return r;     // a previous asynchronous bake still owns the stats buffers
+    if (int r = sky_upload_join(ctx)) return r;        // vlb_skybox_set_async: the bake samples the new texels
     ctx->last_bake = vlb_bake_stats{};
     if (n_probes == 0) return VLB_OK;
     const int W = s->dir_w, H = s->dir_h;

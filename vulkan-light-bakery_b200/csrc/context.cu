@@ -131,6 +131,10 @@ void vlb_ctx_destroy(vlb_ctx* ctx) {
                       &ctx->d_proj_partials, &ctx->d_proj_counters, &ctx->d_row_tab, &ctx->d_col_tab, &ctx->d_bake_out, &ctx->d_bake_prev,
                       &ctx->d_partials, &ctx->d_work_counter, &ctx->d_axis, &ctx->d_row_sc, &ctx->d_col_sc,
                       &ctx->d_stats, &ctx->d_stream_scratch, &ctx->d_ray_o, &ctx->d_ray_d, &ctx->d_hit_id, &ctx->d_hit_tuv, &ctx->d_hit_key};
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    if (ctx->ev_sky_free) cudaEventDestroy(ctx->ev_sky_free);
+    if (ctx->ev_sky_ready) cudaEventDestroy(ctx->ev_sky_ready);
+    ctx->d_sky_stage.release();
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 4; ++i) if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
@@ -150,9 +154,12 @@ int vlb_ctx_set_stream(vlb_ctx* ctx, uint64_t handle) {
     return VLB_OK;
 }
 
+static int join_sky_upload(vlb_ctx* ctx, cudaStream_t st);
+
 int vlb_ctx_synchronize(vlb_ctx* ctx) {
     if (!ctx) return VLB_ERR_INVALID;
     if (int r = check_device(ctx)) return r;
+    if (int r = join_sky_upload(ctx, ctx->stream)) return r;
     VLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return VLB_OK;
 }
@@ -313,11 +320,50 @@ int vlb_bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats) {
     return bvh_build(ctx, stats);
 }
 
+// An asynchronous skybox upload still in flight is ordered before whatever `st` does next.
+static int join_sky_upload(vlb_ctx* ctx, cudaStream_t st) {
+    if (ctx->sky_upload_pending) {
+        VLB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_sky_ready, 0));
+        ctx->sky_upload_pending = false;
+    }
+    return VLB_OK;
+}
+
+int vlb_skybox_set_async(vlb_ctx* ctx, const void* texels, int format, int width, int height) {
+    if (!ctx) return VLB_ERR_INVALID;
+    if (int r = check_device(ctx)) return r;
+    if (!texels || width <= 0 || height <= 0 || (format != VLB_FMT_RGBA8 && format != VLB_FMT_RGBA32F))
+        return ctx->fail(VLB_ERR_INVALID, "vlb_skybox_set_async: bad arguments");
+    const size_t n = (size_t)width * height;
+    if (!ctx->copy_stream) {
+        VLB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        VLB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_sky_free, cudaEventDisableTiming));
+        VLB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_sky_ready, cudaEventDisableTiming));
+    }
+    VLB_CUDA(ctx, ctx->d_sky.reserve(n * sizeof(float4)));
+    // whatever the ctx stream has queued (a bake sampling the old skybox) finishes before the texels are replaced
+    VLB_CUDA(ctx, cudaEventRecord(ctx->ev_sky_free, ctx->stream));
+    VLB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_sky_free, 0));
+    if (format == VLB_FMT_RGBA32F) {
+        VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_sky.p, texels, n * sizeof(float4), cudaMemcpyHostToDevice, ctx->copy_stream));
+    } else {
+        VLB_CUDA(ctx, ctx->d_sky_stage.reserve(n * 4));
+        VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_sky_stage.p, texels, n * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+        k_rgba8_to_f32<<<(unsigned)((n + 255) / 256), 256, 0, ctx->copy_stream>>>(ctx->d_sky_stage.as<uchar4>(), ctx->d_sky.as<float4>(), n);
+        VLB_LAUNCH_CHECK(ctx);
+    }
+    VLB_CUDA(ctx, cudaEventRecord(ctx->ev_sky_ready, ctx->copy_stream));
+    ctx->sky_upload_pending = true;
+    ctx->sky_w = width; ctx->sky_h = height;
+    return VLB_OK;
+}
+
 int vlb_skybox_set(vlb_ctx* ctx, const void* texels, int format, int width, int height) {
     if (!ctx) return VLB_ERR_INVALID;
     if (int r = check_device(ctx)) return r;
     if (!texels || width <= 0 || height <= 0 || (format != VLB_FMT_RGBA8 && format != VLB_FMT_RGBA32F))
         return ctx->fail(VLB_ERR_INVALID, "vlb_skybox_set: bad arguments");
+    if (int r = join_sky_upload(ctx, ctx->stream)) return r;
     const size_t n = (size_t)width * height;
     VLB_CUDA(ctx, ctx->d_sky.reserve(n * sizeof(float4)));
     if (format == VLB_FMT_RGBA32F) {
@@ -555,3 +601,7 @@ int vlb_trace_rays(vlb_ctx* ctx, const float* origins, const float* dirs, uint64
 }
 
 }  // extern "C"
+
+namespace vlb {
+int sky_upload_join(vlb_ctx* ctx) { return join_sky_upload(ctx, ctx->stream); }
+}  // namespace vlb

@@ -77,6 +77,11 @@ struct vlb_ctx {
     // ---- skybox ----
     vlb::DevBuf d_sky;        // RGBA32F
     int sky_w = 0, sky_h = 0;
+    // vlb_skybox_set_async: the upload runs on its own stream, the next bake waits for it
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_sky_free = nullptr, ev_sky_ready = nullptr;
+    bool sky_upload_pending = false;
+    vlb::DevBuf d_sky_stage;  // RGBA8 staging of an asynchronous upload
     // ---- projection (skybox / envmap) ----
     vlb::DevBuf d_proj_in, d_proj_out, d_proj_partials, d_proj_counters, d_row_tab, d_col_tab;
     int tab_w = 0, tab_h = 0, tab_variant = -1;
@@ -136,6 +141,7 @@ int project_sh_device(vlb_ctx* ctx, const void* d_texels, uint64_t map_stride, u
                       int W, int H, int order, int variant, float* d_out, int lane = -1);
 int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_full, float* d_out);
 int bake_collect_stats(vlb_ctx* ctx);
+int sky_upload_join(vlb_ctx* ctx);     // context.cu: orders a pending vlb_skybox_set_async before the ctx stream's next work
 int trace_rays(vlb_ctx* ctx, const float* o, const float* d, uint64_t n, float tmin, float tmax, int accel,
                int kind, int32_t* ids, float* tuv);
 }  // namespace vlb
