@@ -183,9 +183,9 @@ def test_png_reader_filters_palette_grey_and_errors(vlb, scenes, tmp_path):
     got = vlb.gltf_texture(with_image(png(Image.fromarray(rgba)), "rgba.gltf"), 0)
     assert np.array_equal(got["texels"], rgba)
     # unsupported / broken inputs fail loudly with the right code
-    b = io.BytesIO(); Image.fromarray(rgb).save(b, format="JPEG")
+    b = io.BytesIO(); Image.fromarray(rgb).save(b, format="BMP")
     with pytest.raises(vlb.VlbError) as e:
-        vlb.gltf_texture(with_image(b.getvalue(), "jpeg.gltf"), 0)
+        vlb.gltf_texture(with_image(b.getvalue(), "bmp.gltf"), 0)
     assert e.value.code == vlb.ERR_UNSUPPORTED
     wide = Image.fromarray(np.ascontiguousarray((rgb.astype(np.uint16) * 257)[..., 0]))
     with pytest.raises(vlb.VlbError) as e:
@@ -204,6 +204,54 @@ def test_png_reader_filters_palette_grey_and_errors(vlb, scenes, tmp_path):
     json.dump(d, open(str(tmp_path / "unused.gltf"), "w"))
     got = vlb.gltf_texture(str(tmp_path / "unused.gltf"), 0)
     assert not got["used"] and got["texels"].shape == (1, 1, 4)
+
+
+def test_jpeg_reader_vs_libjpeg(vlb, scenes, tmp_path):
+    """csrc/jpeg_decode.cpp (baseline Huffman JPEG) against libjpeg through PIL. JPEG decoding is not bit-normative
+    (IDCT / chroma upsampling arithmetic differ between decoders: "parity unpinned"), so the band is a few levels."""
+    import io
+    import json
+    import base64
+    from PIL import Image
+    rng = np.random.default_rng(1)
+    sc = scenes.small_room()
+    sc["materials"]["textures"][0, 2, 0] = 0
+    doc = json.load(open(scenes.write_gltf(sc, str(tmp_path / "base.gltf"))))
+
+    def with_image(data, name):
+        d = dict(doc)
+        d["images"] = [{"uri": "data:image/jpeg;base64," + base64.b64encode(data).decode()}]
+        d["textures"] = [{"source": 0}]
+        p = str(tmp_path / name)
+        json.dump(d, open(p, "w"))
+        return p
+
+    y, x = np.mgrid[0:97, 0:131]                                   # not a multiple of the MCU size
+    rgb = np.stack([(x * 2) % 256, (y * 3) % 256, (x + y) % 256], -1).astype(np.uint8)
+    rgb[20:50, 30:90] = rng.integers(0, 256, (30, 60, 3), dtype=np.uint8)
+    cases = {"444": dict(subsampling=0), "422": dict(subsampling=1), "420": dict(subsampling=2), "q50": dict(quality=50),
+             "huffopt": dict(optimize=True, quality=90), "restart": dict(quality=85, restart_marker_blocks=3)}
+    for name, kw in cases.items():
+        b = io.BytesIO()
+        Image.fromarray(rgb).save(b, format="JPEG", **({"quality": 92} | kw))
+        ref = np.asarray(Image.open(io.BytesIO(b.getvalue())).convert("RGB")).astype(int)
+        got = vlb.gltf_texture(with_image(b.getvalue(), name + ".gltf"), 0)["texels"]
+        assert got.shape == (97, 131, 4) and (got[..., 3] == 255).all()
+        diff = np.abs(got[..., :3].astype(int) - ref)
+        assert diff.max() <= 6 and diff.mean() <= 0.6, (name, diff.max(), diff.mean())
+    g = io.BytesIO()
+    Image.fromarray(np.ascontiguousarray(rgb[..., 0])).save(g, format="JPEG", quality=90)
+    ref = np.asarray(Image.open(io.BytesIO(g.getvalue()))).astype(int)
+    got = vlb.gltf_texture(with_image(g.getvalue(), "grey.gltf"), 0)["texels"]
+    assert np.abs(got[..., 0].astype(int) - ref).max() <= 2 and np.array_equal(got[..., 0], got[..., 2])
+    pr = io.BytesIO()
+    Image.fromarray(rgb).save(pr, format="JPEG", progressive=True)
+    with pytest.raises(vlb.VlbError) as e:
+        vlb.gltf_texture(with_image(pr.getvalue(), "progressive.gltf"), 0)
+    assert e.value.code == vlb.ERR_UNSUPPORTED
+    with pytest.raises(vlb.VlbError) as e:
+        vlb.gltf_texture(with_image(b.getvalue()[: len(b.getvalue()) // 2], "cut.gltf"), 0)
+    assert e.value.code == vlb.ERR_IO
 
 
 @pytest.mark.gpu

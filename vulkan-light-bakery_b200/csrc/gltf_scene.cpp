@@ -10,7 +10,7 @@
 // float attributes with arbitrary byteStride; u8 / u16 / u32 indices; baseColorFactor and the other
 // factor fields of shader::Factors. Not handled (fail with VLB_ERR_UNSUPPORTED, never silently):
 // sparse accessors, non-triangle primitive modes, Draco / meshopt compression. Textures that a material
-// names as baseColorTexture are decoded (PNG, png_decode.cpp) with their samplers (loadTextures /
+// names as baseColorTexture are decoded (PNG: png_decode.cpp, baseline JPEG: jpeg_decode.cpp) with their samplers (loadTextures /
 // loadSamplers, :941-973, 650-690); the other texture slots are recorded in the material table only, as the
 // bake shader never samples them (env_map.rchit:36-49).
 #include <cmath>
@@ -29,6 +29,7 @@ namespace {
 struct Unsupported : std::runtime_error { using std::runtime_error::runtime_error; };
 }  // namespace
 void png_decode_rgba8(const uint8_t* data, size_t size, std::vector<uint8_t>& rgba, int& width, int& height, bool& unsupported);
+void jpeg_decode_rgba8(const uint8_t* data, size_t size, std::vector<uint8_t>& rgba, int& width, int& height, bool& unsupported);
 namespace {
 
 bool read_all(const std::string& path, std::string& out) {
@@ -379,7 +380,10 @@ void load_textures(const Document& doc, const std::string& base_dir, HostScene& 
         const std::vector<uint8_t> bytes = image_bytes(doc, base_dir, src->integer_value());
         bool unsupported = false;
         try {
-            png_decode_rgba8(bytes.data(), bytes.size(), t.rgba, t.width, t.height, unsupported);
+            if (bytes.size() >= 2 && bytes[0] == 0xFF && bytes[1] == 0xD8)
+                jpeg_decode_rgba8(bytes.data(), bytes.size(), t.rgba, t.width, t.height, unsupported);
+            else
+                png_decode_rgba8(bytes.data(), bytes.size(), t.rgba, t.width, t.height, unsupported);
         } catch (const std::exception& e) {
             const std::string msg = "glTF: baseColor texture " + std::to_string(i) + ": " + e.what();
             if (unsupported) throw Unsupported(msg);

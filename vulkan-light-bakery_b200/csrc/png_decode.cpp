@@ -29,7 +29,7 @@ void png_decode_rgba8(const uint8_t* data, size_t size, std::vector<uint8_t>& rg
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
     if (size < 8 || std::memcmp(data, sig, 8) != 0) {
         unsupported = true;
-        throw std::runtime_error("image is not a PNG (only PNG textures are decoded)");
+        throw std::runtime_error("image is neither PNG nor JPEG (only those are decoded)");
     }
     uint32_t W = 0, H = 0;
     int depth = 0, ctype = -1, interlace = 0;
