@@ -229,6 +229,11 @@ int vlb_scene_bounds(vlb_ctx* ctx, int tight, float out_min_max[6]);
 int vlb_bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats_or_null);
 
 /* --- skybox (replaces Skybox_t) ---------------------------------------------------------- */
+/* Host-only: decode an image file into RGBA8 texels, as the reference's stbi_load(file, &w, &h, &ch, STBI_rgb_alpha)
+ * does for skyboxes (Skybox_t ctor, src/skybox_manager.cpp:14-20). PNG and baseline JPEG (see vlb_scene_load_gltf for
+ * the exact subsets). size[2] = {width, height}; texels may be NULL to query the size first; it receives
+ * width*height*4 bytes if capacity allows. Feed the result to vlb_skybox_set / vlb_skybox_project_sh (VLB_FMT_RGBA8). */
+int vlb_image_load_rgba8(const char* path, void* texels, uint64_t capacity_bytes, int32_t size[2]);
 /* Skybox_t::createTexture (src/skybox_manager.cpp:49-63): the map sampled on ray miss. */
 int vlb_skybox_set(vlb_ctx* ctx, const void* texels, int format, int width, int height);
 /* Same, without blocking: the upload is enqueued on a copy stream of the ctx and the call returns at once; the

@@ -267,3 +267,53 @@ def test_loaded_textured_scene_bakes_like_the_array_scene(ctx, vlb, scenes, tmp_
     ctx.build_bvh()
     b = ctx.bake_probes(s)
     assert rel_l2(b, a) <= 1e-5          # normals are re-normalised by the loader: last-ulp differences only
+
+
+def test_image_file_loader_for_skyboxes(vlb, tmp_path):
+    """vlb_image_load_rgba8 = the reference's stbi_load(file, ..., STBI_rgb_alpha) for skyboxes (skybox_manager.cpp:14-20)."""
+    from PIL import Image
+    rng = np.random.default_rng(3)
+    rgb = rng.integers(0, 256, (32, 64, 3), dtype=np.uint8)
+    Image.fromarray(rgb).save(str(tmp_path / "sky.png"))
+    px = vlb.image_load_rgba8(str(tmp_path / "sky.png"))
+    assert px.shape == (32, 64, 4) and np.array_equal(px[..., :3], rgb) and (px[..., 3] == 255).all()
+    smooth = np.zeros((32, 64, 3), np.uint8)
+    smooth[..., 0] = np.linspace(0, 255, 64)[None, :]
+    smooth[..., 1] = np.linspace(0, 255, 32)[:, None]
+    Image.fromarray(smooth).save(str(tmp_path / "sky.jpg"), quality=95)
+    pj = vlb.image_load_rgba8(str(tmp_path / "sky.jpg"))
+    assert pj.shape == (32, 64, 4) and np.abs(pj[..., :3].astype(int) - smooth).max() <= 8
+    with pytest.raises(vlb.VlbError) as e:
+        vlb.image_load_rgba8(str(tmp_path / "missing.png"))
+    assert e.value.code == vlb.ERR_IO
+    open(str(tmp_path / "junk.png"), "wb").write(b"not an image")
+    with pytest.raises(vlb.VlbError) as e:
+        vlb.image_load_rgba8(str(tmp_path / "junk.png"))
+    assert e.value.code == vlb.ERR_UNSUPPORTED
+
+
+@pytest.mark.gpu
+def test_cli_with_skybox_image_and_textures(ctx, vlb, scenes, tmp_path):
+    """vlb_baker on a textured glTF with --skybox: equals the ABI calls with the same decoded inputs."""
+    import os
+    import subprocess
+    from PIL import Image
+    sc = scenes.small_room_textured()
+    p = scenes.write_gltf(sc, str(tmp_path / "room.gltf"))
+    sky8 = (np.clip(scenes.hdr_sky(64, 32, seed=2), 0, 1) * 255).astype(np.uint8)
+    sky8[..., 3] = 255
+    Image.fromarray(sky8).save(str(tmp_path / "sky.png"))
+    exe = os.path.join(os.path.dirname(vlb.LIB_PATH), "vlb_baker")
+    r = subprocess.run([exe, p, "--probes", "3x2x3", "--dirs", "32x16", "--light", "2,3.5,2", "--skybox", str(tmp_path / "sky.png")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr + r.stdout
+    coeffs, _ = vlb.deserialize_gltf(str(tmp_path / "baked_room.gltf"))
+    ctx.load_gltf(p)
+    ctx.build_bvh()
+    ctx.set_skybox(vlb.image_load_rgba8(str(tmp_path / "sky.png")))
+    s = vlb.default_settings()
+    s.probes[:] = (3, 2, 3); s.dir_w, s.dir_h = 32, 16; s.light_pos[:] = (2.0, 3.5, 2.0)
+    s.flags |= vlb.SKYBOX_ON_MISS
+    vlb.settings_from_bounds(s, ctx.scene_bounds(tight=False))
+    want = ctx.bake_probes(s)
+    assert np.array_equal(np.asarray(coeffs).reshape(want.shape), want)

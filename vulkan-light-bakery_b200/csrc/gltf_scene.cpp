@@ -431,6 +431,25 @@ int vlb_gltf_probe(const char* path, uint64_t counts[5], float ref_bounds[6]) {
     return VLB_OK;
 }
 
+int vlb_image_load_rgba8(const char* path, void* texels, uint64_t capacity, int32_t size[2]) {
+    if (!path || !size) return fail_thread(VLB_ERR_INVALID, "vlb_image_load_rgba8: NULL argument");
+    std::string raw;
+    if (!read_all(path, raw)) return fail_thread(VLB_ERR_IO, std::string("cannot read ") + path);
+    const uint8_t* d = reinterpret_cast<const uint8_t*>(raw.data());
+    std::vector<uint8_t> rgba;
+    int w = 0, h = 0;
+    bool unsupported = false;
+    try {
+        if (raw.size() >= 2 && d[0] == 0xFF && d[1] == 0xD8) jpeg_decode_rgba8(d, raw.size(), rgba, w, h, unsupported);
+        else png_decode_rgba8(d, raw.size(), rgba, w, h, unsupported);
+    } catch (const std::exception& e) {
+        return fail_thread(unsupported ? VLB_ERR_UNSUPPORTED : VLB_ERR_IO, std::string(path) + ": " + e.what());
+    }
+    size[0] = w; size[1] = h;
+    if (texels && capacity >= rgba.size()) std::memcpy(texels, rgba.data(), rgba.size());
+    return VLB_OK;
+}
+
 int vlb_gltf_texture(const char* path, uint32_t index, void* texels, uint64_t capacity, int32_t info[6]) {
     if (!path || !info) return fail_thread(VLB_ERR_INVALID, "vlb_gltf_texture: NULL argument");
     try {

@@ -23,7 +23,7 @@
 namespace {
 
 struct Options {
-    std::string scene, out;
+    std::string scene, out, skybox;
     int probes[3] = {0, 0, 0};      // 0 = reference default
     int dirs[2] = {0, 0};
     int order = 0;
@@ -81,6 +81,7 @@ void usage() {
          "  --no-shadows --no-srgb --quantize8 --reference-order --world-frame   behaviour flags (vlb_bake.h)\n"
          "  --device N           CUDA device (default 0)\n"
          "  --out path           output file (default baked_<scene>)\n"
+         "  --skybox image       equirect PNG / JPEG sampled where a ray leaves the scene (main.rmiss:18-40); default: none\n"
          "  --dry-run            parse the scene and print what would be baked; needs no GPU");
 }
 
@@ -111,6 +112,7 @@ int main(int argc, char** argv) {
         else if (a == "--gain") { o.gain = strtof(need("--gain"), nullptr); }
         else if (a == "--device") { o.device = atoi(need("--device")); }
         else if (a == "--out") { o.out = need("--out"); }
+        else if (a == "--skybox") { o.skybox = need("--skybox"); }
         else if (a == "--tight-bounds") o.tight = true;
         else if (a == "--no-shadows") o.flags_clear |= VLB_BAKE_SHADOW_RAYS;
         else if (a == "--no-srgb") o.flags_clear |= VLB_BAKE_SRGB_ENCODE;
@@ -135,9 +137,10 @@ int main(int argc, char** argv) {
     if (o.dirs[0]) { s.dir_w = o.dirs[0]; s.dir_h = o.dirs[1]; }
     if (o.order) s.sh_order = o.order;
     if (o.have_light) for (int k = 0; k < 3; ++k) s.light_pos[k] = o.light[k];
-    // no skybox can be given on this command line (decoding image files is outside the bake path), and the
-    // reference's own bake pipeline has no skybox bound either: misses contribute 0
-    s.flags = (s.flags | o.flags_set) & ~(o.flags_clear | VLB_BAKE_SKYBOX_ON_MISS);
+    // without --skybox misses contribute 0, as in the reference's own bake pipeline, which binds no skybox
+    // (SURVEY App. B-5); with it the evident intent of main.rmiss is what runs
+    s.flags = (s.flags | o.flags_set) & ~o.flags_clear;
+    if (o.skybox.empty()) s.flags &= ~(unsigned)VLB_BAKE_SKYBOX_ON_MISS; else s.flags |= VLB_BAKE_SKYBOX_ON_MISS;
     s.bounces = o.bounces;
     if (o.gain >= 0.f) s.indirect_gain = o.gain;
 
@@ -166,6 +169,14 @@ int main(int argc, char** argv) {
         }
     };
     check(vlb_scene_load_gltf(ctx, o.scene.c_str()));                        // LightBaker ctor, light_baker.cpp:40-53
+    if (!o.skybox.empty()) {                                                  // Skybox_t ctor: stbi_load -> RGBA8 (skybox_manager.cpp:14-20)
+        int32_t wh[2] = {0, 0};
+        if (vlb_image_load_rgba8(o.skybox.c_str(), nullptr, 0, wh) != VLB_OK) { const std::string m = vlb_last_error(nullptr); vlb_ctx_destroy(ctx); die(m); }
+        std::vector<unsigned char> px((size_t)wh[0] * wh[1] * 4);
+        if (vlb_image_load_rgba8(o.skybox.c_str(), px.data(), px.size(), wh) != VLB_OK) { const std::string m = vlb_last_error(nullptr); vlb_ctx_destroy(ctx); die(m); }
+        check(vlb_skybox_set(ctx, px.data(), VLB_FMT_RGBA8, wh[0], wh[1]));
+        printf("skybox %s: %dx%d\n", o.skybox.c_str(), wh[0], wh[1]);
+    }
     vlb_bvh_stats bs;
     check(vlb_bvh_build(ctx, &bs));                                          // Scene_t::buildAccelerationStructures
     float bounds[6];
