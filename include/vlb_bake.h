@@ -234,6 +234,10 @@ int vlb_bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats_or_null);
  * the exact subsets). size[2] = {width, height}; texels may be NULL to query the size first; it receives
  * width*height*4 bytes if capacity allows. Feed the result to vlb_skybox_set / vlb_skybox_project_sh (VLB_FMT_RGBA8). */
 int vlb_image_load_rgba8(const char* path, void* texels, uint64_t capacity_bytes, int32_t size[2]);
+/* Host-only: decode a Radiance RGBE (.hdr) file into linear RGBA32F texels (alpha 1): the usual container of the
+ * RGBA32F equirect skyboxes the BASELINE configs use. Same calling convention as vlb_image_load_rgba8; texels
+ * receives width*height*16 bytes. Feed the result to vlb_skybox_set / vlb_skybox_project_sh (VLB_FMT_RGBA32F). */
+int vlb_image_load_rgba32f(const char* path, void* texels, uint64_t capacity_bytes, int32_t size[2]);
 /* Skybox_t::createTexture (src/skybox_manager.cpp:49-63): the map sampled on ray miss. */
 int vlb_skybox_set(vlb_ctx* ctx, const void* texels, int format, int width, int height);
 /* Same, without blocking: the upload is enqueued on a copy stream of the ctx and the call returns at once; the

@@ -317,3 +317,60 @@ def test_cli_with_skybox_image_and_textures(ctx, vlb, scenes, tmp_path):
     vlb.settings_from_bounds(s, ctx.scene_bounds(tight=False))
     want = ctx.bake_probes(s)
     assert np.array_equal(np.asarray(coeffs).reshape(want.shape), want)
+
+
+def test_radiance_hdr_loader(vlb, scenes, tmp_path):
+    """vlb_image_load_rgba32f: Radiance RGBE -> linear RGBA32F (csrc/hdr_decode.cpp), flat and run-length coded
+    scanlines; checked against the source within RGBE's 8-bit mantissa and, when OpenCV is there, exactly against it."""
+    sky = scenes.hdr_sky(128, 64, seed=3)[..., :3]
+
+    def to_rgbe(rgb):
+        m = rgb.max(-1)
+        e = np.where(m > 1e-32, np.floor(np.log2(np.maximum(m, 1e-38))) + 1, 0).astype(int)      # m < 2^e
+        scale = np.where(m > 1e-32, 256.0 / np.exp2(e), 0.0)
+        out = np.zeros(rgb.shape[:2] + (4,), np.uint8)
+        out[..., :3] = np.clip(np.floor(rgb * scale[..., None]), 0, 255).astype(np.uint8)
+        out[..., 3] = np.where(m > 1e-32, e + 128, 0).astype(np.uint8)
+        return out
+
+    rgbe = to_rgbe(sky)
+    flat = b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y 64 +X 128\n" + rgbe.tobytes()
+    open(str(tmp_path / "flat.hdr"), "wb").write(flat)
+    px = vlb.image_load_rgba32f(str(tmp_path / "flat.hdr"))
+    assert px.shape == (64, 128, 4) and (px[..., 3] == 1).all()
+    want = rgbe[..., :3].astype(np.float32) * np.exp2(rgbe[..., 3:4].astype(np.float32) - 136)
+    assert np.array_equal(px[..., :3], want)
+    assert np.abs(px[..., :3] - sky).max() <= sky.max() / 128
+    # new-style RLE: every scanline = 2 2 hi lo, then the 4 channels as runs / literals
+    body = bytearray()
+    for y in range(64):
+        body += bytes([2, 2, 0, 128])
+        for c in range(4):
+            ch = rgbe[y, :, c]
+            x = 0
+            while x < 128:
+                run = 1
+                while x + run < 128 and run < 127 and ch[x + run] == ch[x]:
+                    run += 1
+                if run >= 3:
+                    body += bytes([128 + run, int(ch[x])]); x += run
+                else:
+                    n = min(128 - x, 5)
+                    body += bytes([n]) + ch[x:x + n].tobytes(); x += n
+    open(str(tmp_path / "rle.hdr"), "wb").write(b"#?RADIANCE\n# made by the test\nFORMAT=32-bit_rle_rgbe\n\n-Y 64 +X 128\n" + bytes(body))
+    assert np.array_equal(vlb.image_load_rgba32f(str(tmp_path / "rle.hdr")), px)
+    try:
+        import cv2
+    except ImportError:
+        cv2 = None
+    if cv2 is not None and cv2.imwrite(str(tmp_path / "cv.hdr"), np.ascontiguousarray(sky[..., ::-1])):
+        ref = cv2.imread(str(tmp_path / "cv.hdr"), cv2.IMREAD_UNCHANGED)[..., ::-1]
+        assert np.array_equal(vlb.image_load_rgba32f(str(tmp_path / "cv.hdr"))[..., :3], ref)
+    open(str(tmp_path / "cut.hdr"), "wb").write(flat[: len(flat) // 2])
+    with pytest.raises(vlb.VlbError) as e:
+        vlb.image_load_rgba32f(str(tmp_path / "cut.hdr"))
+    assert e.value.code == vlb.ERR_IO
+    open(str(tmp_path / "xy.hdr"), "wb").write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n+Y 64 +X 128\n" + rgbe.tobytes())
+    with pytest.raises(vlb.VlbError) as e:
+        vlb.image_load_rgba32f(str(tmp_path / "xy.hdr"))
+    assert e.value.code == vlb.ERR_UNSUPPORTED

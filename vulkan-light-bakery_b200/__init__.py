@@ -128,7 +128,7 @@ class VlbError(RuntimeError):
 ABI_SYMBOLS = [
     "vlb_abi_version", "vlb_ctx_create", "vlb_ctx_destroy", "vlb_ctx_set_stream", "vlb_ctx_synchronize",
     "vlb_last_error", "vlb_ctx_launch_count", "vlb_scene_set_triangles", "vlb_scene_load_gltf", "vlb_gltf_probe", "vlb_scene_bounds", "vlb_bvh_build",
-    "vlb_scene_set_textures", "vlb_gltf_texture", "vlb_image_load_rgba8", "vlb_skybox_set", "vlb_skybox_set_async", "vlb_skybox_project_sh", "vlb_skybox_project_sh_batched", "vlb_skybox_project_sh_device",
+    "vlb_scene_set_textures", "vlb_gltf_texture", "vlb_image_load_rgba8", "vlb_image_load_rgba32f", "vlb_skybox_set", "vlb_skybox_set_async", "vlb_skybox_project_sh", "vlb_skybox_project_sh_batched", "vlb_skybox_project_sh_device",
     "vlb_skybox_project_sh_device_ptrs", "vlb_envmap_project_sh", "vlb_bake_settings_default", "vlb_bake_settings_from_bounds", "vlb_probe_positions",
     "vlb_bake_probes", "vlb_bake_probes_device", "vlb_bake_gather_device", "vlb_bake_last_stats", "vlb_trace_rays",
     "vlb_bake_serialize_gltf", "vlb_bake_deserialize_gltf",
@@ -164,6 +164,7 @@ def load_library():
         "vlb_scene_set_textures": (i32, [vp, vp, u32]),
         "vlb_gltf_texture": (i32, [ctypes.c_char_p, u32, vp, u64, vp]),
         "vlb_image_load_rgba8": (i32, [ctypes.c_char_p, vp, u64, vp]),
+        "vlb_image_load_rgba32f": (i32, [ctypes.c_char_p, vp, u64, vp]),
         "vlb_skybox_set": (i32, [vp, vp, i32, i32, i32]),
         "vlb_skybox_set_async": (i32, [vp, vp, i32, i32, i32]),
         "vlb_skybox_project_sh": (i32, [vp, vp, i32, i32, i32, i32, vp]),
@@ -392,6 +393,20 @@ def image_load_rgba8(path):
         raise VlbError(r, lib.vlb_last_error(None).decode())
     px = np.zeros((int(size[1]), int(size[0]), 4), np.uint8)
     r = lib.vlb_image_load_rgba8(os.fsencode(path), _ptr(px), px.nbytes, _ptr(size))
+    if r != 0:
+        raise VlbError(r, lib.vlb_last_error(None).decode())
+    return px
+
+
+def image_load_rgba32f(path):
+    """Radiance RGBE (.hdr) -> linear float32 [H, W, 4] (alpha 1): RGBA32F equirect skyboxes from a file."""
+    lib = load_library()
+    size = np.zeros(2, np.int32)
+    r = lib.vlb_image_load_rgba32f(os.fsencode(path), None, 0, _ptr(size))
+    if r != 0:
+        raise VlbError(r, lib.vlb_last_error(None).decode())
+    px = np.zeros((int(size[1]), int(size[0]), 4), np.float32)
+    r = lib.vlb_image_load_rgba32f(os.fsencode(path), _ptr(px), px.nbytes, _ptr(size))
     if r != 0:
         raise VlbError(r, lib.vlb_last_error(None).decode())
     return px

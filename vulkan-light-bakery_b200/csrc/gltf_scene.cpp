@@ -30,6 +30,7 @@ struct Unsupported : std::runtime_error { using std::runtime_error::runtime_erro
 }  // namespace
 void png_decode_rgba8(const uint8_t* data, size_t size, std::vector<uint8_t>& rgba, int& width, int& height, bool& unsupported);
 void jpeg_decode_rgba8(const uint8_t* data, size_t size, std::vector<uint8_t>& rgba, int& width, int& height, bool& unsupported);
+void hdr_decode_rgba32f(const uint8_t* data, size_t size, std::vector<float>& rgba, int& width, int& height, bool& unsupported);
 namespace {
 
 bool read_all(const std::string& path, std::string& out) {
@@ -447,6 +448,23 @@ int vlb_image_load_rgba8(const char* path, void* texels, uint64_t capacity, int3
     }
     size[0] = w; size[1] = h;
     if (texels && capacity >= rgba.size()) std::memcpy(texels, rgba.data(), rgba.size());
+    return VLB_OK;
+}
+
+int vlb_image_load_rgba32f(const char* path, void* texels, uint64_t capacity, int32_t size[2]) {
+    if (!path || !size) return fail_thread(VLB_ERR_INVALID, "vlb_image_load_rgba32f: NULL argument");
+    std::string raw;
+    if (!read_all(path, raw)) return fail_thread(VLB_ERR_IO, std::string("cannot read ") + path);
+    std::vector<float> rgba;
+    int w = 0, h = 0;
+    bool unsupported = false;
+    try {
+        hdr_decode_rgba32f(reinterpret_cast<const uint8_t*>(raw.data()), raw.size(), rgba, w, h, unsupported);
+    } catch (const std::exception& e) {
+        return fail_thread(unsupported ? VLB_ERR_UNSUPPORTED : VLB_ERR_IO, std::string(path) + ": " + e.what());
+    }
+    size[0] = w; size[1] = h;
+    if (texels && capacity >= rgba.size() * sizeof(float)) std::memcpy(texels, rgba.data(), rgba.size() * sizeof(float));
     return VLB_OK;
 }
 

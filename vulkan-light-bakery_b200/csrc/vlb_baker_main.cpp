@@ -81,7 +81,7 @@ void usage() {
          "  --no-shadows --no-srgb --quantize8 --reference-order --world-frame   behaviour flags (vlb_bake.h)\n"
          "  --device N           CUDA device (default 0)\n"
          "  --out path           output file (default baked_<scene>)\n"
-         "  --skybox image       equirect PNG / JPEG sampled where a ray leaves the scene (main.rmiss:18-40); default: none\n"
+         "  --skybox image       equirect PNG / JPEG / Radiance .hdr sampled where a ray leaves the scene (main.rmiss:18-40); default: none\n"
          "  --dry-run            parse the scene and print what would be baked; needs no GPU");
 }
 
@@ -171,10 +171,12 @@ int main(int argc, char** argv) {
     check(vlb_scene_load_gltf(ctx, o.scene.c_str()));                        // LightBaker ctor, light_baker.cpp:40-53
     if (!o.skybox.empty()) {                                                  // Skybox_t ctor: stbi_load -> RGBA8 (skybox_manager.cpp:14-20)
         int32_t wh[2] = {0, 0};
-        if (vlb_image_load_rgba8(o.skybox.c_str(), nullptr, 0, wh) != VLB_OK) { const std::string m = vlb_last_error(nullptr); vlb_ctx_destroy(ctx); die(m); }
-        std::vector<unsigned char> px((size_t)wh[0] * wh[1] * 4);
-        if (vlb_image_load_rgba8(o.skybox.c_str(), px.data(), px.size(), wh) != VLB_OK) { const std::string m = vlb_last_error(nullptr); vlb_ctx_destroy(ctx); die(m); }
-        check(vlb_skybox_set(ctx, px.data(), VLB_FMT_RGBA8, wh[0], wh[1]));
+        const bool hdr = o.skybox.size() >= 4 && o.skybox.compare(o.skybox.size() - 4, 4, ".hdr") == 0;   // Radiance RGBE -> RGBA32F
+        auto load = hdr ? vlb_image_load_rgba32f : vlb_image_load_rgba8;
+        if (load(o.skybox.c_str(), nullptr, 0, wh) != VLB_OK) { const std::string m = vlb_last_error(nullptr); vlb_ctx_destroy(ctx); die(m); }
+        std::vector<unsigned char> px((size_t)wh[0] * wh[1] * (hdr ? 16 : 4));
+        if (load(o.skybox.c_str(), px.data(), px.size(), wh) != VLB_OK) { const std::string m = vlb_last_error(nullptr); vlb_ctx_destroy(ctx); die(m); }
+        check(vlb_skybox_set(ctx, px.data(), hdr ? VLB_FMT_RGBA32F : VLB_FMT_RGBA8, wh[0], wh[1]));
         printf("skybox %s: %dx%d\n", o.skybox.c_str(), wh[0], wh[1]);
     }
     vlb_bvh_stats bs;
