@@ -95,3 +95,43 @@ def test_sharded_bake_oracle_world2(cyclic):
         assert p.exitcode == 0
     tag, equal, shape = q.get(timeout=5)
     assert tag == "ok" and equal and shape == (12, 48)
+
+
+def _sky_worker(rank, world, port, n_maps, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    par = importlib.import_module("vulkan-light-bakery_b200.parallel")
+    scenes = importlib.import_module("vulkan-light-bakery_b200.scenes")
+    from oracle import oracle_api as oa
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        def project(ids, out):
+            for row, i in enumerate(ids):
+                out[row].copy_(torch.from_numpy(oa.skybox_project(scenes.hdr_sky(32, 16, seed=100 + i), order=2).reshape(48)))
+        full = par.project_maps_sharded(project, n_maps, rank, world, device="cpu")
+        if rank == world - 1:
+            ref = torch.empty((n_maps, 48))
+            project(list(range(n_maps)), ref)
+            q.put(("ok", bool(torch.equal(full, ref)), tuple(full.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_maps", [(2, 5), (3, 7), (3, 2), (2, 4)])
+def test_sharded_skybox_batch(world, n_maps):
+    """BASELINE configs[4] across GPUs: maps dealt round-robin, one all-gather of 192 bytes per map."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sky_worker, args=(r, world, port, n_maps, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    tag, equal, shape = q.get(timeout=5)
+    assert tag == "ok" and equal and shape == (n_maps, 48)

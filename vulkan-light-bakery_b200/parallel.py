@@ -99,3 +99,34 @@ def bake_multibounce_sharded(bake_pass, settings, rank, world, device=None, grou
         full = gather_slabs(out, settings, rank, world, group, cyclic)
         prev = full.contiguous()
     return prev
+
+
+# ---- batched skybox projection (BASELINE configs[4]) ------------------------------------------------------
+def map_share(n_maps, rank, world):
+    """Maps of `rank` under the round-robin deal: rank, rank + world, ..."""
+    return list(range(int(rank), int(n_maps), int(world)))
+
+
+def project_maps_sharded(project, n_maps, rank, world, device=None, group=None):
+    """Batched skybox SH projection over `world` GPUs: maps are independent, so they are dealt round-robin,
+    every rank projects its share with project(map_ids, out) (out: [len(map_ids), 48] float32 on `device`,
+    e.g. Context.skybox_project_sh_device over its resident maps) and ONE all-gather of the padded shares gives
+    every rank all n_maps x 48 coefficients in map order. No other collective: 192 bytes per map."""
+    import torch
+    import torch.distributed as dist
+    mine = map_share(n_maps, rank, world)
+    out = torch.zeros((max(len(mine), 1), 48), dtype=torch.float32, device=device)[: len(mine)]
+    if mine:
+        project(mine, out)
+    if world == 1:
+        return out
+    pad = (int(n_maps) + world - 1) // world
+    send = out
+    if out.shape[0] != pad:
+        send = torch.zeros((pad, 48), dtype=torch.float32, device=device)
+        send[: out.shape[0]] = out
+    recv = torch.empty((world * pad, 48), dtype=torch.float32, device=device)
+    dist.all_gather_into_tensor(recv, send.contiguous(), group=group)
+    # recv[r, i] is map r + i * world
+    full = recv.view(world, pad, 48).transpose(0, 1).reshape(pad * world, 48)
+    return full[: int(n_maps)].contiguous()
