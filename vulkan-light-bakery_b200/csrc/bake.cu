@@ -506,6 +506,9 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
         kern = K == 9 ? VLB_PICK(9) : VLB_PICK(16);
 #undef VLB_PICK
     }
+    // the kernel uses no shared memory: ask for the whole 228 KB as L1 (BVH nodes, per-warp queues)
+    if (env_flag("VLB_BAKE_CARVEOUT", 0) >= 0)
+        VLB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, env_flag("VLB_BAKE_CARVEOUT", 0)));
     int per_sm = 0;
     VLB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBakeBlock, 0));
     per_sm = std::max(per_sm, 1);
