@@ -67,3 +67,21 @@ def test_slab_partition(vlb):
             assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
             sizes = [b - a for a, b in ranges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/vlb_bake.h must compile as C99 (no C++ / CUDA / torch types) and a C caller
+    must link against the library."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "vlb_bake.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    src = tmp_path / "caller.c"
+    src.write_text('#include "vlb_bake.h"\n#include <stdio.h>\n'
+                   'int main(void) { vlb_bake_settings s; vlb_bake_settings_default(&s);\n'
+                   '  printf("%d %d %d %d\\n", vlb_abi_version(), s.probes[0], s.dir_w, (int)sizeof(vlb_material)); return 0; }\n')
+    lib_dir = os.path.join(ROOT, "vulkan-light-bakery_b200")
+    exe = tmp_path / "caller"
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", lib_dir,
+                           "-lvlb_bake", "-Wl,-rpath," + lib_dir])
+    out = subprocess.check_output([str(exe)]).decode().split()
+    assert out == ["1", "7", "3141", "144"]
