@@ -281,6 +281,15 @@ int vlb_probe_positions(const vlb_bake_settings* s, float* out_xyz);
  * (float[probe][16][3], light_baker.cpp:294-322). With s->bounces > 0 the call must cover the whole
  * grid (no slab) and runs 1 + bounces passes on the device, returning the last one. */
 int vlb_bake_probes(vlb_ctx* ctx, const vlb_bake_settings* s, float* out);
+/* The same bake spread over several GPUs from ONE host process (how the reference's single-process `baker` would
+ * use a multi-GPU box): ctxs[r] are n distinct contexts (normally one per device) that already hold the same
+ * scene, LBVH and skybox; ctx r bakes z-slices r, r + n, ... on its own device and host thread, and every share
+ * lands in its rows of the one host grid `out` (Nx*Ny*Nz x 48 floats). No inter-GPU traffic on the direct pass;
+ * with s->bounces > 0 the previous pass is redistributed to every device between passes. Bit-identical to
+ * vlb_bake_probes on one ctx. (One process per GPU with an NCCL all-gather, as bench.py runs it, keeps the
+ * gathered grid on the devices instead: vulkan-light-bakery_b200/parallel.py.) Errors: the code of the first
+ * failing ctx, text in vlb_last_error(ctxs[0]). */
+int vlb_bake_probes_multi(vlb_ctx* const* ctxs, uint32_t n_ctx, const vlb_bake_settings* s, float* out);
 /* Device-resident output; enqueues on the ctx stream and returns WITHOUT synchronising. */
 int vlb_bake_probes_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out);
 /* One gather pass with a device-resident source: bakes the slab exactly like

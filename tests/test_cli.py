@@ -66,3 +66,16 @@ def test_cli_bake_equals_abi_bake(ctx, vlb, scenes, tmp_path):
     want = ctx.bake_probes(s)
     assert np.array_equal(np.asarray(coeffs).reshape(want.shape), want)
     assert np.allclose(step, list(s.step))
+
+
+@pytest.mark.gpu
+def test_cli_devices_equals_single_device(vlb, scenes, tmp_path):
+    """`--devices 0,0`: two contexts in one process (vlb_bake_probes_multi) write the same file as one."""
+    p = scenes.write_gltf(scenes.small_room(), str(tmp_path / "room.gltf"))
+    args = ["--probes", "3x2x4", "--dirs", "32x16", "--light", "2,3.5,2"]
+    r1 = _run(vlb, p, *args, "--out", str(tmp_path / "one.gltf"))
+    r2 = _run(vlb, p, *args, "--devices", "0,0", "--out", str(tmp_path / "two.gltf"))
+    assert r1.returncode == 0 and r2.returncode == 0, r1.stderr + r2.stderr
+    a, _ = vlb.deserialize_gltf(str(tmp_path / "one.gltf"))
+    b, _ = vlb.deserialize_gltf(str(tmp_path / "two.gltf"))
+    assert np.array_equal(a, b) and "2 GPU(s)" in r2.stdout

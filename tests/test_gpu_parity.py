@@ -372,3 +372,35 @@ def test_bake_cube_reference_defaults_scaled(ctx, vlb, oa, scenes):
         osc = oa.Scene(sc)
         osc.set_skybox(sky)
         assert rel_l2(got, osc.bake_probes(s)[0]) <= PROBE_TOL
+
+
+def test_bake_probes_multi_one_process_several_contexts(vlb, scenes, room):
+    """vlb_bake_probes_multi: one host process, n contexts (here all on device 0, which exercises the same threads,
+    cyclic shares and strided copies as n GPUs) == one context, bit for bit; with and without gather passes."""
+    sc, _ = room
+    sky = scenes.hdr_sky(64, 32, seed=2)
+    s = vlb.default_settings()
+    s.probes[:] = (3, 2, 5); s.dir_w, s.dir_h = 32, 16; s.sh_order = 3; s.light_pos[:] = (2.0, 3.5, 2.0)
+    s.flags = vlb.SHADOW_RAYS | vlb.SKYBOX_ON_MISS | vlb.SRGB_ENCODE
+    vlb.settings_from_bounds(s, (0.3, 0.3, 0.3, 3.7, 3.7, 3.7))
+    ctxs = [vlb.Context(0) for _ in range(3)]
+    try:
+        for c in ctxs:
+            c.set_scene(sc); c.build_bvh(); c.set_skybox(sky)
+        want = ctxs[0].bake_probes(s)
+        for n in (1, 2, 3):
+            assert np.array_equal(vlb.bake_probes_multi(ctxs[:n], s), want), n
+        s.bounces, s.indirect_gain = 2, 0.7
+        want2 = ctxs[0].bake_probes(s)
+        assert not np.array_equal(want2, want)
+        for n in (2, 3):
+            assert np.array_equal(vlb.bake_probes_multi(ctxs[:n], s), want2), n
+        s.bounces = 0
+        with pytest.raises(vlb.VlbError):
+            vlb.bake_probes_multi([ctxs[0], ctxs[0]], s)
+        t = s.copy(); t.slab_k0, t.slab_k1 = 0, 2
+        with pytest.raises(vlb.VlbError):
+            vlb.bake_probes_multi(ctxs[:2], t)
+    finally:
+        for c in ctxs:
+            c.close()

@@ -128,7 +128,7 @@ class VlbError(RuntimeError):
 ABI_SYMBOLS = [
     "vlb_abi_version", "vlb_ctx_create", "vlb_ctx_destroy", "vlb_ctx_set_stream", "vlb_ctx_synchronize",
     "vlb_last_error", "vlb_ctx_launch_count", "vlb_scene_set_triangles", "vlb_scene_load_gltf", "vlb_gltf_probe", "vlb_scene_bounds", "vlb_bvh_build",
-    "vlb_scene_set_textures", "vlb_gltf_texture", "vlb_image_load_rgba8", "vlb_image_load_rgba32f", "vlb_skybox_set", "vlb_skybox_set_async", "vlb_skybox_project_sh", "vlb_skybox_project_sh_batched", "vlb_skybox_project_sh_device",
+    "vlb_scene_set_textures", "vlb_gltf_texture", "vlb_image_load_rgba8", "vlb_image_load_rgba32f", "vlb_bake_probes_multi", "vlb_skybox_set", "vlb_skybox_set_async", "vlb_skybox_project_sh", "vlb_skybox_project_sh_batched", "vlb_skybox_project_sh_device",
     "vlb_skybox_project_sh_device_ptrs", "vlb_envmap_project_sh", "vlb_bake_settings_default", "vlb_bake_settings_from_bounds", "vlb_probe_positions",
     "vlb_bake_probes", "vlb_bake_probes_device", "vlb_bake_gather_device", "vlb_bake_last_stats", "vlb_trace_rays",
     "vlb_bake_serialize_gltf", "vlb_bake_deserialize_gltf",
@@ -165,6 +165,7 @@ def load_library():
         "vlb_gltf_texture": (i32, [ctypes.c_char_p, u32, vp, u64, vp]),
         "vlb_image_load_rgba8": (i32, [ctypes.c_char_p, vp, u64, vp]),
         "vlb_image_load_rgba32f": (i32, [ctypes.c_char_p, vp, u64, vp]),
+        "vlb_bake_probes_multi": (i32, [vp, u32, S, vp]),
         "vlb_skybox_set": (i32, [vp, vp, i32, i32, i32]),
         "vlb_skybox_set_async": (i32, [vp, vp, i32, i32, i32]),
         "vlb_skybox_project_sh": (i32, [vp, vp, i32, i32, i32, i32, vp]),
@@ -382,6 +383,18 @@ def gltf_probe(path):
         raise VlbError(r, lib.vlb_last_error(None).decode())
     keys = ("vertices", "indices", "instances", "materials", "triangles")
     return dict(zip(keys, (int(c) for c in counts))), bounds
+
+
+def bake_probes_multi(contexts, s):
+    """vlb_bake_probes_multi: one host process, several contexts (one per GPU) holding the same scene; returns the
+    whole grid [n_probes, 16, 3]."""
+    lib = load_library()
+    arr = (ctypes.c_void_p * len(contexts))(*[c._h for c in contexts])
+    out = np.zeros((s.n_probes, 16, 3), np.float32)
+    r = lib.vlb_bake_probes_multi(ctypes.cast(arr, ctypes.c_void_p), len(contexts), ctypes.byref(s), _ptr(out))
+    if r != 0:
+        raise VlbError(r, lib.vlb_last_error(contexts[0]._h).decode())
+    return out
 
 
 def image_load_rgba8(path):

@@ -61,7 +61,7 @@ def build(force=False, verbose=False):
             if r.returncode:
                 raise RuntimeError("nvcc failed: " + " ".join(cmd))
     if jobs or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lz"]
+        cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lz", "-lpthread"]
         subprocess.check_call(cmd)
     cli_src = os.path.join(CSRC, "vlb_baker_main.cpp")
     if not TAG and (force or _stale(CLI, [cli_src, LIB] + hdrs)):

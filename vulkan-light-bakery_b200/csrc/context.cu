@@ -4,6 +4,8 @@
 #include <cmath>
 #include <cstring>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "vlb_context.h"
 #include "vlb_math.cuh"
@@ -578,6 +580,61 @@ int vlb_bake_probes(vlb_ctx* ctx, const vlb_bake_settings* s, float* out) {
     ctx->last_bake = total;
     VLB_CUDA(ctx, cudaMemcpyAsync(out, buf[cur ^ 1], n * VLB_SH_STRIDE * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     VLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return VLB_OK;
+}
+
+// One rank of vlb_bake_probes_multi: bakes the cyclic share of ctx `r` for one pass and copies it into its rows of
+// the host grid (one strided copy: slice k = r + i * n goes to out + k * nxy * 192 bytes).
+static int multi_rank_pass(vlb_ctx* ctx, const vlb_bake_settings* s, uint32_t r, uint32_t n, const float* prev_host, float* out) {
+    if (int rc = check_device(ctx)) return rc;
+    const int Nz = s->probes[2];
+    const size_t nxy = (size_t)s->probes[0] * s->probes[1];
+    const size_t n_slices = (size_t)(Nz > (int)r ? (Nz - (int)r + (int)n - 1) / (int)n : 0);
+    if (n_slices == 0) return VLB_OK;
+    vlb_bake_settings mine = *s;
+    mine.slab_k0 = (int32_t)r; mine.slab_k1 = Nz; mine.slab_stride = (int32_t)n; mine.bounces = 0;
+    VLB_CUDA(ctx, ctx->d_bake_out.reserve(n_slices * nxy * VLB_SH_STRIDE * sizeof(float)));
+    const float* d_prev = nullptr;
+    if (prev_host) {       // gather pass: every device needs the whole previous grid
+        const size_t bytes = nxy * (size_t)Nz * VLB_SH_STRIDE * sizeof(float);
+        VLB_CUDA(ctx, ctx->d_bake_prev.reserve(bytes));
+        VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_bake_prev.p, prev_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        d_prev = ctx->d_bake_prev.as<float>();
+    }
+    if (int rc = vlb_bake_gather_device(ctx, &mine, d_prev, ctx->d_bake_out.as<float>())) return rc;
+    const size_t row = nxy * VLB_SH_STRIDE * sizeof(float);
+    VLB_CUDA(ctx, cudaMemcpy2DAsync(reinterpret_cast<char*>(out) + (size_t)r * row, (size_t)n * row, ctx->d_bake_out.p, row, row, n_slices,
+                                    cudaMemcpyDeviceToHost, ctx->stream));
+    vlb_bake_stats st;
+    return vlb_bake_last_stats(ctx, &st);      // synchronises; surfaces a traversal stack overflow
+}
+
+int vlb_bake_probes_multi(vlb_ctx* const* ctxs, uint32_t n_ctx, const vlb_bake_settings* s, float* out) {
+    if (!ctxs || n_ctx == 0 || !ctxs[0]) return VLB_ERR_INVALID;
+    vlb_ctx* c0 = ctxs[0];
+    if (!s || !out) return c0->fail(VLB_ERR_INVALID, "vlb_bake_probes_multi: NULL settings or output");
+    for (uint32_t r = 0; r < n_ctx; ++r) {
+        if (!ctxs[r]) return c0->fail(VLB_ERR_INVALID, "vlb_bake_probes_multi: ctx %u is NULL", r);
+        for (uint32_t q = 0; q < r; ++q) if (ctxs[q] == ctxs[r]) return c0->fail(VLB_ERR_INVALID, "vlb_bake_probes_multi: ctx %u given twice", r);
+    }
+    if (s->slab_k1 >= 0) return c0->fail(VLB_ERR_INVALID, "vlb_bake_probes_multi: takes the whole grid (slab_k1 < 0) and shards it itself");
+    if (s->probes[0] <= 0 || s->probes[1] <= 0 || s->probes[2] <= 0) return c0->fail(VLB_ERR_INVALID, "bake: probe counts must be positive");
+    const size_t grid_floats = (size_t)s->probes[0] * s->probes[1] * (size_t)s->probes[2] * VLB_SH_STRIDE;
+    std::vector<float> prev;                                   // previous pass over the whole grid (host)
+    for (int pass = 0; pass <= std::max(0, (int)s->bounces); ++pass) {
+        if (pass > 0) prev.assign(out, out + grid_floats);
+        std::vector<int> rc(n_ctx, VLB_OK);
+        std::vector<std::thread> workers;
+        for (uint32_t r = 1; r < n_ctx; ++r)
+            workers.emplace_back([&, r] { rc[r] = multi_rank_pass(ctxs[r], s, r, n_ctx, pass ? prev.data() : nullptr, out); });
+        rc[0] = multi_rank_pass(c0, s, 0, n_ctx, pass ? prev.data() : nullptr, out);
+        for (std::thread& t : workers) t.join();
+        for (uint32_t r = 0; r < n_ctx; ++r)
+            if (rc[r] != VLB_OK) {
+                if (r != 0) c0->fail(rc[r], "vlb_bake_probes_multi: ctx %u: %s", r, vlb_last_error(ctxs[r]));
+                return rc[r];
+            }
+    }
     return VLB_OK;
 }
 

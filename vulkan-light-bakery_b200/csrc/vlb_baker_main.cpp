@@ -28,6 +28,7 @@ struct Options {
     int dirs[2] = {0, 0};
     int order = 0;
     int device = 0;
+    std::vector<int> devices;       // --devices a,b,...: one context per GPU, vlb_bake_probes_multi
     int bounces = 0;
     float gain = -1.f;
     bool tight = false, have_light = false, dry = false;
@@ -80,6 +81,7 @@ void usage() {
          "  --tight-bounds       lay the grid over the true world AABB instead of Scene_t::getBounds()\n"
          "  --no-shadows --no-srgb --quantize8 --reference-order --world-frame   behaviour flags (vlb_bake.h)\n"
          "  --device N           CUDA device (default 0)\n"
+         "  --devices a,b,...    bake on several GPUs from this one process (probe z-slices dealt cyclically)\n"
          "  --out path           output file (default baked_<scene>)\n"
          "  --skybox image       equirect PNG / JPEG / Radiance .hdr sampled where a ray leaves the scene (main.rmiss:18-40); default: none\n"
          "  --dry-run            parse the scene and print what would be baked; needs no GPU");
@@ -111,6 +113,18 @@ int main(int argc, char** argv) {
         else if (a == "--bounces") { o.bounces = atoi(need("--bounces")); if (o.bounces < 0) die("--bounces expects >= 0"); }
         else if (a == "--gain") { o.gain = strtof(need("--gain"), nullptr); }
         else if (a == "--device") { o.device = atoi(need("--device")); }
+        else if (a == "--devices") {
+            const char* v = need("--devices");
+            while (*v) {
+                char* end = nullptr;
+                const long d = strtol(v, &end, 10);
+                if (end == v || d < 0) die("--devices expects a comma separated list of CUDA device ids");
+                o.devices.push_back((int)d);
+                v = *end == ',' ? end + 1 : end;
+                if (*end && *end != ',') die("--devices expects a comma separated list of CUDA device ids");
+            }
+            if (o.devices.empty()) die("--devices expects at least one device id");
+        }
         else if (a == "--out") { o.out = need("--out"); }
         else if (a == "--skybox") { o.skybox = need("--skybox"); }
         else if (a == "--tight-bounds") o.tight = true;
@@ -159,45 +173,65 @@ int main(int argc, char** argv) {
         return EXIT_SUCCESS;
     }
 
-    vlb_ctx* ctx = nullptr;
-    if (vlb_ctx_create(o.device, &ctx) != VLB_OK) die(vlb_last_error(nullptr));
+    if (o.devices.empty()) o.devices.push_back(o.device);
+    std::vector<vlb_ctx*> ctxs;
+    auto destroy_all = [&] { for (vlb_ctx* c : ctxs) vlb_ctx_destroy(c); ctxs.clear(); };
+    for (int d : o.devices) {
+        vlb_ctx* c = nullptr;
+        if (vlb_ctx_create(d, &c) != VLB_OK) { const std::string m = vlb_last_error(nullptr); destroy_all(); die(m); }
+        ctxs.push_back(c);
+    }
+    vlb_ctx* ctx = ctxs[0];
+    vlb_ctx* cur = ctx;                    // the context whose error text `check` reports
     auto check = [&](int r) {
         if (r != VLB_OK) {
-            const std::string msg = vlb_last_error(ctx);
-            vlb_ctx_destroy(ctx);
+            const std::string msg = vlb_last_error(cur);
+            destroy_all();
             die(msg);
         }
     };
-    check(vlb_scene_load_gltf(ctx, o.scene.c_str()));                        // LightBaker ctor, light_baker.cpp:40-53
+    std::vector<unsigned char> sky_px;
+    int32_t sky_wh[2] = {0, 0};
+    bool sky_hdr = false;
     if (!o.skybox.empty()) {                                                  // Skybox_t ctor: stbi_load -> RGBA8 (skybox_manager.cpp:14-20)
-        int32_t wh[2] = {0, 0};
-        const bool hdr = o.skybox.size() >= 4 && o.skybox.compare(o.skybox.size() - 4, 4, ".hdr") == 0;   // Radiance RGBE -> RGBA32F
-        auto load = hdr ? vlb_image_load_rgba32f : vlb_image_load_rgba8;
-        if (load(o.skybox.c_str(), nullptr, 0, wh) != VLB_OK) { const std::string m = vlb_last_error(nullptr); vlb_ctx_destroy(ctx); die(m); }
-        std::vector<unsigned char> px((size_t)wh[0] * wh[1] * (hdr ? 16 : 4));
-        if (load(o.skybox.c_str(), px.data(), px.size(), wh) != VLB_OK) { const std::string m = vlb_last_error(nullptr); vlb_ctx_destroy(ctx); die(m); }
-        check(vlb_skybox_set(ctx, px.data(), hdr ? VLB_FMT_RGBA32F : VLB_FMT_RGBA8, wh[0], wh[1]));
-        printf("skybox %s: %dx%d\n", o.skybox.c_str(), wh[0], wh[1]);
+        sky_hdr = o.skybox.size() >= 4 && o.skybox.compare(o.skybox.size() - 4, 4, ".hdr") == 0;   // Radiance RGBE -> RGBA32F
+        auto load = sky_hdr ? vlb_image_load_rgba32f : vlb_image_load_rgba8;
+        if (load(o.skybox.c_str(), nullptr, 0, sky_wh) != VLB_OK) { const std::string m = vlb_last_error(nullptr); destroy_all(); die(m); }
+        sky_px.resize((size_t)sky_wh[0] * sky_wh[1] * (sky_hdr ? 16 : 4));
+        if (load(o.skybox.c_str(), sky_px.data(), sky_px.size(), sky_wh) != VLB_OK) { const std::string m = vlb_last_error(nullptr); destroy_all(); die(m); }
+        printf("skybox %s: %dx%d\n", o.skybox.c_str(), sky_wh[0], sky_wh[1]);
     }
     vlb_bvh_stats bs;
-    check(vlb_bvh_build(ctx, &bs));                                          // Scene_t::buildAccelerationStructures
+    for (vlb_ctx* c : ctxs) {               // scene, LBVH and skybox are replicated on every GPU
+        cur = c;
+        check(vlb_scene_load_gltf(c, o.scene.c_str()));                      // LightBaker ctor, light_baker.cpp:40-53
+        check(vlb_bvh_build(c, &bs));                                        // Scene_t::buildAccelerationStructures
+        if (!sky_px.empty()) check(vlb_skybox_set(c, sky_px.data(), sky_hdr ? VLB_FMT_RGBA32F : VLB_FMT_RGBA8, sky_wh[0], sky_wh[1]));
+    }
+    cur = ctx;
     float bounds[6];
     check(vlb_scene_bounds(ctx, o.tight ? 1 : 0, bounds));                   // Scene_t::getBounds
     check(vlb_bake_settings_from_bounds(&s, bounds));                        // probePositionsFromBoudingBox
-    printf("LBVH: %llu nodes in %.2f ms; grid %dx%dx%d over (%g %g %g)-(%g %g %g)\n", (unsigned long long)bs.n_nodes, bs.build_ms,
-           s.probes[0], s.probes[1], s.probes[2], bounds[0], bounds[1], bounds[2], bounds[3], bounds[4], bounds[5]);
+    printf("LBVH: %llu nodes in %.2f ms; grid %dx%dx%d over (%g %g %g)-(%g %g %g); %zu GPU(s)\n", (unsigned long long)bs.n_nodes, bs.build_ms,
+           s.probes[0], s.probes[1], s.probes[2], bounds[0], bounds[1], bounds[2], bounds[3], bounds[4], bounds[5], ctxs.size());
 
     std::vector<float> coeffs((size_t)n_probes * VLB_SH_STRIDE);
-    check(vlb_bake_probes(ctx, &s, coeffs.data()));                          // LightBaker::bake
-    vlb_bake_stats st;
-    check(vlb_bake_last_stats(ctx, &st));
-    const double rays = (double)st.n_primary_rays + (double)st.n_shadow_rays;
-    printf("baked %llu probes: %llu primary + %llu shadow rays in %.2f ms (%.3f Grays/s)\n", (unsigned long long)st.n_probes,
-           (unsigned long long)st.n_primary_rays, (unsigned long long)st.n_shadow_rays, st.total_ms,
-           st.total_ms > 0.f ? rays / (st.total_ms * 1e-3) / 1e9 : 0.0);
+    if (ctxs.size() == 1) check(vlb_bake_probes(ctx, &s, coeffs.data()));    // LightBaker::bake
+    else check(vlb_bake_probes_multi(ctxs.data(), (uint32_t)ctxs.size(), &s, coeffs.data()));
+    double rays_p = 0, rays_s = 0, ms = 0;
+    for (vlb_ctx* c : ctxs) {               // every GPU's share of the last pass; the slowest one is the bake time
+        cur = c;
+        vlb_bake_stats st;
+        check(vlb_bake_last_stats(c, &st));
+        rays_p += (double)st.n_primary_rays; rays_s += (double)st.n_shadow_rays;
+        if (st.total_ms > ms) ms = st.total_ms;
+    }
+    cur = ctx;
+    printf("baked %llu probes: %.0f primary + %.0f shadow rays in %.2f ms (%.3f Grays/s)\n", (unsigned long long)n_probes, rays_p, rays_s, ms,
+           ms > 0 ? (rays_p + rays_s) / (ms * 1e-3) / 1e9 : 0.0);
     check(vlb_bake_serialize_gltf(o.scene.c_str(), o.out.c_str(), coeffs.data(), n_probes, &s));   // LightBaker::serialize
     printf("wrote %s\n", o.out.c_str());
-    vlb_ctx_destroy(ctx);
+    destroy_all();
     puts("exiting...");                                                      // main.cpp:42
     return EXIT_SUCCESS;
 }
