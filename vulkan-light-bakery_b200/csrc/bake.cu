@@ -15,7 +15,12 @@
 namespace vlb {
 
 constexpr int kBakeBlock = 128;
-constexpr int kTileW = 8, kTileH = 4;   // one warp = an 8x4 tile of adjacent direction texels
+// One warp-sized direction tile = 2^lw x 2^(5-lw) adjacent texels of the equirect direction grid. The shape is picked
+// per direction grid so that the tile is as square as possible in ANGLE (a texel spans 360/W x 180/H degrees): 4x8
+// texels for W = H (the 32x32 / 64x64 grids of the BASELINE configs; measured +1.4 % over 8x4 on C3), 8x4 for
+// W >= 2H (the reference's 3141x1000). Rays in flight in a warp then cover the smallest solid angle.
+__host__ __device__ inline int tile_x(int tile, int w, int tiles_x, int lw) { return ((tile % tiles_x) << lw) + (w & ((1 << lw) - 1)); }
+__host__ __device__ inline int tile_y(int tile, int w, int tiles_x, int lw) { return ((tile / tiles_x) << (5 - lw)) + (w >> lw); }
 
 struct WarpQueues;
 struct BakeParams {
@@ -26,7 +31,7 @@ struct BakeParams {
     const float2* row_sc;                                // (sin, cos) theta per direction row
     const float2* col_cs;                                // (cos, sin) phi per direction column
     int Nx, Ny, Nz, k0, kstride;   // the call bakes z-slices k0, k0 + kstride, ...
-    int W, H, tiles_x, n_tiles;
+    int W, H, tiles_x, n_tiles, tile_lw;   // tile_lw: log2 of the direction tile's width
     int chunks, tiles_per_chunk;
     uint32_t n_items;
     float pixel_area;
@@ -67,8 +72,8 @@ __global__ void __launch_bounds__(kBakeBlock) k_bake(const BakeParams p) {
         const int t0 = chunk * p.tiles_per_chunk;
         const int t1 = min(t0 + p.tiles_per_chunk, p.n_tiles);
         for (int tile = t0; tile < t1; ++tile) {
-            const int x = (tile % p.tiles_x) * kTileW + (lane & (kTileW - 1));
-            const int y = (tile / p.tiles_x) * kTileH + (lane / kTileW);
+            const int x = tile_x(tile, lane, p.tiles_x, p.tile_lw);
+            const int y = tile_y(tile, lane, p.tiles_x, p.tile_lw);
             if (x < p.W && y < p.H) {
                 const float2 row = __ldg(p.row_sc + y), col = __ldg(p.col_cs + x);
                 const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);   // sh_common.h:8-12
@@ -211,8 +216,8 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                     } else if (!busy && rank - take_sh < take_new) {
                         const int cand = next + rank - take_sh;
                         const int tile = base_tile + (cand >> 5), w = cand & 31;
-                        const int x = (tile % p.tiles_x) * kTileW + (w & (kTileW - 1));
-                        const int y = (tile / p.tiles_x) * kTileH + (w / kTileW);
+                        const int x = tile_x(tile, w, p.tiles_x, p.tile_lw);
+                        const int y = tile_y(tile, w, p.tiles_x, p.tile_lw);
                         if (x < p.W && y < p.H) {
                             const float2 row = __ldg(p.row_sc + y), col = __ldg(p.col_cs + x);
                             const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);   // sh_common.h:8-12
@@ -248,8 +253,8 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                         HitRec h; h.id = S.hq_id[e]; h.t = S.hq_t[e]; h.u = S.hq_u[e]; h.v = S.hq_v[e];
                         dir = S.hq_dir[e];
                         const int tile = base_tile + (dir >> 5), w = dir & 31;
-                        const int x = (tile % p.tiles_x) * kTileW + (w & (kTileW - 1));
-                        const int y = (tile / p.tiles_x) * kTileH + (w / kTileW);
+                        const int x = tile_x(tile, w, p.tiles_x, p.tile_lw);
+                        const int y = tile_y(tile, w, p.tiles_x, p.tile_lw);
                         const float2 row = __ldg(p.row_sc + y), col = __ldg(p.col_cs + x);
                         const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);
                         const Vec3 r = mk3(t.x, t.z, t.y);
@@ -338,8 +343,8 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
             for (int i = 0; i < V; ++i) acc[i] = 0.f;
             for (int tt = 0; tt * 32 < n_dirs; ++tt) {
                 const int tile = base_tile + tt;
-                const int x = (tile % p.tiles_x) * kTileW + (lane & (kTileW - 1));
-                const int y = (tile / p.tiles_x) * kTileH + (lane / kTileW);
+                const int x = tile_x(tile, lane, p.tiles_x, p.tile_lw);
+                const int y = tile_y(tile, lane, p.tiles_x, p.tile_lw);
                 if (x < p.W && y < p.H) {
                     const float2 row = __ldg(p.row_sc + y), col = __ldg(p.col_cs + x);
                     const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);
@@ -455,8 +460,11 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     p.px = ctx->d_axis.as<float>(); p.py = p.px + Nx; p.pz = p.py + Ny;
     p.row_sc = ctx->d_row_sc.as<float2>(); p.col_cs = ctx->d_col_sc.as<float2>();
     p.Nx = Nx; p.Ny = Ny; p.Nz = Nz; p.k0 = k0; p.kstride = kstride; p.W = W; p.H = H;
-    p.tiles_x = (W + kTileW - 1) / kTileW;
-    p.n_tiles = p.tiles_x * ((H + kTileH - 1) / kTileH);
+    p.tile_lw = env_flag("VLB_BAKE_TILE_LW", (long long)W < 2ll * H ? 2 : 3);     // a function of the direction grid only
+    p.tile_lw = std::max(0, std::min(5, p.tile_lw));
+    const int tile_w = 1 << p.tile_lw, tile_h = 32 >> p.tile_lw;
+    p.tiles_x = (W + tile_w - 1) / tile_w;
+    p.n_tiles = p.tiles_x * ((H + tile_h - 1) / tile_h);
     // Work decomposition: a function of the WHOLE grid and the direction grid only (never of the
     // slab), so that a probe's coefficients are bit-identical however the grid is sharded. An item is
     // one 256-direction chunk of one probe (8 tiles: measured best on B200 for large grids); for
