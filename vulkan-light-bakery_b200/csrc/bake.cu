@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kBakeBlock) k_bake(const BakeParams p) {
 //
 // A warp owns a work item = (probe, run of 256-direction chunks). Inside a chunk every LANE is a ray
 // slot: an idle lane first takes a queued shadow ray, otherwise the next direction of the chunk
-// (ballot + popc ranks; directions in 8x4-texel tile order so the rays in flight stay angularly
+// (ballot + popc ranks; directions in tile order (32-texel tiles, square in angle: tile_x / tile_y) so the rays in flight stay angularly
 // adjacent), and traverses the LBVH. Primary (closest-hit) and shadow (any-hit) rays share one
 // "while-while" loop: all lanes step through internal nodes until most of them hold a leaf, then
 // the leaves are intersected. A finished primary ray only pushes its hit record into a per-warp
