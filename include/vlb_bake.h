@@ -211,7 +211,8 @@ int vlb_scene_set_textures(vlb_ctx* ctx, const vlb_texture* textures, uint32_t n
  * (:257-337); then the same upload as vlb_scene_set_triangles. vlb_scene_bounds(tight=0) afterwards
  * returns the reference's bounds including its local-matrix quirk (:497-507). Textures referenced by
  * baseColorTexture are decoded (PNG: 1-8 bit grey / palette, 8-bit RGB / RGBA, non-interlaced; JPEG:
- * 8-bit baseline, grey or YCbCr 4:4:4 / 4:2:2 / 4:4:0 / 4:2:0; anything else is VLB_ERR_UNSUPPORTED) and set
+ * 8-bit baseline or progressive, grey or YCbCr 4:4:4 / 4:2:2 / 4:4:0 / 4:2:0; anything else is
+ * VLB_ERR_UNSUPPORTED) and set
  * with their samplers (:650-690) as by vlb_scene_set_textures. */
 int vlb_scene_load_gltf(vlb_ctx* ctx, const char* gltf_path);
 /* Host-only: parse a glTF and report counts = {vertices, indices, instances (node x primitive),

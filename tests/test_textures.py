@@ -207,7 +207,7 @@ def test_png_reader_filters_palette_grey_and_errors(vlb, scenes, tmp_path):
 
 
 def test_jpeg_reader_vs_libjpeg(vlb, scenes, tmp_path):
-    """csrc/jpeg_decode.cpp (baseline Huffman JPEG) against libjpeg through PIL. JPEG decoding is not bit-normative
+    """csrc/jpeg_decode.cpp (baseline and progressive Huffman JPEG) against libjpeg through PIL. JPEG decoding is not bit-normative
     (IDCT / chroma upsampling arithmetic differ between decoders: "parity unpinned"), so the band is a few levels."""
     import io
     import json
@@ -230,7 +230,9 @@ def test_jpeg_reader_vs_libjpeg(vlb, scenes, tmp_path):
     rgb = np.stack([(x * 2) % 256, (y * 3) % 256, (x + y) % 256], -1).astype(np.uint8)
     rgb[20:50, 30:90] = rng.integers(0, 256, (30, 60, 3), dtype=np.uint8)
     cases = {"444": dict(subsampling=0), "422": dict(subsampling=1), "420": dict(subsampling=2), "q50": dict(quality=50),
-             "huffopt": dict(optimize=True, quality=90), "restart": dict(quality=85, restart_marker_blocks=3)}
+             "huffopt": dict(optimize=True, quality=90), "restart": dict(quality=85, restart_marker_blocks=3),
+             "prog444": dict(progressive=True, subsampling=0), "prog420": dict(progressive=True, subsampling=2, quality=80),
+             "prog_restart": dict(progressive=True, optimize=True, restart_marker_blocks=4, subsampling=1)}
     for name, kw in cases.items():
         b = io.BytesIO()
         Image.fromarray(rgb).save(b, format="JPEG", **({"quality": 92} | kw))
@@ -244,10 +246,14 @@ def test_jpeg_reader_vs_libjpeg(vlb, scenes, tmp_path):
     ref = np.asarray(Image.open(io.BytesIO(g.getvalue()))).astype(int)
     got = vlb.gltf_texture(with_image(g.getvalue(), "grey.gltf"), 0)["texels"]
     assert np.abs(got[..., 0].astype(int) - ref).max() <= 2 and np.array_equal(got[..., 0], got[..., 2])
-    pr = io.BytesIO()
-    Image.fromarray(rgb).save(pr, format="JPEG", progressive=True)
+    pg = io.BytesIO()
+    Image.fromarray(np.ascontiguousarray(rgb[..., 1])).save(pg, format="JPEG", quality=90, progressive=True)
+    ref = np.asarray(Image.open(io.BytesIO(pg.getvalue()))).astype(int)
+    assert np.abs(vlb.gltf_texture(with_image(pg.getvalue(), "prog_grey.gltf"), 0)["texels"][..., 0].astype(int) - ref).max() <= 2
+    cm = io.BytesIO()
+    Image.fromarray(np.concatenate([rgb, rgb[..., :1]], -1), "CMYK").save(cm, format="JPEG")     # 4 components
     with pytest.raises(vlb.VlbError) as e:
-        vlb.gltf_texture(with_image(pr.getvalue(), "progressive.gltf"), 0)
+        vlb.gltf_texture(with_image(cm.getvalue(), "cmyk.gltf"), 0)
     assert e.value.code == vlb.ERR_UNSUPPORTED
     with pytest.raises(vlb.VlbError) as e:
         vlb.gltf_texture(with_image(b.getvalue()[: len(b.getvalue()) // 2], "cut.gltf"), 0)

@@ -1,9 +1,10 @@
-// jpeg_decode.cpp — baseline JPEG reader for glTF baseColor textures; with png_decode.cpp it replaces the
+// jpeg_decode.cpp — baseline + progressive JPEG reader for glTF baseColor textures; with png_decode.cpp it replaces the
 // stb_image decode tinygltf performs for the reference (Scene_t::loadTextures, src/scene_manager.cpp:941-973).
 // Host-side ingest, off the bake path. Handles what glTF exporters write: 8-bit baseline / extended-sequential
 // Huffman JPEG (SOF0 / SOF1), greyscale or YCbCr, sampling 4:4:4 / 4:2:2 / 4:4:0 / 4:2:0 (chroma upsampled with
-// the triangle filter libjpeg calls "fancy upsampling"), restart intervals. Progressive, arithmetic-coded,
-// lossless, 12-bit and CMYK files are reported as unsupported, never guessed.
+// the triangle filter libjpeg calls "fancy upsampling"), restart intervals, and progressive files (SOF2: spectral
+// selection + successive approximation, any scan script). Arithmetic-coded, lossless, hierarchical, 12-bit and
+// CMYK files are reported as unsupported, never guessed.
 // "Parity unpinned": JPEG decoders legitimately differ by a level or two (IDCT and upsampling arithmetic are not
 // normative); this one uses an exact double-precision IDCT, and tests compare it with libjpeg within that band.
 #include <algorithm>
@@ -142,28 +143,179 @@ uint8_t clamp8(double v) { const long r = std::lround(v); return (uint8_t)(r < 0
 
 }  // namespace
 
+// One scan of a (possibly progressive) JPEG: which components, which band of coefficients, which bit.
+struct Scan {
+    std::vector<Component*> comps;
+    int ss = 0, se = 63, ah = 0, al = 0;
+};
+
+struct Decoder {
+    const uint8_t* data; size_t size;
+    uint16_t qt[4][64];
+    bool have_qt[4] = {false, false, false, false};
+    HuffTable dc[4], ac[4];
+    std::vector<Component> comps;
+    std::vector<std::vector<int16_t>> coefs;      // per component: bw * bh blocks x 64 coefficients, natural order
+    int W = 0, H = 0, hmax = 1, vmax = 1, restart = 0, mcus_x = 0, mcus_y = 0;
+    bool progressive = false;
+    int eobrun = 0;
+
+    int16_t* block(const Component& c, int bx, int by) { return &coefs[&c - comps.data()][((size_t)by * c.bw + bx) * 64]; }
+
+    void decode_block(BitReader& br, Component& c, int16_t* coef, const Scan& sc) {
+        if (!progressive) {                                              // sequential: the whole block at once
+            const int t = decode_symbol(br, dc[c.td]);
+            if (t > 11) throw std::runtime_error("JPEG: bad DC size");
+            c.pred += extend(br.bits(t), t);
+            coef[0] = (int16_t)c.pred;
+            for (int k = 1; k < 64;) {
+                const int rs = decode_symbol(br, ac[c.ta]);
+                const int r = rs >> 4, sz = rs & 15;
+                if (sz == 0) {
+                    if (r != 15) break;                                  // EOB
+                    k += 16;
+                    continue;
+                }
+                k += r;
+                if (k > 63) throw std::runtime_error("JPEG: AC run past the block");
+                coef[kZigzag[k]] = (int16_t)extend(br.bits(sz), sz);
+                ++k;
+            }
+            return;
+        }
+        if (sc.ss == 0) {                                                // progressive DC scan
+            if (sc.ah == 0) {
+                const int t = decode_symbol(br, dc[c.td]);
+                if (t > 11) throw std::runtime_error("JPEG: bad DC size");
+                c.pred += extend(br.bits(t), t);
+                coef[0] = (int16_t)(c.pred * (1 << sc.al));
+            } else if (br.bit()) {
+                coef[0] = (int16_t)(coef[0] | (1 << sc.al));
+            }
+            return;
+        }
+        const int p1 = 1 << sc.al, m1 = -(1 << sc.al);
+        if (sc.ah == 0) {                                                // progressive AC, first pass over this band
+            if (eobrun > 0) { --eobrun; return; }
+            for (int k = sc.ss; k <= sc.se;) {
+                const int rs = decode_symbol(br, ac[c.ta]);
+                const int r = rs >> 4, sz = rs & 15;
+                if (sz == 0) {
+                    if (r < 15) {
+                        eobrun = (1 << r) - 1;
+                        if (r) eobrun += br.bits(r);
+                        break;
+                    }
+                    k += 16;
+                } else {
+                    k += r;
+                    if (k > sc.se) throw std::runtime_error("JPEG: AC run past the band");
+                    coef[kZigzag[k]] = (int16_t)(extend(br.bits(sz), sz) * p1);
+                    ++k;
+                }
+            }
+            return;
+        }
+        // progressive AC refinement: one more bit for the coefficients that are already non-zero, new +-1 ones
+        int k = sc.ss;
+        if (eobrun <= 0) {
+            for (; k <= sc.se; ++k) {
+                const int rs = decode_symbol(br, ac[c.ta]);
+                int r = rs >> 4;
+                const int sz = rs & 15;
+                int val = 0;
+                if (sz == 0) {
+                    if (r < 15) {
+                        eobrun = 1 << r;
+                        if (r) eobrun += br.bits(r);
+                        break;
+                    }
+                } else {
+                    if (sz != 1) throw std::runtime_error("JPEG: bad refinement symbol");
+                    val = br.bit() ? p1 : m1;
+                }
+                while (k <= sc.se) {
+                    int16_t& cf = coef[kZigzag[k]];
+                    if (cf != 0) {
+                        if (br.bit() && (cf & p1) == 0) cf = (int16_t)(cf + (cf > 0 ? p1 : m1));
+                    } else {
+                        if (r == 0) { if (val) cf = (int16_t)val; break; }
+                        --r;
+                    }
+                    ++k;
+                }
+            }
+        }
+        if (eobrun > 0) {
+            for (; k <= sc.se; ++k) {
+                int16_t& cf = coef[kZigzag[k]];
+                if (cf != 0 && br.bit() && (cf & p1) == 0) cf = (int16_t)(cf + (cf > 0 ? p1 : m1));
+            }
+            --eobrun;
+        }
+    }
+
+    // Entropy-coded segment of one scan, starting at `pos`; returns the position of the marker that ends it.
+    size_t decode_scan(size_t pos, const Scan& sc) {
+        BitReader br{data + pos, data + size};
+        for (Component* c : sc.comps) c->pred = 0;
+        eobrun = 0;
+        const bool interleaved = sc.comps.size() > 1;
+        int units_x = mcus_x, units_y = mcus_y;
+        if (!interleaved) {                                              // one block per "MCU", over the component's own size
+            const Component& c = *sc.comps[0];
+            units_x = ((W * c.h + hmax - 1) / hmax + 7) / 8;
+            units_y = ((H * c.v + vmax - 1) / vmax + 7) / 8;
+        }
+        int until_restart = restart;
+        for (int uy = 0; uy < units_y; ++uy)
+            for (int ux = 0; ux < units_x; ++ux) {
+                if (restart && until_restart == 0) {                     // RSTn: byte-align, skip the marker, reset the predictors
+                    const uint8_t* q = br.p;
+                    while (q + 1 < br.end && !(q[0] == 0xFF && q[1] >= 0xD0 && q[1] <= 0xD7)) ++q;
+                    if (q + 1 >= br.end) throw std::runtime_error("JPEG: restart marker missing");
+                    br.p = q + 2;
+                    br.reset();
+                    for (Component* c : sc.comps) c->pred = 0;
+                    eobrun = 0;
+                    until_restart = restart;
+                }
+                if (interleaved) {
+                    for (Component* c : sc.comps)
+                        for (int by = 0; by < c->v; ++by)
+                            for (int bx = 0; bx < c->h; ++bx) decode_block(br, *c, block(*c, ux * c->h + bx, uy * c->v + by), sc);
+                } else {
+                    decode_block(br, *sc.comps[0], block(*sc.comps[0], ux, uy), sc);
+                }
+                --until_restart;
+            }
+        const uint8_t* q = br.p;                                          // the next marker (not a stuffed zero, not RSTn)
+        while (q + 1 < data + size && !(q[0] == 0xFF && q[1] != 0x00 && q[1] != 0xFF && !(q[1] >= 0xD0 && q[1] <= 0xD7))) ++q;
+        return (size_t)(q - data);
+    }
+};
+
 // Decodes `data` into RGBA8 (row 0 first, alpha 255). Throws std::runtime_error; `unsupported` is set when the
 // file is a JPEG variant this reader does not handle.
 void jpeg_decode_rgba8(const uint8_t* data, size_t size, std::vector<uint8_t>& rgba, int& width, int& height, bool& unsupported) {
     unsupported = false;
     try {
         if (size < 4 || data[0] != 0xFF || data[1] != 0xD8) throw std::runtime_error("JPEG: missing SOI");
-        uint16_t qt[4][64];
-        bool have_qt[4] = {false, false, false, false};
-        HuffTable dc[4], ac[4];
-        std::vector<Component> comps;
-        int W = 0, H = 0, hmax = 1, vmax = 1, restart = 0;
+        Decoder d;
+        d.data = data; d.size = size;
+        std::vector<Component>& comps = d.comps;
         bool have_sof = false, adobe = false;
-        int adobe_transform = -1;
+        int adobe_transform = -1, n_scans = 0;
         size_t pos = 2;
         bool done = false;
         while (!done) {
-            if (pos + 4 > size) throw std::runtime_error("JPEG: truncated before the scan");
+            if (pos + 2 > size) { if (n_scans) break; throw std::runtime_error("JPEG: truncated before the scan"); }
             if (data[pos] != 0xFF) throw std::runtime_error("JPEG: marker expected");
             while (pos < size && data[pos] == 0xFF) ++pos;           // fill bytes
+            if (pos >= size) { if (n_scans) break; throw std::runtime_error("JPEG: truncated before the scan"); }
             const int m = data[pos++];
             if (m == 0xD8 || (m >= 0xD0 && m <= 0xD7) || m == 0x01) continue;
-            if (m == 0xD9) throw std::runtime_error("JPEG: EOI before any scan");
+            if (m == 0xD9) { if (n_scans) break; throw std::runtime_error("JPEG: EOI before any scan"); }
             if (pos + 2 > size) throw std::runtime_error("JPEG: truncated segment");
             const size_t len = ((size_t)data[pos] << 8) | data[pos + 1];
             if (len < 2 || pos + len > size) throw std::runtime_error("JPEG: truncated segment");
@@ -176,10 +328,10 @@ void jpeg_decode_rgba8(const uint8_t* data, size_t size, std::vector<uint8_t>& r
                     ++i;
                     if (tq > 3 || i + (pq ? 128 : 64) > n) throw std::runtime_error("JPEG: bad DQT");
                     for (int k = 0; k < 64; ++k) {
-                        qt[tq][kZigzag[k]] = pq ? (uint16_t)((s[i] << 8) | s[i + 1]) : s[i];
+                        d.qt[tq][kZigzag[k]] = pq ? (uint16_t)((s[i] << 8) | s[i + 1]) : s[i];
                         i += pq ? 2 : 1;
                     }
-                    have_qt[tq] = true;
+                    d.have_qt[tq] = true;
                 }
             } else if (m == 0xC4) {                                   // DHT
                 size_t i = 0;
@@ -187,7 +339,7 @@ void jpeg_decode_rgba8(const uint8_t* data, size_t size, std::vector<uint8_t>& r
                     if (i + 17 > n) throw std::runtime_error("JPEG: bad DHT");
                     const int tc = s[i] >> 4, th = s[i] & 15;
                     if (tc > 1 || th > 3) throw std::runtime_error("JPEG: bad DHT id");
-                    HuffTable& t = tc ? ac[th] : dc[th];
+                    HuffTable& t = tc ? d.ac[th] : d.dc[th];
                     int total = 0;
                     for (int k = 1; k <= 16; ++k) { t.counts[k] = s[i + k]; total += t.counts[k]; }
                     i += 17;
@@ -197,12 +349,14 @@ void jpeg_decode_rgba8(const uint8_t* data, size_t size, std::vector<uint8_t>& r
                     t.present = true;
                     t.build();
                 }
-            } else if (m == 0xC0 || m == 0xC1) {                      // SOF0 / SOF1
+            } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {         // SOF0 / SOF1 / SOF2 (progressive)
+                if (have_sof) throw std::runtime_error("JPEG: more than one frame");
                 if (n < 6) throw std::runtime_error("JPEG: bad SOF");
                 if (s[0] != 8) throw Unsup("JPEG: only 8-bit samples are decoded");
-                H = (s[1] << 8) | s[2]; W = (s[3] << 8) | s[4];
+                d.progressive = m == 0xC2;
+                d.H = (s[1] << 8) | s[2]; d.W = (s[3] << 8) | s[4];
                 const int nc = s[5];
-                if (W <= 0 || H <= 0 || W > 32768 || H > 32768) throw std::runtime_error("JPEG: bad size");
+                if (d.W <= 0 || d.H <= 0 || d.W > 32768 || d.H > 32768) throw std::runtime_error("JPEG: bad size");
                 if (nc != 1 && nc != 3) throw Unsup("JPEG: only greyscale and YCbCr images are decoded (" + std::to_string(nc) + " components)");
                 if (n < (size_t)(6 + 3 * nc)) throw std::runtime_error("JPEG: bad SOF");
                 comps.assign(nc, Component());
@@ -210,86 +364,69 @@ void jpeg_decode_rgba8(const uint8_t* data, size_t size, std::vector<uint8_t>& r
                     comps[c].id = s[6 + 3 * c]; comps[c].h = s[7 + 3 * c] >> 4; comps[c].v = s[7 + 3 * c] & 15; comps[c].tq = s[8 + 3 * c];
                     if (comps[c].h < 1 || comps[c].h > 2 || comps[c].v < 1 || comps[c].v > 2 || comps[c].tq > 3)
                         throw Unsup("JPEG: sampling factors other than 1 and 2 are not decoded");
-                    hmax = std::max(hmax, comps[c].h); vmax = std::max(vmax, comps[c].v);
+                    d.hmax = std::max(d.hmax, comps[c].h); d.vmax = std::max(d.vmax, comps[c].v);
                 }
                 if (nc == 3 && (comps[1].h != 1 || comps[1].v != 1 || comps[2].h != 1 || comps[2].v != 1))
                     throw Unsup("JPEG: subsampled luma / oversampled chroma layouts are not decoded");
+                if (nc == 1) { comps[0].h = comps[0].v = 1; d.hmax = d.vmax = 1; }   // a single component is never subsampled
+                d.mcus_x = (d.W + 8 * d.hmax - 1) / (8 * d.hmax); d.mcus_y = (d.H + 8 * d.vmax - 1) / (8 * d.vmax);
+                d.coefs.resize(nc);
+                for (int c = 0; c < nc; ++c) {
+                    comps[c].bw = d.mcus_x * comps[c].h; comps[c].bh = d.mcus_y * comps[c].v;
+                    d.coefs[c].assign((size_t)comps[c].bw * comps[c].bh * 64, 0);
+                }
                 have_sof = true;
-            } else if (m == 0xC2 || m == 0xC3 || (m >= 0xC5 && m <= 0xCF && m != 0xC8)) {
-                throw Unsup("JPEG: progressive / lossless / arithmetic-coded files are not decoded (SOF marker 0x" +
+            } else if (m == 0xC3 || (m >= 0xC5 && m <= 0xCF && m != 0xC8)) {
+                throw Unsup("JPEG: lossless / hierarchical / arithmetic-coded files are not decoded (SOF marker 0x" +
                             std::string(1, "0123456789ABCDEF"[m >> 4]) + std::string(1, "0123456789ABCDEF"[m & 15]) + ")");
             } else if (m == 0xDD) {                                   // DRI
                 if (n < 2) throw std::runtime_error("JPEG: bad DRI");
-                restart = (s[0] << 8) | s[1];
+                d.restart = (s[0] << 8) | s[1];
             } else if (m == 0xEE && n >= 12 && !std::memcmp(s, "Adobe", 5)) {
                 adobe = true; adobe_transform = s[11];
             } else if (m == 0xDA) {                                   // SOS
                 if (!have_sof) throw std::runtime_error("JPEG: SOS before SOF");
-                const int ns = s[0];
-                if (ns != (int)comps.size() || n < (size_t)(4 + 2 * ns)) throw Unsup("JPEG: non-interleaved multi-scan files are not decoded");
+                const int ns = n ? s[0] : 0;
+                if (ns < 1 || ns > (int)comps.size() || n < (size_t)(4 + 2 * ns)) throw std::runtime_error("JPEG: bad SOS");
+                Scan sc;
                 for (int k = 0; k < ns; ++k) {
                     const int cid = s[1 + 2 * k];
                     Component* c = nullptr;
                     for (Component& cc : comps) if (cc.id == cid) c = &cc;
                     if (!c) throw std::runtime_error("JPEG: scan names an unknown component");
                     c->td = s[2 + 2 * k] >> 4; c->ta = s[2 + 2 * k] & 15;
-                    if (c->td > 3 || c->ta > 3 || !dc[c->td].present || !ac[c->ta].present || !have_qt[c->tq]) throw std::runtime_error("JPEG: scan uses a missing table");
+                    if (c->td > 3 || c->ta > 3) throw std::runtime_error("JPEG: bad table id");
+                    sc.comps.push_back(c);
                 }
-                pos += len;
-                done = true;
+                sc.ss = s[1 + 2 * ns]; sc.se = s[2 + 2 * ns]; sc.ah = s[3 + 2 * ns] >> 4; sc.al = s[3 + 2 * ns] & 15;
+                if (!d.progressive) { sc.ss = 0; sc.se = 63; sc.ah = sc.al = 0; }
+                if (sc.ss > sc.se || sc.se > 63 || sc.al > 13 || (d.progressive && sc.ss == 0 && sc.se != 0) || (sc.ss > 0 && ns != 1))
+                    throw std::runtime_error("JPEG: bad progressive scan parameters");
+                for (Component* c : sc.comps) {
+                    const bool need_dc = !d.progressive || (sc.ss == 0 && sc.ah == 0), need_ac = !d.progressive || sc.ss > 0;
+                    if ((need_dc && !d.dc[c->td].present) || (need_ac && !d.ac[c->ta].present)) throw std::runtime_error("JPEG: scan uses a missing Huffman table");
+                }
+                pos = d.decode_scan(pos + len, sc);
+                ++n_scans;
                 continue;
             }
             pos += len;
         }
         if (adobe && comps.size() == 3 && adobe_transform == 0) throw Unsup("JPEG: Adobe RGB (untransformed) files are not decoded");
+        const int W = d.W, H = d.H, hmax = d.hmax, vmax = d.vmax;
 
-        // ---- entropy-coded data: interleaved MCUs ----
-        const int mcu_w = 8 * hmax, mcu_h = 8 * vmax;
-        const int mcus_x = (W + mcu_w - 1) / mcu_w, mcus_y = (H + mcu_h - 1) / mcu_h;
+        // ---- dequantise + inverse DCT of every block ----
         for (Component& c : comps) {
-            c.bw = mcus_x * c.h; c.bh = mcus_y * c.v;
+            if (!d.have_qt[c.tq]) throw std::runtime_error("JPEG: missing quantisation table");
             c.plane.assign((size_t)c.bw * 8 * c.bh * 8, 0);
-        }
-        BitReader br{data + pos, data + size};
-        int coef[64];
-        int until_restart = restart;
-        for (int my = 0; my < mcus_y; ++my)
-            for (int mx = 0; mx < mcus_x; ++mx) {
-                if (restart && until_restart == 0) {                 // RSTn: byte-align, skip the marker, reset predictors
-                    const uint8_t* q = br.p;
-                    while (q + 1 < br.end && !(q[0] == 0xFF && q[1] >= 0xD0 && q[1] <= 0xD7)) ++q;
-                    if (q + 1 >= br.end) throw std::runtime_error("JPEG: restart marker missing");
-                    br.p = q + 2;
-                    br.reset();
-                    for (Component& c : comps) c.pred = 0;
-                    until_restart = restart;
+            int coef[64];
+            for (int by = 0; by < c.bh; ++by)
+                for (int bx = 0; bx < c.bw; ++bx) {
+                    const int16_t* src = d.block(c, bx, by);
+                    for (int k = 0; k < 64; ++k) coef[k] = (int)src[k] * d.qt[c.tq][k];
+                    idct8x8(coef, &c.plane[(size_t)by * 8 * c.bw * 8 + (size_t)bx * 8], c.bw * 8);
                 }
-                for (Component& c : comps)
-                    for (int by = 0; by < c.v; ++by)
-                        for (int bx = 0; bx < c.h; ++bx) {
-                            std::memset(coef, 0, sizeof coef);
-                            const int t = decode_symbol(br, dc[c.td]);
-                            if (t > 11) throw std::runtime_error("JPEG: bad DC size");
-                            c.pred += extend(br.bits(t), t);
-                            coef[0] = c.pred * qt[c.tq][0];
-                            for (int k = 1; k < 64;) {
-                                const int rs = decode_symbol(br, ac[c.ta]);
-                                const int r = rs >> 4, sz = rs & 15;
-                                if (sz == 0) {
-                                    if (r != 15) break;              // EOB
-                                    k += 16;
-                                    continue;
-                                }
-                                k += r;
-                                if (k > 63) throw std::runtime_error("JPEG: AC run past the block");
-                                coef[kZigzag[k]] = extend(br.bits(sz), sz) * qt[c.tq][kZigzag[k]];
-                                ++k;
-                            }
-                            const int px = (mx * c.h + bx) * 8, py = (my * c.v + by) * 8;
-                            idct8x8(coef, &c.plane[(size_t)py * c.bw * 8 + px], c.bw * 8);
-                        }
-                --until_restart;
-            }
+        }
 
         // ---- chroma upsampling + colour conversion ----
         width = W; height = H;
