@@ -34,10 +34,12 @@ struct BakeParams {
     int W, H, tiles_x, n_tiles, tile_lw;   // tile_lw: log2 of the direction tile's width
     int chunks, tiles_per_chunk;
     uint32_t n_items;
+    uint32_t n_whole;            // items [0, n_whole) are whole probes; item n_whole + j is chunk run j % chunks of probe n_whole + j / chunks
     float pixel_area;
-    float* out;                  // chunks == 1: final [slot][48]; else partials [item][48]
+    float* out;                  // final [slot][48]
+    float* partials;             // [item - n_whole][48] of the chunk-run items
     unsigned int* work_counter;
-    unsigned long long* stats;   // [0] shadow rays, [1] nodes visited, [2] triangles tested
+    unsigned long long* stats;   // [0] shadow rays, [1] nodes visited, [2] triangles tested, [4..11] COUNT builds: phase utilisation
     int ref_order, world_frame;
     WarpQueues* stream_scratch;  // k_bake_stream: per-warp radiance tile + ray queues, [grid * warps per block]
     int node_min;                // k_bake_stream: the node loop yields to the leaf phase below this many lanes
@@ -52,72 +54,6 @@ __device__ __forceinline__ size_t out_slot(const BakeParams& p, uint32_t q) {
     return (k == 0) ? s : (size_t)p.Nx * p.Ny + s * (p.Nz - 1) + (k - 1);
 }
 
-template <int K, bool COUNT>
-__global__ void __launch_bounds__(kBakeBlock) k_bake(const BakeParams p) {
-    constexpr int V = (K * 3 <= 32) ? 32 : 64;
-    const int lane = threadIdx.x & 31;
-    TraceCounters cnt; cnt.nodes = 0; cnt.tris = 0;
-    uint32_t shadow = 0;
-    for (;;) {
-        unsigned item = 0;
-        if (lane == 0) item = atomicAdd(p.work_counter, 1u);
-        item = __shfl_sync(0xffffffffu, item, 0);
-        if (item >= p.n_items) break;
-        const uint32_t q = item / (uint32_t)p.chunks, chunk = item % (uint32_t)p.chunks;
-        const uint32_t nxy = (uint32_t)(p.Nx * p.Ny), in_slice = q % nxy;
-        const Vec3 o = mk3(p.px[in_slice % p.Nx], p.py[in_slice / p.Nx], p.pz[p.k0 + (q / nxy) * p.kstride]);
-        float acc[V];
-#pragma unroll
-        for (int i = 0; i < V; ++i) acc[i] = 0.f;
-        const int t0 = chunk * p.tiles_per_chunk;
-        const int t1 = min(t0 + p.tiles_per_chunk, p.n_tiles);
-        for (int tile = t0; tile < t1; ++tile) {
-            const int x = tile_x(tile, lane, p.tiles_x, p.tile_lw);
-            const int y = tile_y(tile, lane, p.tiles_x, p.tile_lw);
-            if (x < p.W && y < p.H) {
-                const float2 row = __ldg(p.row_sc + y), col = __ldg(p.col_cs + x);
-                const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);   // sh_common.h:8-12
-                const Vec3 r = mk3(t.x, t.z, t.y);                         // env_map.rgen:21 .xzy
-                float rgb[3];
-                probe_ray_radiance<COUNT, K>(p.bvh, p.shade, p.c, o, r, rgb, &cnt, &shadow, &p.g);
-                const float w = p.pixel_area * row.x;                      // sh.comp:32-33
-                float b[K];
-                sh_basis<K>(p.world_frame ? r : t, b);                     // sh.comp:30,39
-#pragma unroll
-                for (int i = 0; i < K; ++i) {
-                    const float bw = b[i] * w;
-                    acc[3 * i + 0] = fmaf(bw, rgb[0], acc[3 * i + 0]);
-                    acc[3 * i + 1] = fmaf(bw, rgb[1], acc[3 * i + 1]);
-                    acc[3 * i + 2] = fmaf(bw, rgb[2], acc[3 * i + 2]);
-                }
-            }
-            __syncwarp();
-        }
-        warp_transpose_reduce<V>(acc, lane);
-        float* dst = p.out + (p.chunks == 1 ? out_slot(p, q) : (size_t)item) * VLB_SH_STRIDE;
-        if (V == 32) {
-            if (lane < K * 3) dst[lane] = acc[0];
-            if (lane + 32 < VLB_SH_STRIDE) dst[lane + 32] = 0.f;
-            if (lane >= K * 3) dst[lane] = 0.f;
-        } else {
-            if (2 * lane < VLB_SH_STRIDE) {
-                dst[2 * lane] = acc[0];
-                dst[2 * lane + 1] = acc[1];
-            }
-        }
-    }
-    // statistics: one atomic per warp
-    unsigned long long s = shadow, nn = cnt.nodes, nt = cnt.tris;
-    for (int off = 16; off > 0; off >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, off);
-        if (COUNT) { nn += __shfl_xor_sync(0xffffffffu, nn, off); nt += __shfl_xor_sync(0xffffffffu, nt, off); }
-    }
-    if (lane == 0) {
-        atomicAdd(p.stats + 0, s);
-        if (COUNT) { atomicAdd(p.stats + 1, nn); atomicAdd(p.stats + 2, nt); }
-    }
-}
-
 // =========================================================================================
 // k_bake_stream — the production bake kernel: a warp is a small wavefront path tracer.
 //
@@ -129,12 +65,22 @@ __global__ void __launch_bounds__(kBakeBlock) k_bake(const BakeParams p) {
 // the leaves are intersected. A finished primary ray only pushes its hit record into a per-warp
 // queue and frees its lane; once 32 records are queued the whole warp shades them
 // together (env_map.rchit / main.rmiss arithmetic at full SIMD width) and pushes the shadow rays
-// that are needed into a second queue. A finished shadow ray selects the lit or dark radiance
-// computed at shading time. Radiance goes to a shared-memory tile indexed by direction; when the
-// chunk is drained the warp projects its 256 radiances onto SH cooperatively (lane l takes
-// directions l, l+32, ... in a fixed order, so the result is bitwise reproducible whatever the
-// run-time ray scheduling was), reduces with shuffles and keeps one or two running coefficients per
-// lane. Radiance never leaves the SM; HBM sees 192 bytes per item.
+// that are needed into a second queue. Shading stores the radiance of the OCCLUDED outcome in the
+// warp's radiance tile and hands the lit radiance to the shadow ray, which overwrites the tile entry
+// when it escapes. When the chunk is drained the warp projects its 256 radiances onto SH cooperatively
+// (lane l takes directions l, l+32, ... in a fixed order, so the result is bitwise reproducible
+// whatever the run-time ray scheduling was), reduces with shuffles and keeps one or two running
+// coefficients per lane. Radiance never leaves the SM; HBM sees 192 bytes per probe.
+//
+// Where the per-ray state lives (round 2; round 1 kept all of it in local / global memory behind the
+// L1 LSU pipe, which ncu showed to be the binding unit):
+//   traversal stack   the top kSmemStack entries of every lane in SHARED memory, laid out [entry][lane] so
+//                     that lane l only ever touches bank l: a push or pop is one conflict-free wavefront
+//                     however far the lanes' depths have diverged (a per-thread local array costs one
+//                     wavefront per distinct depth). Deeper entries overflow to a global scratch slab
+//                     (rare: the short stack covers > 99 % of pushes on the BASELINE scenes).
+//   hit queue         shared memory (SoA, 20 bytes per record).
+//   shadow-ray queue, radiance tile   global scratch, L1/L2-resident, touched with coalesced accesses.
 // The per-ray arithmetic is exactly that of probe_ray_radiance (vlb_shade.cuh).
 // =========================================================================================
 constexpr int kChunkTiles = 8;
@@ -143,48 +89,94 @@ constexpr int kRayDone = kNoChild;          // traversal finished
 constexpr int kHitCap = 64;                 // queued hit records per warp (<= 31 waiting + 32 arriving)
 constexpr int kShadowCap = 64;              // queued shadow rays per warp (shading needs 32 free slots)
 constexpr int kStreamWarps = kBakeBlock / 32;
+#ifndef VLB_BAKE_SMEM_STACK
+#define VLB_BAKE_SMEM_STACK 12              // stack entries per lane in shared memory; 0 = round-1 per-thread local array
+#endif
+#ifndef VLB_BAKE_SMEM_HQ
+#define VLB_BAKE_SMEM_HQ 1                  // hit queue in shared memory
+#endif
+constexpr int kSmemStack = VLB_BAKE_SMEM_STACK;
+constexpr bool kSmemHq = VLB_BAKE_SMEM_HQ != 0;
+constexpr int kOvfStack = kSmemStack > 0 ? kStackSize - kSmemStack : 1;
 
+// hit queue (SoA): flat triangle id (-1: miss), t, u, v, direction index
+struct HitQueue {
+    int id[kHitCap]; float t[kHitCap], u[kHitCap], v[kHitCap]; int dir[kHitCap];
+};
 struct WarpQueues {
     float rad[3][kChunkDirs];      // radiance of the current chunk, by direction
-    // hit queue (SoA): flat triangle id (-1: miss), t, u, v, direction index
-    int hq_id[kHitCap]; float hq_t[kHitCap], hq_u[kHitCap], hq_v[kHitCap]; int hq_dir[kHitCap];
-    // shadow-ray queue: origin, unit direction, length, direction index, radiance if lit / if occluded
+    // shadow-ray queue: origin, unit direction, length, direction index, radiance if the light is visible
     float sq_o[3][kShadowCap], sq_d[3][kShadowCap], sq_len[kShadowCap]; int sq_dir[kShadowCap];
-    float sq_rgb[6][kShadowCap];
-    float lane_rgb[6][32];         // the same two radiances for the shadow ray a lane is tracing
+    float sq_rgb[3][kShadowCap];
+    HitQueue hq;                   // used when the hit queue is not in shared memory
+    int ovf[kOvfStack][32];        // stack entries beyond the shared-memory short stack, [entry][lane]
+};
+
+// Short stack in shared memory + overflow in global scratch; same interface as LocalStack (vlb_bvh.cuh).
+struct WarpStack {
+    int* sm;      // &s_stack[warp][0][lane]; entry e lives at sm[32 * e]
+    int* ovf;     // &scratch.ovf[0][lane]
+    int sp;
+    __device__ __forceinline__ void clear() { sp = 0; }
+    __device__ __forceinline__ bool empty() const { return sp == 0; }
+    __device__ __forceinline__ bool room(int n) const { return sp + n <= kStackSize; }
+    __device__ __forceinline__ void push(int v) {
+        if (sp < kSmemStack) sm[32 * sp] = v; else ovf[32 * (sp - kSmemStack)] = v;
+        ++sp;
+    }
+    __device__ __forceinline__ int pop() {
+        --sp;
+        return sp < kSmemStack ? sm[32 * sp] : ovf[32 * (sp - kSmemStack)];
+    }
 };
 
 #ifndef VLB_BAKE_MIN_BLOCKS
 #define VLB_BAKE_MIN_BLOCKS 8      // resident 128-thread blocks per SM the register allocation is held to (8 -> 64 registers)
 #endif
+constexpr size_t kBakeSmemPerBlock = (kSmemStack > 0 ? (size_t)kStreamWarps * kSmemStack * 32 * sizeof(int) : 0) +
+                                     (kSmemHq ? (size_t)kStreamWarps * sizeof(HitQueue) : 0);
+
 template <int K, bool COUNT, bool GATHER, bool TEX>
 __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) k_bake_stream(const BakeParams p) {
     constexpr int V = (K * 3 <= 32) ? 32 : 64;
-    // The per-warp queues live in a global scratch buffer (L1/L2 resident, ~9 KB per resident warp),
-    // not in shared memory: measured on B200, leaving the SM's 228 KB to the L1 cache (BVH nodes)
-    // and fitting 8 blocks per SM is worth more than shared-memory latency for the queue traffic
-    // (about 100 bytes per ray against ~1.5 KB of node and triangle reads).
+    __shared__ int s_stack[kSmemStack > 0 ? kStreamWarps : 1][kSmemStack > 0 ? kSmemStack : 1][32];
+    __shared__ HitQueue s_hq[kSmemHq ? kStreamWarps : 1];
     WarpQueues* s_all = p.stream_scratch + (size_t)blockIdx.x * kStreamWarps;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     WarpQueues& S = s_all[warp];
+    HitQueue& HQ = kSmemHq ? s_hq[warp] : S.hq;
     const BvhView& bvh = p.bvh;
     const bool want_shadow = (p.c.flags & 1u) != 0;
     TraceCounters cnt; cnt.nodes = 0; cnt.tris = 0;
     uint32_t shadow = 0;
-    int stack[kStackSize];
+    // COUNT builds: warp-level utilisation of the three phases (iterations, active lanes summed)
+    uint32_t u_node_it = 0, u_node_ln = 0, u_leaf_it = 0, u_leaf_ln = 0, u_shade_it = 0, u_shade_ln = 0, u_outer = 0, u_ovf = 0;
+#if VLB_BAKE_SMEM_STACK > 0
+    WarpStack stk;
+    stk.sm = &s_stack[warp][0][lane];
+    stk.ovf = &S.ovf[0][lane];
+#else
+    LocalStack stk;
+#endif
+    stk.clear();
 
     for (;;) {
         unsigned item = 0;
         if (lane == 0) item = atomicAdd(p.work_counter, 1u);
         item = __shfl_sync(full, item, 0);
         if (item >= p.n_items) break;
-        const uint32_t q = item / (uint32_t)p.chunks, part = item % (uint32_t)p.chunks;
+        // items [0, n_whole): one whole probe each, written straight to the output; the rest: one chunk run of a
+        // probe each, written as a partial (bake_device explains why the two give bit-identical sums)
+        uint32_t q, part;
+        const bool whole = item < p.n_whole;
+        if (whole) { q = item; part = 0; }
+        else { const uint32_t j = item - p.n_whole; q = p.n_whole + j / (uint32_t)p.chunks; part = j % (uint32_t)p.chunks; }
         const uint32_t nxy = (uint32_t)(p.Nx * p.Ny), in_slice = q % nxy;
         const Vec3 po = mk3(p.px[in_slice % p.Nx], p.py[in_slice / p.Nx], p.pz[p.k0 + (q / nxy) * p.kstride]);
-        const int tile_begin = part * p.tiles_per_chunk;
-        const int tile_end = min(tile_begin + p.tiles_per_chunk, p.n_tiles);
+        const int tile_begin = whole ? 0 : part * p.tiles_per_chunk;
+        const int tile_end = whole ? p.n_tiles : min(tile_begin + p.tiles_per_chunk, p.n_tiles);
         float coef0 = 0.f, coef1 = 0.f;   // running sums of coefficient `lane` (V=32) / 2*lane, 2*lane+1 (V=64)
 
         for (int base_tile = tile_begin; base_tile < tile_end; base_tile += kChunkTiles) {
@@ -193,26 +185,29 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
             int next = 0, n_hit = 0, n_sh = 0;   // warp-uniform: directions handed out, queue fills
             bool busy = false;
             int kind = 0;                        // 0 primary (closest hit), 1 shadow (any hit)
-            int my_dir = 0, cur = kRayDone, sp = 0;
+            int my_dir = 0, cur = kRayDone;
             Vec3 ro = po, rd = po, idir = po, ood = po;
             float tmin = 0.f, tcull = 0.f;
+            // primary ray: the closest hit so far. Shadow ray: id = -1 until occluded, (t, u, v) = the radiance of
+            // the direction if the light turns out to be visible (an any-hit ray has no use for them).
             HitRec best; best.id = -1; best.t = 0.f; best.u = 0.f; best.v = 0.f;
             for (;;) {
+                if (COUNT) ++u_outer;
                 // ---- 1. refill idle lanes: queued shadow rays first, then new directions ----
                 const unsigned idle = __ballot_sync(full, !busy);
                 if (idle != 0u && (n_sh > 0 || next < n_dirs)) {
                     const int n_idle = __popc(idle), rank = __popc(idle & lt_mask);
                     const int take_sh = min(n_idle, n_sh);
                     const int take_new = min(n_idle - take_sh, n_dirs - next);
+                    bool fresh = false;
                     if (!busy && rank < take_sh) {
                         const int e = n_sh - 1 - rank;
                         ro = mk3(S.sq_o[0][e], S.sq_o[1][e], S.sq_o[2][e]);
                         rd = mk3(S.sq_d[0][e], S.sq_d[1][e], S.sq_d[2][e]);
                         tmin = 0.0f; tcull = S.sq_len[e];                               // env_map.rchit:87
                         my_dir = S.sq_dir[e];
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) S.lane_rgb[k][lane] = S.sq_rgb[k][e];
-                        kind = 1; busy = true;
+                        best.id = -1; best.t = S.sq_rgb[0][e]; best.u = S.sq_rgb[1][e]; best.v = S.sq_rgb[2][e];
+                        kind = 1; busy = true; fresh = true;
                     } else if (!busy && rank - take_sh < take_new) {
                         const int cand = next + rank - take_sh;
                         const int tile = base_tile + (cand >> 5), w = cand & 31;
@@ -224,16 +219,16 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                             rd = mk3(t.x, t.z, t.y);                                   // env_map.rgen:21 .xzy
                             ro = po;
                             tmin = p.c.tmin; tcull = p.c.tmax;
-                            my_dir = cand; kind = 0; busy = true;
+                            best.id = -1; best.t = tcull; best.u = 0.f; best.v = 0.f;
+                            my_dir = cand; kind = 0; busy = true; fresh = true;
                         } else {
                             S.rad[0][cand] = 0.f; S.rad[1][cand] = 0.f; S.rad[2][cand] = 0.f;   // outside the direction grid
                         }
                     }
-                    if (busy && cur == kRayDone) {     // freshly started ray
+                    if (fresh) {
                         idir = mk3(safe_inv(rd.x), safe_inv(rd.y), safe_inv(rd.z));
                         ood = mk3(ro.x * idir.x, ro.y * idir.y, ro.z * idir.z);
-                        best.id = -1; best.t = tcull; best.u = 0.f; best.v = 0.f;
-                        sp = 0;
+                        stk.clear();
                         cur = bvh.n_tris ? 0 : kRayDone;
                     }
                     n_sh -= take_sh;
@@ -245,13 +240,14 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                 if ((n_hit >= 32 && n_sh <= kShadowCap - 32) || (running == 0u && n_hit > 0)) {
                     const int take = min(n_hit, 32);
                     const int e = n_hit - take + lane;
+                    if (COUNT) { ++u_shade_it; u_shade_ln += take; }
                     bool push = false;
-                    float lit_rgb[3] = {0.f, 0.f, 0.f}, dark_rgb[3] = {0.f, 0.f, 0.f};
+                    float lit_rgb[3] = {0.f, 0.f, 0.f};
                     ShadePrelude pre;
                     int dir = 0;
                     if (lane < take) {
-                        HitRec h; h.id = S.hq_id[e]; h.t = S.hq_t[e]; h.u = S.hq_u[e]; h.v = S.hq_v[e];
-                        dir = S.hq_dir[e];
+                        HitRec h; h.id = HQ.id[e]; h.t = HQ.t[e]; h.u = HQ.u[e]; h.v = HQ.v[e];
+                        dir = HQ.dir[e];
                         const int tile = base_tile + (dir >> 5), w = dir & 31;
                         const int x = tile_x(tile, w, p.tiles_x, p.tile_lw);
                         const int y = tile_y(tile, w, p.tiles_x, p.tile_lw);
@@ -266,9 +262,10 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                             // right here, per lane (main.rchit:143-163); only the sun shadow ray is queued
                             if (GATHER) gather_indirect<K, COUNT>(bvh, p.g, pre, ind, &cnt);
                             if (lit && want_shadow) {
-                                // radiance for both outcomes now, the shadow ray decides (env_map.rchit:83-99)
+                                // radiance for both outcomes now, the shadow ray decides (env_map.rchit:83-99):
+                                // the tile gets the occluded one, the ray carries the lit one
                                 shade_finish(p.c, pre, r, false, ind, lit_rgb);
-                                shade_finish(p.c, pre, r, true, ind, dark_rgb);
+                                shade_finish(p.c, pre, r, true, ind, rgb);
                                 push = true;
                             } else {
                                 shade_finish(p.c, pre, r, !lit, ind, rgb);
@@ -277,10 +274,8 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                             sky_lookup(p.shade, r, rgb);
                             if (p.c.flags & 4u) { rgb[0] = srgb_encode(rgb[0]); rgb[1] = srgb_encode(rgb[1]); rgb[2] = srgb_encode(rgb[2]); }
                         }
-                        if (!push) {
-                            if (p.c.flags & 8u) { rgb[0] = quant8(rgb[0]); rgb[1] = quant8(rgb[1]); rgb[2] = quant8(rgb[2]); }
-                            S.rad[0][dir] = rgb[0]; S.rad[1][dir] = rgb[1]; S.rad[2][dir] = rgb[2];
-                        }
+                        if (p.c.flags & 8u) { rgb[0] = quant8(rgb[0]); rgb[1] = quant8(rgb[1]); rgb[2] = quant8(rgb[2]); }
+                        S.rad[0][dir] = rgb[0]; S.rad[1][dir] = rgb[1]; S.rad[2][dir] = rgb[2];
                     }
                     const unsigned pm = __ballot_sync(full, push);
                     if (push) {
@@ -289,7 +284,7 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                         S.sq_d[0][d] = pre.Ln.x; S.sq_d[1][d] = pre.Ln.y; S.sq_d[2][d] = pre.Ln.z;
                         S.sq_len[d] = pre.llen; S.sq_dir[d] = dir;
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) { S.sq_rgb[k][d] = lit_rgb[k]; S.sq_rgb[3 + k][d] = dark_rgb[k]; }
+                        for (int k = 0; k < 3; ++k) S.sq_rgb[k][d] = lit_rgb[k];
                         ++shadow;
                     }
                     n_sh += __popc(pm);
@@ -306,16 +301,25 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                     const bool at_node = busy && cur >= 0;
                     const unsigned nm = __ballot_sync(full, at_node);
                     if (nm == 0u || (__popc(nm) < p.node_min && __popc(running) - __popc(nm) >= p.node_min)) break;
+                    if (COUNT) { ++u_node_it; u_node_ln += __popc(nm); }
                     if (at_node) {
-                        if (COUNT) cnt.nodes++;
-                        cur = bvh4_step<true>(bvh, cur, idir, ood, tmin, tcull, stack, sp);   // one code path for both ray kinds
+                        if (COUNT) { cnt.nodes++; if (stk.sp > kSmemStack) ++u_ovf; }
+                        cur = bvh4_step<true>(bvh, cur, idir, ood, tmin, tcull, stk);   // one code path for both ray kinds
                     }
                 }
                 // ---- 4. leaves ----
-                if (busy && cur < 0 && cur != kRayDone) {
-                    const bool terminated = kind ? leaf_step<true, COUNT>(bvh, cur, ro, rd, tmin, tcull, best, &cnt)
-                                                 : leaf_step<false, COUNT>(bvh, cur, ro, rd, tmin, tcull, best, &cnt);
-                    cur = (terminated || sp == 0) ? kRayDone : stack[--sp];
+                const bool at_leaf = busy && cur < 0 && cur != kRayDone;
+                if (COUNT) { const unsigned lm = __ballot_sync(full, at_leaf); if (lm) { ++u_leaf_it; u_leaf_ln += __popc(lm); } }
+                if (at_leaf) {
+                    bool terminated;
+                    if (kind) {
+                        HitRec occ; occ.id = -1; occ.t = tcull; occ.u = 0.f; occ.v = 0.f;
+                        terminated = leaf_step<true, COUNT>(bvh, cur, ro, rd, tmin, tcull, occ, &cnt);
+                        if (terminated) best.id = 0;                                    // occluded (shadow.rmiss did not run)
+                    } else {
+                        terminated = leaf_step<false, COUNT>(bvh, cur, ro, rd, tmin, tcull, best, &cnt);
+                    }
+                    cur = (terminated || stk.empty()) ? kRayDone : stk.pop();
                 }
                 // ---- 5. finished rays free their lane ----
                 const bool fin = busy && cur == kRayDone;
@@ -323,10 +327,9 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                 if (fin) {
                     if (kind == 0) {
                         const int e = n_hit + __popc(fp & lt_mask);
-                        S.hq_id[e] = best.id; S.hq_t[e] = best.t; S.hq_u[e] = best.u; S.hq_v[e] = best.v; S.hq_dir[e] = my_dir;
-                    } else {
-                        const int o3 = best.id >= 0 ? 3 : 0;                            // occluded -> dark
-                        float rgb[3] = {S.lane_rgb[o3 + 0][lane], S.lane_rgb[o3 + 1][lane], S.lane_rgb[o3 + 2][lane]};
+                        HQ.id[e] = best.id; HQ.t[e] = best.t; HQ.u[e] = best.u; HQ.v[e] = best.v; HQ.dir[e] = my_dir;
+                    } else if (best.id < 0) {                                           // light visible: the lit radiance replaces the occluded one
+                        float rgb[3] = {best.t, best.u, best.v};
                         if (p.c.flags & 8u) { rgb[0] = quant8(rgb[0]); rgb[1] = quant8(rgb[1]); rgb[2] = quant8(rgb[2]); }  // QUANTIZE_RGBA8
                         S.rad[0][my_dir] = rgb[0]; S.rad[1][my_dir] = rgb[1]; S.rad[2][my_dir] = rgb[2];
                     }
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
             if (V == 64) coef1 += acc[1];
             __syncwarp();
         }
-        float* dst = p.out + (p.chunks == 1 ? out_slot(p, q) : (size_t)item) * VLB_SH_STRIDE;
+        float* dst = whole ? p.out + out_slot(p, q) * VLB_SH_STRIDE : p.partials + (size_t)(item - p.n_whole) * VLB_SH_STRIDE;
         if (V == 32) {
             dst[lane] = lane < K * 3 ? coef0 : 0.f;
             if (lane + 32 < VLB_SH_STRIDE) dst[lane + 32] = 0.f;
@@ -380,20 +383,30 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
         s += __shfl_xor_sync(full, s, off);
         if (COUNT) { nn += __shfl_xor_sync(full, nn, off); nt += __shfl_xor_sync(full, nt, off); }
     }
+    if (COUNT) {
+        unsigned long long ov = u_ovf;
+        for (int off = 16; off > 0; off >>= 1) ov += __shfl_xor_sync(full, ov, off);
+        if (lane == 0) {
+            atomicAdd(p.stats + 4, (unsigned long long)u_node_it); atomicAdd(p.stats + 5, (unsigned long long)u_node_ln);
+            atomicAdd(p.stats + 6, (unsigned long long)u_leaf_it); atomicAdd(p.stats + 7, (unsigned long long)u_leaf_ln);
+            atomicAdd(p.stats + 8, (unsigned long long)u_shade_it); atomicAdd(p.stats + 9, (unsigned long long)u_shade_ln);
+            atomicAdd(p.stats + 10, (unsigned long long)u_outer); atomicAdd(p.stats + 11, ov);
+        }
+    }
     if (lane == 0) {
         atomicAdd(p.stats + 0, s);
         if (COUNT) { atomicAdd(p.stats + 1, nn); atomicAdd(p.stats + 2, nt); }
     }
 }
 
-// chunks > 1: per-probe sum of the chunk partials in chunk order (fixed order => deterministic).
-__global__ void k_sum_partials(const BakeParams p, const float* __restrict__ partials, uint32_t n_probes, float* out) {
+// Probes baked as chunk-run items: per-probe sum of the partials in chunk order (fixed order => deterministic).
+__global__ void k_sum_partials(const BakeParams p, uint32_t n_probes) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_probes * VLB_SH_STRIDE) return;
-    const uint32_t q = idx / VLB_SH_STRIDE, c = idx % VLB_SH_STRIDE;
+    if (idx >= (n_probes - p.n_whole) * VLB_SH_STRIDE) return;
+    const uint32_t j = idx / VLB_SH_STRIDE, c = idx % VLB_SH_STRIDE;
     float s = 0.f;
-    for (int k = 0; k < p.chunks; ++k) s += partials[((size_t)q * p.chunks + k) * VLB_SH_STRIDE + c];
-    out[out_slot(p, q) * VLB_SH_STRIDE + c] = s;
+    for (int k = 0; k < p.chunks; ++k) s += p.partials[((size_t)j * p.chunks + k) * VLB_SH_STRIDE + c];
+    p.out[out_slot(p, p.n_whole + j) * VLB_SH_STRIDE + c] = s;
 }
 
 // VLB_BAKE_ACCUMULATE_ACROSS_PROBES: the reference never re-zeroes its SSBO (light_baker.cpp:110-121),
@@ -438,10 +451,10 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     }
     VLB_CUDA(ctx, ctx->d_axis.reserve(axis.size() * sizeof(float)));
     VLB_CUDA(ctx, ctx->d_work_counter.reserve(16));
-    VLB_CUDA(ctx, ctx->d_stats.reserve(4 * sizeof(unsigned long long)));
+    VLB_CUDA(ctx, ctx->d_stats.reserve(16 * sizeof(unsigned long long)));
     VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_axis.p, axis.data(), axis.size() * sizeof(float), cudaMemcpyHostToDevice, st));
     VLB_CUDA(ctx, cudaMemsetAsync(ctx->d_work_counter.p, 0, 16, st));
-    VLB_CUDA(ctx, cudaMemsetAsync(ctx->d_stats.p, 0, 4 * sizeof(unsigned long long), st));
+    VLB_CUDA(ctx, cudaMemsetAsync(ctx->d_stats.p, 0, 16 * sizeof(unsigned long long), st));
 
     BakeParams p{};
     p.bvh.nodes = ctx->d_nodes.as<float4>(); p.bvh.tris = ctx->d_tris.as<float4>(); p.bvh.n_tris = (uint32_t)ctx->n_tris;
@@ -465,22 +478,7 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     const int tile_w = 1 << p.tile_lw, tile_h = 32 >> p.tile_lw;
     p.tiles_x = (W + tile_w - 1) / tile_w;
     p.n_tiles = p.tiles_x * ((H + tile_h - 1) / tile_h);
-    // Work decomposition: a function of the WHOLE grid and the direction grid only (never of the
-    // slab), so that a probe's coefficients are bit-identical however the grid is sharded. An item is
-    // one 256-direction chunk of one probe (8 tiles: measured best on B200 for large grids); for
-    // small grids the chunk is halved down to one tile until the whole grid has >= 2^18 items, i.e.
-    // every GPU of an 8-way shard still sees several waves of warps.
-    const uint64_t total_probes = (uint64_t)Nx * Ny * Nz;
-    int tiles_per_item = kChunkTiles;
-    while (tiles_per_item > 1 && total_probes * (uint64_t)((p.n_tiles + tiles_per_item - 1) / tiles_per_item) < (1ull << 18))
-        tiles_per_item >>= 1;
-    int chunks = (p.n_tiles + tiles_per_item - 1) / tiles_per_item;
-    chunks = env_flag("VLB_BAKE_CHUNKS", chunks);
-    chunks = std::max(1, std::min(chunks, p.n_tiles));
-    p.tiles_per_chunk = (p.n_tiles + chunks - 1) / chunks;
-    p.chunks = (p.n_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
-    if (n_probes * (uint64_t)p.chunks >= (1ull << 32)) return ctx->fail(VLB_ERR_UNSUPPORTED, "bake: too many work items");
-    p.n_items = (uint32_t)(n_probes * (uint64_t)p.chunks);
+    p.tiles_per_chunk = 0;       // the work decomposition follows the kernel choice (it needs the resident warp count)
     p.pixel_area = (2.0f * kPi / (float)W) * (kPi / (float)H);            // sh.comp:32
     p.work_counter = ctx->d_work_counter.as<unsigned int>();
     p.stats = ctx->d_stats.as<unsigned long long>();
@@ -491,38 +489,65 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     for (int k = 0; k < 3; ++k) { p.g.origin[k] = s->origin[k]; p.g.step[k] = s->step[k]; }
     p.g.gain = s->indirect_gain; p.g.world_frame = p.world_frame;
     const bool gather = d_prev_full != nullptr;
-    if (p.chunks > 1) {
-        VLB_CUDA(ctx, ctx->d_partials.reserve((size_t)p.n_items * VLB_SH_STRIDE * sizeof(float)));
-        p.out = ctx->d_partials.as<float>();
-    } else {
-        p.out = d_out;
-    }
+    p.out = d_out;
 
     const bool count = env_flag("VLB_BAKE_COUNTERS", 0) != 0;
     const int K = s->sh_order == 2 ? 9 : 16;
-    void (*kern)(const BakeParams) = nullptr;
-    if (env_flag("VLB_BAKE_KERNEL", 2) == 1) {      // the round-1 tile-per-warp kernel, kept for A/B runs
-        if (K == 9) kern = count ? k_bake<9, true> : k_bake<9, false>;
-        else        kern = count ? k_bake<16, true> : k_bake<16, false>;
-    } else {
-        // TEX: only scenes with a textured material pay for the texture branch of the hit shading
-        const bool tex = ctx->max_tex_index >= 0;
+    // TEX: only scenes with a textured material pay for the texture branch of the hit shading
+    const bool tex = ctx->max_tex_index >= 0;
 #define VLB_PICK(KK) (gather ? (tex ? (count ? k_bake_stream<KK, true, true, true> : k_bake_stream<KK, false, true, true>)     \
                                     : (count ? k_bake_stream<KK, true, true, false> : k_bake_stream<KK, false, true, false>))   \
                              : (tex ? (count ? k_bake_stream<KK, true, false, true> : k_bake_stream<KK, false, false, true>)   \
                                     : (count ? k_bake_stream<KK, true, false, false> : k_bake_stream<KK, false, false, false>)))
-        kern = K == 9 ? VLB_PICK(9) : VLB_PICK(16);
+    void (*kern)(const BakeParams) = K == 9 ? VLB_PICK(9) : VLB_PICK(16);
 #undef VLB_PICK
-    }
-    // the kernel uses no shared memory: ask for the whole 228 KB as L1 (BVH nodes, per-warp queues)
-    if (env_flag("VLB_BAKE_CARVEOUT", 0) >= 0)
-        VLB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, env_flag("VLB_BAKE_CARVEOUT", 0)));
+    // Shared memory holds the short stacks and the hit queues (kBakeSmemPerBlock per block); everything else of the
+    // SM's 228 KB stays L1 (BVH nodes, triangles, shadow-ray queues, radiance tiles).
+    const int min_blocks = gather ? 6 : VLB_BAKE_MIN_BLOCKS;
+    int carve = (int)((min_blocks * (kBakeSmemPerBlock + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+    carve = env_flag("VLB_BAKE_CARVEOUT", std::min(100, carve));
+    if (carve >= 0) VLB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     int per_sm = 0;
     VLB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kBakeBlock, 0));
     per_sm = std::max(per_sm, 1);
-    const uint32_t warps_needed = p.n_items;
-    uint32_t grid = (uint32_t)(ctx->sm_count * per_sm);
-    grid = std::max(1u, std::min(grid, (warps_needed + (kBakeBlock / 32) - 1) / (kBakeBlock / 32)));
+    const uint32_t full_grid = (uint32_t)(ctx->sm_count * per_sm);
+
+    // Work decomposition. A probe's directions are traced in chunks of 8 tiles = 256 directions whose SH sums are
+    // added up in chunk order, so a probe can be ONE work item (a warp walks all its chunks and writes the 192-byte
+    // result itself) or one item PER CHUNK (each writes a partial, k_sum_partials adds them in chunk order): both
+    // give bit-identical coefficients, because 0 + a_0 + a_1 + ... is evaluated left to right either way. Whole-probe
+    // items need no partials (round 1 wrote and re-read 403 MB of them at C3) but are long (16 chunks at 64x64
+    // directions); so the first probes of the call are whole-probe items and the last ones, about `tail_waves`
+    // rounds of all resident warps, are per-chunk items that fill the gaps while the long items retire. Which probes
+    // fall into the tail depends on the call; the coefficients do not, so a probe's result is bit-identical however
+    // the grid is sharded. Direction grids of less than one chunk per item (small grids: the chunk is halved down to
+    // one tile until the whole grid has >= 2^18 items) are all partial items, as in round 1; that choice is a function
+    // of the WHOLE grid and the direction grid only.
+    const uint64_t total_probes = (uint64_t)Nx * Ny * Nz;
+    int tiles_per_item = kChunkTiles;
+    while (tiles_per_item > 1 && total_probes * (uint64_t)((p.n_tiles + tiles_per_item - 1) / tiles_per_item) < (1ull << 18))
+        tiles_per_item >>= 1;
+    int chunks = (p.n_tiles + tiles_per_item - 1) / tiles_per_item;
+    chunks = std::max(1, std::min(chunks, p.n_tiles));
+    p.tiles_per_chunk = (p.n_tiles + chunks - 1) / chunks;
+    p.chunks = (p.n_tiles + p.tiles_per_chunk - 1) / p.tiles_per_chunk;
+    uint64_t n_whole = 0;
+    if (p.chunks == 1) {
+        n_whole = n_probes;
+    } else if (p.tiles_per_chunk == kChunkTiles) {
+        const uint64_t tail_waves = (uint64_t)std::max(0, env_flag("VLB_BAKE_TAIL_WAVES", 8));
+        const uint64_t tail_probes = env_flag("VLB_BAKE_TAIL_WAVES", 8) < 0 ? n_probes
+                                     : std::min<uint64_t>(n_probes, (tail_waves * full_grid * kStreamWarps + p.chunks - 1) / p.chunks);
+        n_whole = n_probes - tail_probes;
+    }
+    const uint64_t n_items = n_whole + (n_probes - n_whole) * (uint64_t)p.chunks;
+    if (n_items >= (1ull << 32)) return ctx->fail(VLB_ERR_UNSUPPORTED, "bake: too many work items");
+    p.n_items = (uint32_t)n_items; p.n_whole = (uint32_t)n_whole;
+    if (n_whole < n_probes) {
+        VLB_CUDA(ctx, ctx->d_partials.reserve((size_t)(n_items - n_whole) * VLB_SH_STRIDE * sizeof(float)));
+        p.partials = ctx->d_partials.as<float>();
+    }
+    const uint32_t grid = std::max(1u, std::min(full_grid, (p.n_items + kStreamWarps - 1) / kStreamWarps));
 
     VLB_CUDA(ctx, ctx->d_stream_scratch.reserve((size_t)grid * kStreamWarps * sizeof(WarpQueues)));
     p.stream_scratch = ctx->d_stream_scratch.as<WarpQueues>();
@@ -531,9 +556,9 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     kern<<<grid, kBakeBlock, 0, st>>>(p);
     VLB_LAUNCH_CHECK(ctx);
     VLB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
-    if (p.chunks > 1) {
-        const uint32_t n = (uint32_t)n_probes * VLB_SH_STRIDE;
-        k_sum_partials<<<(n + 255) / 256, 256, 0, st>>>(p, ctx->d_partials.as<float>(), (uint32_t)n_probes, d_out);
+    if (p.n_whole < n_probes) {
+        const uint32_t n = (uint32_t)(n_probes - p.n_whole) * VLB_SH_STRIDE;
+        k_sum_partials<<<(n + 255) / 256, 256, 0, st>>>(p, (uint32_t)n_probes);
         VLB_LAUNCH_CHECK(ctx);
     }
     if (s->flags & VLB_BAKE_ACCUMULATE_ACROSS_PROBES) {
@@ -543,10 +568,11 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     VLB_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     // statistics + overflow flag travel to pinned host memory asynchronously; bake_collect_stats() waits for them.
     // (The axis table above was copied from pageable memory, which is staged before cudaMemcpyAsync returns.)
-    if (!ctx->h_bake_stats) VLB_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_bake_stats), 4 * sizeof(unsigned long long), cudaHostAllocDefault));
+    if (!ctx->h_bake_stats) VLB_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_bake_stats), 16 * sizeof(unsigned long long), cudaHostAllocDefault));
     ctx->h_bake_stats[3] = 0;
     VLB_CUDA(ctx, cudaMemcpyAsync(ctx->h_bake_stats, ctx->d_stats.p, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     VLB_CUDA(ctx, cudaMemcpyAsync(ctx->h_bake_stats + 3, ctx->d_scratch.as<float>() + 13, 4, cudaMemcpyDeviceToHost, st));
+    VLB_CUDA(ctx, cudaMemcpyAsync(ctx->h_bake_stats + 4, ctx->d_stats.as<unsigned long long>() + 4, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     VLB_CUDA(ctx, cudaEventRecord(ctx->ev_done, st));
     ctx->last_bake.n_probes = n_probes;
     ctx->last_bake.n_primary_rays = n_probes * (uint64_t)W * H;
@@ -563,6 +589,13 @@ int bake_collect_stats(vlb_ctx* ctx) {
     b.n_shadow_rays = ctx->h_bake_stats[0]; b.n_nodes_visited = ctx->h_bake_stats[1]; b.n_tris_tested = ctx->h_bake_stats[2];
     VLB_CUDA(ctx, cudaEventElapsedTime(&b.kernel_ms, ctx->ev[2], ctx->ev[3]));
     VLB_CUDA(ctx, cudaEventElapsedTime(&b.total_ms, ctx->ev[0], ctx->ev[1]));
+    if (env_flag("VLB_BAKE_COUNTERS", 0) >= 2) {     // phase utilisation of the instrumented kernel (diagnostics)
+        const unsigned long long* h = ctx->h_bake_stats;
+        fprintf(stderr, "[vlb bake counters] node steps: %llu warp iterations, %.2f lanes active | leaf steps: %llu, %.2f lanes | "
+                        "shade: %llu, %.2f lanes | outer iterations %llu | node steps with the stack beyond %d entries: %.4f %%\n",
+                h[4], h[4] ? (double)h[5] / h[4] : 0.0, h[6], h[6] ? (double)h[7] / h[6] : 0.0, h[8], h[8] ? (double)h[9] / h[8] : 0.0,
+                h[10], kSmemStack, h[1] ? 100.0 * h[11] / h[1] : 0.0);
+    }
     if (ctx->h_bake_stats[3])
         return ctx->fail(VLB_ERR_UNSUPPORTED, "bake: BVH traversal stack overflow (more than %d pending nodes on a ray)", kStackSize);
     return VLB_OK;

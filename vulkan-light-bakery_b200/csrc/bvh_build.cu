@@ -63,7 +63,9 @@ __global__ void k_scene_bounds(const float4* __restrict__ tri_flat, uint32_t n, 
     }
 }
 
-__global__ void k_morton(const float4* __restrict__ tri_flat, uint32_t n, const float* __restrict__ scratch,
+// cubic: all three axes are normalised by the LARGEST centroid extent, so Morton cells are cubes and a flat scene
+// spends no key bits (= no tree levels) on splits along its short axes; else every axis is stretched to [0, 1].
+__global__ void k_morton(const float4* __restrict__ tri_flat, uint32_t n, const float* __restrict__ scratch, int cubic,
                          uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
@@ -71,8 +73,9 @@ __global__ void k_morton(const float4* __restrict__ tri_flat, uint32_t n, const 
     tri_aabb(tri_flat[3ull * t], tri_flat[3ull * t + 1], tri_flat[3ull * t + 2], &lo, &hi);
     const float c[3] = {0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z)};
     float nrm[3];
+    const float ext_max = fmaxf(scratch[9] - scratch[6], fmaxf(scratch[10] - scratch[7], scratch[11] - scratch[8]));
     for (int k = 0; k < 3; ++k) {
-        const float ext = scratch[9 + k] - scratch[6 + k];
+        const float ext = cubic ? ext_max : scratch[9 + k] - scratch[6 + k];
         nrm[k] = ext > 0.f ? (c[k] - scratch[6 + k]) / ext : 0.f;
     }
     keys[t] = morton63(nrm[0], nrm[1], nrm[2]);
@@ -183,7 +186,8 @@ int bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats) {
         const unsigned red_grid = std::min<unsigned>(grid_n, (unsigned)ctx->sm_count * 8u);
         k_scene_bounds<<<red_grid, B, 0, st>>>(ctx->d_tri_flat.as<float4>(), n, ctx->d_scratch.as<float>());
         VLB_LAUNCH_CHECK(ctx);
-        k_morton<<<grid_n, B, 0, st>>>(ctx->d_tri_flat.as<float4>(), n, ctx->d_scratch.as<float>(),
+        const char* cubic_env = getenv("VLB_BVH_CUBIC");
+        k_morton<<<grid_n, B, 0, st>>>(ctx->d_tri_flat.as<float4>(), n, ctx->d_scratch.as<float>(), cubic_env && *cubic_env ? atoi(cubic_env) : 0,
                                       ctx->d_keys.as<uint64_t>(), ctx->d_vals.as<uint32_t>());
         VLB_LAUNCH_CHECK(ctx);
 

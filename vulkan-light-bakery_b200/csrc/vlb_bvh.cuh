@@ -367,13 +367,25 @@ VLB_HD float min3(float a, float b, float c) {
 #endif
 }
 
+// Traversal stack of one ray as a per-thread array (local memory on the device). The bake kernel uses the
+// warp-shared-memory stack of bake.cu instead; bvh4_step takes either.
+struct LocalStack {
+    int a[kStackSize];
+    int sp;
+    VLB_HD void clear() { sp = 0; }
+    VLB_HD bool empty() const { return sp == 0; }
+    VLB_HD bool room(int n) const { return sp + n <= kStackSize; }
+    VLB_HD void push(int v) { a[sp++] = v; }
+    VLB_HD int pop() { return a[--sp]; }
+};
+
 // One step through 4-wide node `cur`: slab-tests the four children against (tmin, tcull). ORDERED
 // (closest-hit rays): returns the nearest hit child and pushes the others so that they pop in
 // near-to-far order. Unordered (any-hit rays): returns the first hit child, pushes the rest. With
 // no hit child it pops. Returns kNoChild when the traversal is finished. THE node step of every
 // traversal in the library (closest hit, any hit, the bake kernel).
-template <bool ORDERED>
-VLB_HD int bvh4_step(const BvhView& b, int cur, Vec3 idir, Vec3 ood, float tmin, float tcull, int* stack, int& sp) {
+template <bool ORDERED, class STACK>
+VLB_HD int bvh4_step(const BvhView& b, int cur, Vec3 idir, Vec3 ood, float tmin, float tcull, STACK& stk) {
     const float4* q = b.nodes + (size_t)kNodeQuads * cur;
     // near / far planes by the sign of the direction: no per-child min/max pairs
     const int sx = idir.x < 0.0f, sy = idir.y < 0.0f, sz = idir.z < 0.0f;
@@ -426,27 +438,27 @@ VLB_HD int bvh4_step(const BvhView& b, int cur, Vec3 idir, Vec3 ood, float tmin,
         order2(tn[0], r[0], tn[2], r[2]);
         order2(tn[1], r[1], tn[3], r[3]);
         order2(tn[1], r[1], tn[2], r[2]);
-        if (r[0] == kNoChild) return sp ? stack[--sp] : kNoChild;
+        if (r[0] == kNoChild) return stk.empty() ? kNoChild : stk.pop();
         if (r[1] != kNoChild) {
-            if (sp + 3 > kStackSize) {      // never silently drop subtrees: flag it
+            if (!stk.room(3)) {             // never silently drop subtrees: flag it
                 if (b.overflow) *b.overflow = 1u;
             } else {
-                if (r[3] != kNoChild) stack[sp++] = r[3];
-                if (r[2] != kNoChild) stack[sp++] = r[2];
-                stack[sp++] = r[1];
+                if (r[3] != kNoChild) stk.push(r[3]);
+                if (r[2] != kNoChild) stk.push(r[2]);
+                stk.push(r[1]);
             }
         }
         return r[0];
     }
-    if (sp + 4 > kStackSize) {
+    if (!stk.room(4)) {
         if (b.overflow) *b.overflow = 1u;
     } else {
-        if (r[3] != kNoChild) stack[sp++] = r[3];
-        if (r[2] != kNoChild) stack[sp++] = r[2];
-        if (r[1] != kNoChild) stack[sp++] = r[1];
-        if (r[0] != kNoChild) stack[sp++] = r[0];
+        if (r[3] != kNoChild) stk.push(r[3]);
+        if (r[2] != kNoChild) stk.push(r[2]);
+        if (r[1] != kNoChild) stk.push(r[1]);
+        if (r[0] != kNoChild) stk.push(r[0]);
     }
-    return sp ? stack[--sp] : kNoChild;
+    return stk.empty() ? kNoChild : stk.pop();
 }
 
 // Intersects the triangles of leaf `ref` (< 0). Closest-hit rays update `best` and the culling
@@ -482,17 +494,17 @@ VLB_HD HitRec trace_closest(const BvhView& b, Vec3 o, Vec3 d, float tmin, float 
     if (b.n_tris == 0) return best;
     const Vec3 idir = mk3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
     const Vec3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
-    int stack[kStackSize];
-    int sp = 0;
+    LocalStack stk;
+    stk.clear();
     int cur = 0;
     float tcull = tmax;
     while (cur != kNoChild) {
         if (cur >= 0) {
             if (COUNT) cnt->nodes++;
-            cur = bvh4_step<true>(b, cur, idir, ood, tmin, tcull, stack, sp);
+            cur = bvh4_step<true>(b, cur, idir, ood, tmin, tcull, stk);
         } else {
             leaf_step<false, COUNT>(b, cur, o, d, tmin, tcull, best, cnt);
-            cur = sp ? stack[--sp] : kNoChild;
+            cur = stk.empty() ? kNoChild : stk.pop();
         }
     }
     return best;
@@ -504,21 +516,21 @@ VLB_HD bool trace_any(const BvhView& b, Vec3 o, Vec3 d, float tmin, float tmax, 
     if (b.n_tris == 0) return false;
     const Vec3 idir = mk3(safe_inv(d.x), safe_inv(d.y), safe_inv(d.z));
     const Vec3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
-    int stack[kStackSize];
-    int sp = 0;
+    LocalStack stk;
+    stk.clear();
     int cur = 0;
     float tcull = tmax;
     HitRec h; h.id = -1; h.t = tmax; h.u = 0.f; h.v = 0.f;
     while (cur != kNoChild) {
         if (cur >= 0) {
             if (COUNT) cnt->nodes++;
-            cur = bvh4_step<false>(b, cur, idir, ood, tmin, tcull, stack, sp);
+            cur = bvh4_step<false>(b, cur, idir, ood, tmin, tcull, stk);
         } else {
             if (leaf_step<true, COUNT>(b, cur, o, d, tmin, tcull, h, cnt)) {
                 if (out) *out = h;
                 return true;
             }
-            cur = sp ? stack[--sp] : kNoChild;
+            cur = stk.empty() ? kNoChild : stk.pop();
         }
     }
     return false;
