@@ -2,8 +2,10 @@
 
   build_oracle()  g++ oracle/vlb_oracle.cpp            -> oracle/libvlb_oracle.so
   build_ref()     g++ oracle/ref_shim.cpp + the reference's own shaders/sh_common.h, compiled
-                  from where it lies under /root/reference -> oracle/_ref/libvlb_refsh.so
-                  (only when /root/reference exists; the GPU box uses the prebuilt file).
+                  from where it lies under /root/reference -> oracle/_ref/libvlb_refsh.so, and
+                  oracle/make_ref_shaders.py: the reference's shader sources (env_map.rgen/.rchit, main.rmiss,
+                  shadow.rmiss, sh.comp, skybox_sh.comp) behind oracle/glsl_shim.h -> oracle/_ref/libvlb_refshaders.so
+                  (only when /root/reference exists; the GPU box uses the prebuilt files).
 """
 import os
 import subprocess
@@ -34,6 +36,11 @@ def build_oracle(force=False):
 
 
 def build_ref(force=False):
+    try:                                   # works as `oracle.build_oracle` and as a script
+        from . import make_ref_shaders
+    except ImportError:
+        import make_ref_shaders
+    make_ref_shaders.build(force)          # oracle/_ref/libvlb_refshaders.so: the reference's shaders behind oracle/glsl_shim.h
     header = os.path.join(REFERENCE, "shaders", "sh_common.h")
     if not os.path.exists(header):
         return REF_SO if os.path.exists(REF_SO) else None

@@ -9,6 +9,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(_HERE, "libvlb_oracle.so")
 REF_SO = os.path.join(_HERE, "_ref", "libvlb_refsh.so")
+REF_SHADERS_SO = os.path.join(_HERE, "_ref", "libvlb_refshaders.so")
 
 _vp, _u64, _i32, _f32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_float
 _lib = None
@@ -36,6 +37,9 @@ def lib():
         L.vo_to_vector.argtypes = [_f32, _f32, _vp]
         L.vo_srgb.restype = _f32
         L.vo_srgb.argtypes = [_f32]
+        L.vo_dir2uv.argtypes = [_vp, _vp]
+        L.vo_sky_lookup.argtypes = [_vp, _vp, _vp]
+        L.vo_base_color.argtypes = [_vp, ctypes.c_uint32, _f32, _f32, _vp]
         L.vo_probe_dirs.argtypes = [_i32, _i32, _vp, _vp, _vp]
         L.vo_skybox_project.argtypes = [_vp, _i32, _i32, _i32, _i32, _vp]
         L.vo_envmap_project.argtypes = [_vp, _i32, _i32, _i32, _i32, _vp]
@@ -78,6 +82,138 @@ def ref_lib():
         R.ref_PI.restype = _f32
         _ref = R
     return _ref
+
+
+_refsh = None
+
+
+def ref_shaders_lib():
+    """The reference's own shaders (env_map.rgen/.rchit, main.rmiss, shadow.rmiss, sh.comp, skybox_sh.comp) compiled
+    as C++ by oracle/make_ref_shaders.py into oracle/_ref/libvlb_refshaders.so; None if unavailable."""
+    global _refsh
+    if _refsh is None and os.path.exists(REF_SHADERS_SO):
+        R = ctypes.CDLL(REF_SHADERS_SO)
+        for name in ("ref_rchit_srgb", "ref_rmiss_srgb", "ref_rmiss_dir2uv"):
+            getattr(R, name).argtypes = [_vp, _vp]
+        R.ref_rchit_get_base_color.argtypes = [_vp, _vp, _vp, _vp]
+        R.ref_rchit_get_light.argtypes = [_vp]
+        R.ref_rmiss_run.argtypes = [_vp, _vp, _i32, _i32, _vp]
+        R.ref_sh_comp_dispatch.argtypes = [_vp, _i32, _i32, _vp]
+        R.ref_skybox_sh_comp_dispatch.argtypes = [_vp, _i32, _i32, _vp]
+        R.rp_create.restype = _vp
+        R.rp_create.argtypes = [_vp, _vp, _vp, ctypes.c_uint32, _vp, _vp, _vp]
+        R.rp_destroy.argtypes = [_vp]
+        R.rp_set_skybox.argtypes = [_vp, _vp, _i32, _i32]
+        R.rp_set_textures.argtypes = [_vp, _vp, _vp, ctypes.c_uint32]
+        R.rp_bake_probe.restype = _u64
+        R.rp_bake_probe.argtypes = [_vp, _vp, _i32, _i32, ctypes.c_uint32, _vp, _vp, _vp]
+        _refsh = R
+    return _refsh
+
+
+class RefShaders:
+    """Thin numpy front end of oracle/_ref/libvlb_refshaders.so: the reference's shader functions, one call each."""
+
+    def __init__(self):
+        self.R = ref_shaders_lib()
+        if self.R is None:
+            raise RuntimeError("oracle/_ref/libvlb_refshaders.so not built (needs /root/reference: python oracle/make_ref_shaders.py)")
+
+    def _map4(self, fn, rgba):
+        a = np.ascontiguousarray(rgba, np.float32).reshape(-1, 4)
+        out = np.zeros_like(a)
+        for i in range(a.shape[0]):
+            fn(_p(a[i:i + 1]), _p(out[i:i + 1]))
+        return out
+
+    def srgb_rchit(self, rgba):            # shaders/env_map.rchit:27-34
+        return self._map4(self.R.ref_rchit_srgb, rgba)
+
+    def srgb_rmiss(self, rgba):            # shaders/main.rmiss:9-16
+        return self._map4(self.R.ref_rmiss_srgb, rgba)
+
+    def dir2uv(self, dirs):                # shaders/main.rmiss:18-35
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        out = np.zeros((d.shape[0], 2), np.float32)
+        for i in range(d.shape[0]):
+            self.R.ref_rmiss_dir2uv(_p(d[i:i + 1]), _p(out[i:i + 1]))
+        return out
+
+    def miss(self, dirs, sky):             # shaders/main.rmiss:37-41 (texture lookup: oracle/glsl_shim.h)
+        d = np.ascontiguousarray(dirs, np.float32).reshape(-1, 3)
+        t = np.ascontiguousarray(sky, np.float32)
+        out = np.zeros((d.shape[0], 3), np.float32)
+        for i in range(d.shape[0]):
+            self.R.ref_rmiss_run(_p(d[i:i + 1]), _p(t), t.shape[1], t.shape[0], _p(out[i:i + 1]))
+        return out
+
+    def base_color(self, material, uv, textures_f32=()):   # shaders/env_map.rchit:36-49
+        """material: one element of a MATERIAL_DTYPE array; textures_f32: list of float32 [H, W, 4] arrays."""
+        m = np.ascontiguousarray(material).reshape(1)
+        tex = [np.ascontiguousarray(t, np.float32) for t in textures_f32]
+        samplers = np.zeros(max(len(tex), 1), np.dtype([("texels", "<u8"), ("w", "<i4"), ("h", "<i4")]))
+        for i, t in enumerate(tex):
+            samplers[i] = (t.ctypes.data, t.shape[1], t.shape[0])
+        u = np.ascontiguousarray(uv, np.float32).reshape(2)
+        out = np.zeros(4, np.float32)
+        self.R.ref_rchit_get_base_color(_p(m), _p(u), _p(samplers), _p(out))
+        return out
+
+    def default_light(self):               # shaders/env_map.rchit:25
+        out = np.zeros(3, np.float32)
+        self.R.ref_rchit_get_light(_p(out))
+        return out
+
+    def skybox_sh(self, texels_f32):       # the whole dispatch of shaders/skybox_sh.comp, coeffs in double
+        t = np.ascontiguousarray(texels_f32, np.float32)
+        out = np.zeros((16, 3), np.float64)
+        self.R.ref_skybox_sh_comp_dispatch(_p(t), t.shape[1], t.shape[0], _p(out))
+        return out
+
+    def envmap_sh(self, texels_f32):       # the whole dispatch of shaders/sh.comp, coeffs in double
+        t = np.array(texels_f32, np.float32, order="C")
+        out = np.zeros((16, 3), np.float64)
+        self.R.ref_sh_comp_dispatch(_p(t), t.shape[1], t.shape[0], _p(out))
+        return out
+
+
+class RefPipeline:
+    """The reference's bake pipeline (env_map.rgen -> env_map.rchit / main.rmiss / shadow.rmiss -> sh.comp) run from
+    its own shader code, one probe at a time; ray / triangle intersection is the oracle scene's (oracle/ref_pipeline.cpp)."""
+
+    def __init__(self, scene, oracle_scene, sky=None, textures_f32=()):
+        self.R = ref_shaders_lib()
+        if self.R is None:
+            raise RuntimeError("oracle/_ref/libvlb_refshaders.so not built")
+        self._keep = [np.ascontiguousarray(scene[k]) for k in ("vertices", "indices", "instances", "materials")]
+        v, i, inst, m = self._keep
+        self._osc = oracle_scene
+        trace = ctypes.cast(lib().vo_trace_rays, _vp)
+        self._h = self.R.rp_create(_p(v), _p(i), _p(inst), inst.size, _p(m), trace, oracle_scene._h)
+        if sky is not None:
+            self._sky = np.ascontiguousarray(sky, np.float32)
+            self.R.rp_set_skybox(self._h, _p(self._sky), self._sky.shape[1], self._sky.shape[0])
+        if textures_f32:
+            self._tex = [np.ascontiguousarray(t, np.float32) for t in textures_f32]
+            ptrs = (ctypes.c_void_p * len(self._tex))(*[t.ctypes.data for t in self._tex])
+            wh = np.array([[t.shape[1], t.shape[0]] for t in self._tex], np.int32)
+            self._wh = wh
+            self.R.rp_set_textures(self._h, ctypes.cast(ptrs, _vp), _p(wh), len(self._tex))
+            self._ptrs = ptrs
+
+    def bake_probe(self, origin, W, H, flags, light):
+        """-> (coeffs [16,3] float64, image [H,W,4] float32, shadow rays)"""
+        o = np.ascontiguousarray(origin, np.float32).reshape(3)
+        l = np.ascontiguousarray(light, np.float32).reshape(3)
+        img = np.zeros((H, W, 4), np.float32)
+        out = np.zeros((16, 3), np.float64)
+        n = self.R.rp_bake_probe(self._h, _p(o), W, H, int(flags), _p(l), _p(img), _p(out))
+        return out, img, int(n)
+
+    def close(self):
+        if self._h:
+            self.R.rp_destroy(self._h)
+            self._h = None
 
 
 def num_threads():

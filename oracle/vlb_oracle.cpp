@@ -475,7 +475,8 @@ static bool trace_any(const Scene& s, V3 o, V3 d, float tmin, float tmax, bool b
 static inline float glsl_mod(float x, float y) { return x - y * std::floor(x / y); }
 static inline float clampf(float x, float a, float b) { return std::min(std::max(x, a), b); }
 
-static void sky_lookup(const Scene& s, V3 dir, float rgb[3]) {
+// dir2SkyboxUV, main.rmiss:18-35
+static void dir_to_sky_uv(V3 dir, float* u_out, float* v_out) {
     float theta = (float)std::acos((double)clampf(dir.y, -1.0f, 1.0f));
     float phi = (float)std::atan2((double)dir.x, (double)dir.z);
     theta = glsl_mod(theta, 2.0f * PI_F);
@@ -483,7 +484,12 @@ static void sky_lookup(const Scene& s, V3 dir, float rgb[3]) {
     if (theta > PI_F) { theta = 2.0f * PI_F - theta; phi += PI_F; }
     phi = glsl_mod(phi, 2.0f * PI_F);
     phi = clampf(phi, 0.0f, 2.0f * PI_F);
-    const float u = phi / (2.0f * PI_F), v = theta / PI_F;
+    *u_out = phi / (2.0f * PI_F); *v_out = theta / PI_F;
+}
+
+static void sky_lookup(const Scene& s, V3 dir, float rgb[3]) {
+    float u, v;
+    dir_to_sky_uv(dir, &u, &v);
     const int W = s.skyW, H = s.skyH;
     const float fx = u * (float)W - 0.5f, fy = v * (float)H - 0.5f;
     const float flx = std::floor(fx), fly = std::floor(fy);
@@ -751,6 +757,7 @@ void vo_to_vector(float phi, float theta, float* out3) {
     out3[0] = v.x; out3[1] = v.y; out3[2] = v.z;
 }
 float vo_srgb(float c) { return srgb1(c); }
+void vo_dir2uv(const float dir[3], float uv[2]) { dir_to_sky_uv(v3(dir[0], dir[1], dir[2]), &uv[0], &uv[1]); }
 
 // probe direction table: t (un-swizzled), ray dir r = t.xzy, weight per texel
 void vo_probe_dirs(int W, int H, float* t_out, float* r_out, float* w_out) {
@@ -899,6 +906,13 @@ void vo_scene_set_skybox(void* h, const void* texels, int fmt, int W, int H) {
     }
 }
 // world-space triangle soup as the oracle flattened it: v0,e1,e2 (9 floats per triangle)
+// texture(skybox, dir2SkyboxUV(dir)) of main.rmiss:39 (before sRGB) and getBaseColor of env_map.rchit:36-49
+void vo_sky_lookup(void* h, const float dir[3], float rgb[3]) { sky_lookup(*(Scene*)h, v3(dir[0], dir[1], dir[2]), rgb); }
+void vo_base_color(void* h, uint32_t material, float u, float v, float out4[4]) {
+    Scene* s = (Scene*)h;
+    base_color(*s, s->mats[material], u, v, out4);
+}
+
 void vo_scene_triangles(void* h, float* out9) {
     Scene* s = (Scene*)h;
     for (size_t i = 0; i < s->tris.size(); ++i) {

@@ -20,7 +20,7 @@ def build(force=False, so=None, defines=()):
     srcs = [os.path.join(_HERE, "emu_driver.cpp"),
             os.path.join(_ROOT, "vulkan-light-bakery_b200", "csrc", "host_tables.cpp")]
     csrc = os.path.join(_ROOT, "vulkan-light-bakery_b200", "csrc")
-    deps = srcs + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
+    deps = srcs + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))] + [os.path.join(_HERE, "vlb_ploc.cuh")]
     if not force and os.path.exists(so) and all(os.path.getmtime(d) <= os.path.getmtime(so) for d in deps):
         return so
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
@@ -40,6 +40,7 @@ def lib():
         L.emu_scene_create.restype = _vp
         L.emu_scene_create.argtypes = [_vp, _vp, _vp, ctypes.c_uint32, _vp, ctypes.c_uint32, _i32]
         L.emu_scene_destroy.argtypes = [_vp]
+        L.emu_set_builder.argtypes = [_i32, _i32]
         L.emu_scene_max_depth.restype = _i32
         L.emu_scene_max_depth.argtypes = [_vp]
         L.emu_scene_set_skybox.argtypes = [_vp, _vp, _i32, _i32]
@@ -54,7 +55,8 @@ def lib():
 
 
 class Scene:
-    def __init__(self, scene, max_leaf=4):
+    def __init__(self, scene, max_leaf=4, builder="lbvh", ploc_radius=16):
+        lib().emu_set_builder({"lbvh": 0, "ploc": 1}[builder], ploc_radius)
         self._keep = [np.ascontiguousarray(scene[k]) for k in ("vertices", "indices", "instances", "materials")]
         v, i, inst, m = self._keep
         self._h = lib().emu_scene_create(_p(v), _p(i), _p(inst), inst.size, _p(m), m.size, max_leaf)

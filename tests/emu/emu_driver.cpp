@@ -13,6 +13,7 @@
 
 #include "../../vulkan-light-bakery_b200/csrc/vlb_context.h"
 #include "../../vulkan-light-bakery_b200/csrc/vlb_shade.cuh"
+#include "vlb_ploc.cuh"
 
 using namespace vlb;
 
@@ -27,6 +28,44 @@ struct EmuScene {
 };
 
 static float4 mk4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+
+static int g_builder = 0, g_ploc_radius = 16;    // 0: Karras LBVH, 1: PLOC (vlb_ploc.cuh)
+
+// PLOC (experiment, see vlb_ploc.cuh), round by round; fills the arrays emit_node4 consumes and reorders the
+// triangles / leaf boxes into depth-first order.
+static void emu_ploc(EmuScene* s, std::vector<float4>& lbox, std::vector<float4>& ibox, int radius) {
+    const int n = (int)s->n;
+    std::vector<float4> box(2 * (size_t)(2 * n - 1));
+    std::copy(lbox.begin(), lbox.end(), box.begin());
+    std::vector<int> C(n), Cn(n), nn(n), left(n - 1), right(n - 1), parent(2 * n - 1, -1), count(2 * n - 1, 1), leftmost(2 * n - 1);
+    std::iota(C.begin(), C.end(), 0);
+    std::iota(leftmost.begin(), leftmost.begin() + n, 0);
+    int m = n, created = 0;
+    while (m > 1) {
+        for (int i = 0; i < m; ++i) nn[i] = ploc_nearest(C.data(), m, i, radius, box.data());
+        int out = 0;
+        for (int i = 0; i < m; ++i) {
+            const int role = ploc_role(nn.data(), i);
+            if (role == 2) continue;
+            Cn[out++] = role == 1 ? ploc_merge(C.data(), nn.data(), i, created++, n, box.data(), left.data(), right.data(), parent.data(),
+                                               count.data(), leftmost.data())
+                                  : C[i];
+        }
+        C.swap(Cn);
+        m = out;
+    }
+    std::vector<int> pos(n);
+    for (int i = 0; i < n; ++i) pos[i] = ploc_leaf_position(i, n, left.data(), parent.data(), count.data());
+    std::vector<float4> tris(s->tris.size()), lb(lbox.size());
+    for (int i = 0; i < n; ++i) {
+        for (int k = 0; k < 3; ++k) tris[3 * (size_t)pos[i] + k] = s->tris[3 * (size_t)i + k];
+        lb[2 * (size_t)pos[i]] = lbox[2 * (size_t)i]; lb[2 * (size_t)pos[i] + 1] = lbox[2 * (size_t)i + 1];
+    }
+    s->tris.swap(tris); lbox.swap(lb);
+    for (int k = 0; k < n - 1; ++k)
+        ploc_finish_node(k, n, left.data(), right.data(), count.data(), leftmost.data(), pos.data(), box.data(), s->left.data(), s->right.data(),
+                         s->first.data(), s->last.data(), ibox.data());
+}
 
 extern "C" {
 
@@ -114,24 +153,28 @@ void* emu_scene_create(const vlb_vertex* verts, const uint32_t* indices, const v
     }
     s->left.assign(n, 0); s->right.assign(n, 0); s->first.assign(n, 0); s->last.assign(n, 0);
     s->parent_i.assign(n, -1); s->parent_l.assign(n, -1);
-    for (int i = 0; i < (int)n - 1; ++i)   // k_karras
-        karras_node(ks.data(), (int)n, i, s->left.data(), s->right.data(), s->first.data(), s->last.data(),
-                    s->parent_i.data(), s->parent_l.data());
-    s->parent_i[0] = -1;
-    std::vector<int> flags(n, 0);
-    for (int j = 0; j < (int)n; ++j) {     // k_refit
-        int cur = s->parent_l[j];
-        while (cur >= 0) {
-            if (flags[cur]++ == 0) break;
-            float4 l[2], h[2];
-            const int ch[2] = {s->left[cur], s->right[cur]};
-            for (int c = 0; c < 2; ++c) {
-                if (ch[c] < 0) { l[c] = lbox[2 * (~ch[c])]; h[c] = lbox[2 * (~ch[c]) + 1]; }
-                else { l[c] = ibox[2 * ch[c]]; h[c] = ibox[2 * ch[c] + 1]; }
+    if (g_builder == 1) {
+        emu_ploc(s, lbox, ibox, g_ploc_radius);
+    } else {
+        for (int i = 0; i < (int)n - 1; ++i)   // k_karras
+            karras_node(ks.data(), (int)n, i, s->left.data(), s->right.data(), s->first.data(), s->last.data(),
+                        s->parent_i.data(), s->parent_l.data());
+        s->parent_i[0] = -1;
+        std::vector<int> flags(n, 0);
+        for (int j = 0; j < (int)n; ++j) {     // k_refit
+            int cur = s->parent_l[j];
+            while (cur >= 0) {
+                if (flags[cur]++ == 0) break;
+                float4 l[2], h[2];
+                const int ch[2] = {s->left[cur], s->right[cur]};
+                for (int c = 0; c < 2; ++c) {
+                    if (ch[c] < 0) { l[c] = lbox[2 * (~ch[c])]; h[c] = lbox[2 * (~ch[c]) + 1]; }
+                    else { l[c] = ibox[2 * ch[c]]; h[c] = ibox[2 * ch[c] + 1]; }
+                }
+                ibox[2 * cur] = mk4(fminf(l[0].x, l[1].x), fminf(l[0].y, l[1].y), fminf(l[0].z, l[1].z), 0);
+                ibox[2 * cur + 1] = mk4(fmaxf(h[0].x, h[1].x), fmaxf(h[0].y, h[1].y), fmaxf(h[0].z, h[1].z), 0);
+                cur = s->parent_i[cur];
             }
-            ibox[2 * cur] = mk4(fminf(l[0].x, l[1].x), fminf(l[0].y, l[1].y), fminf(l[0].z, l[1].z), 0);
-            ibox[2 * cur + 1] = mk4(fmaxf(h[0].x, h[1].x), fmaxf(h[0].y, h[1].y), fmaxf(h[0].z, h[1].z), 0);
-            cur = s->parent_i[cur];
         }
     }
     {   // k_emit_level, level by level as bvh_build.cu does
@@ -175,6 +218,7 @@ void emu_scene_node_stats(void* h, uint64_t out[3]) {
     }
 }
 void emu_scene_destroy(void* h) { delete (EmuScene*)h; }
+void emu_set_builder(int builder, int ploc_radius) { g_builder = builder; g_ploc_radius = ploc_radius > 0 ? ploc_radius : 16; }
 int emu_scene_max_depth(void* h) { return ((EmuScene*)h)->max_depth; }
 // vlb_scene_set_textures, as context.cu lays the atlas out
 void emu_scene_set_textures(void* h, const vlb_texture* tex, uint32_t n) {

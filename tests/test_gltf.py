@@ -92,6 +92,42 @@ def test_unsupported_and_malformed_inputs_fail_loudly(vlb, tmp_path):
         vlb.gltf_probe(str(tmp_path / "bad.gltf"))
 
 
+def test_crafted_accessor_numbers_are_rejected_not_wrapped(vlb, tmp_path):
+    # numbers straight from the file must be validated without wrapping arithmetic: count = 2^60 with byteStride 16 and
+    # byteOffset 4 makes off + (count - 1) * stride + elem wrap to a small value (this used to pass the check and read far
+    # out of bounds); negative and fractional numbers, and a stride smaller than the element, are refused as well
+    for patch in ({"count": 2 ** 60}, {"count": -3}, {"count": 2.5}, {"byteOffset": -4}, {"byteOffset": 2 ** 62}):
+        doc = _tri_doc([{"mesh": 0}])
+        doc["bufferViews"][0]["byteStride"] = 16
+        doc["accessors"][0]["byteOffset"] = 4
+        doc["accessors"][0].update(patch)
+        with pytest.raises(vlb.VlbError):
+            vlb.gltf_probe(_write(tmp_path, doc))
+    doc = _tri_doc([{"mesh": 0}])
+    doc["bufferViews"][0]["byteStride"] = 8                             # smaller than a float VEC3
+    with pytest.raises(vlb.VlbError):
+        vlb.gltf_probe(_write(tmp_path, doc))
+    doc = _tri_doc([{"mesh": 0}])
+    doc["bufferViews"][0]["byteOffset"] = 2 ** 63                       # view offset + accessor offset would wrap
+    with pytest.raises(vlb.VlbError):
+        vlb.gltf_probe(_write(tmp_path, doc))
+
+
+def test_non_float_normals_and_uvs_are_refused_not_dropped(vlb, tmp_path):
+    import base64
+    for attr, comp, typ in (("TEXCOORD_0", 5123, "VEC2"), ("TEXCOORD_0", 5126, "SCALAR"), ("NORMAL", 5120, "VEC3")):
+        doc = _tri_doc([{"mesh": 0}])
+        extra = np.zeros(3 * 16, np.uint8).tobytes()
+        blob = base64.b64decode(doc["buffers"][0]["uri"].split(",", 1)[1]) + extra
+        doc["buffers"][0] = {"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}
+        doc["bufferViews"].append({"buffer": 0, "byteOffset": 40, "byteLength": 48})
+        doc["accessors"].append({"bufferView": 2, "componentType": comp, "count": 3, "type": typ})
+        doc["meshes"][0]["primitives"][0]["attributes"][attr] = 2
+        with pytest.raises(vlb.VlbError) as e:
+            vlb.gltf_probe(_write(tmp_path, doc))
+        assert e.value.code == vlb.ERR_UNSUPPORTED
+
+
 # ------------------------------------------------------------------------------- GPU ------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("container", ["gltf", "glb"])

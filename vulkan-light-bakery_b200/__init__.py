@@ -1,8 +1,9 @@
 """vulkan-light-bakery_b200 — host-side Python mirror of the reference's bake interface over
 the C ABI of libvlb_bake.so (include/vlb_bake.h).
 
-The reference's host code is C++ (src/baker, src/scene_manager.cpp, src/skybox_manager.cpp); the
-C++ mirror of those classes lives in host/. This module is the thin ctypes layer the parity tests
+The reference's host code is C++ (src/baker, src/scene_manager.cpp, src/skybox_manager.cpp); its C++
+counterpart here is inside the library (csrc/context.cu, gltf_scene.cpp, ...) and the `vlb_baker` executable
+(csrc/vlb_baker_main.cpp). This module is the thin ctypes layer the parity tests
 and bench.py use: same entry points, same argument meaning, same error behaviour (a failing call
 raises VlbError carrying vlb_last_error(), as the reference throws std::runtime_error).
 
@@ -229,6 +230,7 @@ class Context:
         if r:
             raise VlbError(r, self._lib.vlb_last_error(None).decode())
         self._h = h
+        self.stream_handle = None      # None: the ctx's own stream (set_stream)
         self.device = device
 
     def close(self):
@@ -256,6 +258,7 @@ class Context:
     def set_stream(self, handle):
         """handle: cudaStream_t as int (0 = CUDA's legacy default stream); None = the ctx's own stream."""
         self._check(self._lib.vlb_ctx_set_stream(self._h, STREAM_OWN if handle is None else int(handle)))
+        self.stream_handle = None if handle is None else int(handle)     # parallel.order_after_bake compares it with torch's stream
 
     def synchronize(self):
         self._check(self._lib.vlb_ctx_synchronize(self._h))

@@ -113,20 +113,32 @@ struct WarpQueues {
 };
 
 // Short stack in shared memory + overflow in global scratch; same interface as LocalStack (vlb_bvh.cuh).
+// `sm` is the 32-bit shared-window address of this lane's entry 0; it is produced by an opaque asm move so that
+// the compiler keeps it in a register instead of re-deriving it (S2R tid, shifts, IMAD: ten instructions) at every
+// push and pop, which is what it does with a plain pointer under the kernel's 64-register cap.
 struct WarpStack {
-    int* sm;      // &s_stack[warp][0][lane]; entry e lives at sm[32 * e]
+    uint32_t sm;  // shared address of s_stack[warp][0][lane]; entry e lives 128 * e bytes further
     int* ovf;     // &scratch.ovf[0][lane]
     int sp;
+    __device__ __forceinline__ void bind(const int* entry0, int* overflow) {
+        const uint32_t a = (uint32_t)__cvta_generic_to_shared(entry0);
+        asm volatile("mov.u32 %0, %1;" : "=r"(sm) : "r"(a));
+        ovf = overflow;
+    }
     __device__ __forceinline__ void clear() { sp = 0; }
     __device__ __forceinline__ bool empty() const { return sp == 0; }
     __device__ __forceinline__ bool room(int n) const { return sp + n <= kStackSize; }
     __device__ __forceinline__ void push(int v) {
-        if (sp < kSmemStack) sm[32 * sp] = v; else ovf[32 * (sp - kSmemStack)] = v;
+        if (sp < kSmemStack) asm volatile("st.shared.b32 [%0], %1;" ::"r"(sm + 128u * (uint32_t)sp), "r"(v) : "memory");
+        else ovf[32 * (sp - kSmemStack)] = v;
         ++sp;
     }
     __device__ __forceinline__ int pop() {
         --sp;
-        return sp < kSmemStack ? sm[32 * sp] : ovf[32 * (sp - kSmemStack)];
+        int v;
+        if (sp < kSmemStack) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(sm + 128u * (uint32_t)sp) : "memory");
+        else v = ovf[32 * (sp - kSmemStack)];
+        return v;
     }
 };
 
@@ -155,8 +167,7 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
     uint32_t u_node_it = 0, u_node_ln = 0, u_leaf_it = 0, u_leaf_ln = 0, u_shade_it = 0, u_shade_ln = 0, u_outer = 0, u_ovf = 0;
 #if VLB_BAKE_SMEM_STACK > 0
     WarpStack stk;
-    stk.sm = &s_stack[warp][0][lane];
-    stk.ovf = &S.ovf[0][lane];
+    stk.bind(&s_stack[warp][0][lane], &S.ovf[0][lane]);
 #else
     LocalStack stk;
 #endif
@@ -484,7 +495,7 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     p.stats = ctx->d_stats.as<unsigned long long>();
     p.ref_order = (s->flags & VLB_BAKE_REFERENCE_PROBE_ORDER) ? 1 : 0;
     p.world_frame = (s->flags & VLB_BAKE_SH_WORLD_FRAME) ? 1 : 0;
-    p.node_min = std::max(1, std::min(32, env_flag("VLB_BAKE_NODE_MIN", 8)));
+    p.node_min = std::max(1, std::min(32, env_flag("VLB_BAKE_NODE_MIN", 16)));
     p.g.prev = d_prev_full; p.g.px = p.px; p.g.py = p.py; p.g.pz = p.pz; p.g.Nx = Nx; p.g.Ny = Ny; p.g.Nz = Nz;
     for (int k = 0; k < 3; ++k) { p.g.origin[k] = s->origin[k]; p.g.step[k] = s->step[k]; }
     p.g.gain = s->indirect_gain; p.g.world_frame = p.world_frame;

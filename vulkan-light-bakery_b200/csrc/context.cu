@@ -277,6 +277,7 @@ int vlb_scene_set_triangles(vlb_ctx* ctx, const vlb_vertex* vertices, uint64_t n
 
 int vlb_scene_set_textures(vlb_ctx* ctx, const vlb_texture* textures, uint32_t n_textures) {
     if (!ctx) return VLB_ERR_INVALID;
+    if (int r = check_device(ctx)) return r;
     if (n_textures && !textures) return ctx->fail(VLB_ERR_INVALID, "vlb_scene_set_textures: null textures");
     std::vector<int4> desc(n_textures);
     size_t total = 0;
@@ -555,8 +556,11 @@ int vlb_bake_probes(vlb_ctx* ctx, const vlb_bake_settings* s, float* out) {
     if (s->bounces <= 0) {
         if (int r = vlb_bake_probes_device(ctx, s, ctx->d_bake_out.as<float>())) return r;
         VLB_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_bake_out.p, n * VLB_SH_STRIDE * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+        // the copy was enqueued AFTER the bake recorded its completion event: wait for the stream itself, so that a
+        // pinned `out` is complete when this blocking call returns (a pageable one is staged synchronously anyway)
+        VLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         vlb_bake_stats st;
-        return vlb_bake_last_stats(ctx, &st);      // synchronises and surfaces a traversal stack overflow
+        return vlb_bake_last_stats(ctx, &st);      // surfaces a traversal stack overflow
     }
     // Multi-bounce: pass 0 is the direct bake, pass b gathers from pass b-1 (two device buffers,
     // ping-pong). Every pass needs the previous one over the WHOLE grid, so a sharded grid has to be
@@ -605,8 +609,9 @@ static int multi_rank_pass(vlb_ctx* ctx, const vlb_bake_settings* s, uint32_t r,
     const size_t row = nxy * VLB_SH_STRIDE * sizeof(float);
     VLB_CUDA(ctx, cudaMemcpy2DAsync(reinterpret_cast<char*>(out) + (size_t)r * row, (size_t)n * row, ctx->d_bake_out.p, row, row, n_slices,
                                     cudaMemcpyDeviceToHost, ctx->stream));
+    VLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));    // the strided copy follows the bake's completion event: wait for it too
     vlb_bake_stats st;
-    return vlb_bake_last_stats(ctx, &st);      // synchronises; surfaces a traversal stack overflow
+    return vlb_bake_last_stats(ctx, &st);      // surfaces a traversal stack overflow
 }
 
 int vlb_bake_probes_multi(vlb_ctx* const* ctxs, uint32_t n_ctx, const vlb_bake_settings* s, float* out) {

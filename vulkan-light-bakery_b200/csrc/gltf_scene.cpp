@@ -106,17 +106,31 @@ struct Document {
         if (!bi || bi->integer_value() < 0 || (size_t)bi->integer_value() >= buffers.size()) throw std::runtime_error("glTF: buffer index out of range");
         const std::vector<uint8_t>& buf = buffers[(size_t)bi->integer_value()];
         Accessor r;
-        r.component = (int)(a.find("componentType") ? a.find("componentType")->integer_value() : 0);
-        r.count = (size_t)(a.find("count") ? a.find("count")->integer_value() : 0);
+        // every number below comes straight from the file: reject negatives and validate without wrapping arithmetic
+        auto field = [](const Json& o, const char* key) -> size_t {
+            const Json* f = o.find(key);
+            if (!f) return 0;
+            const double d = f->num();
+            if (!(d >= 0.0) || d > 9.0e15 || d != std::floor(d)) throw std::runtime_error(std::string("glTF: ") + key + " is not a non-negative integer");
+            return (size_t)d;
+        };
+        r.component = (int)field(a, "componentType");
+        if (r.component < 5120 || r.component > 5126 || r.component == 5124) throw Unsupported("glTF: accessor componentType is not one glTF 2.0 defines");
+        r.count = field(a, "count");
         const std::string type = a.find("type") ? a.find("type")->s : "";
         r.ncomp = type == "SCALAR" ? 1 : type == "VEC2" ? 2 : type == "VEC3" ? 3 : type == "VEC4" ? 4 : 0;
         if (!r.ncomp) throw Unsupported("glTF: accessor type " + type + " is not used by the bake path");
         const size_t csize = (r.component == 5120 || r.component == 5121) ? 1 : (r.component == 5122 || r.component == 5123) ? 2 : 4;
-        const size_t off = (size_t)(a.find("byteOffset") ? a.find("byteOffset")->integer_value() : 0) +
-                           (size_t)(v.find("byteOffset") ? v.find("byteOffset")->integer_value() : 0);
-        const size_t bstride = (size_t)(v.find("byteStride") ? v.find("byteStride")->integer_value() : 0);
-        r.stride = bstride ? bstride : csize * r.ncomp;
-        if (r.count && off + (r.count - 1) * r.stride + csize * r.ncomp > buf.size()) throw std::runtime_error("glTF: accessor exceeds its buffer");
+        const size_t elem = csize * r.ncomp;
+        const size_t off_a = field(a, "byteOffset"), off_v = field(v, "byteOffset");
+        const size_t bstride = field(v, "byteStride");
+        r.stride = bstride ? bstride : elem;
+        if (r.stride < elem) throw std::runtime_error("glTF: byteStride smaller than the accessor's element");
+        if (off_a > buf.size() || off_v > buf.size() - off_a) throw std::runtime_error("glTF: accessor exceeds its buffer");
+        const size_t off = off_a + off_v;
+        if (r.count) {
+            if (elem > buf.size() - off || r.count - 1 > (buf.size() - off - elem) / r.stride) throw std::runtime_error("glTF: accessor exceeds its buffer");
+        }
         r.base = buf.data() + off;
         return r;
     }
@@ -254,6 +268,10 @@ void load_node(const Document& doc, long long index, const M4& parent_world, Hos
             if (const Json* a = attrs->find("NORMAL")) nrm = doc.accessor(a->integer_value());
             if (const Json* a = attrs->find("TEXCOORD_0")) uv0 = doc.accessor(a->integer_value());
             if (const Json* a = attrs->find("TEXCOORD_1")) uv1 = doc.accessor(a->integer_value());
+            // only float attributes are read (fetchVertices, :257-290); anything else is refused, never dropped silently
+            if (nrm.base && (nrm.component != 5126 || nrm.ncomp != 3)) throw Unsupported("glTF: NORMAL must be a float VEC3 accessor");
+            for (const Accessor* uv : {&uv0, &uv1})
+                if (uv->base && (uv->component != 5126 || uv->ncomp < 2)) throw Unsupported("glTF: TEXCOORD_n must be a float VEC2 accessor (normalised integer texture coordinates are not supported)");
             vlb_instance inst;
             std::memset(&inst, 0, sizeof inst);
             inst.first_vertex = (uint32_t)hs.vertices.size();

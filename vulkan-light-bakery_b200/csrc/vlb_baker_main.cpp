@@ -79,7 +79,7 @@ void usage() {
          "  --bounces B          gather passes after the direct pass (default 0 = the reference bake)\n"
          "  --gain g             indirect gain of the gather passes\n"
          "  --tight-bounds       lay the grid over the true world AABB instead of Scene_t::getBounds()\n"
-         "  --no-shadows --no-srgb --quantize8 --reference-order --world-frame   behaviour flags (vlb_bake.h)\n"
+         "  --no-shadows --no-srgb --no-quantize8 --reference-order --world-frame   behaviour flags (vlb_bake.h)\n"
          "  --device N           CUDA device (default 0)\n"
          "  --devices a,b,...    bake on several GPUs from this one process (probe z-slices dealt cyclically)\n"
          "  --out path           output file (default baked_<scene>)\n"
@@ -130,7 +130,8 @@ int main(int argc, char** argv) {
         else if (a == "--tight-bounds") o.tight = true;
         else if (a == "--no-shadows") o.flags_clear |= VLB_BAKE_SHADOW_RAYS;
         else if (a == "--no-srgb") o.flags_clear |= VLB_BAKE_SRGB_ENCODE;
-        else if (a == "--quantize8") o.flags_set |= VLB_BAKE_QUANTIZE_RGBA8;
+        else if (a == "--no-quantize8") o.flags_clear |= VLB_BAKE_QUANTIZE_RGBA8;   // the RGBA8 image store (env_map_generator.hpp:39) is in the defaults
+        else if (a == "--quantize8") {}                                              // accepted for compatibility: already the default
         else if (a == "--reference-order") o.flags_set |= VLB_BAKE_REFERENCE_PROBE_ORDER;
         else if (a == "--world-frame") o.flags_set |= VLB_BAKE_SH_WORLD_FRAME;
         else if (a == "--dry-run") o.dry = true;

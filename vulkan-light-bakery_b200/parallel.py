@@ -41,12 +41,30 @@ def shard_settings(settings, rank, world, cyclic=False):
     return s
 
 
-def gather_slabs(local, settings, rank, world, group=None, cyclic=False):
+def order_after_bake(ctx):
+    """Stream contract of this module. The collectives below are issued on torch's CURRENT stream, a vlb Context by
+    default works on its own non-blocking stream: unless the two are the same stream, the all-gather could read the
+    slab before k_bake_stream has written it (and the next gather pass a stale `prev`). Pass the Context as `ctx`
+    to the functions below: if it was put on torch's current stream (ctx.set_stream(torch.cuda.current_stream().cuda_stream),
+    what bench.py does) nothing more is needed, otherwise the bake is waited for here."""
+    if ctx is None:
+        return
+    import torch
+    if not torch.cuda.is_available():
+        return
+    cur = torch.cuda.current_stream().cuda_stream
+    if getattr(ctx, "stream_handle", None) != cur:
+        ctx.synchronize()
+
+
+def gather_slabs(local, settings, rank, world, group=None, cyclic=False, ctx=None):
     """All-gathers the per-rank buffers ([n_local_probes, 48] torch tensors on the bake device) into
     the full [Nx*Ny*Nz, 48] buffer in x-fastest order, identical on every rank. Buffers are padded to
-    the largest share so a single equal-size all_gather_into_tensor moves everything."""
+    the largest share so a single equal-size all_gather_into_tensor moves everything.
+    `ctx`: the vlb Context that baked `local` (see order_after_bake)."""
     import torch
     import torch.distributed as dist
+    order_after_bake(ctx)
     if world == 1:
         return local
     nz = settings.probes[2]
@@ -69,19 +87,19 @@ def gather_slabs(local, settings, rank, world, group=None, cyclic=False):
     return torch.cat(parts, 0)
 
 
-def bake_sharded(bake_slab, settings, rank, world, device=None, group=None, cyclic=False):
+def bake_sharded(bake_slab, settings, rank, world, device=None, group=None, cyclic=False, ctx=None):
     """bake_slab(slab_settings, out_tensor) fills out_tensor ([n_local, 48] float32 on `device`)
-    with this rank's share; returns the gathered full grid on every rank."""
+    with this rank's share; returns the gathered full grid on every rank. `ctx`: see order_after_bake."""
     import torch
     s = shard_settings(settings, rank, world, cyclic)
     n_local = s.n_slab_probes
     out = torch.empty((max(n_local, 1), 48), dtype=torch.float32, device=device)[:n_local]
     if n_local:
         bake_slab(s, out)
-    return gather_slabs(out, settings, rank, world, group, cyclic)
+    return gather_slabs(out, settings, rank, world, group, cyclic, ctx)
 
 
-def bake_multibounce_sharded(bake_pass, settings, rank, world, device=None, group=None, cyclic=False):
+def bake_multibounce_sharded(bake_pass, settings, rank, world, device=None, group=None, cyclic=False, ctx=None):
     """Multi-bounce bake of a sharded grid (include/vlb_bake.h: vlb_bake_gather_device). Every pass needs
     the PREVIOUS pass over the whole grid, so this is the one place on the path with a real exchange
     step: 1 + settings.bounces passes, each followed by one all-gather of the slabs.
@@ -96,7 +114,7 @@ def bake_multibounce_sharded(bake_pass, settings, rank, world, device=None, grou
         out = torch.empty((max(n_local, 1), 48), dtype=torch.float32, device=device)[:n_local]
         if n_local:
             bake_pass(s, prev, out)
-        full = gather_slabs(out, settings, rank, world, group, cyclic)
+        full = gather_slabs(out, settings, rank, world, group, cyclic, ctx)
         prev = full.contiguous()
     return prev
 
@@ -107,7 +125,7 @@ def map_share(n_maps, rank, world):
     return list(range(int(rank), int(n_maps), int(world)))
 
 
-def project_maps_sharded(project, n_maps, rank, world, device=None, group=None):
+def project_maps_sharded(project, n_maps, rank, world, device=None, group=None, ctx=None):
     """Batched skybox SH projection over `world` GPUs: maps are independent, so they are dealt round-robin,
     every rank projects its share with project(map_ids, out) (out: [len(map_ids), 48] float32 on `device`,
     e.g. Context.skybox_project_sh_device over its resident maps) and ONE all-gather of the padded shares gives
@@ -118,6 +136,7 @@ def project_maps_sharded(project, n_maps, rank, world, device=None, group=None):
     out = torch.zeros((max(len(mine), 1), 48), dtype=torch.float32, device=device)[: len(mine)]
     if mine:
         project(mine, out)
+    order_after_bake(ctx)
     if world == 1:
         return out
     pad = (int(n_maps) + world - 1) // world
