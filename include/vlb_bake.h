@@ -185,6 +185,9 @@ void vlb_ctx_destroy(vlb_ctx* ctx);
  * default stream, as everywhere in CUDA); VLB_STREAM_OWN restores the ctx's own stream. */
 #define VLB_STREAM_OWN (~(uint64_t)0)
 int  vlb_ctx_set_stream(vlb_ctx* ctx, uint64_t cuda_stream_handle);
+/* The cudaStream_t the ctx currently enqueues on, as an integer handle (its own non-blocking stream unless
+ * vlb_ctx_set_stream changed it): lets a caller record events on it or make other streams wait for it. */
+uint64_t vlb_ctx_stream(const vlb_ctx* ctx);
 int  vlb_ctx_synchronize(vlb_ctx* ctx);
 /* Last error text of this ctx (or of the calling thread when ctx == NULL). Never NULL. */
 const char* vlb_last_error(const vlb_ctx* ctx);

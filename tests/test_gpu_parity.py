@@ -404,3 +404,38 @@ def test_bake_probes_multi_one_process_several_contexts(vlb, scenes, room):
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_skybox_chained_device_projections_on_own_stream(vlb, oa, scenes):
+    """Back-to-back vlb_skybox_project_sh_device calls on the ctx's own stream are chained with programmatic dependent
+    launch (the next launch streams its texels while the previous one reduces and retires): every result must still be
+    exact, also when other calls (which close the chain) are interleaved and when the shape changes in between."""
+    import torch
+    with vlb.Context(0) as c:
+        W, H = 640, 160
+        host = [scenes.hdr_sky(W, H, seed=500 + i) for i in range(6)]
+        dev = [torch.from_numpy(m).cuda() for m in host]
+        small = scenes.hdr_sky(128, 64, seed=77)
+        dsmall = torch.from_numpy(small).cuda()
+        out = torch.full((8, 48), -1.0, device="cuda")
+        torch.cuda.synchronize()
+        want = [oa.skybox_project(m, 3) for m in host]
+        for rep in range(3):
+            out.fill_(-1.0)
+            torch.cuda.synchronize()
+            for i in range(6):                      # chain of six launches
+                c.skybox_project_sh_device(dev[i].data_ptr(), H * W * 16, 1, vlb.FMT_RGBA32F, W, H, 3, out[i].data_ptr())
+            c.skybox_project_sh_device(dsmall.data_ptr(), 64 * 128 * 16, 1, vlb.FMT_RGBA32F, 128, 64, 3, out[6].data_ptr())   # new shape: tables re-uploaded
+            c.skybox_project_sh_device(dev[0].data_ptr(), H * W * 16, 1, vlb.FMT_RGBA32F, W, H, 2, out[7].data_ptr())
+            c.synchronize()
+            got = out.cpu().numpy().reshape(8, 16, 3)
+            for i in range(6):
+                assert rel_l2(got[i], want[i]) <= SKY_TOL
+                assert np.array_equal(got[i], c.skybox_project_sh(host[i], 3))          # the host path (never chained), bit for bit
+            assert rel_l2(got[6], oa.skybox_project(small, 3)) <= SKY_TOL
+            assert rel_l2(got[7], oa.skybox_project(host[0], 2)) <= SKY_TOL and np.all(got[7, 9:] == 0)
+        # the same output buffer written by consecutive launches: the last one wins
+        for i in range(6):
+            c.skybox_project_sh_device(dev[i].data_ptr(), H * W * 16, 1, vlb.FMT_RGBA32F, W, H, 3, out[0].data_ptr())
+        c.synchronize()
+        assert rel_l2(out[0].cpu().numpy(), want[5]) <= SKY_TOL

@@ -127,7 +127,7 @@ class VlbError(RuntimeError):
 
 # every symbol include/vlb_bake.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
-    "vlb_abi_version", "vlb_ctx_create", "vlb_ctx_destroy", "vlb_ctx_set_stream", "vlb_ctx_synchronize",
+    "vlb_abi_version", "vlb_ctx_create", "vlb_ctx_destroy", "vlb_ctx_set_stream", "vlb_ctx_stream", "vlb_ctx_synchronize",
     "vlb_last_error", "vlb_ctx_launch_count", "vlb_scene_set_triangles", "vlb_scene_load_gltf", "vlb_gltf_probe", "vlb_scene_bounds", "vlb_bvh_build",
     "vlb_scene_set_textures", "vlb_gltf_texture", "vlb_image_load_rgba8", "vlb_image_load_rgba32f", "vlb_bake_probes_multi", "vlb_skybox_set", "vlb_skybox_set_async", "vlb_skybox_project_sh", "vlb_skybox_project_sh_batched", "vlb_skybox_project_sh_device",
     "vlb_skybox_project_sh_device_ptrs", "vlb_envmap_project_sh", "vlb_bake_settings_default", "vlb_bake_settings_from_bounds", "vlb_probe_positions",
@@ -157,6 +157,7 @@ def load_library():
         "vlb_ctx_synchronize": (i32, [vp]),
         "vlb_last_error": (ctypes.c_char_p, [vp]),
         "vlb_ctx_launch_count": (u64, [vp]),
+        "vlb_ctx_stream": (u64, [vp]),
         "vlb_scene_set_triangles": (i32, [vp, vp, u64, vp, u64, vp, u32, vp, u32]),
         "vlb_scene_load_gltf": (i32, [vp, ctypes.c_char_p]),
         "vlb_gltf_probe": (i32, [ctypes.c_char_p, vp, vp]),
@@ -259,6 +260,11 @@ class Context:
         """handle: cudaStream_t as int (0 = CUDA's legacy default stream); None = the ctx's own stream."""
         self._check(self._lib.vlb_ctx_set_stream(self._h, STREAM_OWN if handle is None else int(handle)))
         self.stream_handle = None if handle is None else int(handle)     # parallel.order_after_bake compares it with torch's stream
+
+    @property
+    def stream(self):
+        """cudaStream_t (int) the ctx enqueues on; wrap it with torch.cuda.ExternalStream to record events on it."""
+        return int(self._lib.vlb_ctx_stream(self._h))
 
     def synchronize(self):
         self._check(self._lib.vlb_ctx_synchronize(self._h))

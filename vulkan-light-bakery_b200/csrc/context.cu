@@ -66,6 +66,7 @@ static int env_lanes() {
 }
 
 static int check_device(vlb_ctx* ctx) {
+    ctx->proj_chain = false;       // whatever this call enqueues, the next projection launch must not overtake it (skybox_sh.cu)
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return ctx->fail(VLB_ERR_NO_DEVICE, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
     return VLB_OK;
@@ -153,8 +154,11 @@ void vlb_ctx_destroy(vlb_ctx* ctx) {
 int vlb_ctx_set_stream(vlb_ctx* ctx, uint64_t handle) {
     if (!ctx) return VLB_ERR_INVALID;
     ctx->stream = handle == VLB_STREAM_OWN ? ctx->own_stream : reinterpret_cast<cudaStream_t>(handle);
+    ctx->proj_chain = false;
     return VLB_OK;
 }
+
+uint64_t vlb_ctx_stream(const vlb_ctx* ctx) { return ctx ? (uint64_t)reinterpret_cast<uintptr_t>(ctx->stream) : 0; }
 
 static int join_sky_upload(vlb_ctx* ctx, cudaStream_t st);
 
@@ -423,10 +427,12 @@ int vlb_envmap_project_sh(vlb_ctx* ctx, const void* texels, int format, int widt
 int vlb_skybox_project_sh_device(vlb_ctx* ctx, const void* d_texels, uint64_t map_stride_bytes, uint32_t n_maps,
                                  int format, int width, int height, int sh_order, float* d_out) {
     if (!ctx) return VLB_ERR_INVALID;
+    const bool chain_was_open = ctx->proj_chain;
     if (int r = check_device(ctx)) return r;
     if (!d_texels || !d_out || n_maps == 0 || width <= 0 || height <= 0 || (sh_order != 2 && sh_order != 3) ||
         (format != VLB_FMT_RGBA8 && format != VLB_FMT_RGBA32F))
         return ctx->fail(VLB_ERR_INVALID, "vlb_skybox_project_sh_device: bad arguments");
+    ctx->proj_chain = chain_was_open;      // check_device closed it; the launch below may chain onto the previous projection
     return project_sh_device(ctx, d_texels, map_stride_bytes, n_maps, format, width, height, sh_order, 0, d_out);
 }
 

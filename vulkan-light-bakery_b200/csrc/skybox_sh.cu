@@ -286,7 +286,8 @@ constexpr int kTPhases = 4;                // row phases: 64 columns x 4 phases 
 constexpr int kTConsumers = kTCols * kTPhases;
 constexpr int kTThreads = kTConsumers + 32;
 constexpr int kTMaxStages = 8;
-constexpr int kTCtasPerSm = 2;             // two CTAs share an SM: one streams while the other starts up or flushes
+constexpr int kTCtasPerSm = 2;             // a long launch fills two CTA slots per SM (5 stages each): one streams while the other flushes
+constexpr int kTRegSlots = 3;              // registers are held to 72 so that THREE short launches (3 stages each) of a chain share an SM
 // rows per tile (= pipeline stage): 16 KB of texels per TMA instruction in either format
 __host__ __device__ constexpr int tile_rows(int fmt) { return fmt == VLB_FMT_RGBA32F ? 16 : 64; }
 constexpr int kTRowsMax = 64;
@@ -331,7 +332,7 @@ __device__ __forceinline__ uint32_t cta_of_tile(const ProjParams& p, uint32_t t)
 }
 
 template <int K, int FMT>
-__global__ void __launch_bounds__(kTThreads, kTCtasPerSm) k_project_tiles(const __grid_constant__ CUtensorMap tmap, const ProjParams p) {
+__global__ void __launch_bounds__(kTThreads, kTRegSlots) k_project_tiles(const __grid_constant__ CUtensorMap tmap, const ProjParams p) {
     constexpr int NG = K > 9 ? 7 : 5;
     constexpr int BPT = FMT == VLB_FMT_RGBA32F ? 16 : 4;
     constexpr int TR = tile_rows(FMT);
@@ -352,6 +353,12 @@ __global__ void __launch_bounds__(kTThreads, kTCtasPerSm) k_project_tiles(const 
     const uint32_t t0 = b * p.split_q + min(b, p.split_r);
     const uint32_t nt = p.split_q + (b < p.split_r ? 1u : 0u);
     VLB_STAMP(0);
+    // Programmatic dependent launch (project_sh_device chains back-to-back projections on the ctx's own stream): the next
+    // launch of the chain may be scheduled as soon as every CTA of this one has started, and streams its texels while this
+    // launch reduces and retires. Texels are never written by a projection, so only the shared scratch (partials, counters)
+    // and the output need ordering: griddep_wait() below, right before the first of those writes. Both instructions are
+    // no-ops for an ordinary launch.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kTConsumers / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -460,6 +467,7 @@ __global__ void __launch_bounds__(kTThreads, kTCtasPerSm) k_project_tiles(const 
                 const uint32_t b_first = cta_of_tile(p, map * p.tiles_per_map);
                 const uint32_t b_last = cta_of_tile(p, (map + 1) * p.tiles_per_map - 1);
                 const uint32_t P = b_last - b_first + 1;
+                asm volatile("griddepcontrol.wait;" ::: "memory");      // the previous launch of the chain has retired: scratch and output are ours
                 if (P == 1) {
                     if (tid < VLB_SH_STRIDE) p.out[(size_t)map * VLB_SH_STRIDE + tid] = macc;
                 } else {
@@ -477,6 +485,14 @@ __global__ void __launch_bounds__(kTThreads, kTCtasPerSm) k_project_tiles(const 
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return v && *v ? atoi(v) : dflt;
+}
+
+// Tuning knobs read once (a projection of one map is a 5 microsecond launch: no getenv on that path).
+struct ProjEnv { int tma, ctas_per_sm, stages, pdl, blocks_per_sm, rows; };
+static const ProjEnv& proj_env() {
+    static const ProjEnv e = {env_int("VLB_PROJ_TMA", 1), env_int("VLB_PROJ_CTAS_PER_SM", 0), env_int("VLB_PROJ_STAGES", 0),
+                              env_int("VLB_PROJ_PDL", 1), env_int("VLB_PROJ_BLOCKS_PER_SM", 2), env_int("VLB_PROJ_ROWS", 0)};
+    return e;
 }
 
 #ifdef VLB_PROJ_TIMING
@@ -507,15 +523,20 @@ int proj_timing_dump(vlb_ctx* ctx, int n_launches) {
 #endif
 
 template <int K, int FMT>
-static cudaError_t launch_tiles(const CUtensorMap& tmap, const ProjParams& p, unsigned grid, size_t smem, cudaStream_t st) {
+static cudaError_t launch_tiles(const CUtensorMap& tmap, const ProjParams& p, unsigned grid, size_t smem, cudaStream_t st, bool chained) {
     static size_t allowed = 0;   // per instantiation; raising the limit is idempotent, so a race is harmless
     if (smem > allowed) {
         cudaError_t e = cudaFuncSetAttribute(k_project_tiles<K, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         allowed = smem;
     }
-    k_project_tiles<K, FMT><<<grid, kTThreads, smem, st>>>(tmap, p);
-    return cudaSuccess;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = chained ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k_project_tiles<K, FMT>, tmap, p);
 }
 
 // Partials + arrival counters of scratch set `set` (0: ctx stream, 1 + lane: auxiliary lanes). Growing a
@@ -558,8 +579,14 @@ static EncodeTiledFn encode_tiled_fn() {
 int project_sh_device(vlb_ctx* ctx, const void* d_texels, uint64_t map_stride, uint32_t n_maps, int fmt, int W, int H,
                       int order, int variant, float* d_out, int lane) {
     cudaStream_t st = lane < 0 ? ctx->stream : ctx->lane_stream[lane];
+    const ProjEnv& env = proj_env();
+    // chain onto the previous projection launch (programmatic dependent launch, see k_project_tiles) only when this
+    // ctx knows that nothing else was enqueued on the stream in between: its own stream, previous call = a projection
+    bool chained = lane < 0 && ctx->proj_chain && st == ctx->own_stream && env.pdl != 0;
+    ctx->proj_chain = false;
     // tables (cached per size/variant): per-row quadrature factors (zero-padded to whole tiles), per-column cos/sin(phi)
     if (ctx->tab_w != W || ctx->tab_h != H || ctx->tab_variant != variant) {
+        chained = false;
         const size_t h_pad = ((size_t)H + kTRowsMax - 1) / kTRowsMax * kTRowsMax;
         std::vector<float> row_tab(8 * h_pad, 0.f), row_sc(2 * (size_t)H), col(2 * (size_t)W);
         host_proj_row_table(W, H, row_tab.data());
@@ -579,7 +606,7 @@ int project_sh_device(vlb_ctx* ctx, const void* d_texels, uint64_t map_stride, u
     // TMA needs a 16-byte aligned base and 16-byte multiples for the row and map pitches
     const bool aligned = ((size_t)W * bpt) % 16 == 0 && (n_maps == 1 || map_stride % 16 == 0) &&
                          (reinterpret_cast<uintptr_t>(d_texels) % 16) == 0 && (uint64_t)W * 4 < (1ull << 32);
-    const bool use_tma = aligned && env_int("VLB_PROJ_TMA", 1) != 0 && encode_tiled_fn() != nullptr;
+    const bool use_tma = aligned && env.tma != 0 && encode_tiled_fn() != nullptr;
 
     if (use_tma) {
         p.strips = (W + kTCols - 1) / kTCols;
@@ -593,26 +620,38 @@ int project_sh_device(vlb_ctx* ctx, const void* d_texels, uint64_t map_stride, u
         // slot per SM, so that a launch on another lane / stream runs in the other slot and streams
         // while this one flushes, publishes and sums.
         const bool long_launch = n_tiles >= (uint64_t)ctx->sm_count * kTCtasPerSm * 16;
-        const int per_sm = env_int("VLB_PROJ_CTAS_PER_SM", long_launch ? kTCtasPerSm : 1);
+        const int per_sm = env.ctas_per_sm > 0 ? env.ctas_per_sm : (long_launch ? kTCtasPerSm : 1);
         const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)ctx->sm_count * std::max(1, std::min(per_sm, kTCtasPerSm)));
         p.split_q = p.n_tiles / grid; p.split_r = p.n_tiles % grid;
 
-        CUtensorMap tmap;
-        const cuuint64_t gdim[3] = {(cuuint64_t)W * 4, (cuuint64_t)H, (cuuint64_t)n_maps};
-        const cuuint64_t gstride[2] = {(cuuint64_t)W * bpt, n_maps == 1 ? (cuuint64_t)W * bpt * H : (cuuint64_t)map_stride};
-        const cuuint32_t box[3] = {(cuuint32_t)kTCols * 4, (cuuint32_t)TR, 1};
-        const cuuint32_t estride[3] = {1, 1, 1};
-        const CUresult cr = encode_tiled_fn()(&tmap, bpt == 16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
-                                              const_cast<void*>(d_texels), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) return ctx->fail(VLB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+        // the encoded tensor map is cached per (pointer, shape): encoding costs about as much as the launch itself
+        vlb_ctx::TmapEntry* hit = nullptr;
+        for (vlb_ctx::TmapEntry& e : ctx->tmap_cache)
+            if (e.ptr == d_texels && e.W == W && e.H == H && e.fmt == fmt && e.n_maps == n_maps && e.stride == map_stride) { hit = &e; break; }
+        if (!hit) {
+            hit = &ctx->tmap_cache[ctx->tmap_next++ % (sizeof ctx->tmap_cache / sizeof ctx->tmap_cache[0])];
+            static_assert(sizeof(CUtensorMap) <= sizeof hit->map, "tensor map cache slot too small");
+            CUtensorMap* tm = reinterpret_cast<CUtensorMap*>(hit->map);
+            const cuuint64_t gdim[3] = {(cuuint64_t)W * 4, (cuuint64_t)H, (cuuint64_t)n_maps};
+            const cuuint64_t gstride[2] = {(cuuint64_t)W * bpt, n_maps == 1 ? (cuuint64_t)W * bpt * H : (cuuint64_t)map_stride};
+            const cuuint32_t box[3] = {(cuuint32_t)kTCols * 4, (cuuint32_t)TR, 1};
+            const cuuint32_t estride[3] = {1, 1, 1};
+            const CUresult cr = encode_tiled_fn()(tm, bpt == 16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 3,
+                                                  const_cast<void*>(d_texels), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (cr != CUDA_SUCCESS) { hit->ptr = nullptr; return ctx->fail(VLB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr); }
+            hit->ptr = d_texels; hit->stride = map_stride; hit->n_maps = n_maps; hit->W = W; hit->H = H; hit->fmt = fmt;
+        }
+        const CUtensorMap& tmap = *reinterpret_cast<const CUtensorMap*>(hit->map);
 
         const int stage_bytes = TR * kTCols * bpt + TR * 32;
         const int ng3 = (order == 2 ? 5 : 7) * 3;
         const size_t merge_bytes = (size_t)kTPhases * kTCols * ng3 * sizeof(float);
         // lanes: 3 stages (52 KB in flight per CTA) so that three launches fit on an SM side by side
-        int stages = env_int("VLB_PROJ_STAGES", lane < 0 ? 5 : 3);
+        // one launch takes one CTA slot per SM (unless it is a long batch): with 3 stages (52 KB in flight per CTA) three
+        // launches of a chain / of the lanes fit on an SM side by side, one streaming while its neighbours start up or retire
+        int stages = env.stages > 0 ? env.stages : (long_launch ? 5 : 3);
         stages = std::max(2, std::min(stages, kTMaxStages));
         p.n_stages = stages;
         const size_t smem = (size_t)stages * stage_bytes + merge_bytes + 128;
@@ -625,20 +664,21 @@ int project_sh_device(vlb_ctx* ctx, const void* d_texels, uint64_t map_stride, u
         g_tgrid = grid;
 #endif
         cudaError_t e;
-        if (order == 2) e = fmt == VLB_FMT_RGBA32F ? launch_tiles<9, VLB_FMT_RGBA32F>(tmap, p, grid, smem, st) : launch_tiles<9, VLB_FMT_RGBA8>(tmap, p, grid, smem, st);
-        else            e = fmt == VLB_FMT_RGBA32F ? launch_tiles<16, VLB_FMT_RGBA32F>(tmap, p, grid, smem, st) : launch_tiles<16, VLB_FMT_RGBA8>(tmap, p, grid, smem, st);
+        if (order == 2) e = fmt == VLB_FMT_RGBA32F ? launch_tiles<9, VLB_FMT_RGBA32F>(tmap, p, grid, smem, st, chained) : launch_tiles<9, VLB_FMT_RGBA8>(tmap, p, grid, smem, st, chained);
+        else            e = fmt == VLB_FMT_RGBA32F ? launch_tiles<16, VLB_FMT_RGBA32F>(tmap, p, grid, smem, st, chained) : launch_tiles<16, VLB_FMT_RGBA8>(tmap, p, grid, smem, st, chained);
         VLB_CUDA(ctx, e);
         VLB_LAUNCH_CHECK(ctx);
+        ctx->proj_chain = lane < 0 && st == ctx->own_stream;     // the next device projection may chain onto this launch
         return VLB_OK;
     }
 
     p.strips = (W + kProjBlock - 1) / kProjBlock;
     // launch geometry: about 2 blocks per SM for a single map, whole columns for big batches
-    const long long target = (long long)ctx->sm_count * env_int("VLB_PROJ_BLOCKS_PER_SM", 2);
+    const long long target = (long long)ctx->sm_count * env.blocks_per_sm;
     long long rbw = std::max<long long>(1, target / std::max<long long>(1, (long long)n_maps * p.strips));
     int rows = (int)((H + rbw - 1) / rbw);
     rows = std::max(rows, kProjUnroll);
-    rows = env_int("VLB_PROJ_ROWS", rows);
+    if (env.rows > 0) rows = env.rows;
     rows = std::max(1, std::min(rows, H));
     p.rows_per_block = rows;
     p.row_blocks = (H + rows - 1) / rows;

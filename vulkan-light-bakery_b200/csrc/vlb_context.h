@@ -85,6 +85,13 @@ struct vlb_ctx {
     // ---- projection (skybox / envmap) ----
     vlb::DevBuf d_proj_in, d_proj_out, d_proj_partials, d_proj_counters, d_row_tab, d_col_tab;
     int tab_w = 0, tab_h = 0, tab_variant = -1;
+    // Back-to-back projections of device-resident maps on the ctx's OWN stream are chained with programmatic dependent
+    // launch (skybox_sh.cu): `proj_chain` says that the last thing this ctx enqueued on its stream was such a launch.
+    // Every other API entry point clears it (check_device), so a chained launch never overtakes foreign work.
+    bool proj_chain = false;
+    struct TmapEntry { const void* ptr = nullptr; uint64_t stride = 0; uint32_t n_maps = 0; int W = 0, H = 0, fmt = -1; alignas(64) unsigned char map[128]; };
+    TmapEntry tmap_cache[8];
+    unsigned tmap_next = 0;
     // ---- bake ----
     vlb::DevBuf d_bake_out, d_bake_prev, d_partials, d_work_counter, d_axis, d_row_sc, d_col_sc, d_stats, d_stream_scratch;
     int dir_w = 0, dir_h = 0;
