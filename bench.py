@@ -165,25 +165,31 @@ def ncu_pipes(kernel):
         return None
 
 
-def measure_bake(torch, dist, par, ctx, scene, sky, s, rank, world, dev, stream, K, W, e2e_steps, flush):
-    """Times the bake of settings `s` (this rank's cyclic share) two ways; returns a dict of local times."""
+def measure_bake(torch, dist, par, ctx, scene, sky, s, rank, world, dev, stream, K, W, e2e_steps, flush, gather="abi"):
+    """Times the bake of the whole grid `s` (this rank's cyclic share + the all-gather) two ways; returns local times.
+    gather="abi": vlb_bake_probes_sharded_device (NCCL all-gather + un-interleave inside libvlb_bake.so, the path a
+    C++ host takes); gather="torch": the bake through the ABI, the all-gather through torch.distributed (parallel.py)."""
     mine = par.shard_settings(s, rank, world, cyclic=True)
     n_local = mine.n_slab_probes
-    out = torch.zeros((n_local, 48), dtype=torch.float32, device=dev)
+    out = torch.zeros((max(n_local, 1), 48), dtype=torch.float32, device=dev)
+    full = torch.zeros((s.n_probes, 48), dtype=torch.float32, device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
+    def bake_and_gather():
+        if gather == "abi":
+            ctx.bake_probes_sharded_device(s, 0, full.data_ptr())
+            return full
         ctx.bake_probes_device(mine, out.data_ptr())
-        return par.gather_slabs(out, s, rank, world, cyclic=True)
+        return par.gather_slabs(out[:n_local], s, rank, world, cyclic=True)
 
     # ---- value: inputs resident in HBM ------------------------------------------------------
     for _ in range(W):
         flush.zero_()
-        step_resident()
+        bake_and_gather()
     barrier()
     launches0 = ctx.launch_count
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -192,7 +198,7 @@ def measure_bake(torch, dist, par, ctx, scene, sky, s, rank, world, dev, stream,
     for i in range(K):
         flush.zero_()                      # L2 flush, outside the per-step event pair
         ev[i][0].record(stream)
-        step_resident()
+        bake_and_gather()
         ev[i][1].record(stream)
         st = ctx.last_bake_stats()
         kernel_ms.append(st.kernel_ms)
@@ -202,19 +208,28 @@ def measure_bake(torch, dist, par, ctx, scene, sky, s, rank, world, dev, stream,
     t_ms = sum(a.elapsed_time(b) for a, b in ev)
 
     # ---- e2e: host buffers in, host buffer out, every step -----------------------------------
+    # Every rank holds the same host arrays (one box, one scene file). With a communicator the uploads are
+    # replicated uploads (vlb_comm_sharded_uploads): each rank copies 1/world of the vertex, index and texel arrays
+    # over PCIe and an NVLink all-gather completes them; the gathered grid is read back ONCE, by rank 0 (round 1:
+    # every rank uploaded everything and read the whole grid back, 8 x 63.6 MB through one host per 27 ms step).
     pins = {k: pinned_like(torch, np.ascontiguousarray(scene[k])) for k in ("vertices", "indices", "instances", "materials")}
     pscene = {k: v[0] for k, v in pins.items()}
     psky, _keep_sky = pinned_like(torch, sky)
-    h2d = sum(v[0].nbytes for v in pins.values()) + psky.nbytes
-    full_host = torch.empty((s.n_probes, 48), dtype=torch.float32, pin_memory=True)
+    big = pins["vertices"][0].nbytes + pins["indices"][0].nbytes + psky.nbytes
+    small = pins["instances"][0].nbytes + pins["materials"][0].nbytes
+    sharded_up = gather == "abi" and world > 1
+    h2d = (big // world if sharded_up else big) + small          # this rank's bytes over PCIe per step
+    full_host = torch.empty((s.n_probes, 48), dtype=torch.float32, pin_memory=True) if rank == 0 else None
+    if sharded_up:
+        ctx.comm_sharded_uploads(True)
 
     def step_e2e():
-        ctx.set_skybox_async(psky)          # 33.5 MB H2D on the ctx's copy stream, overlapping the two calls below
+        ctx.set_skybox_async(psky)          # H2D on the ctx's copy stream, overlapping the two calls below
         ctx.set_scene(pscene)
         ctx.build_bvh()
-        ctx.bake_probes_device(mine, out.data_ptr())
-        g = par.gather_slabs(out, s, rank, world, cyclic=True)
-        full_host.copy_(g, non_blocking=True)
+        g = bake_and_gather()
+        if full_host is not None:
+            full_host.copy_(g, non_blocking=True)
         torch.cuda.synchronize()
 
     for _ in range(2):
@@ -226,8 +241,11 @@ def measure_bake(torch, dist, par, ctx, scene, sky, s, rank, world, dev, stream,
         step_e2e()
     e1.record(stream)
     barrier()
+    if sharded_up:
+        ctx.comm_sharded_uploads(False)
     return {"t_ms": t_ms, "e2e_ms": e0.elapsed_time(e1) / e2e_steps, "kern_ms": float(np.mean(kernel_ms)),
-            "shadow": int(shadow), "launches": int(launches), "h2d": int(h2d), "d2h": int(full_host.numel() * 4),
+            "shadow": int(shadow), "launches": int(launches), "h2d": int(h2d),
+            "d2h": int(full_host.numel() * 4) if full_host is not None else 0,
             "mine": mine, "out": out}
 
 
@@ -255,6 +273,14 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)     # one stream for torch, NCCL and the library
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
+    gather = args.gather
+    if world > 1 and gather == "abi":
+        # the library's own communicator (vlb_comm_*): rank 0 makes the NCCL id, torch.distributed carries the 128 bytes
+        uid = torch.zeros(vlb.COMM_ID_BYTES, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(vlb.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        ctx.comm_init_rank(bytes(uid.cpu().numpy().tobytes()), rank, world)
     ctx.set_scene(scene)
     bvh_first = ctx.build_bvh()                # first call: includes the one-off device allocations
     bvh = ctx.build_bvh()                      # steady state (what every e2e step pays)
@@ -265,7 +291,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     m = measure_bake(torch, dist, par, ctx, scene, sky, s, rank, world, dev, stream, K, W,
-                     max(3, min(K, 50 if which == "c2" else 10)), flush)
+                     max(3, min(K, 50 if which == "c2" else 10)), flush, gather)
     clocks = sampler.finish()
     t_ms, e2e_ms, kern_ms = m["t_ms"], m["e2e_ms"], m["kern_ms"]
 
@@ -274,11 +300,11 @@ def run_ours(args):
         tt = torch.tensor([t_ms, e2e_ms, kern_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_ms, e2e_ms, kern_ms = (float(x) for x in tt.tolist())
-        sh = torch.tensor([m["shadow"]], dtype=torch.int64, device=dev)
+        sh = torch.tensor([m["shadow"], m["h2d"], m["d2h"], m["launches"]], dtype=torch.int64, device=dev)
         dist.all_reduce(sh)
-        shadow_total = int(sh.item())
+        shadow_total, h2d_total, d2h_total, launches_total = (int(x) for x in sh.tolist())
     else:
-        shadow_total = m["shadow"]
+        shadow_total, h2d_total, d2h_total, launches_total = m["shadow"], m["h2d"], m["d2h"], m["launches"]
     ms_per_step = t_ms / K
     value = rays_total / (ms_per_step * 1e-3) / 1e9
 
@@ -294,17 +320,28 @@ def run_ours(args):
         alg_bytes = st.n_nodes_visited * 112 + st.n_tris_tested * 48     # per launch (this rank's share)
         peak, peak_src = measured_peaks()
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
-        kname = "vlb::k_bake_stream<9,false,false,false>"
-        roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": ncu_traffic(kname + ":" + which), "ncu": ncu_pipes(kname + ":" + which), "peak_source": peak_src,
+        # the instantiation bake_device picks: K from sh_order, no counters, direct pass, TEX iff a material is textured
+        kname = "vlb::k_bake_stream<%d,false,false,%s>" % (9 if s.sh_order == 2 else 16, "true" if scene.get("textures") else "false")
+        sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+        l1_peak = 148 * 128 * sm_mhz * 1e6 / 1e9                          # 128 B per clock per SM through the L1 data pipe
+        traffic = ncu_traffic(kname + ":" + which)
+        roofline = {"bound": "l1", "kernel": kname, "achieved": achieved, "peak": l1_peak, "unit": "GB/s",
+                    "frac": achieved / l1_peak, "traffic": traffic,
+                    "peak_source": "148 SMs x 128 B/clk x %.0f MHz (SM clock sampled during the timed region): the L1 data pipe, the "
+                                   "unit ncu names as binding for this kernel" % sm_mhz,
+                    "hbm": {"dram_bytes_per_launch": traffic, "achieved": (traffic / (kern_ms * 1e-3) / 1e9) if traffic else None,
+                            "peak": peak, "peak_source": peak_src, "frac": (traffic / (kern_ms * 1e-3) / 1e9 / peak) if traffic else None},
+                    "ncu": ncu_pipes(kname + ":" + which),
                     "algorithmic_bytes_per_launch": int(alg_bytes),
                     "nodes_per_ray": st.n_nodes_visited / max(nrays, 1), "tris_per_ray": st.n_tris_tested / max(nrays, 1),
                     "kernel_ms": kern_ms,
-                    "note": "traversal reads 112 B of each 4-wide node + 48 B per triangle, all L1/L2-resident (BVH + "
-                            "triangles < 30 MB); algorithmic bytes = nodes visited x 112 + triangles tested x 48 from the "
-                            "instrumented build of the same kernel; the kernel is bound by the L1 data pipe, the ALU pipe and latency, "
-                            "not by HBM (see the `ncu` block: DRAM throughput < 1 %), so this fraction is NOT an HBM utilisation "
-                            "and can exceed 1"}
+                    "note": "the traversal reads 112 B of each 4-wide node + 48 B per triangle, all L1/L2-resident (BVH + triangles "
+                            "< 30 MB), so the kernel is NOT HBM-bound: `achieved` = (nodes visited x 112 + triangles tested x 48, "
+                            "counted by the instrumented build of the same kernel) / kernel time, against the L1 data-pipe peak. "
+                            "The bytes are scattered 16-byte loads (about 8 wavefronts per load instruction), so the pipe saturates "
+                            "in wavefronts long before it does in bytes: the binding figures are the `ncu` block's "
+                            "l1tex data-pipe and issue-slot utilisation (profiles/, captured this round on the same build); "
+                            "`hbm` is the measured DRAM traffic of one launch against the HBM copy peak"}
         extra["roofline"] = roofline
         extra["skybox"] = bench_skybox(torch, ctx, scenes, dev, stream, peak, peak_src)
         extra["cpu_baseline"] = cpu_baseline(scene, sky, settings_for(scenes, which, 1), which)
@@ -314,7 +351,7 @@ def run_ours(args):
             # BASELINE configs[1] beside the headline: the small grid whose bake is one 0.9 ms launch
             s2 = settings_for(scenes, "c2", 1)
             K2 = 50
-            m2 = measure_bake(torch, dist, par, ctx, scene, sky, s2, 0, 1, dev, stream, K2, 5, 30, flush)
+            m2 = measure_bake(torch, dist, par, ctx, scene, sky, s2, 0, 1, dev, stream, K2, 5, 30, flush, gather)
             rays2 = s2.n_probes * s2.dir_w * s2.dir_h
             extra["c2"] = {"workload": config_dict(1, s2, "c2")["workload"], "value": rays2 / (m2["t_ms"] / K2 * 1e-3) / 1e9,
                            "unit": UNIT, "ms_per_step": m2["t_ms"] / K2, "kernel_ms": m2["kern_ms"], "steps": K2,
@@ -327,10 +364,15 @@ def run_ours(args):
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if which == "c2" else "strong",
                 "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config_dict(world, s, which), "clocks": clocks,
-                "e2e": {"value": rays_total / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": m["h2d"],
-                        "d2h_bytes_per_step": m["d2h"], "ms_per_step": e2e_ms,
-                        "includes": "scene upload + LBVH build + skybox upload + bake + all-gather + coefficient read-back"},
-                "gpu_launches": m["launches"],
+                "e2e": {"value": rays_total / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d_total,
+                        "d2h_bytes_per_step": d2h_total, "ms_per_step": e2e_ms,
+                        "includes": "scene upload + LBVH build + skybox upload + bake + all-gather + coefficient read-back; "
+                                    "bytes are summed over the ranks: with the library's communicator every rank copies 1/N of "
+                                    "the vertex/index/skybox arrays over PCIe (NVLink all-gather replicates them) and rank 0 "
+                                    "reads the gathered grid back once"},
+                "gpu_launches": launches_total,
+                "gather": ("vlb_bake_probes_sharded_device: ncclAllGather + k_uninterleave inside libvlb_bake.so" if gather == "abi"
+                           else "torch.distributed all_gather_into_tensor (parallel.py)") if world > 1 else "none (1 GPU)",
                 "probes_per_s": s.n_probes / (ms_per_step * 1e-3),
                 "rays_incl_shadow_per_s_G": (rays_total + shadow_total) / (ms_per_step * 1e-3) / 1e9,
                 "shadow_rays_per_step": shadow_total}
@@ -412,6 +454,24 @@ def cpu_baseline(scene, sky, s, which="c3", budget_s=12.0):
 
 
 # =============================================================================================
+def vulkan_probe():
+    """the reference's shaders could only run here through a Vulkan loader + a CPU driver (Mesa
+    lavapipe) + a GLSL compiler. Probed at run time; what is missing is reported in the reference line."""
+    import ctypes
+    import shutil
+    missing = []
+    try:
+        ctypes.CDLL("libvulkan.so.1")
+    except OSError:
+        missing.append("libvulkan.so.1 (Vulkan loader)")
+    icd_dirs = ["/usr/share/vulkan/icd.d", "/etc/vulkan/icd.d"]
+    if not any(os.path.isdir(d) and any("lvp" in f for f in os.listdir(d)) for d in icd_dirs):
+        missing.append("lavapipe ICD (lvp_icd.*.json)")
+    if not (shutil.which("glslangValidator") or shutil.which("glslc")):
+        missing.append("glslangValidator / glslc")
+    return missing
+
+
 def run_reference(args):
     """Reference arm: the reference's path on the host CPU. The reference itself cannot be built
     here (needs Vulkan + an RT-capable driver / lavapipe + glslang, none in the image), so this is
@@ -427,6 +487,7 @@ def run_reference(args):
     from oracle import oracle_api as oa
     scene, sky, s = workload(vlb, scenes, world, args.workload)
     oa.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1
+    missing = vulkan_probe()
     K, W = args.steps, args.warmup
     n = s.n_probes
     # The sample is a bounded fraction of the grid, so the one-off costs (flatten + CPU BVH build) are
@@ -476,7 +537,11 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(world, s, args.workload),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": oa.num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "oracle port of the reference shaders on host cores; the Vulkan reference cannot run in this image"}
+            "note": "oracle port of the reference shaders on host cores (pinned to the reference's own shader sources compiled "
+                    "through oracle/glsl_shim.h, tests/test_ref_shaders.py); the Vulkan reference itself cannot run on this box: "
+                    + ("missing " + ", ".join(missing) if missing else "loader, lavapipe and a GLSL compiler are present but the build "
+                       "needs Vulkan-Hpp, GLFW, glm, imgui and tinygltf, none vendored"),
+            "vulkan_probe_missing": missing}
     print(json.dumps(line), flush=True)
 
 
@@ -487,6 +552,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c3", choices=["c2", "c3"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--gather", default="abi", choices=["abi", "torch"],
+                    help="N > 1: all-gather inside libvlb_bake.so (its own NCCL communicator) or through torch.distributed")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -288,12 +288,44 @@ int vlb_bake_probes(vlb_ctx* ctx, const vlb_bake_settings* s, float* out);
 /* The same bake spread over several GPUs from ONE host process (how the reference's single-process `baker` would
  * use a multi-GPU box): ctxs[r] are n distinct contexts (normally one per device) that already hold the same
  * scene, LBVH and skybox; ctx r bakes z-slices r, r + n, ... on its own device and host thread, and every share
- * lands in its rows of the one host grid `out` (Nx*Ny*Nz x 48 floats). No inter-GPU traffic on the direct pass;
- * with s->bounces > 0 the previous pass is redistributed to every device between passes. Bit-identical to
- * vlb_bake_probes on one ctx. (One process per GPU with an NCCL all-gather, as bench.py runs it, keeps the
- * gathered grid on the devices instead: vulkan-light-bakery_b200/parallel.py.) Errors: the code of the first
- * failing ctx, text in vlb_last_error(ctxs[0]). */
+ * lands in the one host grid `out` (Nx*Ny*Nz x 48 floats). Contexts on distinct devices become the ranks of an NCCL
+ * communicator (vlb_comm_init_all, done here on first use): the shares are all-gathered on the devices over NVLink,
+ * also between the gather passes of s->bounces > 0, and ctx 0 copies the grid out (vlb_bake_probes_sharded per
+ * ctx). Contexts that share a device, or a process without NCCL, take the host route instead: every share is copied
+ * straight into its rows of `out` and the previous pass is redistributed from the host between passes. Either way
+ * bit-identical to vlb_bake_probes on one ctx. Errors: the code of the first failing ctx, text in
+ * vlb_last_error(ctxs[0]). */
 int vlb_bake_probes_multi(vlb_ctx* const* ctxs, uint32_t n_ctx, const vlb_bake_settings* s, float* out);
+/* --- multi-GPU: the exchange step of the sharded bake, behind the ABI ----------------------------------------
+ * The reference is single-device (src/application.cpp:90-136 always takes physical device 0); BASELINE.json shards
+ * the probe grid over the GPUs of one box (scene + LBVH + skybox replicated, z-slices dealt cyclically: rank r of N
+ * bakes k = r, r + N, ...) and gathers the per-GPU SH shares with ONE NCCL all-gather over NVLink. One communicator
+ * rank per ctx: one process per GPU (vlb_comm_get_unique_id on rank 0, the 128 bytes carried to the other ranks by
+ * whatever the host program uses -- MPI, a file, torch.distributed --, then vlb_comm_init_rank everywhere) or several
+ * ctxs of one process (vlb_comm_init_all). NCCL is resolved at run time (libnccl.so.2); without it these calls
+ * return VLB_ERR_UNSUPPORTED. Collective calls (init, sharded bakes, and every upload while sharded uploads are on)
+ * must be made by all ranks in the same order. */
+#define VLB_COMM_ID_BYTES 128
+int vlb_comm_get_unique_id(void* id_out, uint64_t capacity_bytes);
+int vlb_comm_init_rank(vlb_ctx* ctx, const void* id, int rank, int world);
+int vlb_comm_init_all(vlb_ctx* const* ctxs, uint32_t n_ctx);      /* ctx r becomes rank r of n_ctx; distinct devices */
+int vlb_comm_destroy(vlb_ctx* ctx);                                /* also done by vlb_ctx_destroy                    */
+int vlb_comm_info(const vlb_ctx* ctx, int32_t* rank, int32_t* world, int32_t* nccl_version);   /* any pointer may be NULL */
+/* Replicated uploads: with this on, every rank must pass IDENTICAL host arrays to vlb_scene_set_triangles /
+ * vlb_scene_load_gltf / vlb_skybox_set[_async]; each rank then copies only its 1/N-th of the vertex, index and texel
+ * arrays over PCIe and one in-place all-gather over NVLink completes them on every GPU (the box's host memory and
+ * PCIe root see the scene once instead of N times). Off by default. */
+int vlb_comm_sharded_uploads(vlb_ctx* ctx, int enable);
+/* LightBaker::bake over the communicator: `s` describes the WHOLE grid (slab_k1 < 0); this rank bakes its cyclic
+ * z-slices, the shares are all-gathered and un-interleaved, and d_full_out ([Nx*Ny*Nz][48] floats, x-fastest, 16-byte
+ * aligned) holds the whole grid on EVERY rank when the ctx stream reaches this point. d_prev_full as in
+ * vlb_bake_gather_device (NULL = direct pass). Enqueues on the ctx stream, does not synchronise. Without a
+ * communicator it is vlb_bake_gather_device over the whole grid. Bit-identical to the one-GPU bake. */
+int vlb_bake_probes_sharded_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_full, float* d_full_out);
+/* Host-pointer variant: 1 + s->bounces passes on the devices with the all-gather between passes; the last pass is
+ * copied to `out` (Nx*Ny*Nz x 48 floats) on the ranks that pass a non-NULL pointer. Synchronous. */
+int vlb_bake_probes_sharded(vlb_ctx* ctx, const vlb_bake_settings* s, float* out_or_null);
+
 /* Device-resident output; enqueues on the ctx stream and returns WITHOUT synchronising. */
 int vlb_bake_probes_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out);
 /* One gather pass with a device-resident source: bakes the slab exactly like

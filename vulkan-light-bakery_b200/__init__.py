@@ -133,6 +133,8 @@ ABI_SYMBOLS = [
     "vlb_skybox_project_sh_device_ptrs", "vlb_envmap_project_sh", "vlb_bake_settings_default", "vlb_bake_settings_from_bounds", "vlb_probe_positions",
     "vlb_bake_probes", "vlb_bake_probes_device", "vlb_bake_gather_device", "vlb_bake_last_stats", "vlb_trace_rays",
     "vlb_bake_serialize_gltf", "vlb_bake_deserialize_gltf",
+    "vlb_comm_get_unique_id", "vlb_comm_init_rank", "vlb_comm_init_all", "vlb_comm_destroy", "vlb_comm_info",
+    "vlb_comm_sharded_uploads", "vlb_bake_probes_sharded_device", "vlb_bake_probes_sharded",
 ]
 
 _lib = None
@@ -185,6 +187,14 @@ def load_library():
         "vlb_trace_rays": (i32, [vp, vp, vp, u64, f32, f32, i32, i32, vp, vp]),
         "vlb_bake_serialize_gltf": (i32, [ctypes.c_char_p, ctypes.c_char_p, vp, u64, S]),
         "vlb_bake_deserialize_gltf": (i32, [ctypes.c_char_p, vp, u64, ctypes.POINTER(u64), vp]),
+        "vlb_comm_get_unique_id": (i32, [vp, u64]),
+        "vlb_comm_init_rank": (i32, [vp, vp, i32, i32]),
+        "vlb_comm_init_all": (i32, [vp, u32]),
+        "vlb_comm_destroy": (i32, [vp]),
+        "vlb_comm_info": (i32, [vp, vp, vp, vp]),
+        "vlb_comm_sharded_uploads": (i32, [vp, i32]),
+        "vlb_bake_probes_sharded_device": (i32, [vp, S, vp, vp]),
+        "vlb_bake_probes_sharded": (i32, [vp, S, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -371,6 +381,34 @@ class Context:
         self._check(self._lib.vlb_bake_last_stats(self._h, ctypes.byref(st)))
         return st
 
+    # -- multi-GPU: one NCCL rank per Context (include/vlb_bake.h, "multi-GPU")
+    def comm_init_rank(self, unique_id, rank, world):
+        """unique_id: the COMM_ID_BYTES bytes rank 0 got from comm_unique_id(), carried here by the host program."""
+        buf = ctypes.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        self._check(self._lib.vlb_comm_init_rank(self._h, ctypes.cast(buf, ctypes.c_void_p), int(rank), int(world)))
+
+    def comm_destroy(self):
+        self._check(self._lib.vlb_comm_destroy(self._h))
+
+    def comm_info(self):
+        """(rank, world, NCCL version code) -- (0, 1, v) without a communicator."""
+        r, w, v = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        self._check(self._lib.vlb_comm_info(self._h, ctypes.byref(r), ctypes.byref(w), ctypes.byref(v)))
+        return r.value, w.value, v.value
+
+    def comm_sharded_uploads(self, enable=True):
+        self._check(self._lib.vlb_comm_sharded_uploads(self._h, int(bool(enable))))
+
+    def bake_probes_sharded_device(self, s, d_prev_full, d_full_out):
+        """This rank's cyclic z-slices + all-gather: d_full_out ([n_probes, 48] device floats) holds the whole grid on every rank."""
+        self._check(self._lib.vlb_bake_probes_sharded_device(self._h, ctypes.byref(s), int(d_prev_full) if d_prev_full else None, int(d_full_out)))
+
+    def bake_probes_sharded(self, s, want_output=True):
+        """1 + s.bounces passes over the communicator; returns the whole grid [n_probes, 16, 3] (None if not wanted)."""
+        out = np.zeros((s.n_probes, 16, 3), np.float32) if want_output else None
+        self._check(self._lib.vlb_bake_probes_sharded(self._h, ctypes.byref(s), _ptr(out)))
+        return out
+
     # -- validation
     def trace_rays(self, origins, dirs, tmin=0.001, tmax=10000.0, accel=TRACE_BVH, kind=TRACE_CLOSEST):
         o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
@@ -392,6 +430,28 @@ def gltf_probe(path):
         raise VlbError(r, lib.vlb_last_error(None).decode())
     keys = ("vertices", "indices", "instances", "materials", "triangles")
     return dict(zip(keys, (int(c) for c in counts))), bounds
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """vlb_comm_get_unique_id (rank 0): bytes to hand to every rank's Context.comm_init_rank."""
+    lib = load_library()
+    buf = ctypes.create_string_buffer(COMM_ID_BYTES)
+    r = lib.vlb_comm_get_unique_id(ctypes.cast(buf, ctypes.c_void_p), COMM_ID_BYTES)
+    if r != 0:
+        raise VlbError(r, lib.vlb_last_error(None).decode())
+    return buf.raw
+
+
+def comm_init_all(contexts):
+    """vlb_comm_init_all: the contexts of ONE process (distinct devices) become ranks 0..n-1."""
+    lib = load_library()
+    arr = (ctypes.c_void_p * len(contexts))(*[c._h for c in contexts])
+    r = lib.vlb_comm_init_all(ctypes.cast(arr, ctypes.c_void_p), len(contexts))
+    if r != 0:
+        raise VlbError(r, lib.vlb_last_error(contexts[0]._h).decode())
 
 
 def bake_probes_multi(contexts, s):

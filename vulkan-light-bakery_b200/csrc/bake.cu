@@ -92,6 +92,9 @@ constexpr int kStreamWarps = kBakeBlock / 32;
 #ifndef VLB_BAKE_SMEM_STACK
 #define VLB_BAKE_SMEM_STACK 12              // stack entries per lane in shared memory; 0 = round-1 per-thread local array
 #endif
+#ifndef VLB_BAKE_FAST_PUSH
+#define VLB_BAKE_FAST_PUSH 1                // branch-free pushes of a node step's far children (WarpStack::push_far)
+#endif
 #ifndef VLB_BAKE_SMEM_HQ
 #define VLB_BAKE_SMEM_HQ 1                  // hit queue in shared memory
 #endif
@@ -132,6 +135,26 @@ struct WarpStack {
         if (sp < kSmemStack) asm volatile("st.shared.b32 [%0], %1;" ::"r"(sm + 128u * (uint32_t)sp), "r"(v) : "memory");
         else ovf[32 * (sp - kSmemStack)] = v;
         ++sp;
+    }
+    // bvh4_step's far children (r1 valid, r3 valid implies r2 valid), r1 on top. Fast path (all three slots inside the
+    // shared short stack): three UNCONDITIONAL stores and no branch -- entry r_k goes to slot sp + max(n - k, 0) with
+    // n = number of valid refs, so an invalid r3 / r2 is written first to the slot the next valid one overwrites (or,
+    // for n = 1, to the slot above the new top, which is dead).
+    __device__ __forceinline__ void push_far(int r3, int r2, int r1) {
+#if VLB_BAKE_FAST_PUSH
+        if (sp + 3 <= kSmemStack) {
+            const int v3 = r3 != kNoChild, v2 = r2 != kNoChild;
+            const uint32_t base = sm + 128u * (uint32_t)sp;
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(base), "r"(r3) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + 128u * (uint32_t)v3), "r"(r2) : "memory");
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + 128u * (uint32_t)(v3 + v2)), "r"(r1) : "memory");
+            sp += 1 + v3 + v2;
+            return;
+        }
+#endif
+        if (r3 != kNoChild) push(r3);
+        if (r2 != kNoChild) push(r2);
+        push(r1);
     }
     __device__ __forceinline__ int pop() {
         --sp;

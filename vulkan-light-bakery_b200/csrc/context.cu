@@ -126,7 +126,8 @@ void vlb_ctx_destroy(vlb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* bufs[] = {&ctx->d_verts, &ctx->d_indices, &ctx->d_insts_in, &ctx->d_tri_offsets, &ctx->d_tri_flat,
+    comm_destroy(ctx);
+    DevBuf* bufs[] = {&ctx->d_share, &ctx->d_gather_stage, &ctx->d_verts, &ctx->d_indices, &ctx->d_insts_in, &ctx->d_tri_offsets, &ctx->d_tri_flat,
                       &ctx->d_frontier[0], &ctx->d_frontier[1], &ctx->d_frontier_n, &ctx->d_tri_shade, &ctx->d_tri_uv, &ctx->d_tex_desc, &ctx->d_tex_texels, &ctx->d_inst, &ctx->d_base_color, &ctx->d_tris, &ctx->d_nodes, &ctx->d_keys,
                       &ctx->d_keys_sorted, &ctx->d_vals, &ctx->d_vals_sorted, &ctx->d_sort_tmp, &ctx->d_left,
                       &ctx->d_right, &ctx->d_first, &ctx->d_last, &ctx->d_parent_i, &ctx->d_parent_l, &ctx->d_flags,
@@ -247,8 +248,8 @@ int vlb_scene_set_triangles(vlb_ctx* ctx, const vlb_vertex* vertices, uint64_t n
 
     ctx->n_tris = tri_total; ctx->n_verts = n_vertices; ctx->n_indices = n_indices;
     ctx->n_insts = n_instances; ctx->n_mats = n_materials;
-    VLB_CUDA(ctx, ctx->d_verts.reserve(n_vertices * sizeof(vlb_vertex)));
-    VLB_CUDA(ctx, ctx->d_indices.reserve(n_indices * sizeof(uint32_t)));
+    VLB_CUDA(ctx, ctx->d_verts.reserve(comm_padded_bytes(ctx, n_vertices * sizeof(vlb_vertex))));
+    VLB_CUDA(ctx, ctx->d_indices.reserve(comm_padded_bytes(ctx, n_indices * sizeof(uint32_t))));
     VLB_CUDA(ctx, ctx->d_insts_in.reserve(insts.size() * sizeof(InstanceDev)));
     VLB_CUDA(ctx, ctx->d_tri_offsets.reserve(offsets.size() * sizeof(uint32_t)));
     VLB_CUDA(ctx, ctx->d_inst.reserve(inst_rec.size() * sizeof(float4)));
@@ -257,8 +258,9 @@ int vlb_scene_set_triangles(vlb_ctx* ctx, const vlb_vertex* vertices, uint64_t n
     VLB_CUDA(ctx, ctx->d_tri_shade.reserve(3 * tri_total * sizeof(float4)));
     VLB_CUDA(ctx, ctx->d_tri_uv.reserve(2 * tri_total * sizeof(float4)));
     cudaStream_t st = ctx->stream;
-    if (n_vertices) VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_verts.p, vertices, n_vertices * sizeof(vlb_vertex), cudaMemcpyHostToDevice, st));
-    if (n_indices) VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_indices.p, indices, n_indices * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    // the two big arrays: plain H2D copies, or (vlb_comm_sharded_uploads) 1/world over PCIe + an NVLink all-gather
+    if (int r = upload_replicated(ctx, ctx->d_verts.p, vertices, n_vertices * sizeof(vlb_vertex), st)) return r;
+    if (int r = upload_replicated(ctx, ctx->d_indices.p, indices, n_indices * sizeof(uint32_t), st)) return r;
     if (n_instances) {
         VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_insts_in.p, insts.data(), insts.size() * sizeof(InstanceDev), cudaMemcpyHostToDevice, st));
         VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_inst.p, inst_rec.data(), inst_rec.size() * sizeof(float4), cudaMemcpyHostToDevice, st));
@@ -347,15 +349,15 @@ int vlb_skybox_set_async(vlb_ctx* ctx, const void* texels, int format, int width
         VLB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_sky_free, cudaEventDisableTiming));
         VLB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_sky_ready, cudaEventDisableTiming));
     }
-    VLB_CUDA(ctx, ctx->d_sky.reserve(n * sizeof(float4)));
+    VLB_CUDA(ctx, ctx->d_sky.reserve(comm_padded_bytes(ctx, n * sizeof(float4))));
     // whatever the ctx stream has queued (a bake sampling the old skybox) finishes before the texels are replaced
     VLB_CUDA(ctx, cudaEventRecord(ctx->ev_sky_free, ctx->stream));
     VLB_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_sky_free, 0));
     if (format == VLB_FMT_RGBA32F) {
-        VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_sky.p, texels, n * sizeof(float4), cudaMemcpyHostToDevice, ctx->copy_stream));
+        if (int r = upload_replicated(ctx, ctx->d_sky.p, texels, n * sizeof(float4), ctx->copy_stream)) return r;
     } else {
-        VLB_CUDA(ctx, ctx->d_sky_stage.reserve(n * 4));
-        VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_sky_stage.p, texels, n * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+        VLB_CUDA(ctx, ctx->d_sky_stage.reserve(comm_padded_bytes(ctx, n * 4)));
+        if (int r = upload_replicated(ctx, ctx->d_sky_stage.p, texels, n * 4, ctx->copy_stream)) return r;
         k_rgba8_to_f32<<<(unsigned)((n + 255) / 256), 256, 0, ctx->copy_stream>>>(ctx->d_sky_stage.as<uchar4>(), ctx->d_sky.as<float4>(), n);
         VLB_LAUNCH_CHECK(ctx);
     }
@@ -372,12 +374,12 @@ int vlb_skybox_set(vlb_ctx* ctx, const void* texels, int format, int width, int 
         return ctx->fail(VLB_ERR_INVALID, "vlb_skybox_set: bad arguments");
     if (int r = join_sky_upload(ctx, ctx->stream)) return r;
     const size_t n = (size_t)width * height;
-    VLB_CUDA(ctx, ctx->d_sky.reserve(n * sizeof(float4)));
+    VLB_CUDA(ctx, ctx->d_sky.reserve(comm_padded_bytes(ctx, n * sizeof(float4))));
     if (format == VLB_FMT_RGBA32F) {
-        VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_sky.p, texels, n * sizeof(float4), cudaMemcpyHostToDevice, ctx->stream));
+        if (int r = upload_replicated(ctx, ctx->d_sky.p, texels, n * sizeof(float4), ctx->stream)) return r;
     } else {
-        VLB_CUDA(ctx, ctx->d_proj_in.reserve(n * 4));
-        VLB_CUDA(ctx, cudaMemcpyAsync(ctx->d_proj_in.p, texels, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        VLB_CUDA(ctx, ctx->d_proj_in.reserve(comm_padded_bytes(ctx, n * 4)));
+        if (int r = upload_replicated(ctx, ctx->d_proj_in.p, texels, n * 4, ctx->stream)) return r;
         k_rgba8_to_f32<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_proj_in.as<uchar4>(), ctx->d_sky.as<float4>(), n);
         VLB_LAUNCH_CHECK(ctx);
     }
@@ -630,6 +632,31 @@ int vlb_bake_probes_multi(vlb_ctx* const* ctxs, uint32_t n_ctx, const vlb_bake_s
     }
     if (s->slab_k1 >= 0) return c0->fail(VLB_ERR_INVALID, "vlb_bake_probes_multi: takes the whole grid (slab_k1 < 0) and shards it itself");
     if (s->probes[0] <= 0 || s->probes[1] <= 0 || s->probes[2] <= 0) return c0->fail(VLB_ERR_INVALID, "bake: probe counts must be positive");
+    // Distinct devices: one NCCL rank per ctx (vlb_comm_init_all, done here on first use), the shares are all-gathered
+    // on the devices (NVLink) and between gather passes nothing touches the host; ctx 0 copies the grid out once.
+    // Several ctxs on ONE device (NCCL allows one rank per GPU), or no NCCL in the process: the host-side path below.
+    bool distinct = n_ctx > 1;
+    for (uint32_t r = 0; r < n_ctx; ++r) for (uint32_t q = 0; q < r; ++q) if (ctxs[q]->device == ctxs[r]->device) distinct = false;
+    bool have_comm = distinct;
+    for (uint32_t r = 0; r < n_ctx && have_comm; ++r) have_comm = ctxs[r]->comm && ctxs[r]->comm_world == (int)n_ctx && ctxs[r]->comm_rank == (int)r;
+    if (distinct && !have_comm) {
+        bool none = true;
+        for (uint32_t r = 0; r < n_ctx; ++r) none = none && !ctxs[r]->comm;
+        have_comm = none && vlb_comm_init_all(ctxs, n_ctx) == VLB_OK;
+    }
+    if (have_comm) {
+        std::vector<int> rc(n_ctx, VLB_OK);
+        std::vector<std::thread> workers;
+        for (uint32_t r = 1; r < n_ctx; ++r) workers.emplace_back([&, r] { rc[r] = vlb_bake_probes_sharded(ctxs[r], s, nullptr); });
+        rc[0] = vlb_bake_probes_sharded(c0, s, out);
+        for (std::thread& t : workers) t.join();
+        for (uint32_t r = 0; r < n_ctx; ++r)
+            if (rc[r] != VLB_OK) {
+                if (r != 0) c0->fail(rc[r], "vlb_bake_probes_multi: ctx %u: %s", r, vlb_last_error(ctxs[r]));
+                return rc[r];
+            }
+        return VLB_OK;
+    }
     const size_t grid_floats = (size_t)s->probes[0] * s->probes[1] * (size_t)s->probes[2] * VLB_SH_STRIDE;
     std::vector<float> prev;                                   // previous pass over the whole grid (host)
     for (int pass = 0; pass <= std::max(0, (int)s->bounces); ++pass) {

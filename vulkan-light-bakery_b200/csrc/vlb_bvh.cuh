@@ -367,6 +367,25 @@ VLB_HD float min3(float a, float b, float c) {
 #endif
 }
 
+#ifndef VLB_FFMA2
+#define VLB_FFMA2 1
+#endif
+#if defined(__CUDA_ARCH__)
+// v = v * s - c on all four components with two packed fp32x2 FMAs (fma.rn.f32x2 -> FFMA2 on sm_100a)
+__device__ __forceinline__ void fma2_planes(float4& v, float s, float c) {
+    unsigned long long a0, a1, ss, cc;
+    const float nc = -c;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a0) : "f"(v.x), "f"(v.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a1) : "f"(v.z), "f"(v.w));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ss) : "f"(s));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(nc));
+    asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a0) : "l"(ss), "l"(cc));
+    asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a1) : "l"(ss), "l"(cc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(a0));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(v.z), "=f"(v.w) : "l"(a1));
+}
+#endif
+
 // Traversal stack of one ray as a per-thread array (local memory on the device). The bake kernel uses the
 // warp-shared-memory stack of bake.cu instead; bvh4_step takes either.
 struct LocalStack {
@@ -377,6 +396,12 @@ struct LocalStack {
     VLB_HD bool room(int n) const { return sp + n <= kStackSize; }
     VLB_HD void push(int v) { a[sp++] = v; }
     VLB_HD int pop() { return a[--sp]; }
+    // r1 is a valid ref; r2 / r3 may be kNoChild (r3 valid implies r2 valid): pushes the valid ones so that r1 pops first
+    VLB_HD void push_far(int r3, int r2, int r1) {
+        if (r3 != kNoChild) push(r3);
+        if (r2 != kNoChild) push(r2);
+        push(r1);
+    }
 };
 
 // One step through 4-wide node `cur`: slab-tests the four children against (tmin, tcull). ORDERED
@@ -414,10 +439,25 @@ VLB_HD int bvh4_step(const BvhView& b, int cur, Vec3 idir, Vec3 ood, float tmin,
         r[k] = hit ? ref : kNoChild;                                                                             \
     }
 #else
-    const float4 nx = ld4(q + sx), fx = ld4(q + 1 - sx);
-    const float4 ny = ld4(q + 2 + sy), fy = ld4(q + 3 - sy);
-    const float4 nz = ld4(q + 4 + sz), fz = ld4(q + 5 - sz);
+    float4 nx = ld4(q + sx), fx = ld4(q + 1 - sx);
+    float4 ny = ld4(q + 2 + sy), fy = ld4(q + 3 - sy);
+    float4 nz = ld4(q + 4 + sz), fz = ld4(q + 5 - sz);
     const float4 rf = ld4(q + 6);
+#if defined(__CUDA_ARCH__) && VLB_FFMA2
+    // the 24 plane distances plane * idir - o * idir as 12 packed fp32x2 FMAs (FFMA2, sm_100): per-element IEEE
+    // round-to-nearest, so bit-identical to the scalar form
+    fma2_planes(nx, idir.x, ood.x); fma2_planes(fx, idir.x, ood.x);
+    fma2_planes(ny, idir.y, ood.y); fma2_planes(fy, idir.y, ood.y);
+    fma2_planes(nz, idir.z, ood.z); fma2_planes(fz, idir.z, ood.z);
+#define VLB_SLAB(k, c)                                                                                           \
+    {                                                                                                            \
+        const float a = fmaxf(max3(nx.c, ny.c, nz.c), tmin);                                                     \
+        const float e = fminf(min3(fx.c, fy.c, fz.c), tcull);                                                    \
+        const bool hit = a <= e;                                                                                 \
+        tn[k] = hit ? a : inf;                                                                                   \
+        r[k] = hit ? f2i(rf.c) : kNoChild;                                                                       \
+    }
+#else
 #define VLB_SLAB(k, c)                                                                                           \
     {                                                                                                            \
         const float a = fmaxf(max3(f_fma(nx.c, idir.x, -ood.x), f_fma(ny.c, idir.y, -ood.y),                      \
@@ -428,6 +468,7 @@ VLB_HD int bvh4_step(const BvhView& b, int cur, Vec3 idir, Vec3 ood, float tmin,
         tn[k] = hit ? a : inf;                                                                                   \
         r[k] = hit ? f2i(rf.c) : kNoChild;                                                                       \
     }
+#endif
 #endif
     VLB_SLAB(0, x) VLB_SLAB(1, y) VLB_SLAB(2, z) VLB_SLAB(3, w)
 #undef VLB_SLAB
@@ -443,9 +484,7 @@ VLB_HD int bvh4_step(const BvhView& b, int cur, Vec3 idir, Vec3 ood, float tmin,
             if (!stk.room(3)) {             // never silently drop subtrees: flag it
                 if (b.overflow) *b.overflow = 1u;
             } else {
-                if (r[3] != kNoChild) stk.push(r[3]);
-                if (r[2] != kNoChild) stk.push(r[2]);
-                stk.push(r[1]);
+                stk.push_far(r[3], r[2], r[1]);
             }
         }
         return r[0];

@@ -105,6 +105,11 @@ struct vlb_ctx {
     cudaEvent_t lane_fork = nullptr, lane_join[VLB_MAX_LANES] = {};
     // ---- trace ----
     vlb::DevBuf d_ray_o, d_ray_d, d_hit_id, d_hit_tuv, d_hit_key;
+    // ---- multi-GPU (comm.cu): one NCCL rank per ctx ----
+    void* comm = nullptr;                  // ncclComm_t
+    int comm_rank = 0, comm_world = 1;
+    bool comm_sharded_uploads = false;     // scene / skybox uploads: every rank copies 1/world over PCIe, NVLink all-gather replicates
+    vlb::DevBuf d_share, d_gather_stage;   // this rank's padded share of a sharded bake, all-gather staging [world][max share]
 
     int fail(int code, const char* fmt, ...) {
         char buf[512];
@@ -149,6 +154,10 @@ int project_sh_device(vlb_ctx* ctx, const void* d_texels, uint64_t map_stride, u
 int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_full, float* d_out);
 int bake_collect_stats(vlb_ctx* ctx);
 int sky_upload_join(vlb_ctx* ctx);     // context.cu: orders a pending vlb_skybox_set_async before the ctx stream's next work
+// comm.cu
+int upload_replicated(vlb_ctx* ctx, void* d_dst, const void* h_src, size_t bytes, cudaStream_t st);
+size_t comm_padded_bytes(const vlb_ctx* ctx, size_t bytes);   // capacity d_dst needs for upload_replicated
+int comm_destroy(vlb_ctx* ctx);
 int trace_rays(vlb_ctx* ctx, const float* o, const float* d, uint64_t n, float tmin, float tmax, int accel,
                int kind, int32_t* ids, float* tuv);
 }  // namespace vlb
