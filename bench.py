@@ -385,9 +385,13 @@ def run_ours(args):
 
 def bench_skybox(torch, ctx, scenes, dev, stream, peak, peak_src, n_buf=8, reps=20):
     """BASELINE configs[0] (C1): one 2048x1024 RGBA32F equirect -> L2 SH. 8 distinct maps (268 MB > 126 MB
-    L2) are rotated so every launch reads from HBM. Three ways of issuing the same kernel:
-      single    one vlb_skybox_project_sh_device call per map, back to back on one stream
-      pipelined vlb_skybox_project_sh_device_ptrs over the 8 maps (one launch per map on internal lanes)
+    L2) are rotated so every launch reads from HBM. Measured on the ctx's OWN stream (where back-to-back projections
+    may be chained with programmatic dependent launch). Three ways of issuing the same kernel:
+      single    one vlb_skybox_project_sh_device call per map, back to back (PDL-chained; the host needs ~6 us to
+                issue a launch, more than the 5 us a map streams in, so this mode is bound by the host thread)
+      pipelined ONE vlb_skybox_project_sh_device_ptrs call over the 8 maps: still one kernel launch per map; a call
+                repeated with the same arguments is replayed from a CUDA graph of those launches (lanes = parallel
+                branches, PDL inside a branch), which takes the host out of the loop
       batched8  the 8 maps as one contiguous batch in ONE launch (how configs[4] runs)"""
     Wd, Hd = SKY_WH
     maps = torch.empty((n_buf, Hd, Wd, 4), dtype=torch.float32, device=dev)
@@ -397,6 +401,9 @@ def bench_skybox(torch, ctx, scenes, dev, stream, peak, peak_src, n_buf=8, reps=
     stride = Hd * Wd * 16
     vlbm = importlib.import_module("vulkan-light-bakery_b200")
     ptrs = [maps[i].data_ptr() for i in range(n_buf)]
+    torch.cuda.synchronize()
+    ctx.set_stream(None)                                   # the ctx's own stream
+    own = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     def single():
         for i in range(n_buf):
@@ -409,25 +416,32 @@ def bench_skybox(torch, ctx, scenes, dev, stream, peak, peak_src, n_buf=8, reps=
         ctx.skybox_project_sh_device(maps.data_ptr(), stride, n_buf, vlbm.FMT_RGBA32F, Wd, Hd, 2, outs.data_ptr())
 
     def timed(fn):
-        for _ in range(3):
+        for _ in range(4):
             fn()
-        torch.cuda.synchronize()
+        ctx.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(stream)
+        a.record(own)
         for _ in range(reps):
             fn()
-        b.record(stream)
-        torch.cuda.synchronize()
+        b.record(own)
+        ctx.synchronize()
         us = a.elapsed_time(b) * 1e3 / (reps * n_buf)        # per map
         return {"us_per_map": us, "achieved": stride / (us * 1e-6) / 1e9, "frac": stride / (us * 1e-6) / 1e9 / peak}
 
-    res = {"single": timed(single), "pipelined": timed(pipelined), "batched8": timed(batched)}
+    try:
+        res = {"single": timed(single), "pipelined": timed(pipelined), "batched8": timed(batched)}
+    finally:
+        ctx.synchronize()
+        ctx.set_stream(stream.cuda_stream)
     best = res["pipelined"]
     return {"workload": "C1 (BASELINE configs[0]): 2048x1024 RGBA32F equirect -> L2 SH, 8 distinct maps rotated",
             "kernel": "vlb::k_project_tiles<9,RGBA32F>", "bound": "hbm", "algorithmic_bytes_per_launch": stride,
             "us_per_launch": best["us_per_map"], "achieved": best["achieved"], "peak": peak, "unit": "GB/s",
             "frac": best["frac"], "traffic": ncu_traffic("vlb::k_project_tiles<9,RGBA32F>:c1"), "frac_of_8TBs_nominal": best["achieved"] / 8000.0, "peak_source": peak_src,
-            "mode": "pipelined (one launch per map, vlb_skybox_project_sh_device_ptrs)", "modes": res}
+            "mode": "pipelined: one kernel launch per 32 MiB map (vlb_skybox_project_sh_device_ptrs, replayed from the CUDA graph the "
+                    "library caches for a repeated call); `single` is the same launches issued one API call at a time and is bound "
+                    "by the host's launch cost, `batched8` is one launch for 8 maps",
+            "modes": res}
 
 
 def cpu_baseline(scene, sky, s, which="c3", budget_s=12.0):

@@ -116,6 +116,38 @@ def test_skybox_device_ptrs_lanes_vs_oracle(ctx, vlb, oa, scenes, order, fmt):
         assert np.all(got[:, 9:] == 0)
 
 
+def test_skybox_device_ptrs_repeated_call_is_replayed_from_a_graph(vlb, oa, scenes):
+    """The same vlb_skybox_project_sh_device_ptrs call issued again and again (direct launches, then the capture, then
+    graph replays) gives the same bits every time; new texels in the same buffers are picked up by the replays; a
+    different argument list in between does not disturb the cached graph."""
+    import torch
+    W, H = 320, 96
+    with vlb.Context(0) as c:
+        host = [scenes.hdr_sky(W, H, seed=900 + i) for i in range(6)]
+        dev = [torch.from_numpy(m).cuda() for m in host]
+        out = torch.zeros((6, 48), device="cuda")
+        other = torch.zeros((2, 48), device="cuda")
+        ptrs = [d.data_ptr() for d in dev]
+        first = None
+        for rep in range(5):
+            out.fill_(-1.0); torch.cuda.synchronize()
+            c.skybox_project_sh_device_ptrs(ptrs, vlb.FMT_RGBA32F, W, H, 3, out.data_ptr())
+            if rep == 2:
+                c.skybox_project_sh_device_ptrs(ptrs[:2], vlb.FMT_RGBA32F, W, H, 2, other.data_ptr())
+            c.synchronize()
+            got = out.cpu().numpy().copy()
+            if first is None:
+                first = got
+                for i in range(6):
+                    assert rel_l2(got[i], oa.skybox_project(host[i], 3)) <= SKY_TOL
+            assert np.array_equal(got, first), rep
+        new = scenes.hdr_sky(W, H, seed=990)
+        dev[3].copy_(torch.from_numpy(new)); torch.cuda.synchronize()
+        c.skybox_project_sh_device_ptrs(ptrs, vlb.FMT_RGBA32F, W, H, 3, out.data_ptr()); c.synchronize()
+        got = out.cpu().numpy()
+        assert rel_l2(got[3], oa.skybox_project(new, 3)) <= SKY_TOL and np.array_equal(got[2], first[2])
+
+
 def test_skybox_device_ptrs_errors(ctx, vlb):
     import torch
     out = torch.zeros((2, 48), device="cuda")

@@ -13,6 +13,7 @@ ap.add_argument("--tag", default="")
 ap.add_argument("--wh", default="2048x1024")
 ap.add_argument("--order", type=int, default=2)
 ap.add_argument("--cpu", action="store_true")
+ap.add_argument("--graph", action="store_true")
 a = ap.parse_args()
 W, H = (int(x) for x in a.wh.split("x"))
 n = 8
@@ -37,8 +38,24 @@ def pipelined():
 def batched():
     ctx.skybox_project_sh_device(maps.data_ptr(), stride, n, vlb.FMT_RGBA32F, W, H, a.order, outs.data_ptr())
 
+def make_graph(fn):
+    """fn's launches captured from the ctx's own stream into a CUDA graph; returns a replay function."""
+    from cuda.bindings import runtime as rt
+    h = ctx.stream
+    fn(); ctx.synchronize()                       # tables, scratch, tensor maps exist before the capture
+    (err,) = rt.cudaStreamBeginCapture(h, rt.cudaStreamCaptureMode.cudaStreamCaptureModeThreadLocal); assert err == 0, err
+    fn()
+    err, graph = rt.cudaStreamEndCapture(h); assert err == 0, err
+    err, ge = rt.cudaGraphInstantiate(graph, 0); assert err == 0, err
+    def replay():
+        (e,) = rt.cudaGraphLaunch(ge, h); assert e == 0, e
+    return replay
+
+modes = [("single", single), ("pipelined", pipelined), ("batched8", batched)]
+if a.graph:
+    modes += [("graph(single x8)", make_graph(single))]
 res = {}
-for name, fn in (("single", single), ("pipelined", pipelined), ("batched8", batched)):
+for name, fn in modes:
     for _ in range(3):
         fn()
     ctx.synchronize()

@@ -44,6 +44,7 @@ struct BakeParams {
     WarpQueues* stream_scratch;  // k_bake_stream: per-warp radiance tile + ray queues, [grid * warps per block]
     int node_min;                // k_bake_stream: the node loop yields to the leaf phase below this many lanes
     GatherView g;                // gather pass source (g.prev == NULL: direct pass)
+    int* vis_ovf;                // gather passes: stack overflow slab of the visibility-ray batches, [grid * warps][kOvfStack][32]
 };
 
 __device__ __forceinline__ size_t out_slot(const BakeParams& p, uint32_t q) {
@@ -83,7 +84,10 @@ __device__ __forceinline__ size_t out_slot(const BakeParams& p, uint32_t q) {
 //   shadow-ray queue, radiance tile   global scratch, L1/L2-resident, touched with coalesced accesses.
 // The per-ray arithmetic is exactly that of probe_ray_radiance (vlb_shade.cuh).
 // =========================================================================================
-constexpr int kChunkTiles = 8;
+#ifndef VLB_BAKE_CHUNK_TILES
+#define VLB_BAKE_CHUNK_TILES 16             // direction tiles (of 32 rays) traced between two drains of the warp
+#endif
+constexpr int kChunkTiles = VLB_BAKE_CHUNK_TILES;
 constexpr int kChunkDirs = kChunkTiles * 32;
 constexpr int kRayDone = kNoChild;          // traversal finished
 constexpr int kHitCap = 64;                 // queued hit records per warp (<= 31 waiting + 32 arriving)
@@ -140,7 +144,7 @@ struct WarpStack {
     // shared short stack): three UNCONDITIONAL stores and no branch -- entry r_k goes to slot sp + max(n - k, 0) with
     // n = number of valid refs, so an invalid r3 / r2 is written first to the slot the next valid one overwrites (or,
     // for n = 1, to the slot above the new top, which is dead).
-    __device__ __forceinline__ void push_far(int r3, int r2, int r1) {
+    __device__ __forceinline__ void push_far(int r3, int r2, int r1, unsigned int* overflow) {
 #if VLB_BAKE_FAST_PUSH
         if (sp + 3 <= kSmemStack) {
             const int v3 = r3 != kNoChild, v2 = r2 != kNoChild;
@@ -152,6 +156,7 @@ struct WarpStack {
             return;
         }
 #endif
+        if (!room(3)) { if (overflow) *overflow = 1u; return; }
         if (r3 != kNoChild) push(r3);
         if (r2 != kNoChild) push(r2);
         push(r1);
@@ -165,17 +170,98 @@ struct WarpStack {
     }
 };
 
+#if VLB_BAKE_SMEM_STACK > 0
+using RayStack = WarpStack;
+#else
+using RayStack = LocalStack;
+#endif
+
+// Per-warp exchange area of a visibility-ray batch (gather passes): what the ray lanes need to know about the 32 hits
+// being shaded -- hit position, biased ray origin (env_map.rchit:82 / main.rchit:143), grid cell -- and the result.
+struct VisExchange {
+    float P[3][32], so[3][32];
+    int cell[3][32];
+    unsigned occluded[32];       // bit c: the ray from hit `lane` to corner c of its cell was blocked
+};
+
+// The 8 visibility rays of each of the (up to 32) hits a warp shades together (shaders/main.rchit:143-163), traced as
+// ONE batch by the whole warp: ray r = (hit r / 8, corner r % 8) goes to whichever lane is idle, lanes step through the
+// tree in the same while-while loop as the main rays and refill as they finish, so the warp stays full although the
+// rays are short and of very different lengths. (Round 1 traced the 8 rays of a hit one after the other inside the
+// shading lane: 32 lanes in lockstep on unrelated rays, a gather pass cost 5.5 direct passes.) `hm`: lanes holding a hit.
+template <bool COUNT>
+__device__ __forceinline__ void trace_vis_batch(const BvhView& bvh, const GatherView& g, RayStack& stk, VisExchange& X, unsigned hm,
+                                                int lane, int node_min, TraceCounters& cnt) {
+    const unsigned full = 0xffffffffu, lt_mask = (1u << lane) - 1u;
+    const int n_rays = 8 * __popc(hm);
+    int next = 0, cur = kRayDone, tag = 0;
+    bool busy = false;
+    Vec3 ro = mk3(0.f, 0.f, 0.f), rd = ro, idir = ro, ood = ro;
+    float tcull = 0.f;
+    for (;;) {
+        const unsigned idle = __ballot_sync(full, !busy);
+        if (idle != 0u && next < n_rays) {
+            const int cand = next + __popc(idle & lt_mask);
+            if (!busy && cand < n_rays) {
+                const int h = __fns(hm, 0, (cand >> 3) + 1), c = cand & 7;
+                const Vec3 P = mk3(X.P[0][h], X.P[1][h], X.P[2][h]);
+                int i, j, k; Vec3 d; float tmax;
+                gather_corner(g, P, X.cell[0][h], X.cell[1][h], X.cell[2][h], c, i, j, k, d, tmax);
+                if (tmax > 0.0f) {                                                     // main.rchit:154-155
+                    ro = mk3(X.so[0][h], X.so[1][h], X.so[2][h]);
+                    rd = mk3(f_div(d.x, tmax), f_div(d.y, tmax), f_div(d.z, tmax));
+                    idir = mk3(safe_inv(rd.x), safe_inv(rd.y), safe_inv(rd.z));
+                    ood = mk3(ro.x * idir.x, ro.y * idir.y, ro.z * idir.z);
+                    tcull = tmax; tag = (h << 3) | c;
+                    stk.clear(); cur = 0; busy = true;
+                }
+            }
+            next = min(n_rays, next + __popc(idle));
+        }
+        const unsigned running = __ballot_sync(full, busy);
+        if (running == 0u) {
+            if (next >= n_rays) break;
+            continue;
+        }
+        for (;;) {
+            const bool at_node = busy && cur >= 0;
+            const unsigned nm = __ballot_sync(full, at_node);
+            if (nm == 0u || (__popc(nm) < node_min && __popc(running) - __popc(nm) >= node_min)) break;
+            if (at_node) {
+                if (COUNT) cnt.nodes++;
+                cur = bvh4_step<true>(bvh, cur, idir, ood, 0.0f, tcull, stk);
+            }
+        }
+        if (busy && cur < 0 && cur != kRayDone) {
+            HitRec occ; occ.id = -1; occ.t = tcull; occ.u = 0.f; occ.v = 0.f;
+            if (leaf_step<true, COUNT>(bvh, cur, ro, rd, 0.0f, tcull, occ, &cnt)) {
+                atomicOr(&X.occluded[tag >> 3], 1u << (tag & 7));
+                cur = kRayDone;
+            } else {
+                cur = stk.empty() ? kRayDone : stk.pop();
+            }
+        }
+        if (busy && cur == kRayDone) busy = false;
+    }
+    __syncwarp();
+}
+
 #ifndef VLB_BAKE_MIN_BLOCKS
 #define VLB_BAKE_MIN_BLOCKS 8      // resident 128-thread blocks per SM the register allocation is held to (8 -> 64 registers)
 #endif
 constexpr size_t kBakeSmemPerBlock = (kSmemStack > 0 ? (size_t)kStreamWarps * kSmemStack * 32 * sizeof(int) : 0) +
                                      (kSmemHq ? (size_t)kStreamWarps * sizeof(HitQueue) : 0);
+// gather passes add the second short stack and the exchange area of the visibility-ray batches
+constexpr size_t kBakeSmemPerBlockGather = kBakeSmemPerBlock + (kSmemStack > 0 ? (size_t)kStreamWarps * kSmemStack * 32 * sizeof(int) : 0) +
+                                           (size_t)kStreamWarps * sizeof(VisExchange);
 
 template <int K, bool COUNT, bool GATHER, bool TEX>
 __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) k_bake_stream(const BakeParams p) {
     constexpr int V = (K * 3 <= 32) ? 32 : 64;
     __shared__ int s_stack[kSmemStack > 0 ? kStreamWarps : 1][kSmemStack > 0 ? kSmemStack : 1][32];
     __shared__ HitQueue s_hq[kSmemHq ? kStreamWarps : 1];
+    __shared__ int s_stack2[GATHER && kSmemStack > 0 ? kStreamWarps : 1][GATHER && kSmemStack > 0 ? kSmemStack : 1][32];
+    __shared__ VisExchange s_vis[GATHER ? kStreamWarps : 1];
     WarpQueues* s_all = p.stream_scratch + (size_t)blockIdx.x * kStreamWarps;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -195,6 +281,11 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
     LocalStack stk;
 #endif
     stk.clear();
+    RayStack stk2;               // visibility-ray batches of the gather passes (the main rays keep `stk` while a batch runs)
+#if VLB_BAKE_SMEM_STACK > 0
+    if (GATHER) stk2.bind(&s_stack2[warp][0][lane], p.vis_ovf + ((size_t)blockIdx.x * kStreamWarps + warp) * kOvfStack * 32 + lane);
+#endif
+    stk2.clear();
 
     for (;;) {
         unsigned item = 0;
@@ -279,6 +370,34 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                     float lit_rgb[3] = {0.f, 0.f, 0.f};
                     ShadePrelude pre;
                     int dir = 0;
+                    unsigned occluded = 0;
+                    if (GATHER) {
+                        // gather passes: first the visibility rays of all hits of this batch (trace_vis_batch); the hit
+                        // shading below then only needs the 8-bit result per hit
+                        VisExchange& X = s_vis[warp];
+                        bool has_hit = false;
+                        if (lane < take && HQ.id[e] >= 0) {
+                            HitRec h; h.id = HQ.id[e]; h.t = HQ.t[e]; h.u = HQ.u[e]; h.v = HQ.v[e];
+                            const int hd = HQ.dir[e];
+                            const int tile = base_tile + (hd >> 5), w = hd & 31;
+                            const float2 row = __ldg(p.row_sc + tile_y(tile, w, p.tiles_x, p.tile_lw)), col = __ldg(p.col_cs + tile_x(tile, w, p.tiles_x, p.tile_lw));
+                            const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);
+                            ShadePrelude q;
+                            shade_prelude<TEX>(p.shade, p.c, h, po, mk3(t.x, t.z, t.y), q);
+                            X.P[0][lane] = q.P.x; X.P[1][lane] = q.P.y; X.P[2][lane] = q.P.z;
+                            X.so[0][lane] = q.so.x; X.so[1][lane] = q.so.y; X.so[2][lane] = q.so.z;
+                            X.cell[0][lane] = gather_cell(q.P.x, p.g.origin[0], p.g.step[0], p.g.Nx);
+                            X.cell[1][lane] = gather_cell(q.P.y, p.g.origin[1], p.g.step[1], p.g.Ny);
+                            X.cell[2][lane] = gather_cell(q.P.z, p.g.origin[2], p.g.step[2], p.g.Nz);
+                            has_hit = true;
+                        }
+                        X.occluded[lane] = 0u;
+                        const unsigned hm = __ballot_sync(full, has_hit);
+                        __syncwarp();
+                        if (hm != 0u && bvh.n_tris) trace_vis_batch<COUNT>(bvh, p.g, stk2, X, hm, lane, p.node_min, cnt);
+                        occluded = X.occluded[lane];
+                        __syncwarp();
+                    }
                     if (lane < take) {
                         HitRec h; h.id = HQ.id[e]; h.t = HQ.t[e]; h.u = HQ.u[e]; h.v = HQ.v[e];
                         dir = HQ.dir[e];
@@ -292,9 +411,7 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                         if (h.id >= 0) {
                             const bool lit = shade_prelude<TEX>(p.shade, p.c, h, po, r, pre);
                             float ind[3] = {0.f, 0.f, 0.f};
-                            // gather passes: the 8 short visibility rays to the surrounding probes are traced
-                            // right here, per lane (main.rchit:143-163); only the sun shadow ray is queued
-                            if (GATHER) gather_indirect<K, COUNT>(bvh, p.g, pre, ind, &cnt);
+                            if (GATHER) gather_accumulate<K>(p.g, pre, occluded, ind);         // main.rchit:156-165
                             if (lit && want_shadow) {
                                 // radiance for both outcomes now, the shadow ray decides (env_map.rchit:83-99):
                                 // the tile gets the occluded one, the ray carries the lit one
@@ -538,7 +655,7 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     // Shared memory holds the short stacks and the hit queues (kBakeSmemPerBlock per block); everything else of the
     // SM's 228 KB stays L1 (BVH nodes, triangles, shadow-ray queues, radiance tiles).
     const int min_blocks = gather ? 6 : VLB_BAKE_MIN_BLOCKS;
-    int carve = (int)((min_blocks * (kBakeSmemPerBlock + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+    int carve = (int)((min_blocks * ((gather ? kBakeSmemPerBlockGather : kBakeSmemPerBlock) + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
     carve = env_flag("VLB_BAKE_CARVEOUT", std::min(100, carve));
     if (carve >= 0) VLB_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
     int per_sm = 0;
@@ -585,6 +702,10 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
 
     VLB_CUDA(ctx, ctx->d_stream_scratch.reserve((size_t)grid * kStreamWarps * sizeof(WarpQueues)));
     p.stream_scratch = ctx->d_stream_scratch.as<WarpQueues>();
+    if (gather) {
+        VLB_CUDA(ctx, ctx->d_vis_ovf.reserve((size_t)grid * kStreamWarps * kOvfStack * 32 * sizeof(int)));
+        p.vis_ovf = ctx->d_vis_ovf.as<int>();
+    }
     VLB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
     VLB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     kern<<<grid, kBakeBlock, 0, st>>>(p);

@@ -127,7 +127,7 @@ void vlb_ctx_destroy(vlb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     comm_destroy(ctx);
-    DevBuf* bufs[] = {&ctx->d_share, &ctx->d_gather_stage, &ctx->d_verts, &ctx->d_indices, &ctx->d_insts_in, &ctx->d_tri_offsets, &ctx->d_tri_flat,
+    DevBuf* bufs[] = {&ctx->d_share, &ctx->d_gather_stage, &ctx->d_vis_ovf, &ctx->d_verts, &ctx->d_indices, &ctx->d_insts_in, &ctx->d_tri_offsets, &ctx->d_tri_flat,
                       &ctx->d_frontier[0], &ctx->d_frontier[1], &ctx->d_frontier_n, &ctx->d_tri_shade, &ctx->d_tri_uv, &ctx->d_tex_desc, &ctx->d_tex_texels, &ctx->d_inst, &ctx->d_base_color, &ctx->d_tris, &ctx->d_nodes, &ctx->d_keys,
                       &ctx->d_keys_sorted, &ctx->d_vals, &ctx->d_vals_sorted, &ctx->d_sort_tmp, &ctx->d_left,
                       &ctx->d_right, &ctx->d_first, &ctx->d_last, &ctx->d_parent_i, &ctx->d_parent_l, &ctx->d_flags,
@@ -136,6 +136,8 @@ void vlb_ctx_destroy(vlb_ctx* ctx) {
                       &ctx->d_partials, &ctx->d_work_counter, &ctx->d_axis, &ctx->d_row_sc, &ctx->d_col_sc,
                       &ctx->d_stats, &ctx->d_stream_scratch, &ctx->d_ray_o, &ctx->d_ray_d, &ctx->d_hit_id, &ctx->d_hit_tuv, &ctx->d_hit_key};
     if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    for (vlb_ctx::ProjGraph& g : ctx->proj_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (ctx->cap_stream) cudaStreamDestroy(ctx->cap_stream);
     if (ctx->ev_sky_free) cudaEventDestroy(ctx->ev_sky_free);
     if (ctx->ev_sky_ready) cudaEventDestroy(ctx->ev_sky_ready);
     ctx->d_sky_stage.release();
@@ -438,6 +440,34 @@ int vlb_skybox_project_sh_device(vlb_ctx* ctx, const void* d_texels, uint64_t ma
     return project_sh_device(ctx, d_texels, map_stride_bytes, n_maps, format, width, height, sh_order, 0, d_out);
 }
 
+// The launches of one vlb_skybox_project_sh_device_ptrs call: one per map, alternating over auxiliary streams forked from /
+// joined to `origin`; the second and later launches of a lane are chained to their predecessor (programmatic dependent launch).
+static int project_ptrs_lanes(vlb_ctx* ctx, cudaStream_t origin, const void* const* d_maps, uint32_t n_maps, int format, int width,
+                              int height, int sh_order, float* d_out) {
+    const int lanes = std::max(1, std::min<int>({env_lanes(), VLB_MAX_LANES, (int)n_maps}));
+    if (!ctx->lane_fork) VLB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_fork, cudaEventDisableTiming));
+    for (int l = 0; l < lanes; ++l) {
+        if (!ctx->lane_stream[l]) VLB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking));
+        if (!ctx->lane_join[l]) VLB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_join[l], cudaEventDisableTiming));
+    }
+    VLB_CUDA(ctx, cudaEventRecord(ctx->lane_fork, origin));
+    for (int l = 0; l < lanes; ++l) VLB_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_stream[l], ctx->lane_fork, 0));
+    int rc = VLB_OK;
+    for (uint32_t i = 0; i < n_maps && rc == VLB_OK; ++i)
+        rc = project_sh_device(ctx, d_maps[i], 0, 1, format, width, height, sh_order, 0,
+                               d_out + (size_t)i * VLB_SH_STRIDE, (int)(i % lanes), /*chain_in_lane=*/i >= (uint32_t)lanes);
+    for (int l = 0; l < lanes; ++l) {      // always join, also after an error, so the streams stay ordered
+        VLB_CUDA(ctx, cudaEventRecord(ctx->lane_join[l], ctx->lane_stream[l]));
+        VLB_CUDA(ctx, cudaStreamWaitEvent(origin, ctx->lane_join[l], 0));
+    }
+    return rc;
+}
+
+static int env_proj_graph() {
+    static const int v = [] { const char* e = getenv("VLB_PROJ_GRAPH"); return e && *e ? atoi(e) : 1; }();
+    return v;
+}
+
 int vlb_skybox_project_sh_device_ptrs(vlb_ctx* ctx, const void* const* d_maps, uint32_t n_maps, int format, int width,
                                       int height, int sh_order, float* d_out) {
     if (!ctx) return VLB_ERR_INVALID;
@@ -447,24 +477,60 @@ int vlb_skybox_project_sh_device_ptrs(vlb_ctx* ctx, const void* const* d_maps, u
         return ctx->fail(VLB_ERR_INVALID, "vlb_skybox_project_sh_device_ptrs: bad arguments");
     for (uint32_t i = 0; i < n_maps; ++i)
         if (!d_maps[i]) return ctx->fail(VLB_ERR_INVALID, "vlb_skybox_project_sh_device_ptrs: d_maps[%u] is NULL", i);
-    // one launch per map, alternating over auxiliary streams forked from / joined to the ctx stream
-    const int lanes = std::max(1, std::min<int>({env_lanes(), VLB_MAX_LANES, (int)n_maps}));
-    cudaStream_t st = ctx->stream;
-    if (!ctx->lane_fork) VLB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_fork, cudaEventDisableTiming));
-    for (int l = 0; l < lanes; ++l) {
-        if (!ctx->lane_stream[l]) VLB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking));
-        if (!ctx->lane_join[l]) VLB_CUDA(ctx, cudaEventCreateWithFlags(&ctx->lane_join[l], cudaEventDisableTiming));
+#ifndef VLB_PROJ_TIMING
+    // A call repeated with the same arguments (re-projecting the pushed skyboxes, src/skybox_manager.cpp:284-298) is
+    // replayed from a CUDA graph: first sighting runs the launches directly, the second captures them, later ones replay.
+    if (env_proj_graph() && n_maps >= 2 && n_maps <= 64) {
+        vlb_ctx::ProjGraph* g = nullptr;
+        for (vlb_ctx::ProjGraph& e : ctx->proj_graphs)
+            if (e.fmt == format && e.W == width && e.H == height && e.order == sh_order && e.out == d_out && e.maps.size() == n_maps &&
+                std::equal(e.maps.begin(), e.maps.end(), d_maps)) { g = &e; break; }
+        if (g && g->exec && (g->partials != ctx->d_proj_partials.p || g->row_tab != ctx->d_row_tab.p || ctx->tab_w != width || ctx->tab_h != height || ctx->tab_variant != 0)) {
+            cudaGraphExecDestroy(g->exec);      // a scratch buffer or the tables moved since the capture
+            g->exec = nullptr; g->seen = 0;
+        }
+        if (g && g->exec) {
+            VLB_CUDA(ctx, cudaGraphLaunch(g->exec, ctx->stream));
+            ctx->launches += n_maps;
+            return VLB_OK;
+        }
+        if (!g) {
+            if (ctx->proj_graphs.size() >= 4) {
+                if (ctx->proj_graphs.front().exec) cudaGraphExecDestroy(ctx->proj_graphs.front().exec);
+                ctx->proj_graphs.erase(ctx->proj_graphs.begin());
+            }
+            ctx->proj_graphs.emplace_back();
+            g = &ctx->proj_graphs.back();
+            g->maps.assign(d_maps, d_maps + n_maps); g->fmt = format; g->W = width; g->H = height; g->order = sh_order; g->out = d_out;
+        }
+        if (++g->seen >= 2 && ctx->tab_w == width && ctx->tab_h == height && ctx->tab_variant == 0) {
+            // tables, scratch and kernel attributes exist (the first sighting ran the same launches): capture
+            if (!ctx->cap_stream) VLB_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->cap_stream, cudaStreamNonBlocking));
+            const uint64_t launches0 = ctx->launches;
+            VLB_CUDA(ctx, cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = project_ptrs_lanes(ctx, ctx->cap_stream, d_maps, n_maps, format, width, height, sh_order, d_out);
+            cudaGraph_t graph = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(ctx->cap_stream, &graph);
+            ctx->launches = launches0;
+            if (rc == VLB_OK && ce == cudaSuccess && graph) {
+                cudaGraphExec_t exec = nullptr;
+                const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ie == cudaSuccess) {
+                    g->exec = exec; g->partials = ctx->d_proj_partials.p; g->row_tab = ctx->d_row_tab.p;
+                    VLB_CUDA(ctx, cudaGraphLaunch(g->exec, ctx->stream));
+                    ctx->launches += n_maps;
+                    return VLB_OK;
+                }
+            } else if (graph) {
+                cudaGraphDestroy(graph);
+            }
+            cudaGetLastError();            // capture not possible here: fall through to the direct launches
+            g->seen = -(1 << 30);          // and do not try again for this argument list
+        }
     }
-    VLB_CUDA(ctx, cudaEventRecord(ctx->lane_fork, st));
-    for (int l = 0; l < lanes; ++l) VLB_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_stream[l], ctx->lane_fork, 0));
-    int rc = VLB_OK;
-    for (uint32_t i = 0; i < n_maps && rc == VLB_OK; ++i)
-        rc = project_sh_device(ctx, d_maps[i], 0, 1, format, width, height, sh_order, 0,
-                               d_out + (size_t)i * VLB_SH_STRIDE, (int)(i % lanes));
-    for (int l = 0; l < lanes; ++l) {      // always join, also after an error, so the streams stay ordered
-        VLB_CUDA(ctx, cudaEventRecord(ctx->lane_join[l], ctx->lane_stream[l]));
-        VLB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->lane_join[l], 0));
-    }
+#endif
+    const int rc = project_ptrs_lanes(ctx, ctx->stream, d_maps, n_maps, format, width, height, sh_order, d_out);
 #ifdef VLB_PROJ_TIMING
     if (rc == VLB_OK) return proj_timing_dump(ctx, (int)n_maps);
 #endif

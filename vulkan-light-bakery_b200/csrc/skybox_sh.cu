@@ -577,12 +577,13 @@ static EncodeTiledFn encode_tiled_fn() {
 // `lane` with that lane's scratch set (vlb_skybox_project_sh_device_ptrs: independent maps alternate
 // over the lanes, so one map streams from HBM while another flushes, reduces and retires).
 int project_sh_device(vlb_ctx* ctx, const void* d_texels, uint64_t map_stride, uint32_t n_maps, int fmt, int W, int H,
-                      int order, int variant, float* d_out, int lane) {
+                      int order, int variant, float* d_out, int lane, bool chain_in_lane) {
     cudaStream_t st = lane < 0 ? ctx->stream : ctx->lane_stream[lane];
     const ProjEnv& env = proj_env();
     // chain onto the previous projection launch (programmatic dependent launch, see k_project_tiles) only when this
-    // ctx knows that nothing else was enqueued on the stream in between: its own stream, previous call = a projection
-    bool chained = lane < 0 && ctx->proj_chain && st == ctx->own_stream && env.pdl != 0;
+    // ctx knows that nothing else was enqueued on the stream in between: its own stream, previous call = a projection;
+    // or (chain_in_lane) the previous launch on this lane belongs to the same vlb_skybox_project_sh_device_ptrs call
+    bool chained = ((lane < 0 && ctx->proj_chain && st == ctx->own_stream) || (lane >= 0 && chain_in_lane)) && env.pdl != 0;
     ctx->proj_chain = false;
     // tables (cached per size/variant): per-row quadrature factors (zero-padded to whole tiles), per-column cos/sin(phi)
     if (ctx->tab_w != W || ctx->tab_h != H || ctx->tab_variant != variant) {

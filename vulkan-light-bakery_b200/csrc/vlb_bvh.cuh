@@ -397,7 +397,9 @@ struct LocalStack {
     VLB_HD void push(int v) { a[sp++] = v; }
     VLB_HD int pop() { return a[--sp]; }
     // r1 is a valid ref; r2 / r3 may be kNoChild (r3 valid implies r2 valid): pushes the valid ones so that r1 pops first
-    VLB_HD void push_far(int r3, int r2, int r1) {
+    // A full stack never drops subtrees silently: *overflow is set (the caller reports VLB_ERR_UNSUPPORTED).
+    VLB_HD void push_far(int r3, int r2, int r1, unsigned int* overflow) {
+        if (!room(3)) { if (overflow) *overflow = 1u; return; }
         if (r3 != kNoChild) push(r3);
         if (r2 != kNoChild) push(r2);
         push(r1);
@@ -480,13 +482,7 @@ VLB_HD int bvh4_step(const BvhView& b, int cur, Vec3 idir, Vec3 ood, float tmin,
         order2(tn[1], r[1], tn[3], r[3]);
         order2(tn[1], r[1], tn[2], r[2]);
         if (r[0] == kNoChild) return stk.empty() ? kNoChild : stk.pop();
-        if (r[1] != kNoChild) {
-            if (!stk.room(3)) {             // never silently drop subtrees: flag it
-                if (b.overflow) *b.overflow = 1u;
-            } else {
-                stk.push_far(r[3], r[2], r[1]);
-            }
-        }
+        if (r[1] != kNoChild) stk.push_far(r[3], r[2], r[1], b.overflow);
         return r[0];
     }
     if (!stk.room(4)) {

@@ -92,8 +92,18 @@ struct vlb_ctx {
     struct TmapEntry { const void* ptr = nullptr; uint64_t stride = 0; uint32_t n_maps = 0; int W = 0, H = 0, fmt = -1; alignas(64) unsigned char map[128]; };
     TmapEntry tmap_cache[8];
     unsigned tmap_next = 0;
+    // vlb_skybox_project_sh_device_ptrs: a call repeated with the same arguments is replayed from a CUDA graph of its
+    // launches (one kernel node per map, lanes = parallel branches): issuing a launch costs the host ~6 us, a
+    // 32 MiB map streams in 5
+    struct ProjGraph {
+        std::vector<const void*> maps; int fmt = 0, W = 0, H = 0, order = 0; float* out = nullptr;
+        const void* partials = nullptr; const void* row_tab = nullptr;   // device buffers baked into the nodes
+        int seen = 0; cudaGraphExec_t exec = nullptr;
+    };
+    std::vector<ProjGraph> proj_graphs;
+    cudaStream_t cap_stream = nullptr;
     // ---- bake ----
-    vlb::DevBuf d_bake_out, d_bake_prev, d_partials, d_work_counter, d_axis, d_row_sc, d_col_sc, d_stats, d_stream_scratch;
+    vlb::DevBuf d_bake_out, d_bake_prev, d_partials, d_work_counter, d_axis, d_row_sc, d_col_sc, d_stats, d_stream_scratch, d_vis_ovf;
     int dir_w = 0, dir_h = 0;
     vlb_bake_stats last_bake{};
     bool bake_pending = false;             // a device bake was enqueued and its statistics not yet collected
@@ -150,7 +160,7 @@ size_t ref_order_index(int i, int j, int k, int Nx, int Ny, int Nz);
 int scene_flatten(vlb_ctx* ctx);
 int bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats);
 int project_sh_device(vlb_ctx* ctx, const void* d_texels, uint64_t map_stride, uint32_t n_maps, int fmt,
-                      int W, int H, int order, int variant, float* d_out, int lane = -1);
+                      int W, int H, int order, int variant, float* d_out, int lane = -1, bool chain_in_lane = false);
 int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_full, float* d_out);
 int bake_collect_stats(vlb_ctx* ctx);
 int sky_upload_join(vlb_ctx* ctx);     // context.cu: orders a pending vlb_skybox_set_async before the ctx stream's next work

@@ -201,11 +201,21 @@ VLB_HD int gather_cell(float p, float origin, float step, int n) {
     return g >= (float)(n - 2) ? n - 2 : (int)g;
 }
 
+// Corner c (gridVertices order, shaders/main.rchit:128-137) of the grid cell (ci, cj, ck) around a hit at P: probe
+// indices, vector from P to the probe and its length (= the visibility ray's direction and tmax, :145,154).
+VLB_HD void gather_corner(const GatherView& g, Vec3 P, int ci, int cj, int ck, int c, int& i, int& j, int& k, Vec3& d, float& tmax) {
+    i = mini(ci + ((c >> 2) & 1), g.Nx - 1); j = mini(cj + ((c >> 1) & 1), g.Ny - 1); k = mini(ck + (c & 1), g.Nz - 1);
+    d = mk3(f_sub(g.px[i], P.x), f_sub(g.py[j], P.y), f_sub(g.pz[k], P.z));
+    tmax = f_sqrt(dot_exact(d, d));
+}
+
 // The reference's run-time gather (shaders/main.rchit:124-163, probe lookup shaders/sh.rmiss:20-36)
 // over the previous pass: visibility-weighted interpolation of the 8 probes around the hit, each
-// probe's SH evaluated on the shading normal. Operation order = oracle gather_indirect.
-template <int K, bool COUNT>
-VLB_HD void gather_indirect(const BvhView& b, const GatherView& g, const ShadePrelude& p, float out[3], TraceCounters* cnt) {
+// probe's SH evaluated on the shading normal. Operation order = oracle gather_indirect. `occluded` has bit c set
+// when the visibility ray to corner c was blocked (:155); the rays themselves are traced by the caller -- inline
+// (gather_indirect below) or, in the bake kernel, as one warp-wide batch per 32 shaded hits (bake.cu).
+template <int K>
+VLB_HD void gather_accumulate(const GatherView& g, const ShadePrelude& p, unsigned occluded, float out[3]) {
     const int ci = gather_cell(p.P.x, g.origin[0], g.step[0], g.Nx);
     const int cj = gather_cell(p.P.y, g.origin[1], g.step[1], g.Ny);
     const int ck = gather_cell(p.P.z, g.origin[2], g.step[2], g.Nz);
@@ -214,14 +224,10 @@ VLB_HD void gather_indirect(const BvhView& b, const GatherView& g, const ShadePr
     sh_basis<K>(g.world_frame ? p.N : mk3(p.N.x, p.N.z, p.N.y), basis);
     float sum[3] = {0.f, 0.f, 0.f}, wsum = 0.f;
     for (int c = 0; c < 8; ++c) {                                       // gridVertices order, :128-137
-        const int i = mini(ci + ((c >> 2) & 1), g.Nx - 1), j = mini(cj + ((c >> 1) & 1), g.Ny - 1), k = mini(ck + (c & 1), g.Nz - 1);
-        const Vec3 d = mk3(f_sub(g.px[i], p.P.x), f_sub(g.py[j], p.P.y), f_sub(g.pz[k], p.P.z));   // :145
-        const float tmax = f_sqrt(dot_exact(d, d));                     // :154
+        if ((occluded >> c) & 1u) continue;
+        int i, j, k; Vec3 d; float tmax;
+        gather_corner(g, p.P, ci, cj, ck, c, i, j, k, d, tmax);
         const float w = fmaxf(f_sub(weight_max, tmax), 0.0f);           // :156
-        bool occluded = false;
-        if (tmax > 0.0f)
-            occluded = trace_any<COUNT>(b, p.so, mk3(f_div(d.x, tmax), f_div(d.y, tmax), f_div(d.z, tmax)), 0.0f, tmax, cnt, nullptr);  // :155
-        if (occluded) continue;
         const float* shp = g.prev + ((size_t)i + (size_t)g.Nx * ((size_t)j + (size_t)g.Ny * (size_t)k)) * 48;   // sh.rmiss:25
         // the probe's K x 3 coefficients as 16-byte loads (a probe record is 192 bytes, 16-byte aligned)
         constexpr int NQ = (K * 3 + 3) / 4;
@@ -240,6 +246,23 @@ VLB_HD void gather_indirect(const BvhView& b, const GatherView& g, const ShadePr
         wsum = f_add(wsum, w);                                          // :161
     }
     for (int c = 0; c < 3; ++c) out[c] = wsum > 0.0f ? f_mul(g.gain, f_div(sum[c], wsum)) : 0.0f;      // :164-165
+}
+
+// Gather with the 8 visibility rays traced right here by the calling thread (tests/emu, probe_ray_radiance).
+template <int K, bool COUNT>
+VLB_HD void gather_indirect(const BvhView& b, const GatherView& g, const ShadePrelude& p, float out[3], TraceCounters* cnt) {
+    const int ci = gather_cell(p.P.x, g.origin[0], g.step[0], g.Nx);
+    const int cj = gather_cell(p.P.y, g.origin[1], g.step[1], g.Ny);
+    const int ck = gather_cell(p.P.z, g.origin[2], g.step[2], g.Nz);
+    unsigned occluded = 0;
+    for (int c = 0; c < 8; ++c) {
+        int i, j, k; Vec3 d; float tmax;
+        gather_corner(g, p.P, ci, cj, ck, c, i, j, k, d, tmax);
+        if (tmax > 0.0f &&
+            trace_any<COUNT>(b, p.so, mk3(f_div(d.x, tmax), f_div(d.y, tmax), f_div(d.z, tmax)), 0.0f, tmax, cnt, nullptr))  // :155
+            occluded |= 1u << c;
+    }
+    gather_accumulate<K>(g, p, occluded, out);
 }
 
 // `ind` = gathered indirect term per channel (zeros in the direct pass: k + 0 == k, so the direct
