@@ -325,28 +325,42 @@ def run_ours(args):
         sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
         l1_peak = 148 * 128 * sm_mhz * 1e6 / 1e9                          # 128 B per clock per SM through the L1 data pipe
         traffic = ncu_traffic(kname + ":" + which)
+        pipes = ncu_pipes(kname + ":" + which)
         roofline = {"bound": "l1", "kernel": kname, "achieved": achieved, "peak": l1_peak, "unit": "GB/s",
                     "frac": achieved / l1_peak, "traffic": traffic,
                     "peak_source": "148 SMs x 128 B/clk x %.0f MHz (SM clock sampled during the timed region): the L1 data pipe, the "
                                    "unit ncu names as binding for this kernel" % sm_mhz,
                     "hbm": {"dram_bytes_per_launch": traffic, "achieved": (traffic / (kern_ms * 1e-3) / 1e9) if traffic else None,
                             "peak": peak, "peak_source": peak_src, "frac": (traffic / (kern_ms * 1e-3) / 1e9 / peak) if traffic else None},
-                    "ncu": ncu_pipes(kname + ":" + which),
+                    "binding_pipe": ({"unit": "l1tex data-pipe wavefronts (ncu l1tex__data_pipe_lsu_wavefronts, % of peak sustained)",
+                                      "frac": pipes["l1_data_pipe_lsu_wavefronts_pct"] / 100.0, "alu_pipe_frac": pipes["alu_pipe_pct"] / 100.0,
+                                      "issue_slots_frac": pipes["issue_slots_pct"] / 100.0, "capture": pipes.get("capture")} if pipes else None),
+                    "ncu": pipes,
                     "algorithmic_bytes_per_launch": int(alg_bytes),
                     "nodes_per_ray": st.n_nodes_visited / max(nrays, 1), "tris_per_ray": st.n_tris_tested / max(nrays, 1),
                     "kernel_ms": kern_ms,
                     "note": "the traversal reads 112 B of each 4-wide node + 48 B per triangle, all L1/L2-resident (BVH + triangles "
                             "< 30 MB), so the kernel is NOT HBM-bound: `achieved` = (nodes visited x 112 + triangles tested x 48, "
                             "counted by the instrumented build of the same kernel) / kernel time, against the L1 data-pipe peak. "
-                            "The bytes are scattered 16-byte loads (about 8 wavefronts per load instruction), so the pipe saturates "
-                            "in wavefronts long before it does in bytes: the binding figures are the `ncu` block's "
-                            "l1tex data-pipe and issue-slot utilisation (profiles/, captured this round on the same build); "
+                            "The bytes are scattered 16-byte loads (about 8 distinct lines, i.e. wavefronts, per load instruction), so the "
+                            "pipe saturates in wavefronts long before it does in bytes: `binding_pipe.frac` is the ncu utilisation of "
+                            "that pipe (static: profiles/, ncu --set full of the same build and workload this round); "
                             "`hbm` is the measured DRAM traffic of one launch against the HBM copy peak"}
         extra["roofline"] = roofline
         extra["skybox"] = bench_skybox(torch, ctx, scenes, dev, stream, peak, peak_src)
         extra["cpu_baseline"] = cpu_baseline(scene, sky, settings_for(scenes, which, 1), which)
         extra["bvh"] = {"build_ms": bvh.build_ms, "first_build_ms": bvh_first.build_ms, "sort_ms": bvh.sort_ms, "nodes": int(bvh.n_nodes),
                         "mtris_per_s": N_TRIS / (bvh.build_ms * 1e-3) / 1e6}
+        if world == 1 and which == "c3" and not args.quick:
+            # the other named configs, beside the headline: C5 (batched skybox sweep) and C4 (3 M triangles, 3 gather passes)
+            try:
+                extra["c5"] = bench_c5(torch, ctx, dev, stream, peak, peak_src)
+            except Exception as e:      # noqa: a full HBM on a shared box must not lose the headline line
+                extra["c5"] = {"error": repr(e)}
+            try:
+                extra["c4"] = bench_c4(torch, vlb, scenes, local)
+            except Exception as e:      # noqa
+                extra["c4"] = {"error": repr(e)}
         if world == 1 and which == "c3":
             # BASELINE configs[1] beside the headline: the small grid whose bake is one 0.9 ms launch
             s2 = settings_for(scenes, "c2", 1)
@@ -442,6 +456,84 @@ def bench_skybox(torch, ctx, scenes, dev, stream, peak, peak_src, n_buf=8, reps=
                     "library caches for a repeated call); `single` is the same launches issued one API call at a time and is bound "
                     "by the host's launch cost, `batched8` is one launch for 8 maps",
             "modes": res}
+
+
+def bench_c5(torch, ctx, dev, stream, peak, peak_src, reps=3):
+    """BASELINE configs[4] (C5): batched skybox projection sweep, 1024 RGBA32F equirect maps per size from 512x256 to
+    4096x2048 (the largest batch is 137 GB resident in HBM), L2 and L3 SH, one batched launch per size and order.
+    Every size is far larger than L2, so all reads come from HBM. A size that does not fit the free memory is
+    run with fewer maps and says so."""
+    vlbm = importlib.import_module("vulkan-light-bakery_b200")
+    free, _total = torch.cuda.mem_get_info(dev)
+    out = []
+    buf = None
+    try:
+        want = 1024 * 4096 * 2048 * 16
+        nbytes = min(want, int(free * 0.92) // (1 << 20) * (1 << 20))
+        buf = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+        for off in range(0, buf.numel(), 1 << 28):                     # 1 GiB slices of uniform [0, 1) texels
+            buf[off: off + (1 << 28)].uniform_(0.0, 1.0)
+        outs = torch.zeros((1024, 48), dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()
+        for (Wd, Hd) in ((512, 256), (1024, 512), (2048, 1024), (4096, 2048)):
+            stride = Wd * Hd * 16
+            n = min(1024, nbytes // stride)
+            for order in (2, 3):
+                def fn():
+                    ctx.skybox_project_sh_device(buf.data_ptr(), stride, n, vlbm.FMT_RGBA32F, Wd, Hd, order, outs.data_ptr())
+                fn(); fn()
+                torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                for _ in range(reps):
+                    fn()
+                b.record(stream)
+                torch.cuda.synchronize()
+                ms = a.elapsed_time(b) / reps
+                gbs = stride * n / (ms * 1e-3) / 1e9
+                out.append({"W": Wd, "H": Hd, "maps": n, "sh_order": order, "ms_per_launch": ms, "maps_per_s": n / (ms * 1e-3),
+                            "achieved": gbs, "unit": "GB/s", "frac": gbs / peak})
+    finally:
+        del buf
+        torch.cuda.empty_cache()
+    return {"workload": "C5 (BASELINE configs[4]): batched skybox projection sweep, 1024 RGBA32F maps per size, device-resident, "
+                        "one launch per size and SH order", "kernel": "vlb::k_project_tiles<K,RGBA32F>", "bound": "hbm", "peak": peak,
+            "peak_source": peak_src, "sizes": out, "min_frac": min(o["frac"] for o in out) if out else None}
+
+
+def bench_c4(torch, vlb, scenes, local, reps=2):
+    """BASELINE configs[3] (C4): ~3 M-triangle procedural scene, 32x16x32 probes x 4,096 rays, L3 SH, direct pass + 3
+    gather passes (the reference's run-time gather, shaders/main.rchit:124-163, applied to the previous pass), on a
+    context of its own; device-resident, kernel times from the library's CUDA events."""
+    t0 = time.perf_counter()
+    scene = scenes.atrium(3 * (1 << 20), seed=11)
+    sky = scenes.hdr_sky(SKY_WH[0], SKY_WH[1], seed=1)
+    gen_s = time.perf_counter() - t0
+    s = scenes.atrium_settings(probes=(32, 16, 32), dirs=(64, 64), order=3, bounds=(0, 0, 0) + tuple(scenes.HALL))
+    s.indirect_gain = 1.0
+    bounces = 3
+    with vlb.Context(local) as c4:
+        c4.set_scene(scene); c4.build_bvh(); bvh = c4.build_bvh(); c4.set_skybox(sky)
+        bufs = [torch.zeros((s.n_probes, 48), device="cuda:%d" % local) for _ in range(2)]
+        best, shadow = None, 0
+        for rep in range(reps + 1):
+            ms, prev = [], 0
+            for pss in range(1 + bounces):
+                o = bufs[pss & 1]
+                c4.bake_gather_device(s, prev, o.data_ptr()); c4.synchronize()
+                st = c4.last_bake_stats()
+                ms.append(st.kernel_ms); shadow = int(st.n_shadow_rays)
+                prev = o.data_ptr()
+            if rep > 0 and (best is None or sum(ms) < sum(best)):
+                best = ms
+        checksum = float(bufs[bounces & 1].double().abs().sum())
+    rays = s.n_probes * s.dir_w * s.dir_h
+    return {"workload": "C4 (BASELINE configs[3]): procedural atrium seed 11, 3,145,728 triangles; 32x16x32 probes x 4,096 rays; "
+                        "L3 SH (16 coeffs); direct pass + 3 gather passes; device-resident",
+            "pass_kernel_ms": best, "total_ms": sum(best), "value": rays * len(best) / (sum(best) * 1e-3) / 1e9, "unit": UNIT,
+            "direct_pass_Grays_per_s": rays / (best[0] * 1e-3) / 1e9, "gather_pass_Grays_per_s": rays / (best[-1] * 1e-3) / 1e9,
+            "probes_per_s": s.n_probes / (sum(best) * 1e-3), "shadow_rays_per_pass": shadow, "bvh_build_ms": bvh.build_ms,
+            "bvh_nodes": int(bvh.n_nodes), "scene_generation_s_host": gen_s, "checksum": checksum}
 
 
 def cpu_baseline(scene, sky, s, which="c3", budget_s=12.0):
@@ -566,6 +658,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c3", choices=["c2", "c3"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--quick", action="store_true", help="N = 1: skip the C4 and C5 blocks (headline C3 + C2 + C1 only)")
     ap.add_argument("--gather", default="abi", choices=["abi", "torch"],
                     help="N > 1: all-gather inside libvlb_bake.so (its own NCCL communicator) or through torch.distributed")
     args = ap.parse_args()

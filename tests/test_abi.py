@@ -57,6 +57,26 @@ def test_no_gpu_means_loud_failure(vlb):
     assert "no CPU path" in str(e.value)
 
 
+def test_comm_host_side(vlb):
+    """The multi-GPU section of the ABI without a GPU: the NCCL id is 128 bytes (run-time libnccl), bad arguments are
+    refused, and a communicator cannot be made without a context."""
+    lib = vlb.load_library()
+    assert vlb.COMM_ID_BYTES == 128
+    small = ctypes.create_string_buffer(16)
+    assert lib.vlb_comm_get_unique_id(ctypes.cast(small, ctypes.c_void_p), 16) == vlb.ERR_INVALID or \
+        lib.vlb_comm_get_unique_id(ctypes.cast(small, ctypes.c_void_p), 16) == vlb.ERR_UNSUPPORTED
+    try:
+        a, b = vlb.comm_unique_id(), vlb.comm_unique_id()
+    except vlb.VlbError as e:                       # a machine without libnccl.so.2: loud, not silent
+        assert e.code == vlb.ERR_UNSUPPORTED and "NCCL" in str(e)
+        return
+    assert len(a) == 128 and len(b) == 128 and a != b
+    assert lib.vlb_comm_init_rank(None, a, 0, 1) == vlb.ERR_INVALID
+    assert lib.vlb_comm_destroy(None) == vlb.ERR_INVALID
+    assert lib.vlb_comm_sharded_uploads(None, 1) == vlb.ERR_INVALID
+    assert lib.vlb_bake_probes_sharded(None, None, None) == vlb.ERR_INVALID
+
+
 def test_slab_partition(vlb):
     import importlib
     par = importlib.import_module("vulkan-light-bakery_b200.parallel")

@@ -97,7 +97,7 @@ constexpr int kStreamWarps = kBakeBlock / 32;
 #define VLB_BAKE_SMEM_STACK 12              // stack entries per lane in shared memory; 0 = round-1 per-thread local array
 #endif
 #ifndef VLB_BAKE_FAST_PUSH
-#define VLB_BAKE_FAST_PUSH 1                // branch-free pushes of a node step's far children (WarpStack::push_far)
+#define VLB_BAKE_FAST_PUSH 1                // branch-free end of a node step in the shared short stack (WarpStack::advance)
 #endif
 #ifndef VLB_BAKE_SMEM_HQ
 #define VLB_BAKE_SMEM_HQ 1                  // hit queue in shared memory
@@ -110,22 +110,28 @@ constexpr int kOvfStack = kSmemStack > 0 ? kStackSize - kSmemStack : 1;
 struct HitQueue {
     int id[kHitCap]; float t[kHitCap], u[kHitCap], v[kHitCap]; int dir[kHitCap];
 };
-struct WarpQueues {
-    float rad[3][kChunkDirs];      // radiance of the current chunk, by direction
+#ifndef VLB_BAKE_DISCARD
+#define VLB_BAKE_DISCARD 1                  // discard.global.L2 of the radiance tile once a chunk is projected
+#endif
+struct alignas(128) WarpQueues {
+    float rad[3][kChunkDirs];      // radiance of the current chunk, by direction (whole 128-byte lines: see the discard below)
     // shadow-ray queue: origin, unit direction, length, direction index, radiance if the light is visible
     float sq_o[3][kShadowCap], sq_d[3][kShadowCap], sq_len[kShadowCap]; int sq_dir[kShadowCap];
     float sq_rgb[3][kShadowCap];
     HitQueue hq;                   // used when the hit queue is not in shared memory
-    int ovf[kOvfStack][32];        // stack entries beyond the shared-memory short stack, [entry][lane]
+    int ovf[kOvfStack * (VLB_STACK_CULL ? 2 : 1)][32];   // stack entries beyond the shared-memory short stack, [entry][word][lane]
 };
 
 // Short stack in shared memory + overflow in global scratch; same interface as LocalStack (vlb_bvh.cuh).
 // `sm` is the 32-bit shared-window address of this lane's entry 0; it is produced by an opaque asm move so that
 // the compiler keeps it in a register instead of re-deriving it (S2R tid, shifts, IMAD: ten instructions) at every
 // push and pop, which is what it does with a plain pointer under the kernel's 64-register cap.
+// An entry is kStackWords words: the ref and (VLB_STACK_CULL) the entry distance of its box, one 128-byte row each.
+constexpr int kStackWords = VLB_STACK_CULL ? 2 : 1;
+constexpr uint32_t kEntryBytes = 128u * kStackWords;
 struct WarpStack {
-    uint32_t sm;  // shared address of s_stack[warp][0][lane]; entry e lives 128 * e bytes further
-    int* ovf;     // &scratch.ovf[0][lane]
+    uint32_t sm;  // shared address of s_stack[warp][0][0][lane]; entry e lives kEntryBytes * e further
+    int* ovf;     // &scratch.ovf[0][lane]: overflow entries, kStackWords rows of 32 lanes each
     int sp;
     __device__ __forceinline__ void bind(const int* entry0, int* overflow) {
         const uint32_t a = (uint32_t)__cvta_generic_to_shared(entry0);
@@ -135,38 +141,78 @@ struct WarpStack {
     __device__ __forceinline__ void clear() { sp = 0; }
     __device__ __forceinline__ bool empty() const { return sp == 0; }
     __device__ __forceinline__ bool room(int n) const { return sp + n <= kStackSize; }
-    __device__ __forceinline__ void push(int v) {
-        if (sp < kSmemStack) asm volatile("st.shared.b32 [%0], %1;" ::"r"(sm + 128u * (uint32_t)sp), "r"(v) : "memory");
-        else ovf[32 * (sp - kSmemStack)] = v;
+    __device__ __forceinline__ void sts(uint32_t addr, int v, float tn) {
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+#if VLB_STACK_CULL
+        asm volatile("st.shared.b32 [%0+128], %1;" ::"r"(addr), "f"(tn) : "memory");
+#endif
+    }
+    __device__ __forceinline__ void push(int v, float tn) {
+        if (sp < kSmemStack) sts(sm + kEntryBytes * (uint32_t)sp, v, tn);
+        else {
+            ovf[32 * kStackWords * (sp - kSmemStack)] = v;
+#if VLB_STACK_CULL
+            ovf[32 * kStackWords * (sp - kSmemStack) + 32] = __float_as_int(tn);
+#endif
+        }
         ++sp;
     }
-    // bvh4_step's far children (r1 valid, r3 valid implies r2 valid), r1 on top. Fast path (all three slots inside the
-    // shared short stack): three UNCONDITIONAL stores and no branch -- entry r_k goes to slot sp + max(n - k, 0) with
-    // n = number of valid refs, so an invalid r3 / r2 is written first to the slot the next valid one overwrites (or,
-    // for n = 1, to the slot above the new top, which is dead).
-    __device__ __forceinline__ void push_far(int r3, int r2, int r1, unsigned int* overflow) {
+    // next pending node / leaf whose box starts within tcull, or kNoChild
+    __device__ __forceinline__ int pop(float tcull) {
+        while (sp > 0) {
+            --sp;
+            int v;
+            float tn = 0.f;
+            if (sp < kSmemStack) {
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(sm + kEntryBytes * (uint32_t)sp) : "memory");
+#if VLB_STACK_CULL
+                asm volatile("ld.shared.b32 %0, [%1+128];" : "=f"(tn) : "r"(sm + kEntryBytes * (uint32_t)sp) : "memory");
+#endif
+            } else {
+                v = ovf[32 * kStackWords * (sp - kSmemStack)];
+#if VLB_STACK_CULL
+                tn = __int_as_float(ovf[32 * kStackWords * (sp - kSmemStack) + 32]);
+#endif
+            }
+            if (!VLB_STACK_CULL || tn <= tcull) return v;
+        }
+        return kNoChild;
+    }
+    // End of an ordered node step (see LocalStack::advance). While the three slots above the top are inside the shared
+    // short stack the pushes are branch-free: three unconditional stores -- entry r_k goes to slot sp + max(n - k, 0)
+    // with n = number of valid refs, so an invalid r3 / r2 is written first to the slot the next valid one overwrites
+    // (or, for n = 0 / 1, to slots above the new top, which are dead). Without VLB_STACK_CULL the pop is branch-free too
+    // (one predicated load): the node loop then has no taken branch besides its back edge (ncu round 2:
+    // no_instruction + branch_resolving = 17 % of the stall samples).
+    __device__ __forceinline__ int advance(int r0, int r1, int r2, int r3, float t1, float t2, float t3, float tcull, unsigned int* overflow) {
 #if VLB_BAKE_FAST_PUSH
         if (sp + 3 <= kSmemStack) {
-            const int v3 = r3 != kNoChild, v2 = r2 != kNoChild;
-            const uint32_t base = sm + 128u * (uint32_t)sp;
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(base), "r"(r3) : "memory");
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + 128u * (uint32_t)v3), "r"(r2) : "memory");
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(base + 128u * (uint32_t)(v3 + v2)), "r"(r1) : "memory");
-            sp += 1 + v3 + v2;
-            return;
+            const int v3 = r3 != kNoChild, v2 = r2 != kNoChild, v1 = r1 != kNoChild;
+            const uint32_t base = sm + kEntryBytes * (uint32_t)sp;
+            sts(base, r3, t3);
+            sts(base + kEntryBytes * (uint32_t)v3, r2, t2);
+            sts(base + kEntryBytes * (uint32_t)(v3 + v2), r1, t1);
+            sp += v1 + v2 + v3;
+#if VLB_STACK_CULL
+            return r0 == kNoChild ? pop(tcull) : r0;                             // nothing hit => nothing was pushed
+#else
+            const bool need_pop = r0 == kNoChild, can_pop = need_pop && sp > 0;   // nothing hit => nothing was pushed
+            int top = kNoChild;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.shared.b32 %0, [%1];\n\t}"
+                         : "+r"(top) : "r"(base - 128u), "r"((int)can_pop) : "memory");
+            sp -= can_pop ? 1 : 0;
+            return need_pop ? top : r0;
+#endif
         }
 #endif
-        if (!room(3)) { if (overflow) *overflow = 1u; return; }
-        if (r3 != kNoChild) push(r3);
-        if (r2 != kNoChild) push(r2);
-        push(r1);
-    }
-    __device__ __forceinline__ int pop() {
-        --sp;
-        int v;
-        if (sp < kSmemStack) asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(sm + 128u * (uint32_t)sp) : "memory");
-        else v = ovf[32 * (sp - kSmemStack)];
-        return v;
+        if (r0 == kNoChild) return pop(tcull);
+        if (r1 != kNoChild) {
+            if (!room(3)) { if (overflow) *overflow = 1u; return r0; }
+            if (r3 != kNoChild) push(r3, t3);
+            if (r2 != kNoChild) push(r2, t2);
+            push(r1, t1);
+        }
+        return r0;
     }
 };
 
@@ -238,7 +284,7 @@ __device__ __forceinline__ void trace_vis_batch(const BvhView& bvh, const Gather
                 atomicOr(&X.occluded[tag >> 3], 1u << (tag & 7));
                 cur = kRayDone;
             } else {
-                cur = stk.empty() ? kRayDone : stk.pop();
+                cur = stk.pop(tcull);
             }
         }
         if (busy && cur == kRayDone) busy = false;
@@ -249,18 +295,18 @@ __device__ __forceinline__ void trace_vis_batch(const BvhView& bvh, const Gather
 #ifndef VLB_BAKE_MIN_BLOCKS
 #define VLB_BAKE_MIN_BLOCKS 8      // resident 128-thread blocks per SM the register allocation is held to (8 -> 64 registers)
 #endif
-constexpr size_t kBakeSmemPerBlock = (kSmemStack > 0 ? (size_t)kStreamWarps * kSmemStack * 32 * sizeof(int) : 0) +
+constexpr size_t kBakeSmemPerBlock = (kSmemStack > 0 ? (size_t)kStreamWarps * kSmemStack * kStackWords * 32 * sizeof(int) : 0) +
                                      (kSmemHq ? (size_t)kStreamWarps * sizeof(HitQueue) : 0);
 // gather passes add the second short stack and the exchange area of the visibility-ray batches
-constexpr size_t kBakeSmemPerBlockGather = kBakeSmemPerBlock + (kSmemStack > 0 ? (size_t)kStreamWarps * kSmemStack * 32 * sizeof(int) : 0) +
+constexpr size_t kBakeSmemPerBlockGather = kBakeSmemPerBlock + (kSmemStack > 0 ? (size_t)kStreamWarps * kSmemStack * kStackWords * 32 * sizeof(int) : 0) +
                                            (size_t)kStreamWarps * sizeof(VisExchange);
 
 template <int K, bool COUNT, bool GATHER, bool TEX>
 __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) k_bake_stream(const BakeParams p) {
     constexpr int V = (K * 3 <= 32) ? 32 : 64;
-    __shared__ int s_stack[kSmemStack > 0 ? kStreamWarps : 1][kSmemStack > 0 ? kSmemStack : 1][32];
+    __shared__ int s_stack[kSmemStack > 0 ? kStreamWarps : 1][kSmemStack > 0 ? kSmemStack : 1][kStackWords][32];
     __shared__ HitQueue s_hq[kSmemHq ? kStreamWarps : 1];
-    __shared__ int s_stack2[GATHER && kSmemStack > 0 ? kStreamWarps : 1][GATHER && kSmemStack > 0 ? kSmemStack : 1][32];
+    __shared__ int s_stack2[GATHER && kSmemStack > 0 ? kStreamWarps : 1][GATHER && kSmemStack > 0 ? kSmemStack : 1][kStackWords][32];
     __shared__ VisExchange s_vis[GATHER ? kStreamWarps : 1];
     WarpQueues* s_all = p.stream_scratch + (size_t)blockIdx.x * kStreamWarps;
     const unsigned full = 0xffffffffu;
@@ -276,14 +322,14 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
     uint32_t u_node_it = 0, u_node_ln = 0, u_leaf_it = 0, u_leaf_ln = 0, u_shade_it = 0, u_shade_ln = 0, u_outer = 0, u_ovf = 0;
 #if VLB_BAKE_SMEM_STACK > 0
     WarpStack stk;
-    stk.bind(&s_stack[warp][0][lane], &S.ovf[0][lane]);
+    stk.bind(&s_stack[warp][0][0][lane], &S.ovf[0][lane]);
 #else
     LocalStack stk;
 #endif
     stk.clear();
     RayStack stk2;               // visibility-ray batches of the gather passes (the main rays keep `stk` while a batch runs)
 #if VLB_BAKE_SMEM_STACK > 0
-    if (GATHER) stk2.bind(&s_stack2[warp][0][lane], p.vis_ovf + ((size_t)blockIdx.x * kStreamWarps + warp) * kOvfStack * 32 + lane);
+    if (GATHER) stk2.bind(&s_stack2[warp][0][0][lane], p.vis_ovf + ((size_t)blockIdx.x * kStreamWarps + warp) * kOvfStack * kStackWords * 32 + lane);
 #endif
     stk2.clear();
 
@@ -470,7 +516,7 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                     } else {
                         terminated = leaf_step<false, COUNT>(bvh, cur, ro, rd, tmin, tcull, best, &cnt);
                     }
-                    cur = (terminated || stk.empty()) ? kRayDone : stk.pop();
+                    cur = terminated ? kRayDone : stk.pop(tcull);
                 }
                 // ---- 5. finished rays free their lane ----
                 const bool fin = busy && cur == kRayDone;
@@ -519,6 +565,15 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
             coef0 += acc[0];
             if (V == 64) coef1 += acc[1];
             __syncwarp();
+#if VLB_BAKE_DISCARD
+            // The tile's radiances are dead now (the next chunk writes every entry before it reads any), but their
+            // lines sit dirty in L2 and would be written back to HBM when the BVH / skybox traffic evicts them:
+            // round 2 measured 4.2 GB of such write-backs per C3 launch. Tell L2 to drop them instead.
+            static_assert(sizeof(S.rad) % 128 == 0, "radiance tile must cover whole 128-byte lines");
+            for (uint32_t off = 128u * lane; off < sizeof(S.rad); off += 32u * 128u)
+                asm volatile("discard.global.L2 [%0], 128;" ::"l"(reinterpret_cast<char*>(&S.rad[0][0]) + off) : "memory");
+            __syncwarp();
+#endif
         }
         float* dst = whole ? p.out + out_slot(p, q) * VLB_SH_STRIDE : p.partials + (size_t)(item - p.n_whole) * VLB_SH_STRIDE;
         if (V == 32) {
@@ -703,7 +758,7 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     VLB_CUDA(ctx, ctx->d_stream_scratch.reserve((size_t)grid * kStreamWarps * sizeof(WarpQueues)));
     p.stream_scratch = ctx->d_stream_scratch.as<WarpQueues>();
     if (gather) {
-        VLB_CUDA(ctx, ctx->d_vis_ovf.reserve((size_t)grid * kStreamWarps * kOvfStack * 32 * sizeof(int)));
+        VLB_CUDA(ctx, ctx->d_vis_ovf.reserve((size_t)grid * kStreamWarps * kOvfStack * kStackWords * 32 * sizeof(int)));
         p.vis_ovf = ctx->d_vis_ovf.as<int>();
     }
     VLB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));

@@ -388,21 +388,54 @@ __device__ __forceinline__ void fma2_planes(float4& v, float s, float c) {
 
 // Traversal stack of one ray as a per-thread array (local memory on the device). The bake kernel uses the
 // warp-shared-memory stack of bake.cu instead; bvh4_step takes either.
+// VLB_STACK_CULL = 1: every stack entry carries the entry distance of its box; a popped entry whose box starts beyond
+// the current culling distance is dropped without a node step (closest-hit rays: after the first hit most pending far
+// children are farther than the hit). Hit ids stay bit-exact: a triangle inside the box is hit no earlier than the box
+// is entered, and tcull already carries kCullSlack.
+#ifndef VLB_STACK_CULL
+#define VLB_STACK_CULL 0
+#endif
 struct LocalStack {
     int a[kStackSize];
+#if VLB_STACK_CULL
+    float t[kStackSize];
+#endif
     int sp;
     VLB_HD void clear() { sp = 0; }
     VLB_HD bool empty() const { return sp == 0; }
     VLB_HD bool room(int n) const { return sp + n <= kStackSize; }
-    VLB_HD void push(int v) { a[sp++] = v; }
-    VLB_HD int pop() { return a[--sp]; }
-    // r1 is a valid ref; r2 / r3 may be kNoChild (r3 valid implies r2 valid): pushes the valid ones so that r1 pops first
-    // A full stack never drops subtrees silently: *overflow is set (the caller reports VLB_ERR_UNSUPPORTED).
-    VLB_HD void push_far(int r3, int r2, int r1, unsigned int* overflow) {
-        if (!room(3)) { if (overflow) *overflow = 1u; return; }
-        if (r3 != kNoChild) push(r3);
-        if (r2 != kNoChild) push(r2);
-        push(r1);
+    VLB_HD void push(int v, float tn) {
+#if VLB_STACK_CULL
+        t[sp] = tn;
+#endif
+        a[sp++] = v;
+    }
+    // next pending node / leaf whose box starts within tcull, or kNoChild
+    VLB_HD int pop(float tcull) {
+#if VLB_STACK_CULL
+        while (sp > 0) {
+            --sp;
+            if (t[sp] <= tcull) return a[sp];
+        }
+        return kNoChild;
+#else
+        (void)tcull;
+        return sp > 0 ? a[--sp] : kNoChild;
+#endif
+    }
+    // End of an ordered node step: r0..r3 = the hit children, nearest first, misses (kNoChild) last, t1..t3 the entry
+    // distances of r1..r3. Returns the next node / leaf of the ray (r0, or the top of the stack when nothing was hit, or
+    // kNoChild when the ray is done) and pushes the other hit children so that they pop near to far.
+    VLB_HD int advance(int r0, int r1, int r2, int r3, float t1, float t2, float t3, float tcull, unsigned int* overflow) {
+        if (r0 == kNoChild) return pop(tcull);
+        if (r1 != kNoChild) {
+            // a full stack never drops subtrees silently: *overflow is set (the caller reports VLB_ERR_UNSUPPORTED)
+            if (!room(3)) { if (overflow) *overflow = 1u; return r0; }
+            if (r3 != kNoChild) push(r3, t3);
+            if (r2 != kNoChild) push(r2, t2);
+            push(r1, t1);
+        }
+        return r0;
     }
 };
 
@@ -481,19 +514,17 @@ VLB_HD int bvh4_step(const BvhView& b, int cur, Vec3 idir, Vec3 ood, float tmin,
         order2(tn[0], r[0], tn[2], r[2]);
         order2(tn[1], r[1], tn[3], r[3]);
         order2(tn[1], r[1], tn[2], r[2]);
-        if (r[0] == kNoChild) return stk.empty() ? kNoChild : stk.pop();
-        if (r[1] != kNoChild) stk.push_far(r[3], r[2], r[1], b.overflow);
-        return r[0];
+        return stk.advance(r[0], r[1], r[2], r[3], tn[1], tn[2], tn[3], tcull, b.overflow);
     }
     if (!stk.room(4)) {
         if (b.overflow) *b.overflow = 1u;
     } else {
-        if (r[3] != kNoChild) stk.push(r[3]);
-        if (r[2] != kNoChild) stk.push(r[2]);
-        if (r[1] != kNoChild) stk.push(r[1]);
-        if (r[0] != kNoChild) stk.push(r[0]);
+        if (r[3] != kNoChild) stk.push(r[3], tn[3]);
+        if (r[2] != kNoChild) stk.push(r[2], tn[2]);
+        if (r[1] != kNoChild) stk.push(r[1], tn[1]);
+        if (r[0] != kNoChild) stk.push(r[0], tn[0]);
     }
-    return stk.empty() ? kNoChild : stk.pop();
+    return stk.pop(tcull);
 }
 
 // Intersects the triangles of leaf `ref` (< 0). Closest-hit rays update `best` and the culling
@@ -539,7 +570,7 @@ VLB_HD HitRec trace_closest(const BvhView& b, Vec3 o, Vec3 d, float tmin, float 
             cur = bvh4_step<true>(b, cur, idir, ood, tmin, tcull, stk);
         } else {
             leaf_step<false, COUNT>(b, cur, o, d, tmin, tcull, best, cnt);
-            cur = stk.empty() ? kNoChild : stk.pop();
+            cur = stk.pop(tcull);
         }
     }
     return best;
@@ -565,7 +596,7 @@ VLB_HD bool trace_any(const BvhView& b, Vec3 o, Vec3 d, float tmin, float tmax, 
                 if (out) *out = h;
                 return true;
             }
-            cur = stk.empty() ? kNoChild : stk.pop();
+            cur = stk.pop(tcull);
         }
     }
     return false;
