@@ -214,6 +214,34 @@ struct WarpStack {
         }
         return r0;
     }
+    // End of an unsorted node step (see LocalStack::advance_unsorted): a0..a3 in visiting order, kNoChild = missed.
+    // Fast path, branch-free: a3, a2, a1 are stored at positions that advance only past valid refs (an invalid one is
+    // overwritten by the next store or left above the new top); the ray continues with a0 if it was hit, else with
+    // the new top of the stack.
+    __device__ __forceinline__ int advance_unsorted(int a0, int a1, int a2, int a3, float tcull, unsigned int* overflow) {
+        static_assert(!(VLB_NODE_ORDER1D && VLB_STACK_CULL), "unsorted node steps carry no entry distances");
+        if (sp + 3 <= kSmemStack) {
+            const int v3 = a3 != kNoChild, v2 = a2 != kNoChild, v1 = a1 != kNoChild;
+            const uint32_t base = sm + kEntryBytes * (uint32_t)sp;
+            sts(base, a3, 0.f);
+            sts(base + kEntryBytes * (uint32_t)v3, a2, 0.f);
+            sts(base + kEntryBytes * (uint32_t)(v3 + v2), a1, 0.f);
+            sp += v1 + v2 + v3;
+            const bool need_pop = a0 == kNoChild, can_pop = need_pop && sp > 0;
+            int top = kNoChild;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.shared.b32 %0, [%1];\n\t}"
+                         : "+r"(top) : "r"(sm + kEntryBytes * (uint32_t)(sp - 1)), "r"((int)can_pop) : "memory");
+            sp -= can_pop ? 1 : 0;
+            return need_pop ? top : a0;
+        }
+        const int a[4] = {a0, a1, a2, a3};
+        int f = 0;
+        while (f < 4 && a[f] == kNoChild) ++f;
+        if (f == 4) return pop(tcull);
+        if (!room(3)) { if (overflow) *overflow = 1u; return a[f]; }
+        for (int k = 3; k > f; --k) if (a[k] != kNoChild) push(a[k], 0.0f);
+        return a[f];
+    }
 };
 
 #if VLB_BAKE_SMEM_STACK > 0

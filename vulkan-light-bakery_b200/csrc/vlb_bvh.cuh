@@ -49,7 +49,16 @@ constexpr int kStackSize = 96;              // up to three pushes per 4-wide nod
 #ifndef VLB_NODE_QUADS
 #define VLB_NODE_QUADS 7
 #endif
+// VLB_NODE_ORDER1D = 1 (8-bit nodes only): the children of a node are stored sorted along the axis on which their
+// centroids spread most, the axis is kept in the node, and a closest-hit ray visits the hit children in slot order
+// (ascending or descending by the sign of its direction on that axis) instead of sorting them by entry distance: the
+// 25 ALU-pipe instructions of the sort network pay for the 8-bit decode. Traversal order never changes a result
+// (culling uses the hit distance with kCullSlack, ties go by flat id), only the number of nodes visited.
+#ifndef VLB_NODE_ORDER1D
+#define VLB_NODE_ORDER1D 0
+#endif
 constexpr bool kNodeQ8 = VLB_NODE_Q8 != 0;
+constexpr bool kOrder1D = VLB_NODE_Q8 != 0 && VLB_NODE_ORDER1D != 0;
 constexpr int kNodeQuads = kNodeQ8 ? 4 : VLB_NODE_QUADS;  // float4s per traversal node
 constexpr int kNoChild = (int)0x80000000;   // empty child slot / "no node": never a valid leaf ref (n_tris < 2^28)
 // Culling slack: a node is skipped only if its entry distance exceeds best_t * kCullSlack, so
@@ -223,7 +232,29 @@ VLB_HD uint32_t quant_hi(float v, float o, float s) {
 }
 
 // Writes one traversal node: `n` valid children (padded boxes lo/hi, refs), the remaining slots empty.
-VLB_HD void store_node4(float4* q, const int* refs, const float4* lo, const float4* hi, int n) {
+VLB_HD void store_node4(float4* q, const int* refs_in, const float4* lo_in, const float4* hi_in, int n) {
+    int refs[4]; float4 lo[4], hi[4];
+    for (int k = 0; k < 4; ++k) { refs[k] = k < n ? refs_in[k] : kNoChild; if (k < n) { lo[k] = lo_in[k]; hi[k] = hi_in[k]; } }
+    int order_axis = 0;
+    if (kOrder1D && n > 1) {
+        // axis on which the child centroids spread most; children sorted ascending along it (insertion sort of <= 4)
+        float cmin[3] = {INFINITY, INFINITY, INFINITY}, cmax[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int k = 0; k < n; ++k) {
+            const float c[3] = {lo[k].x + hi[k].x, lo[k].y + hi[k].y, lo[k].z + hi[k].z};
+            for (int a = 0; a < 3; ++a) { cmin[a] = fminf(cmin[a], c[a]); cmax[a] = fmaxf(cmax[a], c[a]); }
+        }
+        const float e[3] = {cmax[0] - cmin[0], cmax[1] - cmin[1], cmax[2] - cmin[2]};
+        order_axis = e[0] >= e[1] ? (e[0] >= e[2] ? 0 : 2) : (e[1] >= e[2] ? 1 : 2);
+        for (int i = 1; i < n; ++i)
+            for (int j = i; j > 0; --j) {
+                const float a = order_axis == 0 ? lo[j - 1].x + hi[j - 1].x : (order_axis == 1 ? lo[j - 1].y + hi[j - 1].y : lo[j - 1].z + hi[j - 1].z);
+                const float b = order_axis == 0 ? lo[j].x + hi[j].x : (order_axis == 1 ? lo[j].y + hi[j].y : lo[j].z + hi[j].z);
+                if (!(b < a)) break;
+                const float4 tl = lo[j], th = hi[j]; const int tr = refs[j];
+                lo[j] = lo[j - 1]; hi[j] = hi[j - 1]; refs[j] = refs[j - 1];
+                lo[j - 1] = tl; hi[j - 1] = th; refs[j - 1] = tr;
+            }
+    }
     if (kNodeQ8) {
         float o[3], st[3];
         uint32_t lob[3] = {0, 0, 0}, hib[3] = {0, 0, 0};
@@ -241,7 +272,9 @@ VLB_HD void store_node4(float4* q, const int* refs, const float4* lo, const floa
                 lob[a] |= bl << (8 * k); hib[a] |= bh << (8 * k);
             }
         }
-        q[0] = make_float4(o[0], o[1], o[2], st[0] * 32768.0f);
+        // the ordering axis rides in the two lowest mantissa bits of step.x * 2^15 (a power of two: they are free; the
+        // traversal multiplies with them in place, 3 ulp of the scale against a margin of 1/64 step)
+        q[0] = make_float4(o[0], o[1], o[2], kOrder1D ? i2f(f2i(st[0] * 32768.0f) | order_axis) : st[0] * 32768.0f);
         q[1] = make_float4(st[1] * 32768.0f, st[2] * 32768.0f, i2f((int)lob[0]), i2f((int)hib[0]));
         q[2] = make_float4(i2f((int)lob[1]), i2f((int)hib[1]), i2f((int)lob[2]), i2f((int)hib[2]));
         q[3] = make_float4(i2f(refs[0]), i2f(refs[1]), i2f(refs[2]), i2f(refs[3]));
@@ -370,6 +403,25 @@ VLB_HD float min3(float a, float b, float c) {
 #ifndef VLB_FFMA2
 #define VLB_FFMA2 1
 #endif
+VLB_HD float byte_to_unit(uint32_t w, int k);
+// 8-bit node format: the four plane distances v_k * S + C of one plane word (v_k = 1 + byte k * 2^-15). On the device
+// four PRMTs and two packed FFMA2, per-element IEEE, so bit-identical to the scalar host form.
+VLB_HD void q8_planes(uint32_t w, float S, float C, float4& out) {
+#if defined(__CUDA_ARCH__) && VLB_FFMA2
+    unsigned long long a0, a1, ss, cc;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a0) : "f"(byte_to_unit(w, 0)), "f"(byte_to_unit(w, 1)));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a1) : "f"(byte_to_unit(w, 2)), "f"(byte_to_unit(w, 3)));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ss) : "f"(S));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(C));
+    asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a0) : "l"(ss), "l"(cc));
+    asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a1) : "l"(ss), "l"(cc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(out.x), "=f"(out.y) : "l"(a0));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(out.z), "=f"(out.w) : "l"(a1));
+#else
+    out.x = f_fma(byte_to_unit(w, 0), S, C); out.y = f_fma(byte_to_unit(w, 1), S, C);
+    out.z = f_fma(byte_to_unit(w, 2), S, C); out.w = f_fma(byte_to_unit(w, 3), S, C);
+#endif
+}
 #if defined(__CUDA_ARCH__)
 // v = v * s - c on all four components with two packed fp32x2 FMAs (fma.rn.f32x2 -> FFMA2 on sm_100a)
 __device__ __forceinline__ void fma2_planes(float4& v, float s, float c) {
@@ -437,6 +489,18 @@ struct LocalStack {
         }
         return r0;
     }
+    // End of an unsorted node step (VLB_NODE_ORDER1D): a0..a3 = the children in visiting order, kNoChild where the ray
+    // misses. Returns the first hit one (or the top of the stack / kNoChild) and pushes the later ones so that they pop
+    // in visiting order.
+    VLB_HD int advance_unsorted(int a0, int a1, int a2, int a3, float tcull, unsigned int* overflow) {
+        const int a[4] = {a0, a1, a2, a3};
+        int f = 0;
+        while (f < 4 && a[f] == kNoChild) ++f;
+        if (f == 4) return pop(tcull);
+        if (!room(3)) { if (overflow) *overflow = 1u; return a[f]; }
+        for (int k = 3; k > f; --k) if (a[k] != kNoChild) push(a[k], 0.0f);
+        return a[f];
+    }
 };
 
 // One step through 4-wide node `cur`: slab-tests the four children against (tmin, tcull). ORDERED
@@ -462,12 +526,14 @@ VLB_HD int bvh4_step(const BvhView& b, int cur, Vec3 idir, Vec3 ood, float tmin,
     const uint32_t nxw = (uint32_t)f2i(sx ? q1.w : q1.z), fxw = (uint32_t)f2i(sx ? q1.z : q1.w);
     const uint32_t nyw = (uint32_t)f2i(sy ? q2.y : q2.x), fyw = (uint32_t)f2i(sy ? q2.x : q2.y);
     const uint32_t nzw = (uint32_t)f2i(sz ? q2.w : q2.z), fzw = (uint32_t)f2i(sz ? q2.z : q2.w);
+    float4 tnx, tfx, tny, tfy, tnz, tfz;       // plane distances of the four children, near and far, per axis
+    q8_planes(nxw, Sx, Cx, tnx); q8_planes(fxw, Sx, Cx, tfx);
+    q8_planes(nyw, Sy, Cy, tny); q8_planes(fyw, Sy, Cy, tfy);
+    q8_planes(nzw, Sz, Cz, tnz); q8_planes(fzw, Sz, Cz, tfz);
 #define VLB_SLAB(k, c)                                                                                           \
     {                                                                                                            \
-        const float a = fmaxf(max3(f_fma(byte_to_unit(nxw, k), Sx, Cx), f_fma(byte_to_unit(nyw, k), Sy, Cy),      \
-                                   f_fma(byte_to_unit(nzw, k), Sz, Cz)), tmin);                                  \
-        const float e = fminf(min3(f_fma(byte_to_unit(fxw, k), Sx, Cx), f_fma(byte_to_unit(fyw, k), Sy, Cy),      \
-                                   f_fma(byte_to_unit(fzw, k), Sz, Cz)), tcull);                                 \
+        const float a = fmaxf(max3(tnx.c, tny.c, tnz.c), tmin);                                                  \
+        const float e = fminf(min3(tfx.c, tfy.c, tfz.c), tcull);                                                 \
         const int ref = f2i(rf.c);                                                                               \
         const bool hit = a <= e && ref != kNoChild;                                                              \
         tn[k] = hit ? a : inf;                                                                                   \
@@ -507,6 +573,15 @@ VLB_HD int bvh4_step(const BvhView& b, int cur, Vec3 idir, Vec3 ood, float tmin,
 #endif
     VLB_SLAB(0, x) VLB_SLAB(1, y) VLB_SLAB(2, z) VLB_SLAB(3, w)
 #undef VLB_SLAB
+#if VLB_NODE_Q8 && VLB_NODE_ORDER1D
+    if (ORDERED) {
+        // slot order = ascending along the node's ordering axis (store_node4): a ray running against that axis visits
+        // the slots in descending order. No distance sort.
+        const int ax = f2i(q0.w) & 3;
+        const bool rev = (ax == 0 ? sx : (ax == 1 ? sy : sz)) != 0;
+        return stk.advance_unsorted(rev ? r[3] : r[0], rev ? r[2] : r[1], rev ? r[1] : r[2], rev ? r[0] : r[3], tcull, b.overflow);
+    }
+#endif
     if (ORDERED) {
         // sort the (entry distance, ref) pairs ascending; misses carry +inf and sink to the end
         order2(tn[0], r[0], tn[1], r[1]);
