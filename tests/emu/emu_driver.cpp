@@ -148,7 +148,7 @@ void* emu_scene_create(const vlb_vertex* verts, const uint32_t* indices, const v
     const float ext = std::max(hi[0] - lo[0], std::max(hi[1] - lo[1], hi[2] - lo[2]));
     s->nodes.resize((size_t)kNodeQuads * std::max(n - 1, 1u));
     if (n == 1) {
-        emit_single4(lbox.data(), ext * 1e-6f, s->nodes.data());
+        emit_wide_single(lbox.data(), ext * 1e-6f, s->nodes.data());
         return s;
     }
     s->left.assign(n, 0); s->right.assign(n, 0); s->first.assign(n, 0); s->last.assign(n, 0);
@@ -182,7 +182,7 @@ void* emu_scene_create(const vlb_vertex* verts, const uint32_t* indices, const v
         while (!frontier.empty()) {
             unsigned int n_next = 0;
             for (int root : frontier)
-                emit_node4(root, s->left.data(), s->right.data(), s->first.data(), s->last.data(), ibox.data(), lbox.data(), max_leaf,
+                emit_wide_node(root, s->left.data(), s->right.data(), s->first.data(), s->last.data(), ibox.data(), lbox.data(), max_leaf,
                            ext * 1e-6f, s->nodes.data(), next.data(), &n_next);
             frontier.assign(next.begin(), next.begin() + n_next);
         }
@@ -192,9 +192,8 @@ void* emu_scene_create(const vlb_vertex* verts, const uint32_t* indices, const v
     while (!st.empty()) {
         auto [nd, dp] = st.back(); st.pop_back();
         s->max_depth = std::max(s->max_depth, dp);
-        const float4 refs = s->nodes[(size_t)kNodeQuads * nd + (kNodeQ8 ? 3 : 6)];
-        const int r[4] = {f2i(refs.x), f2i(refs.y), f2i(refs.z), f2i(refs.w)};
-        for (int k = 0; k < 4; ++k) if (r[k] >= 0) st.push_back({r[k], dp + 1});
+        const int* r = reinterpret_cast<const int*>(&s->nodes[(size_t)kNodeQuads * nd + kRefQuad]);
+        for (int k = 0; k < kWide; ++k) if (r[k] >= 0) st.push_back({r[k], dp + 1});
     }
     return s;
 }
@@ -208,9 +207,8 @@ void emu_scene_node_stats(void* h, uint64_t out[3]) {
     while (!st.empty()) {
         const int nd = st.back(); st.pop_back();
         ++out[0];
-        const float4 refs = s->nodes[(size_t)kNodeQuads * nd + (kNodeQ8 ? 3 : 6)];
-        const int r[4] = {f2i(refs.x), f2i(refs.y), f2i(refs.z), f2i(refs.w)};
-        for (int k = 0; k < 4; ++k) {
+        const int* r = reinterpret_cast<const int*>(&s->nodes[(size_t)kNodeQuads * nd + kRefQuad]);
+        for (int k = 0; k < kWide; ++k) {
             if (r[k] == kNoChild) continue;
             ++out[1];
             if (r[k] < 0) ++out[2]; else st.push_back(r[k]);

@@ -119,7 +119,7 @@ struct alignas(128) WarpQueues {
     float sq_o[3][kShadowCap], sq_d[3][kShadowCap], sq_len[kShadowCap]; int sq_dir[kShadowCap];
     float sq_rgb[3][kShadowCap];
     HitQueue hq;                   // used when the hit queue is not in shared memory
-    int ovf[kOvfStack * (VLB_STACK_CULL ? 2 : 1)][32];   // stack entries beyond the shared-memory short stack, [entry][word][lane]
+    int ovf[kOvfStack * ((VLB_STACK_CULL || VLB_BVH8) ? 2 : 1)][32];   // stack entries beyond the shared-memory short stack, [entry][word][lane]
 };
 
 // Short stack in shared memory + overflow in global scratch; same interface as LocalStack (vlb_bvh.cuh).
@@ -127,7 +127,7 @@ struct alignas(128) WarpQueues {
 // the compiler keeps it in a register instead of re-deriving it (S2R tid, shifts, IMAD: ten instructions) at every
 // push and pop, which is what it does with a plain pointer under the kernel's 64-register cap.
 // An entry is kStackWords words: the ref and (VLB_STACK_CULL) the entry distance of its box, one 128-byte row each.
-constexpr int kStackWords = VLB_STACK_CULL ? 2 : 1;
+constexpr int kStackWords = (VLB_STACK_CULL || VLB_BVH8) ? 2 : 1;   // 8-wide: an entry is a (node, remaining hit mask) group
 constexpr uint32_t kEntryBytes = 128u * kStackWords;
 struct WarpStack {
     uint32_t sm;  // shared address of s_stack[warp][0][0][lane]; entry e lives kEntryBytes * e further
@@ -214,6 +214,46 @@ struct WarpStack {
         }
         return r0;
     }
+#if VLB_BVH8
+    // 8-wide (see LocalStack::descend / pop_group): the group's two words sit in the entry's two rows.
+    __device__ __forceinline__ void group_store(int e, int node, unsigned mask, bool both) {
+        if (e < kSmemStack) {
+            const uint32_t addr = sm + kEntryBytes * (uint32_t)e;
+            if (both) asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(node) : "memory");
+            asm volatile("st.shared.b32 [%0+128], %1;" ::"r"(addr), "r"(mask) : "memory");
+        } else {
+            if (both) ovf[64 * (e - kSmemStack)] = node;
+            ovf[64 * (e - kSmemStack) + 32] = (int)mask;
+        }
+    }
+    __device__ __forceinline__ int descend(const BvhView& b, int cur, unsigned mask, int flip) {
+        if (mask == 0u) return pop_group(b, flip);
+        const int p = __ffs((int)mask) - 1;
+        mask &= mask - 1u;
+        if (mask != 0u) {
+            if (!room(1)) { if (b.overflow) *b.overflow = 1u; }
+            else { group_store(sp, cur, mask, true); ++sp; }
+        }
+        return ref_of8(b, cur, p ^ flip);
+    }
+    __device__ __forceinline__ int pop_group(const BvhView& b, int flip) {
+        if (sp == 0) return kNoChild;
+        const int e = sp - 1;
+        int node; unsigned mask;
+        if (e < kSmemStack) {
+            const uint32_t addr = sm + kEntryBytes * (uint32_t)e;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(node) : "r"(addr) : "memory");
+            asm volatile("ld.shared.b32 %0, [%1+128];" : "=r"(mask) : "r"(addr) : "memory");
+        } else {
+            node = ovf[64 * (e - kSmemStack)];
+            mask = (unsigned)ovf[64 * (e - kSmemStack) + 32];
+        }
+        const int p = __ffs((int)mask) - 1;
+        mask &= mask - 1u;
+        if (mask != 0u) group_store(e, node, mask, false); else --sp;
+        return ref_of8(b, node, p ^ flip);
+    }
+#endif
     // End of an unsorted node step (see LocalStack::advance_unsorted): a0..a3 in visiting order, kNoChild = missed.
     // Fast path, branch-free: a3, a2, a1 are stored at positions that advance only past valid refs (an invalid one is
     // overwritten by the next store or left above the new top); the ray continues with a0 if it was hit, else with
@@ -303,7 +343,7 @@ __device__ __forceinline__ void trace_vis_batch(const BvhView& bvh, const Gather
             if (nm == 0u || (__popc(nm) < node_min && __popc(running) - __popc(nm) >= node_min)) break;
             if (at_node) {
                 if (COUNT) cnt.nodes++;
-                cur = bvh4_step<true>(bvh, cur, idir, ood, 0.0f, tcull, stk);
+                cur = traverse_step<true>(bvh, cur, idir, ood, 0.0f, tcull, stk);
             }
         }
         if (busy && cur < 0 && cur != kRayDone) {
@@ -312,7 +352,7 @@ __device__ __forceinline__ void trace_vis_batch(const BvhView& bvh, const Gather
                 atomicOr(&X.occluded[tag >> 3], 1u << (tag & 7));
                 cur = kRayDone;
             } else {
-                cur = stk.pop(tcull);
+                cur = traverse_pop(bvh, idir, tcull, stk);
             }
         }
         if (busy && cur == kRayDone) busy = false;
@@ -529,7 +569,7 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                     if (COUNT) { ++u_node_it; u_node_ln += __popc(nm); }
                     if (at_node) {
                         if (COUNT) { cnt.nodes++; if (stk.sp > kSmemStack) ++u_ovf; }
-                        cur = bvh4_step<true>(bvh, cur, idir, ood, tmin, tcull, stk);   // one code path for both ray kinds
+                        cur = traverse_step<true>(bvh, cur, idir, ood, tmin, tcull, stk);   // one code path for both ray kinds
                     }
                 }
                 // ---- 4. leaves ----
@@ -544,7 +584,7 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                     } else {
                         terminated = leaf_step<false, COUNT>(bvh, cur, ro, rd, tmin, tcull, best, &cnt);
                     }
-                    cur = terminated ? kRayDone : stk.pop(tcull);
+                    cur = terminated ? kRayDone : traverse_pop(bvh, idir, tcull, stk);
                 }
                 // ---- 5. finished rays free their lane ----
                 const bool fin = busy && cur == kRayDone;

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) k_emit_levels(int* __restrict__ frontier_
         int* next = (level & 1) ? frontier_a : frontier_b;
         if (gtid == 0) cnt[(level + 2) % 3] = 0;
         for (unsigned int t = gtid; t < n_front; t += gsize)
-            emit_node4(__ldcg(cur + t), left, right, first, last, ibox, lbox, max_leaf, ext * 1e-6f, nodes, next, cnt + (level + 1) % 3);
+            emit_wide_node(__ldcg(cur + t), left, right, first, last, ibox, lbox, max_leaf, ext * 1e-6f, nodes, next, cnt + (level + 1) % 3);
         __threadfence();
         grid.sync();
     }
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) k_emit_levels(int* __restrict__ frontier_
 // n == 1: a single node whose only child is the one-triangle leaf.
 __global__ void k_emit_single(const float4* __restrict__ lbox, const float* __restrict__ scratch, float4* nodes) {
     const float ext = fmaxf(scratch[3] - scratch[0], fmaxf(scratch[4] - scratch[1], scratch[5] - scratch[2]));
-    emit_single4(lbox, ext * 1e-6f, nodes);
+    emit_wide_single(lbox, ext * 1e-6f, nodes);
 }
 
 int bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats) {

@@ -57,9 +57,24 @@ constexpr int kStackSize = 96;              // up to three pushes per 4-wide nod
 #ifndef VLB_NODE_ORDER1D
 #define VLB_NODE_ORDER1D 0
 #endif
+// VLB_BVH8 = 1: 8-wide nodes of 96 bytes (6 float4) with 8-bit planes, the layout of a compressed wide BVH
+// (Ylitie, Karras, Laine 2017) kept with explicit child refs so that the Morton-ordered triangle array stays as it is:
+//   [0] origin.xyz, bits(ex | ey << 8 | ez << 16): plane = origin + byte * 2^(e - 127 - 15)
+//   [1] lo.x bytes of children 0..3, of 4..7, hi.x bytes of 0..3, of 4..7     [2] the same for y     [3] for z
+//   [4] refs of children 0..3      [5] refs of children 4..7   (NOT read by the node step: only the ref of the child
+//                                                                that is entered is fetched, one 4-byte load)
+// Children sit in octant-ordered slots (slot s lies towards ((s&1)?+:-, (s&2)?+:-, (s&4)?+:-) of the node's centre), so
+// a ray visits the hit slots in the order flip ^ 0, flip ^ 1, ..., flip ^ 7 (flip = its three sign bits): no distance
+// sort. The stack holds one (node, remaining hit mask) group per node, not one entry per child.
+#ifndef VLB_BVH8
+#define VLB_BVH8 0
+#endif
+constexpr bool kBvh8 = VLB_BVH8 != 0;
 constexpr bool kNodeQ8 = VLB_NODE_Q8 != 0;
 constexpr bool kOrder1D = VLB_NODE_Q8 != 0 && VLB_NODE_ORDER1D != 0;
-constexpr int kNodeQuads = kNodeQ8 ? 4 : VLB_NODE_QUADS;  // float4s per traversal node
+constexpr int kNodeQuads = kBvh8 ? 6 : (kNodeQ8 ? 4 : VLB_NODE_QUADS);  // float4s per traversal node
+constexpr int kRefQuad = kBvh8 ? 4 : (kNodeQ8 ? 3 : 6);                 // first float4 of the child refs
+constexpr int kWide = kBvh8 ? 8 : 4;                                    // children per node
 constexpr int kNoChild = (int)0x80000000;   // empty child slot / "no node": never a valid leaf ref (n_tris < 2^28)
 // Culling slack: a node is skipped only if its entry distance exceeds best_t * kCullSlack, so
 // that two triangles whose computed t differ by rounding are both reached and the
@@ -351,6 +366,110 @@ VLB_HD void emit_single4(const float4* lbox, float abs_pad, float4* nodes) {
     store_node4(nodes, refs, lo, hi, 1);
 }
 
+// ---- 8-wide nodes (VLB_BVH8) ----
+// Writes one 8-wide node: `n` valid children (padded boxes, refs) assigned to octant slots, the rest empty.
+VLB_HD void store_node8(float4* q, const int* refs_in, const float4* lo_in, const float4* hi_in, int n) {
+    // slot assignment: greedy maximum of dot(child centroid - node centre, diagonal of the slot)
+    float cen[8][3], mid[3] = {0.f, 0.f, 0.f};
+    for (int k = 0; k < n; ++k) {
+        cen[k][0] = 0.5f * (lo_in[k].x + hi_in[k].x); cen[k][1] = 0.5f * (lo_in[k].y + hi_in[k].y); cen[k][2] = 0.5f * (lo_in[k].z + hi_in[k].z);
+        for (int a = 0; a < 3; ++a) mid[a] += cen[k][a] / (float)n;
+    }
+    int slot_of[8], child_in[8];
+    for (int k = 0; k < 8; ++k) { slot_of[k] = -1; child_in[k] = -1; }
+    for (int it = 0; it < n; ++it) {
+        float best = -INFINITY; int bc = -1, bs = -1;
+        for (int c = 0; c < n; ++c) {
+            if (slot_of[c] >= 0) continue;
+            for (int sl = 0; sl < 8; ++sl) {
+                if (child_in[sl] >= 0) continue;
+                const float sc = ((sl & 1) ? 1.f : -1.f) * (cen[c][0] - mid[0]) + ((sl & 2) ? 1.f : -1.f) * (cen[c][1] - mid[1]) +
+                                 ((sl & 4) ? 1.f : -1.f) * (cen[c][2] - mid[2]);
+                if (sc > best) { best = sc; bc = c; bs = sl; }
+            }
+        }
+        slot_of[bc] = bs; child_in[bs] = bc;
+    }
+    float o[3], st[3];
+    uint32_t lob[3][2] = {{0, 0}, {0, 0}, {0, 0}}, hib[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    uint32_t ebits = 0;
+    for (int a = 0; a < 3; ++a) {
+        float l[8], h[8];
+        for (int k = 0; k < n; ++k) {
+            l[k] = a == 0 ? lo_in[k].x : (a == 1 ? lo_in[k].y : lo_in[k].z);
+            h[k] = a == 0 ? hi_in[k].x : (a == 1 ? hi_in[k].y : hi_in[k].z);
+        }
+        quant_frame(l, h, n, &o[a], &st[a]);
+        ebits |= (((uint32_t)f2i(st[a] * 32768.0f) >> 23) & 0xffu) << (8 * a);      // step is a power of two: only its exponent is kept
+        for (int sl = 0; sl < 8; ++sl) {
+            const int c = child_in[sl];
+            // empty slots: inverted (255, 0): near > far for either ray sign
+            const uint32_t bl = c >= 0 ? quant_lo(l[c], o[a], st[a]) : 255u;
+            const uint32_t bh = c >= 0 ? quant_hi(h[c], o[a], st[a]) : 0u;
+            lob[a][sl >> 2] |= bl << (8 * (sl & 3)); hib[a][sl >> 2] |= bh << (8 * (sl & 3));
+        }
+    }
+    q[0] = make_float4(o[0], o[1], o[2], i2f((int)ebits));
+    for (int a = 0; a < 3; ++a)
+        q[1 + a] = make_float4(i2f((int)lob[a][0]), i2f((int)lob[a][1]), i2f((int)hib[a][0]), i2f((int)hib[a][1]));
+    int r[8];
+    for (int sl = 0; sl < 8; ++sl) r[sl] = child_in[sl] >= 0 ? refs_in[child_in[sl]] : kNoChild;
+    q[4] = make_float4(i2f(r[0]), i2f(r[1]), i2f(r[2]), i2f(r[3]));
+    q[5] = make_float4(i2f(r[4]), i2f(r[5]), i2f(r[6]), i2f(r[7]));
+}
+
+// emit_node4's 8-wide twin: open the largest big child until there are eight.
+VLB_HD void emit_node8(int i, const int* left, const int* right, const int* first, const int* last,
+                       const float4* ibox, const float4* lbox, int max_leaf, float abs_pad, float4* nodes,
+                       int* next, unsigned int* n_next) {
+    int c[8] = {left[i], right[i], 0, 0, 0, 0, 0, 0};
+    int n = 2;
+    while (n < 8) {
+        int best = -1;
+        float best_area = -1.0f;
+        for (int k = 0; k < n; ++k) {
+            if (c[k] < 0 || last[c[k]] - first[c[k]] + 1 <= max_leaf) continue;
+            const float area = box_half_area(ibox[2 * c[k]], ibox[2 * c[k] + 1]);
+            if (area > best_area) { best_area = area; best = k; }
+        }
+        if (best < 0) break;
+        const int open = c[best];
+        c[best] = left[open];
+        c[n++] = right[open];
+    }
+    int refs[8];
+    float4 lo[8], hi[8];
+    for (int k = 0; k < n; ++k) {
+        if (classify_child(c[k], first, last, ibox, lbox, max_leaf, &refs[k], &lo[k], &hi[k]) && next) {
+#ifdef __CUDA_ARCH__
+            next[atomicAdd(n_next, 1u)] = c[k];
+#else
+            next[(*n_next)++] = c[k];
+#endif
+        }
+        pad_box(&lo[k], &hi[k], abs_pad);
+    }
+    store_node8(nodes + (size_t)kNodeQuads * i, refs, lo, hi, n);
+}
+
+// The node emitters of the configured width.
+VLB_HD void emit_wide_node(int i, const int* left, const int* right, const int* first, const int* last,
+                           const float4* ibox, const float4* lbox, int max_leaf, float abs_pad, float4* nodes,
+                           int* next, unsigned int* n_next) {
+    if (kBvh8) emit_node8(i, left, right, first, last, ibox, lbox, max_leaf, abs_pad, nodes, next, n_next);
+    else emit_node4(i, left, right, first, last, ibox, lbox, max_leaf, abs_pad, nodes, next, n_next);
+}
+VLB_HD void emit_wide_single(const float4* lbox, float abs_pad, float4* nodes) {
+    if (kBvh8) {
+        float4 lo[1] = {lbox[0]}, hi[1] = {lbox[1]};
+        pad_box(&lo[0], &hi[0], abs_pad);
+        const int refs[1] = {leaf_ref(0, 1)};
+        store_node8(nodes, refs, lo, hi, 1);
+    } else {
+        emit_single4(lbox, abs_pad, nodes);
+    }
+}
+
 struct HitRec {
     int id;       // flat triangle id, -1 = miss
     float t, u, v;
@@ -447,10 +566,51 @@ __device__ __forceinline__ void fma2_planes(float4& v, float s, float c) {
 #ifndef VLB_STACK_CULL
 #define VLB_STACK_CULL 0
 #endif
+VLB_HD int ctz32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+// ref of child `slot` of 8-wide node `node`: the one 4-byte load a descent costs besides the node's four plane loads
+VLB_HD int ref_of8(const BvhView& b, int node, int slot) {
+    const int* r = reinterpret_cast<const int*>(b.nodes + (size_t)kNodeQuads * node + kRefQuad) + slot;
+#ifdef __CUDA_ARCH__
+    return __ldg(r);
+#else
+    return *r;
+#endif
+}
+
 struct LocalStack {
     int a[kStackSize];
 #if VLB_STACK_CULL
     float t[kStackSize];
+#endif
+#if VLB_BVH8
+    unsigned m[kStackSize];     // remaining hit mask of the group (priority order)
+    // 8-wide: enter the first child of node `cur` in priority order (mask bit p = slot p ^ flip was hit), keep the rest
+    // of the group on the stack; with an empty mask continue with the newest group on the stack.
+    VLB_HD int descend(const BvhView& b, int cur, unsigned mask, int flip) {
+        if (mask == 0u) return pop_group(b, flip);
+        const int p = ctz32(mask);
+        mask &= mask - 1u;
+        if (mask != 0u) {
+            if (!room(1)) { if (b.overflow) *b.overflow = 1u; }
+            else { a[sp] = cur; m[sp] = mask; ++sp; }
+        }
+        return ref_of8(b, cur, p ^ flip);
+    }
+    VLB_HD int pop_group(const BvhView& b, int flip) {
+        if (sp == 0) return kNoChild;
+        const int node = a[sp - 1];
+        unsigned mask = m[sp - 1];
+        const int p = ctz32(mask);
+        mask &= mask - 1u;
+        if (mask != 0u) m[sp - 1] = mask; else --sp;
+        return ref_of8(b, node, p ^ flip);
+    }
 #endif
     int sp;
     VLB_HD void clear() { sp = 0; }
@@ -602,6 +762,66 @@ VLB_HD int bvh4_step(const BvhView& b, int cur, Vec3 idir, Vec3 ood, float tmin,
     return stk.pop(tcull);
 }
 
+#if VLB_BVH8
+// One step through 8-wide node `cur` (closest-hit and any-hit rays alike): slab-tests the eight children, enters the
+// first hit one in octant order and leaves the others as one (node, mask) group on the stack.
+template <class STACK>
+VLB_HD int bvh8_step(const BvhView& b, int cur, Vec3 idir, Vec3 ood, float tmin, float tcull, STACK& stk) {
+    const float4* q = b.nodes + (size_t)kNodeQuads * cur;
+    const float4 q0 = ld4(q), q1 = ld4(q + 1), q2 = ld4(q + 2), q3 = ld4(q + 3);
+    const int sx = idir.x < 0.0f, sy = idir.y < 0.0f, sz = idir.z < 0.0f;
+    const uint32_t eb = (uint32_t)f2i(q0.w);
+    // t(byte) = v * S + C with v = 1 + byte * 2^-15, S = step * 2^15 * idir, C = (origin * idir - o * idir) - S (see the 4-wide 8-bit format)
+    const float Sx = f_mul(i2f((int)((eb & 0xffu) << 23)), idir.x), Sy = f_mul(i2f((int)(((eb >> 8) & 0xffu) << 23)), idir.y),
+                Sz = f_mul(i2f((int)(((eb >> 16) & 0xffu) << 23)), idir.z);
+    const float Cx = f_sub(f_fma(q0.x, idir.x, -ood.x), Sx), Cy = f_sub(f_fma(q0.y, idir.y, -ood.y), Sy),
+                Cz = f_sub(f_fma(q0.z, idir.z, -ood.z), Sz);
+    float4 nx0, nx1, fx0, fx1, ny0, ny1, fy0, fy1, nz0, nz1, fz0, fz1;   // near / far plane distances, children 0..3 and 4..7
+    q8_planes((uint32_t)f2i(sx ? q1.z : q1.x), Sx, Cx, nx0); q8_planes((uint32_t)f2i(sx ? q1.w : q1.y), Sx, Cx, nx1);
+    q8_planes((uint32_t)f2i(sx ? q1.x : q1.z), Sx, Cx, fx0); q8_planes((uint32_t)f2i(sx ? q1.y : q1.w), Sx, Cx, fx1);
+    q8_planes((uint32_t)f2i(sy ? q2.z : q2.x), Sy, Cy, ny0); q8_planes((uint32_t)f2i(sy ? q2.w : q2.y), Sy, Cy, ny1);
+    q8_planes((uint32_t)f2i(sy ? q2.x : q2.z), Sy, Cy, fy0); q8_planes((uint32_t)f2i(sy ? q2.y : q2.w), Sy, Cy, fy1);
+    q8_planes((uint32_t)f2i(sz ? q3.z : q3.x), Sz, Cz, nz0); q8_planes((uint32_t)f2i(sz ? q3.w : q3.y), Sz, Cz, nz1);
+    q8_planes((uint32_t)f2i(sz ? q3.x : q3.z), Sz, Cz, fz0); q8_planes((uint32_t)f2i(sz ? q3.y : q3.w), Sz, Cz, fz1);
+    unsigned m = 0u;      // bit k: the ray enters child slot k (empty slots have inverted boxes and never hit)
+#define VLB_SLAB8(k, h, c)                                                                                       \
+    {                                                                                                            \
+        const float a = fmaxf(max3(nx##h.c, ny##h.c, nz##h.c), tmin);                                            \
+        const float e = fminf(min3(fx##h.c, fy##h.c, fz##h.c), tcull);                                           \
+        m |= (a <= e) ? (1u << (k)) : 0u;                                                                        \
+    }
+    VLB_SLAB8(0, 0, x) VLB_SLAB8(1, 0, y) VLB_SLAB8(2, 0, z) VLB_SLAB8(3, 0, w)
+    VLB_SLAB8(4, 1, x) VLB_SLAB8(5, 1, y) VLB_SLAB8(6, 1, z) VLB_SLAB8(7, 1, w)
+#undef VLB_SLAB8
+    // slot order -> priority order: bit p of the result = bit (p ^ flip) of m (an XOR on bit indices = three swap stages)
+    if (sx) m = ((m & 0x55u) << 1) | ((m >> 1) & 0x55u);
+    if (sy) m = ((m & 0x33u) << 2) | ((m >> 2) & 0x33u);
+    if (sz) m = ((m & 0x0fu) << 4) | ((m >> 4) & 0x0fu);
+    return stk.descend(b, cur, m, sx | (sy << 1) | (sz << 2));
+}
+#endif
+
+// The node step / the "what next" after a leaf of the configured tree width. Every traversal in the library goes
+// through these two (closest hit, any hit, the bake kernel's main rays and its visibility-ray batches).
+template <bool ORDERED, class STACK>
+VLB_HD int traverse_step(const BvhView& b, int cur, Vec3 idir, Vec3 ood, float tmin, float tcull, STACK& stk) {
+#if VLB_BVH8
+    return bvh8_step(b, cur, idir, ood, tmin, tcull, stk);
+#else
+    return bvh4_step<ORDERED>(b, cur, idir, ood, tmin, tcull, stk);
+#endif
+}
+template <class STACK>
+VLB_HD int traverse_pop(const BvhView& b, Vec3 idir, float tcull, STACK& stk) {
+#if VLB_BVH8
+    (void)tcull;
+    return stk.pop_group(b, (idir.x < 0.0f ? 1 : 0) | (idir.y < 0.0f ? 2 : 0) | (idir.z < 0.0f ? 4 : 0));
+#else
+    (void)b; (void)idir;
+    return stk.pop(tcull);
+#endif
+}
+
 // Intersects the triangles of leaf `ref` (< 0). Closest-hit rays update `best` and the culling
 // distance; any-hit rays return true at the first triangle inside (tmin, tcull).
 template <bool ANY, bool COUNT>
@@ -642,10 +862,10 @@ VLB_HD HitRec trace_closest(const BvhView& b, Vec3 o, Vec3 d, float tmin, float 
     while (cur != kNoChild) {
         if (cur >= 0) {
             if (COUNT) cnt->nodes++;
-            cur = bvh4_step<true>(b, cur, idir, ood, tmin, tcull, stk);
+            cur = traverse_step<true>(b, cur, idir, ood, tmin, tcull, stk);
         } else {
             leaf_step<false, COUNT>(b, cur, o, d, tmin, tcull, best, cnt);
-            cur = stk.pop(tcull);
+            cur = traverse_pop(b, idir, tcull, stk);
         }
     }
     return best;
@@ -665,13 +885,13 @@ VLB_HD bool trace_any(const BvhView& b, Vec3 o, Vec3 d, float tmin, float tmax, 
     while (cur != kNoChild) {
         if (cur >= 0) {
             if (COUNT) cnt->nodes++;
-            cur = bvh4_step<false>(b, cur, idir, ood, tmin, tcull, stk);
+            cur = traverse_step<false>(b, cur, idir, ood, tmin, tcull, stk);
         } else {
             if (leaf_step<true, COUNT>(b, cur, o, d, tmin, tcull, h, cnt)) {
                 if (out) *out = h;
                 return true;
             }
-            cur = stk.pop(tcull);
+            cur = traverse_pop(b, idir, tcull, stk);
         }
     }
     return false;
