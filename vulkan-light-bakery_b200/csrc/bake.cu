@@ -298,6 +298,39 @@ struct VisExchange {
     unsigned occluded[32];       // bit c: the ray from hit `lane` to corner c of its cell was blocked
 };
 
+// Entry points of the visibility rays (gather passes). A visibility ray runs from a hit inside grid cell (i, j, k) to
+// one of the cell's corners, so it stays inside the cell's box (grown by `margin` for the biased origin): the only
+// triangles it can meet are those reaching into that box. One thread per cell walks down from the root for as long as
+// exactly ONE child box overlaps the cell's box; the node it stops at has every such triangle below it, and the ray may
+// start there -- on a scene much larger than a cell that skips the upper half of every descent. out[cell]: a node
+// index, a leaf ref (< 0) or kNoChild when nothing reaches into the cell at all. fp32 4-wide nodes only.
+__global__ void k_cell_roots(BvhView b, const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz,
+                             int cx, int cy, int cz, float margin, int* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cx * cy * cz) return;
+    const int i = c % cx, j = (c / cx) % cy, k = c / (cx * cy);
+    const float lo[3] = {fminf(px[i], px[i + 1]) - margin, fminf(py[j], py[j + 1]) - margin, fminf(pz[k], pz[k + 1]) - margin};
+    const float hi[3] = {fmaxf(px[i], px[i + 1]) + margin, fmaxf(py[j], py[j + 1]) + margin, fmaxf(pz[k], pz[k + 1]) + margin};
+    int cur = b.n_tris ? 0 : kNoChild;
+#if !VLB_NODE_Q8 && !VLB_BVH8
+    while (cur >= 0) {
+        const float4* q = b.nodes + (size_t)kNodeQuads * cur;
+        const float4 lx = ld4(q), hx = ld4(q + 1), ly = ld4(q + 2), hy = ld4(q + 3), lz = ld4(q + 4), hz = ld4(q + 5), rf = ld4(q + 6);
+        const float clx[4] = {lx.x, lx.y, lx.z, lx.w}, chx[4] = {hx.x, hx.y, hx.z, hx.w}, cly[4] = {ly.x, ly.y, ly.z, ly.w},
+                    chy[4] = {hy.x, hy.y, hy.z, hy.w}, clz[4] = {lz.x, lz.y, lz.z, lz.w}, chz[4] = {hz.x, hz.y, hz.z, hz.w};
+        const int ref[4] = {f2i(rf.x), f2i(rf.y), f2i(rf.z), f2i(rf.w)};
+        int n_over = 0, only = kNoChild;
+        for (int s = 0; s < 4; ++s) {      // empty slots have (+inf, -inf) boxes and never overlap
+            if (clx[s] <= hi[0] && chx[s] >= lo[0] && cly[s] <= hi[1] && chy[s] >= lo[1] && clz[s] <= hi[2] && chz[s] >= lo[2]) { ++n_over; only = ref[s]; }
+        }
+        if (n_over == 0) { cur = kNoChild; break; }
+        if (n_over > 1) break;
+        cur = only;
+    }
+#endif
+    out[c] = cur;
+}
+
 // The 8 visibility rays of each of the (up to 32) hits a warp shades together (shaders/main.rchit:143-163), traced as
 // ONE batch by the whole warp: ray r = (hit r / 8, corner r % 8) goes to whichever lane is idle, lanes step through the
 // tree in the same while-while loop as the main rays and refill as they finish, so the warp stays full although the
@@ -327,7 +360,18 @@ __device__ __forceinline__ void trace_vis_batch(const BvhView& bvh, const Gather
                     idir = mk3(safe_inv(rd.x), safe_inv(rd.y), safe_inv(rd.z));
                     ood = mk3(ro.x * idir.x, ro.y * idir.y, ro.z * idir.z);
                     tcull = tmax; tag = (h << 3) | c;
-                    stk.clear(); cur = 0; busy = true;
+                    stk.clear(); cur = 0;
+                    if (g.cell_root) {
+                        // start below the root when the ray lies inside its cell's (grown) box: origin inside, target = a corner
+                        const int ci = X.cell[0][h], cj = X.cell[1][h], ck = X.cell[2][h];
+                        const float m = g.cell_margin;
+                        const bool inside = g.Nx > 1 && g.Ny > 1 && g.Nz > 1 &&
+                            ro.x >= fminf(g.px[ci], g.px[ci + 1]) - m && ro.x <= fmaxf(g.px[ci], g.px[ci + 1]) + m &&
+                            ro.y >= fminf(g.py[cj], g.py[cj + 1]) - m && ro.y <= fmaxf(g.py[cj], g.py[cj + 1]) + m &&
+                            ro.z >= fminf(g.pz[ck], g.pz[ck + 1]) - m && ro.z <= fmaxf(g.pz[ck], g.pz[ck + 1]) + m;
+                        if (inside) cur = __ldg(g.cell_root + ci + (g.Nx - 1) * (cj + (g.Ny - 1) * ck));
+                    }
+                    busy = cur != kRayDone;          // kNoChild: nothing reaches into the cell, the corner is visible
                 }
             }
             next = min(n_rays, next + __popc(idle));
@@ -825,6 +869,16 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
 
     VLB_CUDA(ctx, ctx->d_stream_scratch.reserve((size_t)grid * kStreamWarps * sizeof(WarpQueues)));
     p.stream_scratch = ctx->d_stream_scratch.as<WarpQueues>();
+    if (gather && Nx > 1 && Ny > 1 && Nz > 1 && env_flag("VLB_BAKE_CELL_ROOTS", 1)) {
+        const int cx = Nx - 1, cy = Ny - 1, cz = Nz - 1;
+        VLB_CUDA(ctx, ctx->d_cell_root.reserve((size_t)cx * cy * cz * sizeof(int)));
+        // the biased ray origin lies within shadow_bias of the hit; a little more for rounding
+        const float ext = std::max({fabsf(s->step[0]) * Nx, fabsf(s->step[1]) * Ny, fabsf(s->step[2]) * Nz});
+        p.g.cell_margin = fabsf(s->shadow_bias) * 1.5f + 1e-5f * ext;
+        k_cell_roots<<<(unsigned)((cx * cy * cz + 127) / 128), 128, 0, st>>>(p.bvh, p.px, p.py, p.pz, cx, cy, cz, p.g.cell_margin, ctx->d_cell_root.as<int>());
+        VLB_LAUNCH_CHECK(ctx);
+        p.g.cell_root = ctx->d_cell_root.as<int>();
+    }
     if (gather) {
         VLB_CUDA(ctx, ctx->d_vis_ovf.reserve((size_t)grid * kStreamWarps * kOvfStack * kStackWords * 32 * sizeof(int)));
         p.vis_ovf = ctx->d_vis_ovf.as<int>();

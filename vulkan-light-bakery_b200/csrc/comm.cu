@@ -198,11 +198,18 @@ int vlb_comm_init_all(vlb_ctx* const* ctxs, uint32_t n) {
     VLB_NCCL(c0, a.GetUniqueId(&uid));
     std::vector<ncclComm_t> comms(n, nullptr);
     VLB_NCCL(c0, a.GroupStart());
-    for (uint32_t r = 0; r < n; ++r) {
-        VLB_CUDA(c0, cudaSetDevice(ctxs[r]->device));
-        VLB_NCCL(c0, a.CommInitRank(&comms[r], (int)n, uid, (int)r));
+    ncclResult_t first_bad = ncclSuccess;
+    cudaError_t dev_bad = cudaSuccess;
+    for (uint32_t r = 0; r < n && first_bad == ncclSuccess && dev_bad == cudaSuccess; ++r) {
+        dev_bad = cudaSetDevice(ctxs[r]->device);
+        if (dev_bad == cudaSuccess) first_bad = a.CommInitRank(&comms[r], (int)n, uid, (int)r);
     }
-    VLB_NCCL(c0, a.GroupEnd());
+    const ncclResult_t end = a.GroupEnd();       // always closed, also after a failed rank, so no group is left open
+    if (dev_bad != cudaSuccess) return c0->fail(VLB_ERR_CUDA, "vlb_comm_init_all: cudaSetDevice -> %s", cudaGetErrorString(dev_bad));
+    if (first_bad != ncclSuccess || end != ncclSuccess) {
+        for (uint32_t r = 0; r < n; ++r) if (comms[r]) a.CommDestroy(comms[r]);
+        return c0->fail(VLB_ERR_CUDA, "vlb_comm_init_all: NCCL: %s", a.GetErrorString(first_bad != ncclSuccess ? first_bad : end));
+    }
     for (uint32_t r = 0; r < n; ++r) { ctxs[r]->comm = comms[r]; ctxs[r]->comm_rank = (int)r; ctxs[r]->comm_world = (int)n; }
     return VLB_OK;
 }

@@ -127,7 +127,7 @@ void vlb_ctx_destroy(vlb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     comm_destroy(ctx);
-    DevBuf* bufs[] = {&ctx->d_share, &ctx->d_gather_stage, &ctx->d_vis_ovf, &ctx->d_verts, &ctx->d_indices, &ctx->d_insts_in, &ctx->d_tri_offsets, &ctx->d_tri_flat,
+    DevBuf* bufs[] = {&ctx->d_share, &ctx->d_gather_stage, &ctx->d_vis_ovf, &ctx->d_cell_root, &ctx->d_verts, &ctx->d_indices, &ctx->d_insts_in, &ctx->d_tri_offsets, &ctx->d_tri_flat,
                       &ctx->d_frontier[0], &ctx->d_frontier[1], &ctx->d_frontier_n, &ctx->d_tri_shade, &ctx->d_tri_uv, &ctx->d_tex_desc, &ctx->d_tex_texels, &ctx->d_inst, &ctx->d_base_color, &ctx->d_tris, &ctx->d_nodes, &ctx->d_keys,
                       &ctx->d_keys_sorted, &ctx->d_vals, &ctx->d_vals_sorted, &ctx->d_sort_tmp, &ctx->d_left,
                       &ctx->d_right, &ctx->d_first, &ctx->d_last, &ctx->d_parent_i, &ctx->d_parent_l, &ctx->d_flags,

@@ -12,7 +12,9 @@
 
 #include "../../include/vlb_bake.h"
 
+#ifndef VLB_MAX_LANES
 #define VLB_MAX_LANES 4
+#endif
 
 namespace vlb {
 
@@ -103,7 +105,7 @@ struct vlb_ctx {
     std::vector<ProjGraph> proj_graphs;
     cudaStream_t cap_stream = nullptr;
     // ---- bake ----
-    vlb::DevBuf d_bake_out, d_bake_prev, d_partials, d_work_counter, d_axis, d_row_sc, d_col_sc, d_stats, d_stream_scratch, d_vis_ovf;
+    vlb::DevBuf d_bake_out, d_bake_prev, d_partials, d_work_counter, d_axis, d_row_sc, d_col_sc, d_stats, d_stream_scratch, d_vis_ovf, d_cell_root;
     int dir_w = 0, dir_h = 0;
     vlb_bake_stats last_bake{};
     bool bake_pending = false;             // a device bake was enqueued and its statistics not yet collected

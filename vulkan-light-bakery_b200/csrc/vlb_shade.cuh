@@ -155,6 +155,11 @@ struct GatherView {
     float origin[3], step[3];
     float gain;
     int world_frame;
+    // bake kernel only: per grid cell, the node (or leaf ref, or kNoChild) below which every triangle that reaches into
+    // the cell lies (k_cell_roots, bake.cu); visibility rays of hits inside the cell start there instead of at the root.
+    // NULL: start at the root.
+    const int* cell_root;
+    float cell_margin;
 };
 
 // TEX = false compiles the texture branch out: the bake kernel is instantiated both ways and scenes without
