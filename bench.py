@@ -171,6 +171,12 @@ def measure_bake(torch, dist, par, ctx, scene, sky, s, rank, world, dev, stream,
     C++ host takes); gather="torch": the bake through the ABI, the all-gather through torch.distributed (parallel.py)."""
     mine = par.shard_settings(s, rank, world, cyclic=True)
     n_local = mine.n_slab_probes
+    # the hierarchy builder the library recommends for this rank's share of the job (vlb_bvh_recommend_builder: PLOC when
+    # the trace is long enough to pay for its build, else the LBVH); the e2e steps below rebuild with the same choice
+    vlbm = importlib.import_module("vulkan-light-bakery_b200")
+    builder = vlbm.recommend_builder(N_TRIS, n_local * s.dir_w * s.dir_h)
+    ctx.set_bvh_builder(builder)
+    ctx.build_bvh()
     out = torch.zeros((max(n_local, 1), 48), dtype=torch.float32, device=dev)
     full = torch.zeros((s.n_probes, 48), dtype=torch.float32, device=dev)
 
@@ -219,17 +225,36 @@ def measure_bake(torch, dist, par, ctx, scene, sky, s, rank, world, dev, stream,
     small = pins["instances"][0].nbytes + pins["materials"][0].nbytes
     sharded_up = gather == "abi" and world > 1
     h2d = (big // world if sharded_up else big) + small          # this rank's bytes over PCIe per step
-    full_host = torch.empty((s.n_probes, 48), dtype=torch.float32, pin_memory=True) if rank == 0 else None
+    # Result read-back. One GPU: the grid to pinned host memory. N ranks with the library's communicator: ONE host grid in
+    # shared memory (/dev/shm, pinned by every process with cudaHostRegister) that every rank fills with the slices it baked
+    # (vlb_bake_probes_sharded_rows): 1/N of the grid per PCIe link instead of rank 0 reading all of it.
+    shared_grid = None
+    full_host = None
     if sharded_up:
+        nbytes = s.n_probes * 48 * 4
+        path = "/dev/shm/vlb_bench_grid_%s" % os.environ.get("MASTER_PORT", "0")
+        if rank == 0:
+            with open(path, "wb") as f:
+                f.truncate(nbytes)
+        dist.barrier()
+        shared_grid = torch.from_file(path, shared=True, size=s.n_probes * 48, dtype=torch.float32)
+        rc = torch.cuda.cudart().cudaHostRegister(shared_grid.data_ptr(), nbytes, 0)
+        if int(rc) != 0:
+            raise RuntimeError("cudaHostRegister of the shared host grid failed: %s" % rc)
         ctx.comm_sharded_uploads(True)
+    elif rank == 0:
+        full_host = torch.empty((s.n_probes, 48), dtype=torch.float32, pin_memory=True)
 
     def step_e2e():
         ctx.set_skybox_async(psky)          # H2D on the ctx's copy stream, overlapping the two calls below
         ctx.set_scene(pscene)
         ctx.build_bvh()
-        g = bake_and_gather()
-        if full_host is not None:
-            full_host.copy_(g, non_blocking=True)
+        if shared_grid is not None:
+            ctx.bake_probes_sharded_rows(s, shared_grid.data_ptr())      # bake + all-gather + this rank's rows to the host grid
+        else:
+            g = bake_and_gather()
+            if full_host is not None:
+                full_host.copy_(g, non_blocking=True)
         torch.cuda.synchronize()
 
     for _ in range(2):
@@ -241,12 +266,22 @@ def measure_bake(torch, dist, par, ctx, scene, sky, s, rank, world, dev, stream,
         step_e2e()
     e1.record(stream)
     barrier()
+    e2e_ok = True
     if sharded_up:
         ctx.comm_sharded_uploads(False)
+        # the shared host grid must be the device grid of the resident run, bit for bit (every rank checks all of it)
+        ctx.bake_probes_sharded_device(s, 0, full.data_ptr())
+        torch.cuda.synchronize()
+        dist.barrier()
+        e2e_ok = bool(torch.equal(shared_grid, full.cpu()))
+        torch.cuda.cudart().cudaHostUnregister(shared_grid.data_ptr())
+        dist.barrier()
+        if rank == 0:
+            os.unlink(path)
+    d2h = n_local * 48 * 4 if sharded_up else (int(full_host.numel() * 4) if full_host is not None else 0)
     return {"t_ms": t_ms, "e2e_ms": e0.elapsed_time(e1) / e2e_steps, "kern_ms": float(np.mean(kernel_ms)),
-            "shadow": int(shadow), "launches": int(launches), "h2d": int(h2d),
-            "d2h": int(full_host.numel() * 4) if full_host is not None else 0,
-            "mine": mine, "out": out}
+            "shadow": int(shadow), "launches": int(launches), "h2d": int(h2d), "d2h": int(d2h),
+            "mine": mine, "out": out, "builder": builder, "e2e_ok": e2e_ok}
 
 
 def run_ours(args):
@@ -349,8 +384,15 @@ def run_ours(args):
         extra["roofline"] = roofline
         extra["skybox"] = bench_skybox(torch, ctx, scenes, dev, stream, peak, peak_src)
         extra["cpu_baseline"] = cpu_baseline(scene, sky, settings_for(scenes, which, 1), which)
-        extra["bvh"] = {"build_ms": bvh.build_ms, "first_build_ms": bvh_first.build_ms, "sort_ms": bvh.sort_ms, "nodes": int(bvh.n_nodes),
-                        "mtris_per_s": N_TRIS / (bvh.build_ms * 1e-3) / 1e6}
+        builds = {}
+        for bname in ("lbvh", "ploc"):                 # steady-state build of both hierarchy builders (what an e2e step pays)
+            ctx.set_bvh_builder(bname)
+            ctx.build_bvh()
+            bs = ctx.build_bvh()
+            builds[bname] = {"build_ms": bs.build_ms, "sort_ms": bs.sort_ms, "nodes": int(bs.n_nodes), "mtris_per_s": N_TRIS / (bs.build_ms * 1e-3) / 1e6}
+        ctx.set_bvh_builder(m["builder"])
+        ctx.build_bvh()
+        extra["bvh"] = {"used": m["builder"], "first_build_ms": bvh_first.build_ms, **builds}
         if world == 1 and which == "c3" and not args.quick:
             # the other named configs, beside the headline: C5 (batched skybox sweep) and C4 (3 M triangles, 3 gather passes)
             try:
@@ -382,9 +424,12 @@ def run_ours(args):
                         "d2h_bytes_per_step": d2h_total, "ms_per_step": e2e_ms,
                         "includes": "scene upload + LBVH build + skybox upload + bake + all-gather + coefficient read-back; "
                                     "bytes are summed over the ranks: with the library's communicator every rank copies 1/N of "
-                                    "the vertex/index/skybox arrays over PCIe (NVLink all-gather replicates them) and rank 0 "
-                                    "reads the gathered grid back once"},
+                                    "the vertex/index/skybox arrays over PCIe (NVLink all-gather replicates them) and copies the "
+                                    "slices it baked into ONE host grid in shared memory (vlb_bake_probes_sharded_rows); the host grid "
+                                    "is checked bit for bit against the device grid after the timed steps",
+                        "host_grid_equals_device_grid": bool(m["e2e_ok"])},
                 "gpu_launches": launches_total,
+                "bvh_builder": m["builder"] + " (vlb_bvh_recommend_builder for %d triangles x %d primary rays per GPU)" % (N_TRIS, rays_total // world),
                 "gather": ("vlb_bake_probes_sharded_device: ncclAllGather + k_uninterleave inside libvlb_bake.so" if gather == "abi"
                            else "torch.distributed all_gather_into_tensor (parallel.py)") if world > 1 else "none (1 GPU)",
                 "probes_per_s": s.n_probes / (ms_per_step * 1e-3),

@@ -231,6 +231,18 @@ int vlb_gltf_texture(const char* gltf_path, uint32_t index, void* texels, uint64
 int vlb_scene_bounds(vlb_ctx* ctx, int tight, float out_min_max[6]);
 /* Scene_t::buildAccelerationStructures (src/scene_manager.cpp:385-443) -> software LBVH. */
 int vlb_bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats_or_null);
+/* The build preference the reference passes to its driver (VK_BUILD_ACCELERATION_STRUCTURE_PREFER_FAST_TRACE_BIT,
+ * src/scene_manager.cpp:346-347): which builder makes the binary hierarchy under the wide nodes. LBVH (default):
+ * Karras 2012, fastest build. PLOC: agglomerative clustering within `ploc_radius` (1..64, 0 = keep / default 16) places
+ * of the Morton order, a few per cent fewer node visits per ray on irregular scenes for about twice the build time.
+ * Results never depend on the builder (hit ids are bit-exact with any tree). Takes effect at the next vlb_bvh_build. */
+enum { VLB_BVH_BUILDER_LBVH = 0, VLB_BVH_BUILDER_PLOC = 1 };
+int vlb_bvh_set_builder(vlb_ctx* ctx, int builder, int ploc_radius);
+/* Host-only: the builder that minimises build + trace time for a bake of n_primary_rays rays (on this GPU / rank) through
+ * a scene of n_triangles, from the measured costs on B200 (PLOC: +2.5 ns per triangle of build time, -4 % of trace time at
+ * ~0.3 ns per primary ray; no gain beyond ~1 M triangles on the scenes measured): PLOC when the trace is long enough to
+ * pay for it. The caller knows the probe grid before it builds, as the reference knows its build flags. */
+int vlb_bvh_recommend_builder(uint64_t n_triangles, uint64_t n_primary_rays);
 
 /* --- skybox (replaces Skybox_t) ---------------------------------------------------------- */
 /* Host-only: decode an image file into RGBA8 texels, as the reference's stbi_load(file, &w, &h, &ch, STBI_rgb_alpha)
@@ -325,6 +337,12 @@ int vlb_bake_probes_sharded_device(vlb_ctx* ctx, const vlb_bake_settings* s, con
 /* Host-pointer variant: 1 + s->bounces passes on the devices with the all-gather between passes; the last pass is
  * copied to `out` (Nx*Ny*Nz x 48 floats) on the ranks that pass a non-NULL pointer. Synchronous. */
 int vlb_bake_probes_sharded(vlb_ctx* ctx, const vlb_bake_settings* s, float* out_or_null);
+/* The same, but this rank copies only the z-slices IT baked into `grid` (the whole grid's layout, Nx*Ny*Nz x 48 floats):
+ * the ranks of one host all pass the SAME buffer -- shared memory between processes (pin it with cudaHostRegister), the
+ * same pointer between the contexts of one process -- and fill it together, every rank over its own PCIe link (1/N of
+ * the grid each, instead of one rank reading all of it). The grid is complete once every rank has returned. The device
+ * side is unchanged: the all-gather still leaves the whole grid on every GPU (the multi-bounce passes read it). */
+int vlb_bake_probes_sharded_rows(vlb_ctx* ctx, const vlb_bake_settings* s, float* grid);
 
 /* Device-resident output; enqueues on the ctx stream and returns WITHOUT synchronising. */
 int vlb_bake_probes_device(vlb_ctx* ctx, const vlb_bake_settings* s, float* d_out);

@@ -20,7 +20,7 @@ def build(force=False, so=None, defines=()):
     srcs = [os.path.join(_HERE, "emu_driver.cpp"),
             os.path.join(_ROOT, "vulkan-light-bakery_b200", "csrc", "host_tables.cpp")]
     csrc = os.path.join(_ROOT, "vulkan-light-bakery_b200", "csrc")
-    deps = srcs + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))] + [os.path.join(_HERE, "vlb_ploc.cuh")]
+    deps = srcs + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".h"))]
     if not force and os.path.exists(so) and all(os.path.getmtime(d) <= os.path.getmtime(so) for d in deps):
         return so
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")

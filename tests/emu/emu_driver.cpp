@@ -13,7 +13,7 @@
 
 #include "../../vulkan-light-bakery_b200/csrc/vlb_context.h"
 #include "../../vulkan-light-bakery_b200/csrc/vlb_shade.cuh"
-#include "vlb_ploc.cuh"
+#include "../../vulkan-light-bakery_b200/csrc/vlb_ploc.cuh"
 
 using namespace vlb;
 

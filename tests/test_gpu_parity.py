@@ -406,6 +406,71 @@ def test_bake_cube_reference_defaults_scaled(ctx, vlb, oa, scenes):
         assert rel_l2(got, osc.bake_probes(s)[0]) <= PROBE_TOL
 
 
+def test_scene_with_an_index_past_its_vertex_range_is_refused(vlb, scenes):
+    """Index validation and the per-instance bounds run on the device (k_instance_checks): a bad index fails the call with
+    VLB_ERR_INVALID (never reads outside the vertex array), the context stays usable, and the reference-mode bounds of a
+    good scene are the ones the host loop used to compute."""
+    good = scenes.small_room()
+    with vlb.Context(0) as c:
+        bad = {k: np.array(v, copy=True) for k, v in good.items() if k in ("vertices", "indices", "instances", "materials")}
+        inst = bad["instances"][0]
+        bad["indices"][int(inst["first_index"]) + 1] = int(inst["vertex_count"]) + 7
+        with pytest.raises(vlb.VlbError) as e:
+            c.set_scene(bad)
+        assert e.value.code == vlb.ERR_INVALID and "index out of range" in str(e.value)
+        with pytest.raises(vlb.VlbError):
+            c.build_bvh()                                   # no scene is set after the failure
+        c.set_scene(good)
+        c.build_bvh()
+        ref = c.scene_bounds(tight=False)
+        # host restatement of Scene_t::loadNode's bounds (scene_manager.cpp:497-507)
+        lo, hi = np.zeros(3), np.zeros(3)
+        for it in good["instances"]:
+            v = good["vertices"]["position"][int(it["first_vertex"]): int(it["first_vertex"]) + int(it["vertex_count"]), :3]
+            m = np.asarray(it["transform"], np.float32).reshape(3, 4)
+            a = m[:, :3] @ v.min(0) + m[:, 3]; b = m[:, :3] @ v.max(0) + m[:, 3]
+            lo = np.minimum(lo, a); hi = np.maximum(hi, b)
+        assert np.allclose(ref[:3], lo, atol=1e-5) and np.allclose(ref[3:], hi, atol=1e-5)
+
+
+@pytest.mark.parametrize("radius", [4, 16, 64])
+def test_ploc_builder_same_hits_same_bake_same_tree_as_host_twin(vlb, scenes, radius):
+    """vlb_bvh_set_builder(PLOC): the agglomerative builder (csrc/vlb_ploc.cuh, all rounds in one cooperative kernel) gives
+    another tree, never another result: hit ids / (t, u, v) identical to the LBVH and to brute force, the bake bitwise
+    identical; and the tree is the one the serial host twin of the same code builds (tests/emu), wide node for wide node."""
+    import emu_api
+    sc = scenes.atrium(20000, seed=3)
+    sky = scenes.hdr_sky(64, 32, seed=2)
+    rng = np.random.default_rng(11)
+    n = 20000
+    o = (rng.uniform(0.03, 0.97, (n, 3)) * np.array(scenes.HALL)).astype(np.float32)
+    d = rng.normal(size=(n, 3)); d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    s = scenes.atrium_settings(probes=(5, 3, 4), dirs=(32, 32), order=3, bounds=(0, 0, 0) + tuple(scenes.HALL))
+    with vlb.Context(0) as c:
+        c.set_scene(sc); c.set_skybox(sky)
+        lb = c.build_bvh()
+        ids0, tuv0 = c.trace_rays(o, d)
+        any0, _ = c.trace_rays(o, d, tmin=0.0, tmax=4.0, kind=vlb.TRACE_ANY)
+        bake0 = c.bake_probes(s)
+        c.set_bvh_builder("ploc", radius)
+        pl = c.build_bvh()
+        ids1, tuv1 = c.trace_rays(o, d)
+        idsb, tuvb = c.trace_rays(o, d, accel=vlb.TRACE_BRUTE_FORCE)
+        any1, _ = c.trace_rays(o, d, tmin=0.0, tmax=4.0, kind=vlb.TRACE_ANY)
+        assert (ids0 >= 0).mean() > 0.5
+        assert np.array_equal(ids1, ids0) and np.array_equal(tuv1, tuv0)
+        assert np.array_equal(ids1, idsb) and np.array_equal(tuv1, tuvb)
+        assert np.array_equal(any1 >= 0, any0 >= 0)
+        assert np.array_equal(c.bake_probes(s), bake0)
+        assert pl.n_triangles == lb.n_triangles and pl.n_nodes != lb.n_nodes
+        twin = emu_api.Scene(sc, max_leaf=int(pl.max_leaf_size), builder="ploc", ploc_radius=radius)
+        assert int(twin.node_stats()[0]) == int(pl.n_nodes)
+        c.set_bvh_builder("lbvh")
+        assert c.build_bvh().n_nodes == lb.n_nodes
+        with pytest.raises(vlb.VlbError):
+            c.set_bvh_builder("ploc", 65)
+
+
 def test_bake_probes_multi_one_process_several_contexts(vlb, scenes, room):
     """vlb_bake_probes_multi: one host process, n contexts (here all on device 0, which exercises the same threads,
     cyclic shares and strided copies as n GPUs) == one context, bit for bit; with and without gather passes."""

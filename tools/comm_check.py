@@ -37,6 +37,13 @@ for probes, bounces in (((8, 4, 8), 0), ((8, 4, 7), 0), ((6, 4, 5), 2), ((4, 4, 
         full = torch.zeros((s.n_probes, 48), device=dev)
         ctx.bake_probes_sharded_device(s, 0, full.data_ptr()); ctx.synchronize()
         same = same and np.array_equal(full.cpu().numpy().reshape(-1, 16, 3), want)
+    # own rows only: this rank's z-slices land in its rows of a host grid, the other rows are left alone
+    grid = np.full((s.n_probes, 16, 3), -7.0, np.float32)
+    ctx.bake_probes_sharded_rows(s, grid.ctypes.data)
+    nxy = probes[0] * probes[1]
+    g4 = grid.reshape(probes[2], nxy, 16, 3); w4 = want.reshape(probes[2], nxy, 16, 3)
+    mine = np.zeros(probes[2], bool); mine[rank::world] = True
+    same = same and np.array_equal(g4[mine], w4[mine]) and bool(np.all(g4[~mine] == -7.0))
     ok = ok and same
     print("rank %d/%d probes %s bounces %d: sharded == single-GPU bitwise: %s" % (rank, world, probes, bounces, same), flush=True)
 ctx.close()

@@ -128,13 +128,13 @@ class VlbError(RuntimeError):
 # every symbol include/vlb_bake.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "vlb_abi_version", "vlb_ctx_create", "vlb_ctx_destroy", "vlb_ctx_set_stream", "vlb_ctx_stream", "vlb_ctx_synchronize",
-    "vlb_last_error", "vlb_ctx_launch_count", "vlb_scene_set_triangles", "vlb_scene_load_gltf", "vlb_gltf_probe", "vlb_scene_bounds", "vlb_bvh_build",
+    "vlb_last_error", "vlb_ctx_launch_count", "vlb_scene_set_triangles", "vlb_scene_load_gltf", "vlb_gltf_probe", "vlb_scene_bounds", "vlb_bvh_build", "vlb_bvh_set_builder", "vlb_bvh_recommend_builder",
     "vlb_scene_set_textures", "vlb_gltf_texture", "vlb_image_load_rgba8", "vlb_image_load_rgba32f", "vlb_bake_probes_multi", "vlb_skybox_set", "vlb_skybox_set_async", "vlb_skybox_project_sh", "vlb_skybox_project_sh_batched", "vlb_skybox_project_sh_device",
     "vlb_skybox_project_sh_device_ptrs", "vlb_envmap_project_sh", "vlb_bake_settings_default", "vlb_bake_settings_from_bounds", "vlb_probe_positions",
     "vlb_bake_probes", "vlb_bake_probes_device", "vlb_bake_gather_device", "vlb_bake_last_stats", "vlb_trace_rays",
     "vlb_bake_serialize_gltf", "vlb_bake_deserialize_gltf",
     "vlb_comm_get_unique_id", "vlb_comm_init_rank", "vlb_comm_init_all", "vlb_comm_destroy", "vlb_comm_info",
-    "vlb_comm_sharded_uploads", "vlb_bake_probes_sharded_device", "vlb_bake_probes_sharded",
+    "vlb_comm_sharded_uploads", "vlb_bake_probes_sharded_device", "vlb_bake_probes_sharded", "vlb_bake_probes_sharded_rows",
 ]
 
 _lib = None
@@ -165,6 +165,8 @@ def load_library():
         "vlb_gltf_probe": (i32, [ctypes.c_char_p, vp, vp]),
         "vlb_scene_bounds": (i32, [vp, i32, vp]),
         "vlb_bvh_build": (i32, [vp, ctypes.POINTER(BvhStats)]),
+        "vlb_bvh_set_builder": (i32, [vp, i32, i32]),
+        "vlb_bvh_recommend_builder": (i32, [u64, u64]),
         "vlb_scene_set_textures": (i32, [vp, vp, u32]),
         "vlb_gltf_texture": (i32, [ctypes.c_char_p, u32, vp, u64, vp]),
         "vlb_image_load_rgba8": (i32, [ctypes.c_char_p, vp, u64, vp]),
@@ -195,6 +197,7 @@ def load_library():
         "vlb_comm_sharded_uploads": (i32, [vp, i32]),
         "vlb_bake_probes_sharded_device": (i32, [vp, S, vp, vp]),
         "vlb_bake_probes_sharded": (i32, [vp, S, vp]),
+        "vlb_bake_probes_sharded_rows": (i32, [vp, S, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -307,6 +310,10 @@ class Context:
         self._check(self._lib.vlb_scene_bounds(self._h, int(bool(tight)), _ptr(out)))
         return out
 
+    def set_bvh_builder(self, builder="lbvh", ploc_radius=0):
+        """vlb_bvh_set_builder: "lbvh" (Karras, default) or "ploc" (agglomerative, radius 1..64, 0 = default 16)."""
+        self._check(self._lib.vlb_bvh_set_builder(self._h, {"lbvh": 0, "ploc": 1}[builder], int(ploc_radius)))
+
     def build_bvh(self):
         st = BvhStats()
         self._check(self._lib.vlb_bvh_build(self._h, ctypes.byref(st)))
@@ -409,6 +416,11 @@ class Context:
         self._check(self._lib.vlb_bake_probes_sharded(self._h, ctypes.byref(s), _ptr(out)))
         return out
 
+    def bake_probes_sharded_rows(self, s, host_grid_ptr):
+        """vlb_bake_probes_sharded_rows: this rank's z-slices land in the host grid at `host_grid_ptr` (address of a
+        [n_probes, 48] float32 buffer every rank of the host shares); synchronous."""
+        self._check(self._lib.vlb_bake_probes_sharded_rows(self._h, ctypes.byref(s), int(host_grid_ptr)))
+
     # -- validation
     def trace_rays(self, origins, dirs, tmin=0.001, tmax=10000.0, accel=TRACE_BVH, kind=TRACE_CLOSEST):
         o = np.ascontiguousarray(origins, np.float32).reshape(-1, 3)
@@ -433,6 +445,11 @@ def gltf_probe(path):
 
 
 COMM_ID_BYTES = 128
+
+
+def recommend_builder(n_triangles, n_primary_rays):
+    """vlb_bvh_recommend_builder: "lbvh" or "ploc" for a bake of that many primary rays (per GPU) through that many triangles."""
+    return ("lbvh", "ploc")[load_library().vlb_bvh_recommend_builder(int(n_triangles), int(n_primary_rays))]
 
 
 def comm_unique_id():

@@ -9,8 +9,12 @@
 //   k_refit          bottom-up AABB refit, atomic arrival flags
 //   k_emit_levels    4-wide traversal nodes (vlb_bvh.cuh), top-down in one cooperative launch: children chosen greedily by
 //                    surface area, small subtrees -> leaves
+// Optional second builder for the binary hierarchy (vlb_bvh_set_builder / VLB_BVH_BUILDER=ploc; replaces k_karras + k_refit):
+//   k_ploc_rounds    PLOC agglomeration (vlb_ploc.cuh), all rounds in one cooperative launch
+//   k_ploc_leaf_pos, k_ploc_permute, k_ploc_finish   depth-first leaf order, triangles moved into it, arrays for k_emit_levels
 
 #include "vlb_bvh.cuh"
+#include "vlb_ploc.cuh"
 #include <cooperative_groups.h>
 
 #include "radix_sort.cuh"
@@ -153,6 +157,228 @@ __global__ void __launch_bounds__(256) k_emit_levels(int* __restrict__ frontier_
     if (gtid == 0) *n_emitted = total;
 }
 
+// ---- PLOC (vlb_ploc.cuh) -------------------------------------------------------------------------------------
+__global__ void k_ploc_init(int n, int* __restrict__ C, int* __restrict__ leftmost, int* __restrict__ count, int* __restrict__ parent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2 * n - 1) { parent[i] = -1; count[i] = 1; leftmost[i] = i; }
+    if (i < n) C[i] = i;
+}
+
+constexpr int kPlocTail = 1024;     // cluster count below which one block finishes the agglomeration alone
+constexpr int kPlocMaxRadius = 64;
+
+// ploc_nearest for the 256 positions [t0, t0 + 256) of the current order, through shared memory: the boxes of positions
+// [t0 - radius, t0 + 256 + radius) are staged once (one coalesced read of the order + one gather of the boxes, instead of
+// 2 * radius dependent trips to L2 per thread), then every thread scans its window there. Same candidates, same
+// arithmetic, same tie-break as ploc_nearest. All threads of the block must call it.
+__device__ __forceinline__ void ploc_nearest_tile(const int* cur, int m, int t0, int radius, const float4* box, int* nn,
+                                                  float4* s_lo, float4* s_hi) {
+    const int tid = threadIdx.x, first = t0 - radius, span = (int)blockDim.x + 2 * radius;
+    for (int k = tid; k < span; k += blockDim.x) {
+        const int j = first + k;
+        if (j >= 0 && j < m) {
+            const int cj = ld_cg(cur + j);
+            s_lo[k] = ld_cg4(box + 2 * (size_t)cj); s_hi[k] = ld_cg4(box + 2 * (size_t)cj + 1);
+        }
+    }
+    __syncthreads();
+    const int i = t0 + tid;
+    if (i < m) {
+        const float4 lo = s_lo[tid + radius], hi = s_hi[tid + radius];
+        const int j0 = i - radius < 0 ? 0 : i - radius, j1 = i + radius > m - 1 ? m - 1 : i + radius;
+        int best = -1;
+        float best_cost = INFINITY;
+        for (int j = j0; j <= j1; ++j) {
+            if (j == i) continue;
+            const float c = merged_half_area(lo, hi, s_lo[j - first], s_hi[j - first]);
+            if (c < best_cost) { best_cost = c; best = j; }
+        }
+        nn[i] = best;
+    }
+    __syncthreads();
+}
+
+// All rounds of the agglomeration in one cooperative launch. A round: (1) every cluster picks its nearest neighbour
+// within `radius` places of the current order; (2) every block counts, over its contiguous chunk of the order, the
+// clusters that stay or create a node and the nodes created; (3) with the block totals every block knows where its
+// chunk lands in the next order and which creation indices it hands out, and an ordered block scan places each
+// cluster. Output position and creation index of a cluster are "how many before it", exactly the serial loop of
+// tests/emu, so the tree is the same whatever the grid size.
+__global__ void __launch_bounds__(256) k_ploc_rounds(int n, int radius, int* C, int* Cn, int* nn, float4* box, int* left, int* right,
+                                                     int* parent, int* count, int* leftmost, int2* block_tot) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ int s_w[4][8];
+    __shared__ float4 s_lo[256 + 2 * kPlocMaxRadius], s_hi[256 + 2 * kPlocMaxRadius];
+    const int nb = gridDim.x, b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    int m = n, created = 0;
+    int* cur = C; int* nxt = Cn;
+    while (m > 1) {
+        if (m <= kPlocTail) {
+            // The last rounds (about half of them) involve a few hundred clusters: block 0 finishes them alone, with block
+            // barriers instead of grid-wide ones (a grid.sync costs microseconds, these rounds nothing).
+            if (b != 0) return;
+            while (m > 1) {
+                for (int t0 = 0; t0 < m; t0 += blockDim.x) ploc_nearest_tile(cur, m, t0, radius, box, nn, s_lo, s_hi);
+                int run_k = 0, run_g = created;
+                for (int base = 0; base < m; base += blockDim.x) {
+                    const int i = base + tid;
+                    const int role = i < m ? ploc_role(nn, i) : 2;
+                    const bool fk = role != 2, fg = role == 1;
+                    const unsigned bk = __ballot_sync(0xffffffffu, fk), bg = __ballot_sync(0xffffffffu, fg);
+                    if (lane == 0) { s_w[0][warp] = __popc(bk); s_w[1][warp] = __popc(bg); }
+                    __syncthreads();
+                    int wk = 0, wg = 0, totk = 0, totg = 0;
+                    for (int w = 0; w < 8; ++w) {
+                        if (w < warp) { wk += s_w[0][w]; wg += s_w[1][w]; }
+                        totk += s_w[0][w]; totg += s_w[1][w];
+                    }
+                    if (fk) {
+                        const int out = run_k + wk + __popc(bk & lt);
+                        nxt[out] = fg ? ploc_merge(cur, nn, i, run_g + wg + __popc(bg & lt), n, box, left, right, parent, count, leftmost)
+                                      : ld_cg(cur + i);
+                    }
+                    run_k += totk; run_g += totg;
+                    __syncthreads();
+                }
+                created = run_g; m = run_k;
+                int* t = cur; cur = nxt; nxt = t;
+                __threadfence_block();
+                __syncthreads();
+            }
+            return;
+        }
+        const int chunk = (m + nb - 1) / nb, lo = min(m, b * chunk), hi = min(m, lo + chunk);
+        for (int t0 = lo; t0 < hi; t0 += blockDim.x) {
+            // a tile may reach past this block's chunk: the positions beyond `hi` are then written twice with the same value
+            ploc_nearest_tile(cur, m, t0, radius, box, nn, s_lo, s_hi);
+        }
+        __threadfence();
+        grid.sync();
+        int kept = 0, merged = 0;
+        for (int i = lo + tid; i < hi; i += blockDim.x) { const int role = ploc_role(nn, i); kept += role != 2; merged += role == 1; }
+        for (int off = 16; off > 0; off >>= 1) { kept += __shfl_xor_sync(0xffffffffu, kept, off); merged += __shfl_xor_sync(0xffffffffu, merged, off); }
+        if (lane == 0) { s_w[0][warp] = kept; s_w[1][warp] = merged; }
+        __syncthreads();
+        if (tid == 0) {
+            int k = 0, g = 0;
+            for (int w = 0; w < 8; ++w) { k += s_w[0][w]; g += s_w[1][w]; }
+            block_tot[b] = make_int2(k, g);
+        }
+        __threadfence();
+        grid.sync();
+        // totals of the round and of the blocks before this one
+        int ok = 0, og = 0, tk = 0, tg = 0;
+        for (int j = tid; j < nb; j += blockDim.x) {
+            const int2 t = __ldcg(block_tot + j);
+            tk += t.x; tg += t.y;
+            if (j < b) { ok += t.x; og += t.y; }
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            ok += __shfl_xor_sync(0xffffffffu, ok, off); og += __shfl_xor_sync(0xffffffffu, og, off);
+            tk += __shfl_xor_sync(0xffffffffu, tk, off); tg += __shfl_xor_sync(0xffffffffu, tg, off);
+        }
+        __syncthreads();
+        if (lane == 0) { s_w[0][warp] = ok; s_w[1][warp] = og; s_w[2][warp] = tk; s_w[3][warp] = tg; }
+        __syncthreads();
+        ok = og = tk = tg = 0;
+        for (int w = 0; w < 8; ++w) { ok += s_w[0][w]; og += s_w[1][w]; tk += s_w[2][w]; tg += s_w[3][w]; }
+        __syncthreads();
+        int run_k = ok, run_g = created + og;
+        for (int base = lo; base < hi; base += blockDim.x) {
+            const int i = base + tid;
+            const int role = i < hi ? ploc_role(nn, i) : 2;
+            const bool fk = role != 2, fg = role == 1;
+            const unsigned bk = __ballot_sync(0xffffffffu, fk), bg = __ballot_sync(0xffffffffu, fg);
+            if (lane == 0) { s_w[0][warp] = __popc(bk); s_w[1][warp] = __popc(bg); }
+            __syncthreads();
+            int wk = 0, wg = 0, totk = 0, totg = 0;
+            for (int w = 0; w < 8; ++w) {
+                if (w < warp) { wk += s_w[0][w]; wg += s_w[1][w]; }
+                totk += s_w[0][w]; totg += s_w[1][w];
+            }
+            if (fk) {
+                const int out = run_k + wk + __popc(bk & lt);
+                nxt[out] = fg ? ploc_merge(cur, nn, i, run_g + wg + __popc(bg & lt), n, box, left, right, parent, count, leftmost)
+                              : ld_cg(cur + i);
+            }
+            run_k += totk; run_g += totg;
+            __syncthreads();
+        }
+        m = tk; created += tg;
+        int* t = cur; cur = nxt; nxt = t;
+        __threadfence();
+        grid.sync();
+    }
+}
+
+__global__ void k_ploc_leaf_pos(int n, const int* __restrict__ left, const int* __restrict__ parent, const int* __restrict__ count, int* __restrict__ pos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pos[i] = ploc_leaf_position(i, n, left, parent, count);
+}
+__global__ void k_ploc_permute(int n, const int* __restrict__ pos, const float4* __restrict__ tris_in, const float4* __restrict__ lbox_in,
+                               float4* __restrict__ tris_out, float4* __restrict__ lbox_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t p = (size_t)pos[i];
+    for (int k = 0; k < 3; ++k) tris_out[3 * p + k] = tris_in[3 * (size_t)i + k];
+    lbox_out[2 * p] = lbox_in[2 * (size_t)i]; lbox_out[2 * p + 1] = lbox_in[2 * (size_t)i + 1];
+}
+__global__ void k_ploc_finish(int n, const int* __restrict__ left, const int* __restrict__ right, const int* __restrict__ count,
+                              const int* __restrict__ leftmost, const int* __restrict__ pos, const float4* __restrict__ box,
+                              int* e_left, int* e_right, int* e_first, int* e_last, float4* e_ibox) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n - 1) ploc_finish_node(k, n, left, right, count, leftmost, pos, box, e_left, e_right, e_first, e_last, e_ibox);
+}
+
+// The PLOC hierarchy over the Morton-ordered triangles in ctx->d_tris / d_lbox; leaves d_left / d_right / d_first / d_last /
+// d_ibox as k_emit_levels reads them and the triangles + leaf boxes in the tree's depth-first order.
+static int ploc_build(vlb_ctx* ctx, uint32_t n_u, cudaStream_t st) {
+    const int n = (int)n_u, B = 256;
+    const size_t n_ref = 2 * (size_t)n - 1;
+    int per_sm = 0;
+    VLB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_ploc_rounds, 256, 0));
+    int want_per_sm = 2;
+    if (const char* v = getenv("VLB_PLOC_BLOCKS_PER_SM")) want_per_sm = std::max(1, atoi(v));
+    const unsigned int grid_c = (unsigned int)std::max(1, std::min(per_sm, want_per_sm) * ctx->sm_count);
+    // one scratch allocation, carved: box | C | Cn | nn | left | right | parent | count | leftmost | pos | block totals
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+    const size_t o_box = carve(2 * n_ref * sizeof(float4)), o_C = carve(n * sizeof(int)), o_Cn = carve(n * sizeof(int)), o_nn = carve(n * sizeof(int)),
+                 o_left = carve(n * sizeof(int)), o_right = carve(n * sizeof(int)), o_parent = carve(n_ref * sizeof(int)),
+                 o_count = carve(n_ref * sizeof(int)), o_lm = carve(n_ref * sizeof(int)), o_pos = carve(n * sizeof(int)),
+                 o_tot = carve(grid_c * sizeof(int2));
+    VLB_CUDA(ctx, ctx->d_ploc.reserve(off));
+    VLB_CUDA(ctx, ctx->d_tris_alt.reserve(3ull * n * sizeof(float4)));
+    VLB_CUDA(ctx, ctx->d_lbox_alt.reserve(2ull * n * sizeof(float4)));
+    char* base = static_cast<char*>(ctx->d_ploc.p);
+    float4* box = reinterpret_cast<float4*>(base + o_box);
+    int* C = reinterpret_cast<int*>(base + o_C); int* Cn = reinterpret_cast<int*>(base + o_Cn); int* nn = reinterpret_cast<int*>(base + o_nn);
+    int* left = reinterpret_cast<int*>(base + o_left); int* right = reinterpret_cast<int*>(base + o_right);
+    int* parent = reinterpret_cast<int*>(base + o_parent); int* count = reinterpret_cast<int*>(base + o_count);
+    int* leftmost = reinterpret_cast<int*>(base + o_lm); int* pos = reinterpret_cast<int*>(base + o_pos);
+    int2* tot = reinterpret_cast<int2*>(base + o_tot);
+    VLB_CUDA(ctx, cudaMemcpyAsync(box, ctx->d_lbox.p, 2ull * n * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    k_ploc_init<<<(unsigned)((n_ref + B - 1) / B), B, 0, st>>>(n, C, leftmost, count, parent);
+    VLB_LAUNCH_CHECK(ctx);
+    int radius = std::max(1, std::min(kPlocMaxRadius, ctx->ploc_radius));
+    int n_arg = n;
+    void* args[] = {&n_arg, &radius, &C, &Cn, &nn, &box, &left, &right, &parent, &count, &leftmost, &tot};
+    VLB_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_ploc_rounds), dim3(grid_c), dim3(256), args, 0, st));
+    VLB_LAUNCH_CHECK(ctx);
+    const unsigned grid_n = (unsigned)((n + B - 1) / B);
+    k_ploc_leaf_pos<<<grid_n, B, 0, st>>>(n, left, parent, count, pos);
+    VLB_LAUNCH_CHECK(ctx);
+    k_ploc_permute<<<grid_n, B, 0, st>>>(n, pos, ctx->d_tris.as<float4>(), ctx->d_lbox.as<float4>(), ctx->d_tris_alt.as<float4>(), ctx->d_lbox_alt.as<float4>());
+    VLB_LAUNCH_CHECK(ctx);
+    std::swap(ctx->d_tris, ctx->d_tris_alt);        // the permuted arrays become the BVH's triangles and leaf boxes
+    std::swap(ctx->d_lbox, ctx->d_lbox_alt);
+    k_ploc_finish<<<grid_n, B, 0, st>>>(n, left, right, count, leftmost, pos, box, ctx->d_left.as<int>(), ctx->d_right.as<int>(),
+                                        ctx->d_first.as<int>(), ctx->d_last.as<int>(), ctx->d_ibox.as<float4>());
+    VLB_LAUNCH_CHECK(ctx);
+    return VLB_OK;
+}
+
 // n == 1: a single node whose only child is the one-triangle leaf.
 __global__ void k_emit_single(const float4* __restrict__ lbox, const float* __restrict__ scratch, float4* nodes) {
     const float ext = fmaxf(scratch[3] - scratch[0], fmaxf(scratch[4] - scratch[1], scratch[5] - scratch[2]));
@@ -209,13 +435,20 @@ int bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats) {
             VLB_LAUNCH_CHECK(ctx);
             ctx->n_nodes = 1;
         } else {
-            VLB_CUDA(ctx, cudaMemsetAsync(ctx->d_flags.p, 0, n * sizeof(int), st));
-            k_karras<<<grid_n, B, 0, st>>>(keys_sorted, (int)n, ctx->d_left.as<int>(), ctx->d_right.as<int>(),
-                                          ctx->d_first.as<int>(), ctx->d_last.as<int>(), ctx->d_parent_i.as<int>(), ctx->d_parent_l.as<int>());
-            VLB_LAUNCH_CHECK(ctx);
-            k_refit<<<grid_n, B, 0, st>>>((int)n, ctx->d_left.as<int>(), ctx->d_right.as<int>(), ctx->d_parent_i.as<int>(),
-                                         ctx->d_parent_l.as<int>(), ctx->d_lbox.as<float4>(), ctx->d_ibox.as<float4>(), ctx->d_flags.as<int>());
-            VLB_LAUNCH_CHECK(ctx);
+            int builder = ctx->bvh_builder;
+            if (const char* v = getenv("VLB_BVH_BUILDER")) builder = (*v == 'p' || *v == 'P' || *v == '1') ? VLB_BVH_BUILDER_PLOC : VLB_BVH_BUILDER_LBVH;
+            if (const char* v = getenv("VLB_PLOC_RADIUS")) ctx->ploc_radius = atoi(v);
+            if (builder == VLB_BVH_BUILDER_PLOC) {
+                if (int r = ploc_build(ctx, n, st)) return r;
+            } else {
+                VLB_CUDA(ctx, cudaMemsetAsync(ctx->d_flags.p, 0, n * sizeof(int), st));
+                k_karras<<<grid_n, B, 0, st>>>(keys_sorted, (int)n, ctx->d_left.as<int>(), ctx->d_right.as<int>(),
+                                              ctx->d_first.as<int>(), ctx->d_last.as<int>(), ctx->d_parent_i.as<int>(), ctx->d_parent_l.as<int>());
+                VLB_LAUNCH_CHECK(ctx);
+                k_refit<<<grid_n, B, 0, st>>>((int)n, ctx->d_left.as<int>(), ctx->d_right.as<int>(), ctx->d_parent_i.as<int>(),
+                                             ctx->d_parent_l.as<int>(), ctx->d_lbox.as<float4>(), ctx->d_ibox.as<float4>(), ctx->d_flags.as<int>());
+                VLB_LAUNCH_CHECK(ctx);
+            }
             // top-down collapse into 4-wide nodes: one cooperative launch (grid.sync per level of the wide tree)
             VLB_CUDA(ctx, ctx->d_frontier[0].reserve(n * sizeof(int)));
             VLB_CUDA(ctx, ctx->d_frontier[1].reserve(n * sizeof(int)));

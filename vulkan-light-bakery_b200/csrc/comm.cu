@@ -248,7 +248,18 @@ int vlb_bake_probes_sharded_device(vlb_ctx* ctx, const vlb_bake_settings* s, con
     return sharded_pass(ctx, s, d_prev_full, d_full_out);
 }
 
+static int bake_sharded_host(vlb_ctx* ctx, const vlb_bake_settings* s, float* out_or_null, bool own_rows_only);
+
 int vlb_bake_probes_sharded(vlb_ctx* ctx, const vlb_bake_settings* s, float* out_or_null) {
+    return bake_sharded_host(ctx, s, out_or_null, false);
+}
+
+int vlb_bake_probes_sharded_rows(vlb_ctx* ctx, const vlb_bake_settings* s, float* grid) {
+    if (ctx && !grid) return ctx->fail(VLB_ERR_INVALID, "vlb_bake_probes_sharded_rows: grid is NULL");
+    return bake_sharded_host(ctx, s, grid, true);
+}
+
+static int bake_sharded_host(vlb_ctx* ctx, const vlb_bake_settings* s, float* out_or_null, bool own_rows_only) {
     if (!ctx) return VLB_ERR_INVALID;
     VLB_CUDA(ctx, cudaSetDevice(ctx->device));
     if (int r = check_whole_grid(ctx, s, "vlb_bake_probes_sharded")) return r;
@@ -269,7 +280,19 @@ int vlb_bake_probes_sharded(vlb_ctx* ctx, const vlb_bake_settings* s, float* out
         }
         cur ^= 1;
     }
-    if (out_or_null) VLB_CUDA(ctx, cudaMemcpyAsync(out_or_null, buf[cur ^ 1], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    const int world = ctx->comm ? ctx->comm_world : 1, rank = ctx->comm ? ctx->comm_rank : 0;
+    if (out_or_null && own_rows_only && world > 1) {
+        // only the z-slices this rank baked (k = rank, rank + world, ...): one strided copy into the caller's grid
+        const int Nz = s->probes[2];
+        const size_t row = (size_t)s->probes[0] * s->probes[1] * VLB_SH_STRIDE * sizeof(float);
+        const size_t n_slices = Nz > rank ? (size_t)(Nz - rank + world - 1) / world : 0;
+        if (n_slices)
+            VLB_CUDA(ctx, cudaMemcpy2DAsync(reinterpret_cast<char*>(out_or_null) + (size_t)rank * row, (size_t)world * row,
+                                            reinterpret_cast<const char*>(buf[cur ^ 1]) + (size_t)rank * row, (size_t)world * row, row, n_slices,
+                                            cudaMemcpyDeviceToHost, ctx->stream));
+    } else if (out_or_null) {
+        VLB_CUDA(ctx, cudaMemcpyAsync(out_or_null, buf[cur ^ 1], bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     VLB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (s->bounces > 0) { ctx->last_bake = total; return VLB_OK; }
     vlb_bake_stats st;

@@ -29,6 +29,7 @@ struct Options {
     int order = 0;
     int device = 0;
     std::vector<int> devices;       // --devices a,b,...: one context per GPU, vlb_bake_probes_multi
+    int builder = -1;               // --builder lbvh|ploc|auto: -1 = auto (vlb_bvh_recommend_builder)
     int bounces = 0;
     float gain = -1.f;
     bool tight = false, have_light = false, dry = false;
@@ -73,6 +74,7 @@ bool parse_floats(const char* s, float* v, int n) {
 void usage() {
     puts("usage: vlb_baker <scene.gltf|scene.glb> [options]\n"
          "  --probes NxNyxNz     probe grid (default 7x7x7, light_baker.cpp:38)\n"
+         "  --builder B          lbvh | ploc | auto (default): hierarchy builder, auto = by job size (vlb_bvh_recommend_builder)\n"
          "  --dirs WxH           equirect direction grid per probe (default 3141x1000, light_baker.cpp:65)\n"
          "  --order 2|3          SH order written: 9 or 16 coefficients (default 3)\n"
          "  --light x,y,z        point light position (default 1,10,1, env_map.rchit:25)\n"
@@ -106,6 +108,11 @@ int main(int argc, char** argv) {
             return argv[++i];
         };
         if (a == "-h" || a == "--help") { usage(); return EXIT_SUCCESS; }
+        else if (a == "--builder") {
+            const std::string b = need("--builder");
+            if (b == "lbvh") o.builder = VLB_BVH_BUILDER_LBVH; else if (b == "ploc") o.builder = VLB_BVH_BUILDER_PLOC;
+            else if (b == "auto") o.builder = -1; else die("--builder expects lbvh, ploc or auto");
+        }
         else if (a == "--probes") { if (!parse_ints(need("--probes"), o.probes, 3)) die("--probes expects NxNyxNz"); }
         else if (a == "--dirs") { if (!parse_ints(need("--dirs"), o.dirs, 2)) die("--dirs expects WxH"); }
         else if (a == "--order") { o.order = atoi(need("--order")); if (o.order != 2 && o.order != 3) die("--order expects 2 or 3"); }
@@ -202,10 +209,21 @@ int main(int argc, char** argv) {
         if (load(o.skybox.c_str(), sky_px.data(), sky_px.size(), sky_wh) != VLB_OK) { const std::string m = vlb_last_error(nullptr); destroy_all(); die(m); }
         printf("skybox %s: %dx%d\n", o.skybox.c_str(), sky_wh[0], sky_wh[1]);
     }
+    // the build preference (the reference passes ePreferFastTrace to its driver, scene_manager.cpp:346-347): chosen from
+    // the size of the job unless --builder says otherwise
+    int builder = o.builder;
+    if (builder < 0) {
+        uint64_t counts[5] = {0, 0, 0, 0, 0};
+        float ref_bounds[6];
+        if (vlb_gltf_probe(o.scene.c_str(), counts, ref_bounds) != VLB_OK) { const std::string m = vlb_last_error(nullptr); destroy_all(); die(m); }
+        const uint64_t rays = n_probes * (uint64_t)s.dir_w * (uint64_t)s.dir_h * (uint64_t)(1 + (s.bounces > 0 ? s.bounces : 0)) / ctxs.size();
+        builder = vlb_bvh_recommend_builder(counts[4], rays);
+    }
     vlb_bvh_stats bs;
     for (vlb_ctx* c : ctxs) {               // scene, LBVH and skybox are replicated on every GPU
         cur = c;
         check(vlb_scene_load_gltf(c, o.scene.c_str()));                      // LightBaker ctor, light_baker.cpp:40-53
+        check(vlb_bvh_set_builder(c, builder, 0));
         check(vlb_bvh_build(c, &bs));                                        // Scene_t::buildAccelerationStructures
         if (!sky_px.empty()) check(vlb_skybox_set(c, sky_px.data(), sky_hdr ? VLB_FMT_RGBA32F : VLB_FMT_RGBA8, sky_wh[0], sky_wh[1]));
     }
@@ -213,7 +231,7 @@ int main(int argc, char** argv) {
     float bounds[6];
     check(vlb_scene_bounds(ctx, o.tight ? 1 : 0, bounds));                   // Scene_t::getBounds
     check(vlb_bake_settings_from_bounds(&s, bounds));                        // probePositionsFromBoudingBox
-    printf("LBVH: %llu nodes in %.2f ms; grid %dx%dx%d over (%g %g %g)-(%g %g %g); %zu GPU(s)\n", (unsigned long long)bs.n_nodes, bs.build_ms,
+    printf("%s: %llu nodes in %.2f ms; grid %dx%dx%d over (%g %g %g)-(%g %g %g); %zu GPU(s)\n", builder == VLB_BVH_BUILDER_PLOC ? "BVH (PLOC)" : "LBVH", (unsigned long long)bs.n_nodes, bs.build_ms,
            s.probes[0], s.probes[1], s.probes[2], bounds[0], bounds[1], bounds[2], bounds[3], bounds[4], bounds[5], ctxs.size());
 
     std::vector<float> coeffs((size_t)n_probes * VLB_SH_STRIDE);

@@ -40,6 +40,7 @@ struct InstanceDev {       // device-side instance record used by the flatten ke
     float m[12];
     float minv[9];
     uint32_t first_index, first_vertex, material, tri_offset;
+    uint32_t index_count, vertex_count;
 };
 
 }  // namespace vlb
@@ -59,7 +60,7 @@ struct vlb_ctx {
     float ref_bounds[6] = {0, 0, 0, 0, 0, 0};
     float tight_bounds[6] = {0, 0, 0, 0, 0, 0};
     bool have_tight_bounds = false;
-    vlb::DevBuf d_verts, d_indices, d_insts_in, d_tri_offsets;
+    vlb::DevBuf d_verts, d_indices, d_insts_in, d_tri_offsets, d_inst_check;   // d_inst_check: per-instance local AABB + bad-index flag (k_instance_checks)
     vlb::DevBuf d_tri_flat;   // 3 float4 per triangle, flat order (before Morton sort)
     vlb::DevBuf d_tri_shade;  // 3 float4 per triangle, flat order
     vlb::DevBuf d_inst;       // 3 float4 per instance
@@ -76,6 +77,8 @@ struct vlb_ctx {
     vlb::DevBuf d_left, d_right, d_first, d_last, d_parent_i, d_parent_l, d_flags, d_ibox, d_lbox, d_scratch;
     uint64_t n_nodes = 0;
     int max_leaf = 3;
+    int bvh_builder = 0, ploc_radius = 16;      // vlb_bvh_set_builder
+    vlb::DevBuf d_ploc, d_tris_alt, d_lbox_alt; // PLOC scratch; the triangles / leaf boxes in the tree's leaf order
     // ---- skybox ----
     vlb::DevBuf d_sky;        // RGBA32F
     int sky_w = 0, sky_h = 0;

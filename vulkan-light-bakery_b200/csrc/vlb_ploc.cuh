@@ -1,10 +1,11 @@
-// vlb_ploc.cuh — TEST-ONLY EXPERIMENT ("higher-quality BVH"): PLOC (parallel locally-ordered
-// clustering, Meister & Bittner 2018) binary hierarchy over the Morton-sorted triangles, as a "prefer fast trace"
-// builder (the reference asks its driver for VK_BUILD_ACCELERATION_STRUCTURE_PREFER_FAST_TRACE_BIT,
-// src/scene_manager.cpp:346-347) next to the Karras LBVH. Evaluated through tests/emu with the product's own
-// collapse (emit_node4) and traversal (bvh4_step / leaf_step): on the BASELINE atrium it saves 2.5-4.6 % of the node
-// visits per ray (radius 8-64), far from the 15 % that would have justified a second GPU builder, so it was NOT
-// moved into the library (profiles/r02_bvh_builder_ab.log). Hit ids stay bit-exact with any tree.
+// vlb_ploc.cuh — PLOC (parallel locally-ordered clustering, Meister & Bittner 2018): the "prefer fast trace" builder
+// (the reference asks its driver for VK_BUILD_ACCELERATION_STRUCTURE_PREFER_FAST_TRACE_BIT,
+// src/scene_manager.cpp:346-347) next to the Karras LBVH. A binary hierarchy over the Morton-sorted
+// triangles built by agglomeration; the wide-node collapse (emit_wide_node) and the traversal are the same for both
+// builders, and hit ids stay bit-exact with any tree. Selected with vlb_bvh_set_builder / VLB_BVH_BUILDER=ploc;
+// bvh_build.cu runs the rounds in one cooperative kernel, tests/emu runs the same per-item bodies serially.
+// Measured on the bake's own ray distribution (profiles/r02_bvh_builder_ab.log): 2.5-4.6 % fewer node visits than
+// the LBVH on the 262,144-triangle atrium (radius 8-64), -0.7..+3.7 % at 1 M triangles.
 //
 // Clusters start as the n leaves in Morton order. Every round, each cluster looks `radius` places left and right
 // in the CURRENT order for the neighbour whose merged box has the smallest surface area (ties: smaller index);
@@ -22,9 +23,28 @@
 // Per-item bodies are `__host__ __device__` so that tests/emu runs the same code serially on the CPU.
 #pragma once
 
-#include "../../vulkan-light-bakery_b200/csrc/vlb_bvh.cuh"
+#include "vlb_bvh.cuh"
 
 namespace vlb {
+
+// Everything another block wrote before the last grid-wide barrier -- the cluster order, the neighbour choices, and
+// the boxes / counts of nodes created in earlier rounds (a new node shares its 128-byte line with older ones, so a line
+// cached before the node existed would be stale) -- is read past the non-coherent L1 on the device.
+VLB_HD int ld_cg(const int* p) {
+#ifdef __CUDA_ARCH__
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+
+VLB_HD float4 ld_cg4(const float4* p) {
+#ifdef __CUDA_ARCH__
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
 
 VLB_HD float merged_half_area(const float4 alo, const float4 ahi, const float4 blo, const float4 bhi) {
     const float dx = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x);
@@ -35,13 +55,15 @@ VLB_HD float merged_half_area(const float4 alo, const float4 ahi, const float4 b
 
 // Nearest neighbour of cluster i among positions [i - radius, i + radius] of the current order `C` (m clusters).
 VLB_HD int ploc_nearest(const int* C, int m, int i, int radius, const float4* box) {
-    const float4 lo = box[2 * (size_t)C[i]], hi = box[2 * (size_t)C[i] + 1];
+    const int ci = ld_cg(C + i);
+    const float4 lo = ld_cg4(box + 2 * (size_t)ci), hi = ld_cg4(box + 2 * (size_t)ci + 1);
     const int j0 = i - radius < 0 ? 0 : i - radius, j1 = i + radius > m - 1 ? m - 1 : i + radius;
     int best = -1;
     float best_cost = INFINITY;
     for (int j = j0; j <= j1; ++j) {
         if (j == i) continue;
-        const float c = merged_half_area(lo, hi, box[2 * (size_t)C[j]], box[2 * (size_t)C[j] + 1]);
+        const int cj = ld_cg(C + j);
+        const float c = merged_half_area(lo, hi, ld_cg4(box + 2 * (size_t)cj), ld_cg4(box + 2 * (size_t)cj + 1));
         if (c < best_cost) { best_cost = c; best = j; }
     }
     return best;
@@ -49,22 +71,22 @@ VLB_HD int ploc_nearest(const int* C, int m, int i, int radius, const float4* bo
 
 // What position i does this round: 0 = stays, 1 = lower member of a mutual pair (creates the node), 2 = upper member (leaves).
 VLB_HD int ploc_role(const int* nn, int i) {
-    const int j = nn[i];
-    if (j < 0 || nn[j] != i) return 0;
+    const int j = ld_cg(nn + i);
+    if (j < 0 || ld_cg(nn + j) != i) return 0;
     return i < j ? 1 : 2;
 }
 
 // Lower member i of a mutual pair creates internal node `k` (creation index) from C[i] (left) and C[nn[i]] (right).
 VLB_HD int ploc_merge(const int* C, const int* nn, int i, int k, int n, float4* box, int* left, int* right, int* parent, int* count,
                       int* leftmost) {
-    const int a = C[i], b = C[nn[i]], node = n + k;
+    const int a = ld_cg(C + i), b = ld_cg(C + ld_cg(nn + i)), node = n + k;
     left[k] = a; right[k] = b;
     parent[a] = node; parent[b] = node;
-    const float4 alo = box[2 * (size_t)a], ahi = box[2 * (size_t)a + 1], blo = box[2 * (size_t)b], bhi = box[2 * (size_t)b + 1];
+    const float4 alo = ld_cg4(box + 2 * (size_t)a), ahi = ld_cg4(box + 2 * (size_t)a + 1), blo = ld_cg4(box + 2 * (size_t)b), bhi = ld_cg4(box + 2 * (size_t)b + 1);
     box[2 * (size_t)node] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.f);
     box[2 * (size_t)node + 1] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.f);
-    count[node] = count[a] + count[b];
-    leftmost[node] = leftmost[a];
+    count[node] = ld_cg(count + a) + ld_cg(count + b);
+    leftmost[node] = ld_cg(leftmost + a);
     return node;
 }
 
