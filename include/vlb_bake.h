@@ -240,8 +240,8 @@ enum { VLB_BVH_BUILDER_LBVH = 0, VLB_BVH_BUILDER_PLOC = 1 };
 int vlb_bvh_set_builder(vlb_ctx* ctx, int builder, int ploc_radius);
 /* Host-only: the builder that minimises build + trace time for a bake of n_primary_rays rays (on this GPU / rank) through
  * a scene of n_triangles, from the measured costs on B200 (PLOC: +2.5 ns per triangle of build time, -4 % of trace time at
- * ~0.3 ns per primary ray; no gain beyond ~1 M triangles on the scenes measured): PLOC when the trace is long enough to
- * pay for it. The caller knows the probe grid before it builds, as the reference knows its build flags. */
+ * ~0.3 ns per primary ray; no gain below a few thousand or beyond ~1 M triangles on the scenes measured): PLOC when the
+ * trace is long enough to pay for it. The caller knows the probe grid before it builds, as the reference knows its build flags. */
 int vlb_bvh_recommend_builder(uint64_t n_triangles, uint64_t n_primary_rays);
 
 /* --- skybox (replaces Skybox_t) ---------------------------------------------------------- */

@@ -7,6 +7,7 @@ timeout 600 python -m pytest tests/test_gpu_comm.py tests/test_gpu_parity.py -m 
 tail -n 5 gpurun_out/pytest_comm.log
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tools/comm_check.py > gpurun_out/comm_check_n$N.log 2>&1; echo "comm_check rc=$?"
 grep "rank" gpurun_out/comm_check_n$N.log | sort | tail -n 40
+timeout 300 bash tools/multi_device_cli_check.sh > gpurun_out/multi_device_cli.log 2>&1; tail -n 4 gpurun_out/multi_device_cli.log
 for g in abi torch; do
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 10 --warmup 3 --gather $g > gpurun_out/bench_n${N}_$g.json 2> gpurun_out/bench_n${N}_$g.err; echo "bench $g rc=$?"
   tail -c 300 gpurun_out/bench_n${N}_$g.err

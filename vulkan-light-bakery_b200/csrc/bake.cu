@@ -854,8 +854,12 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
         n_whole = n_probes;
     } else if (p.tiles_per_chunk == kChunkTiles) {
         const uint64_t tail_waves = (uint64_t)std::max(0, env_flag("VLB_BAKE_TAIL_WAVES", 8));
-        const uint64_t tail_probes = env_flag("VLB_BAKE_TAIL_WAVES", 8) < 0 ? n_probes
-                                     : std::min<uint64_t>(n_probes, (tail_waves * full_grid * kStreamWarps + p.chunks - 1) / p.chunks);
+        const uint64_t warps = (uint64_t)full_grid * kStreamWarps;
+        // Whole-probe items only pay when there are several probes per resident warp; a call with few probes and many
+        // directions (the reference's own 7x7x7 x 3141x1000 bake: 343 probes of 6,141 chunks for 4,736 warps) is all
+        // per-chunk items, or most of the GPU would idle behind 343 long items.
+        const uint64_t tail_probes = (env_flag("VLB_BAKE_TAIL_WAVES", 8) < 0 || n_probes < 2 * warps) ? n_probes
+                                     : std::min<uint64_t>(n_probes, (tail_waves * warps + p.chunks - 1) / p.chunks);
         n_whole = n_probes - tail_probes;
     }
     const uint64_t n_items = n_whole + (n_probes - n_whole) * (uint64_t)p.chunks;

@@ -380,7 +380,7 @@ int vlb_bvh_set_builder(vlb_ctx* ctx, int builder, int ploc_radius) {
 int vlb_bvh_recommend_builder(uint64_t n_triangles, uint64_t n_primary_rays) {
     // PLOC costs ~2.5 ns per triangle more than the LBVH and takes ~4.2 % off ~0.31 ns per primary ray (C3, shadow rays
     // included): worth it above ~190 primary rays per triangle. Measured without gain at 1 M and 3 M triangles.
-    if (n_triangles == 0 || n_triangles > (1u << 20)) return VLB_BVH_BUILDER_LBVH;
+    if (n_triangles < 4096 || n_triangles > (1u << 20)) return VLB_BVH_BUILDER_LBVH;    // a tiny tree has nothing to gain
     return n_primary_rays > 190ull * n_triangles ? VLB_BVH_BUILDER_PLOC : VLB_BVH_BUILDER_LBVH;
 }
 
