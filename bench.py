@@ -403,6 +403,10 @@ def run_ours(args):
                 extra["c4"] = bench_c4(torch, vlb, scenes, local)
             except Exception as e:      # noqa
                 extra["c4"] = {"error": repr(e)}
+            try:
+                extra["reference_default_bake"] = bench_reference_default(torch, vlb, scenes, local)
+            except Exception as e:      # noqa
+                extra["reference_default_bake"] = {"error": repr(e)}
         if world == 1 and which == "c3":
             # BASELINE configs[1] beside the headline: the small grid whose bake is one 0.9 ms launch
             s2 = settings_for(scenes, "c2", 1)
@@ -579,6 +583,27 @@ def bench_c4(torch, vlb, scenes, local, reps=2):
             "direct_pass_Grays_per_s": rays / (best[0] * 1e-3) / 1e9, "gather_pass_Grays_per_s": rays / (best[-1] * 1e-3) / 1e9,
             "probes_per_s": s.n_probes / (sum(best) * 1e-3), "shadow_rays_per_pass": shadow, "bvh_build_ms": bvh.build_ms,
             "bvh_nodes": int(bvh.n_nodes), "scene_generation_s_host": gen_s, "checksum": checksum}
+
+
+def bench_reference_default(torch, vlb, scenes, local, reps=3):
+    """The reference's own workload and constants (`baker default_blender_cube.gltf`): 7x7x7 probes x 3141x1000 rays on the
+    12-triangle cube, 16 coefficients, no skybox (light_baker.cpp:38,65,294); device-resident."""
+    s = vlb.default_settings()
+    s.flags &= ~vlb.SKYBOX_ON_MISS
+    with vlb.Context(local) as c:
+        c.set_scene(scenes.default_cube())
+        c.build_bvh()
+        vlb.settings_from_bounds(s, c.scene_bounds(tight=False))
+        out = torch.zeros((s.n_probes, 48), device="cuda:%d" % local)
+        ms = []
+        for _ in range(reps + 1):
+            c.bake_probes_device(s, out.data_ptr()); c.synchronize()
+            ms.append(c.last_bake_stats().total_ms)
+        st = c.last_bake_stats()
+    best = min(ms[1:])
+    return {"workload": "the reference's default bake: default_blender_cube (12 triangles), 7x7x7 probes x 3141x1000 rays, L3, shadow rays, no skybox",
+            "ms": best, "value": st.n_primary_rays / (best * 1e-3) / 1e9, "unit": UNIT,
+            "rays_incl_shadow_per_s_G": (st.n_primary_rays + st.n_shadow_rays) / (best * 1e-3) / 1e9, "probes_per_s": s.n_probes / (best * 1e-3)}
 
 
 def cpu_baseline(scene, sky, s, which="c3", budget_s=12.0):
