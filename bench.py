@@ -233,16 +233,28 @@ def measure_bake(torch, dist, par, ctx, scene, sky, s, rank, world, dev, stream,
     if sharded_up:
         nbytes = s.n_probes * 48 * 4
         path = "/dev/shm/vlb_bench_grid_%s" % os.environ.get("MASTER_PORT", "0")
-        if rank == 0:
-            with open(path, "wb") as f:
-                f.truncate(nbytes)
+        ok = 1
+        try:
+            if rank == 0:
+                with open(path, "wb") as f:
+                    f.truncate(nbytes)
+        except OSError:
+            ok = 0
         dist.barrier()
-        shared_grid = torch.from_file(path, shared=True, size=s.n_probes * 48, dtype=torch.float32)
-        rc = torch.cuda.cudart().cudaHostRegister(shared_grid.data_ptr(), nbytes, 0)
-        if int(rc) != 0:
-            raise RuntimeError("cudaHostRegister of the shared host grid failed: %s" % rc)
+        try:
+            shared_grid = torch.from_file(path, shared=True, size=s.n_probes * 48, dtype=torch.float32)
+            if int(torch.cuda.cudart().cudaHostRegister(shared_grid.data_ptr(), nbytes, 0)) != 0:
+                ok = 0
+        except Exception:      # noqa: no usable /dev/shm on this box
+            ok = 0
+        agree = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)          # every rank takes the same route
+        if int(agree.item()) == 0:
+            if ok and shared_grid is not None:
+                torch.cuda.cudart().cudaHostUnregister(shared_grid.data_ptr())
+            shared_grid = None
         ctx.comm_sharded_uploads(True)
-    elif rank == 0:
+    if shared_grid is None and rank == 0:
         full_host = torch.empty((s.n_probes, 48), dtype=torch.float32, pin_memory=True)
 
     def step_e2e():
@@ -269,6 +281,7 @@ def measure_bake(torch, dist, par, ctx, scene, sky, s, rank, world, dev, stream,
     e2e_ok = True
     if sharded_up:
         ctx.comm_sharded_uploads(False)
+    if shared_grid is not None:
         # the shared host grid must be the device grid of the resident run, bit for bit (every rank checks all of it)
         ctx.bake_probes_sharded_device(s, 0, full.data_ptr())
         torch.cuda.synchronize()
@@ -278,7 +291,7 @@ def measure_bake(torch, dist, par, ctx, scene, sky, s, rank, world, dev, stream,
         dist.barrier()
         if rank == 0:
             os.unlink(path)
-    d2h = n_local * 48 * 4 if sharded_up else (int(full_host.numel() * 4) if full_host is not None else 0)
+    d2h = n_local * 48 * 4 if shared_grid is not None else (int(full_host.numel() * 4) if full_host is not None else 0)
     return {"t_ms": t_ms, "e2e_ms": e0.elapsed_time(e1) / e2e_steps, "kern_ms": float(np.mean(kernel_ms)),
             "shadow": int(shadow), "launches": int(launches), "h2d": int(h2d), "d2h": int(d2h),
             "mine": mine, "out": out, "builder": builder, "e2e_ok": e2e_ok}

@@ -77,6 +77,16 @@ def test_comm_host_side(vlb):
     assert lib.vlb_bake_probes_sharded(None, None, None) == vlb.ERR_INVALID
 
 
+def test_builder_recommendation(vlb):
+    """vlb_bvh_recommend_builder (host-only): PLOC when the trace is long enough to pay for its build."""
+    assert vlb.recommend_builder(262144, 64 * 32 * 64 * 4096) == "ploc"            # C3 on one GPU
+    assert vlb.recommend_builder(262144, 64 * 32 * 64 * 4096 // 8) == "ploc"       # C3, one of 8 ranks
+    assert vlb.recommend_builder(262144, 16 * 8 * 16 * 1024) == "lbvh"             # C2: a 0.9 ms bake
+    assert vlb.recommend_builder(3 << 20, 32 * 16 * 32 * 4096 * 4) == "lbvh"       # C4: no trace gain measured at 3 M triangles
+    assert vlb.recommend_builder(12, 343 * 3141 * 1000) == "lbvh"                  # the default cube
+    assert vlb.recommend_builder(0, 10 ** 12) == "lbvh"
+
+
 def test_slab_partition(vlb):
     import importlib
     par = importlib.import_module("vulkan-light-bakery_b200.parallel")
