@@ -7,6 +7,8 @@
 // and nothing in the product path can reach it; the GPU parity tests (-m gpu) remain the gate.
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -41,7 +43,10 @@ static void emu_ploc(EmuScene* s, std::vector<float4>& lbox, std::vector<float4>
     std::iota(C.begin(), C.end(), 0);
     std::iota(leftmost.begin(), leftmost.begin() + n, 0);
     int m = n, created = 0;
+    const bool trace = getenv("VLB_EMU_PLOC_TRACE") != nullptr;
+    int round = 0;
     while (m > 1) {
+        if (trace) fprintf(stderr, "ploc round %d: m = %d\n", round++, m);
         for (int i = 0; i < m; ++i) nn[i] = ploc_nearest(C.data(), m, i, radius, box.data());
         int out = 0;
         for (int i = 0; i < m; ++i) {

@@ -406,6 +406,38 @@ def test_bake_cube_reference_defaults_scaled(ctx, vlb, oa, scenes):
         assert rel_l2(got, osc.bake_probes(s)[0]) <= PROBE_TOL
 
 
+def test_whole_probe_items_and_per_chunk_items_give_the_same_bits(vlb, scenes, monkeypatch):
+    """bake_device's work decomposition (a probe as ONE work item whose warp adds the chunk sums in order, or one item per
+    chunk + k_sum_partials adding them in the same order) never shows in the result: all-whole, all-partial and the default
+    mix are bitwise equal. The grid is large enough (10,240 probes > 2 per resident warp) for whole-probe items to be used."""
+    import torch
+    sc = scenes.small_room()
+    sky = scenes.hdr_sky(64, 32, seed=4)
+    s = vlb.default_settings()
+    s.probes[:] = (32, 32, 10); s.dir_w, s.dir_h = 64, 64; s.sh_order = 2; s.light_pos[:] = (2.0, 3.5, 2.0)
+    s.flags = vlb.SHADOW_RAYS | vlb.SKYBOX_ON_MISS | vlb.SRGB_ENCODE
+    vlb.settings_from_bounds(s, (0.3, 0.3, 0.3, 3.7, 3.7, 3.7))
+    with vlb.Context(0) as c:
+        c.set_scene(sc); c.build_bvh(); c.set_skybox(sky)
+        outs = {}
+        for mode in ("default", "0", "-1"):
+            if mode == "default":
+                monkeypatch.delenv("VLB_BAKE_TAIL_WAVES", raising=False)
+            else:
+                monkeypatch.setenv("VLB_BAKE_TAIL_WAVES", mode)
+            out = torch.full((s.n_probes, 48), -1.0, device="cuda")
+            c.bake_probes_device(s, out.data_ptr()); c.synchronize()
+            outs[mode] = out.cpu().numpy()
+        assert np.abs(outs["default"]).sum() > 0
+        assert np.array_equal(outs["0"], outs["default"]) and np.array_equal(outs["-1"], outs["default"])
+        # and a few-probe call (all per-chunk items whatever the setting) reproduces its rows of the large one
+        monkeypatch.delenv("VLB_BAKE_TAIL_WAVES", raising=False)
+        t = s.copy(); t.slab_k0, t.slab_k1 = 3, 4
+        part = torch.zeros((32 * 32, 48), device="cuda")
+        c.bake_probes_device(t, part.data_ptr()); c.synchronize()
+        assert np.array_equal(part.cpu().numpy(), outs["default"][3 * 1024: 4 * 1024])
+
+
 def test_scene_with_an_index_past_its_vertex_range_is_refused(vlb, scenes):
     """Index validation and the per-instance bounds run on the device (k_instance_checks): a bad index fails the call with
     VLB_ERR_INVALID (never reads outside the vertex array), the context stays usable, and the reference-mode bounds of a
