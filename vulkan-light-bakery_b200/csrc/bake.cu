@@ -113,6 +113,15 @@ struct HitQueue {
 #ifndef VLB_BAKE_DISCARD
 #define VLB_BAKE_DISCARD 1                  // discard.global.L2 of the radiance tile once a chunk is projected
 #endif
+// Loads of the per-warp scratch (written by other lanes of the warp): with VLB_L1_HINTS through L2 only, so that the
+// queues and radiance tiles do not compete with the BVH for L1 lines.
+template <class T> __device__ __forceinline__ T ld_scratch(const T* p) {
+#if VLB_L1_HINTS
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
 struct alignas(128) WarpQueues {
     float rad[3][kChunkDirs];      // radiance of the current chunk, by direction (whole 128-byte lines: see the discard below)
     // shadow-ray queue: origin, unit direction, length, direction index, radiance if the light is visible
@@ -485,11 +494,11 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                     bool fresh = false;
                     if (!busy && rank < take_sh) {
                         const int e = n_sh - 1 - rank;
-                        ro = mk3(S.sq_o[0][e], S.sq_o[1][e], S.sq_o[2][e]);
-                        rd = mk3(S.sq_d[0][e], S.sq_d[1][e], S.sq_d[2][e]);
-                        tmin = 0.0f; tcull = S.sq_len[e];                               // env_map.rchit:87
-                        my_dir = S.sq_dir[e];
-                        best.id = -1; best.t = S.sq_rgb[0][e]; best.u = S.sq_rgb[1][e]; best.v = S.sq_rgb[2][e];
+                        ro = mk3(ld_scratch(&S.sq_o[0][e]), ld_scratch(&S.sq_o[1][e]), ld_scratch(&S.sq_o[2][e]));
+                        rd = mk3(ld_scratch(&S.sq_d[0][e]), ld_scratch(&S.sq_d[1][e]), ld_scratch(&S.sq_d[2][e]));
+                        tmin = 0.0f; tcull = ld_scratch(&S.sq_len[e]);                  // env_map.rchit:87
+                        my_dir = ld_scratch(&S.sq_dir[e]);
+                        best.id = -1; best.t = ld_scratch(&S.sq_rgb[0][e]); best.u = ld_scratch(&S.sq_rgb[1][e]); best.v = ld_scratch(&S.sq_rgb[2][e]);
                         kind = 1; busy = true; fresh = true;
                     } else if (!busy && rank - take_sh < take_new) {
                         const int cand = next + rank - take_sh;
@@ -663,7 +672,7 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                     const float w = p.pixel_area * row.x;                               // sh.comp:32-33
                     float b[K];
                     sh_basis<K>(p.world_frame ? mk3(t.x, t.z, t.y) : t, b);             // sh.comp:30,39
-                    const float r0 = S.rad[0][tt * 32 + lane], r1 = S.rad[1][tt * 32 + lane], r2 = S.rad[2][tt * 32 + lane];
+                    const float r0 = ld_scratch(&S.rad[0][tt * 32 + lane]), r1 = ld_scratch(&S.rad[1][tt * 32 + lane]), r2 = ld_scratch(&S.rad[2][tt * 32 + lane]);
 #pragma unroll
                     for (int i = 0; i < K; ++i) {
                         const float bw = b[i] * w;

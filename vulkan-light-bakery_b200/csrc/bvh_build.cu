@@ -59,11 +59,19 @@ __global__ void k_scene_bounds(const float4* __restrict__ tri_flat, uint32_t n, 
             v[k] = is_max ? fmaxf(v[k], o) : fminf(v[k], o);
         }
     }
-    if ((threadIdx.x & 31) == 0) {
-        for (int k = 0; k < 12; ++k) {
-            if ((k / 3) & 1) atomic_max_float(scratch + k, v[k]);
-            else atomic_min_float(scratch + k, v[k]);
-        }
+    // one set of 12 atomics per BLOCK (per warp they were 98 k atomics on 12 addresses at 262 k triangles: the kernel spent
+    // 68 us on a 12 MB read)
+    __shared__ float s_v[12][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31) >> 5;
+    if (lane == 0) for (int k = 0; k < 12; ++k) s_v[k][warp] = v[k];
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        const int k = threadIdx.x;
+        const bool is_max = (k / 3) & 1;
+        float r = s_v[k][0];
+        for (int w = 1; w < n_warps; ++w) r = is_max ? fmaxf(r, s_v[k][w]) : fminf(r, s_v[k][w]);
+        if (is_max) atomic_max_float(scratch + k, r);
+        else atomic_min_float(scratch + k, r);
     }
 }
 
@@ -409,7 +417,7 @@ int bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats) {
             VLB_CUDA(ctx, b->reserve(n * sizeof(int)));
         VLB_CUDA(ctx, ctx->d_ibox.reserve(2ull * n * sizeof(float4)));
 
-        const unsigned red_grid = std::min<unsigned>(grid_n, (unsigned)ctx->sm_count * 8u);
+        const unsigned red_grid = std::min<unsigned>(grid_n, (unsigned)ctx->sm_count * 4u);
         k_scene_bounds<<<red_grid, B, 0, st>>>(ctx->d_tri_flat.as<float4>(), n, ctx->d_scratch.as<float>());
         VLB_LAUNCH_CHECK(ctx);
         const char* cubic_env = getenv("VLB_BVH_CUBIC");

@@ -479,6 +479,23 @@ struct TraceCounters {
     uint32_t nodes, tris;
 };
 
+// A 16-byte load of data with little reuse inside an SM (skybox texels, per-triangle shading records): served through
+// L2 without taking an L1 line away from the BVH nodes and triangles (VLB_L1_HINTS, A/B in DESIGN.md 4.2).
+#ifndef VLB_L1_HINTS
+#define VLB_L1_HINTS 0
+#endif
+VLB_HD float4 ld4_stream(const float4* p) {
+#if defined(__CUDA_ARCH__) && VLB_L1_HINTS
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#elif defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
 VLB_HD float4 ld4(const float4* p) {
 #ifdef __CUDA_ARCH__
     return __ldg(p);

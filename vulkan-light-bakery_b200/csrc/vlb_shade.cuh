@@ -51,10 +51,10 @@ VLB_HD void sky_lookup(const ShadeView& s, Vec3 dir, float rgb[3]) {
     const float ax = fx - flx, ay = fy - fly;
     const int x0 = wrapi((int)flx, W), x1 = wrapi((int)flx + 1, W);
     const int y0 = wrapi((int)fly, H), y1 = wrapi((int)fly + 1, H);
-    const float4 p00 = ld4(s.sky + (size_t)y0 * W + x0);
-    const float4 p10 = ld4(s.sky + (size_t)y0 * W + x1);
-    const float4 p01 = ld4(s.sky + (size_t)y1 * W + x0);
-    const float4 p11 = ld4(s.sky + (size_t)y1 * W + x1);
+    const float4 p00 = ld4_stream(s.sky + (size_t)y0 * W + x0);
+    const float4 p10 = ld4_stream(s.sky + (size_t)y0 * W + x1);
+    const float4 p01 = ld4_stream(s.sky + (size_t)y1 * W + x0);
+    const float4 p11 = ld4_stream(s.sky + (size_t)y1 * W + x1);
     const float t0 = p00.x + (p10.x - p00.x) * ax, b0 = p01.x + (p11.x - p01.x) * ax;
     const float t1 = p00.y + (p10.y - p00.y) * ax, b1 = p01.y + (p11.y - p01.y) * ax;
     const float t2 = p00.z + (p10.z - p00.z) * ax, b2 = p01.z + (p11.z - p01.z) * ax;
@@ -124,7 +124,7 @@ float3 textured_base_color(const float4* tri_uv, const int4* tex_desc, const uch
                            float b0, float b1, float b2) {
     ShadeView s{};
     s.tex_desc = tex_desc; s.tex_texels = tex_texels;
-    const float4 ua = ld4(tri_uv + 2 * (size_t)tri), ub = ld4(tri_uv + 2 * (size_t)tri + 1);
+    const float4 ua = ld4_stream(tri_uv + 2 * (size_t)tri), ub = ld4_stream(tri_uv + 2 * (size_t)tri + 1);
     const float tu = f_add(f_add(f_mul(ua.x, b0), f_mul(ua.z, b1)), f_mul(ub.x, b2));   // :65
     const float tv = f_add(f_add(f_mul(ua.y, b0), f_mul(ua.w, b1)), f_mul(ub.y, b2));
     float rgb[3];
@@ -167,9 +167,9 @@ struct GatherView {
 template <bool TEX = true>
 VLB_HD bool shade_prelude(const ShadeView& s, const BakeConsts& c, const HitRec& h, Vec3 o, Vec3 r,
                           ShadePrelude& p) {
-    const float4 a0 = ld4(s.tri_shade + 3 * (size_t)h.id + 0);
-    const float4 a1 = ld4(s.tri_shade + 3 * (size_t)h.id + 1);
-    const float4 a2 = ld4(s.tri_shade + 3 * (size_t)h.id + 2);
+    const float4 a0 = ld4_stream(s.tri_shade + 3 * (size_t)h.id + 0);
+    const float4 a1 = ld4_stream(s.tri_shade + 3 * (size_t)h.id + 1);
+    const float4 a2 = ld4_stream(s.tri_shade + 3 * (size_t)h.id + 2);
     const int inst = f2i(a0.w);
     const float4 m0 = ld4(s.inst + 3 * (size_t)inst + 0);
     const float4 m1 = ld4(s.inst + 3 * (size_t)inst + 1);
