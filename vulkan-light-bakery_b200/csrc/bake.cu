@@ -299,6 +299,9 @@ using RayStack = WarpStack;
 using RayStack = LocalStack;
 #endif
 
+#ifndef VLB_VIS_CORNER_MAJOR
+#define VLB_VIS_CORNER_MAJOR 0
+#endif
 // Per-warp exchange area of a visibility-ray batch (gather passes): what the ray lanes need to know about the 32 hits
 // being shaded -- hit position, biased ray origin (env_map.rchit:82 / main.rchit:143), grid cell -- and the result.
 struct VisExchange {
@@ -341,7 +344,8 @@ __global__ void k_cell_roots(BvhView b, const float* __restrict__ px, const floa
 }
 
 // The 8 visibility rays of each of the (up to 32) hits a warp shades together (shaders/main.rchit:143-163), traced as
-// ONE batch by the whole warp: ray r = (hit r / 8, corner r % 8) goes to whichever lane is idle, lanes step through the
+// ONE batch by the whole warp: ray r = (hit r / 8, corner r % 8) goes to whichever lane is idle (the corner-major order,
+// VLB_VIS_CORNER_MAJOR, measured 2 % slower), lanes step through the
 // tree in the same while-while loop as the main rays and refill as they finish, so the warp stays full although the
 // rays are short and of very different lengths. (Round 1 traced the 8 rays of a hit one after the other inside the
 // shading lane: 32 lanes in lockstep on unrelated rays, a gather pass cost 5.5 direct passes.) `hm`: lanes holding a hit.
@@ -349,7 +353,7 @@ template <bool COUNT>
 __device__ __forceinline__ void trace_vis_batch(const BvhView& bvh, const GatherView& g, RayStack& stk, VisExchange& X, unsigned hm,
                                                 int lane, int node_min, TraceCounters& cnt) {
     const unsigned full = 0xffffffffu, lt_mask = (1u << lane) - 1u;
-    const int n_rays = 8 * __popc(hm);
+    const int n_hits = __popc(hm), n_rays = 8 * n_hits;
     int next = 0, cur = kRayDone, tag = 0;
     bool busy = false;
     Vec3 ro = mk3(0.f, 0.f, 0.f), rd = ro, idir = ro, ood = ro;
@@ -359,7 +363,13 @@ __device__ __forceinline__ void trace_vis_batch(const BvhView& bvh, const Gather
         if (idle != 0u && next < n_rays) {
             const int cand = next + __popc(idle & lt_mask);
             if (!busy && cand < n_rays) {
+#if VLB_VIS_CORNER_MAJOR
+                // corner-major order: neighbouring lanes trace the rays of neighbouring hits towards the SAME corner of their
+                // cells (near-parallel rays from near-by origins) instead of the eight diverging rays of one hit
+                const int c = cand / n_hits, h = __fns(hm, 0, cand - c * n_hits + 1);
+#else
                 const int h = __fns(hm, 0, (cand >> 3) + 1), c = cand & 7;
+#endif
                 const Vec3 P = mk3(X.P[0][h], X.P[1][h], X.P[2][h]);
                 int i, j, k; Vec3 d; float tmax;
                 gather_corner(g, P, X.cell[0][h], X.cell[1][h], X.cell[2][h], c, i, j, k, d, tmax);
