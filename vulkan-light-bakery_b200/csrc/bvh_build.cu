@@ -208,11 +208,12 @@ __device__ __forceinline__ void ploc_nearest_tile(const int* cur, int m, int t0,
 
 // All rounds of the agglomeration in one cooperative launch. A round: (1) every cluster picks its nearest neighbour
 // within `radius` places of the current order; (2) every block counts, over its contiguous chunk of the order, the
-// clusters that stay or create a node and the nodes created; (3) with the block totals every block knows where its
+// clusters that stay or create a node and the nodes created (no barrier between (1) and (2): see the halo below);
+// (3) with the block totals every block knows where its
 // chunk lands in the next order and which creation indices it hands out, and an ordered block scan places each
 // cluster. Output position and creation index of a cluster are "how many before it", exactly the serial loop of
 // tests/emu, so the tree is the same whatever the grid size.
-__global__ void __launch_bounds__(256) k_ploc_rounds(int n, int radius, int* C, int* Cn, int* nn, float4* box, int* left, int* right,
+__global__ void __launch_bounds__(256) k_ploc_rounds(int n, int radius, int tail, int* C, int* Cn, int* nn, float4* box, int* left, int* right,
                                                      int* parent, int* count, int* leftmost, int2* block_tot) {
     cg::grid_group grid = cg::this_grid();
     __shared__ int s_w[4][8];
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(256) k_ploc_rounds(int n, int radius, int* C, 
     int m = n, created = 0;
     int* cur = C; int* nxt = Cn;
     while (m > 1) {
-        if (m <= kPlocTail) {
+        if (m <= tail) {
             // The last rounds (about half of them) involve a few hundred clusters: block 0 finishes them alone, with block
             // barriers instead of grid-wide ones (a grid.sync costs microseconds, these rounds nothing).
             if (b != 0) return;
@@ -257,12 +258,13 @@ __global__ void __launch_bounds__(256) k_ploc_rounds(int n, int radius, int* C, 
             return;
         }
         const int chunk = (m + nb - 1) / nb, lo = min(m, b * chunk), hi = min(m, lo + chunk);
-        for (int t0 = lo; t0 < hi; t0 += blockDim.x) {
-            // a tile may reach past this block's chunk: the positions beyond `hi` are then written twice with the same value
-            ploc_nearest_tile(cur, m, t0, radius, box, nn, s_lo, s_hi);
-        }
-        __threadfence();
-        grid.sync();
+        // The neighbour choices of this block's chunk AND of `radius` positions on either side: a cluster's role needs its
+        // neighbour's choice, which lies within the radius, so the block can count its chunk without waiting for the
+        // others (two grid-wide barriers per round instead of three). Positions in the overlap are computed by two
+        // blocks and written twice with the same value.
+        if (lo < hi)
+            for (int t0 = max(0, lo - radius); t0 < min(m, hi + radius); t0 += blockDim.x) ploc_nearest_tile(cur, m, t0, radius, box, nn, s_lo, s_hi);
+        __syncthreads();
         int kept = 0, merged = 0;
         for (int i = lo + tid; i < hi; i += blockDim.x) { const int role = ploc_role(nn, i); kept += role != 2; merged += role == 1; }
         for (int off = 16; off > 0; off >>= 1) { kept += __shfl_xor_sync(0xffffffffu, kept, off); merged += __shfl_xor_sync(0xffffffffu, merged, off); }
@@ -370,8 +372,9 @@ static int ploc_build(vlb_ctx* ctx, uint32_t n_u, cudaStream_t st) {
     k_ploc_init<<<(unsigned)((n_ref + B - 1) / B), B, 0, st>>>(n, C, leftmost, count, parent);
     VLB_LAUNCH_CHECK(ctx);
     int radius = std::max(1, std::min(kPlocMaxRadius, ctx->ploc_radius));
-    int n_arg = n;
-    void* args[] = {&n_arg, &radius, &C, &Cn, &nn, &box, &left, &right, &parent, &count, &leftmost, &tot};
+    int n_arg = n, tail = kPlocTail;
+    if (const char* v = getenv("VLB_PLOC_TAIL")) tail = std::max(2, atoi(v));
+    void* args[] = {&n_arg, &radius, &tail, &C, &Cn, &nn, &box, &left, &right, &parent, &count, &leftmost, &tot};
     VLB_CUDA(ctx, cudaLaunchCooperativeKernel(reinterpret_cast<void*>(k_ploc_rounds), dim3(grid_c), dim3(256), args, 0, st));
     VLB_LAUNCH_CHECK(ctx);
     const unsigned grid_n = (unsigned)((n + B - 1) / B);
