@@ -34,6 +34,8 @@ def test_missing_file_and_bad_options(vlb, tmp_path):
     assert r.returncode == 1 and "--probes" in r.stderr
     r = _run(vlb, "sky.png")
     assert r.returncode == 1 and "image input" in r.stderr
+    r = _run(vlb, "a.gltf", "--builder", "sah")
+    assert r.returncode == 1 and "--builder" in r.stderr
 
 
 def test_dry_run_reports_reference_defaults(vlb, scenes, tmp_path):
@@ -66,6 +68,21 @@ def test_cli_bake_equals_abi_bake(ctx, vlb, scenes, tmp_path):
     want = ctx.bake_probes(s)
     assert np.array_equal(np.asarray(coeffs).reshape(want.shape), want)
     assert np.allclose(step, list(s.step))
+
+
+@pytest.mark.gpu
+def test_cli_builder_option_never_changes_the_file(vlb, scenes, tmp_path):
+    """--builder lbvh / ploc / auto: another tree, the same coefficients bit for bit."""
+    p = scenes.write_gltf(scenes.atrium(8192, seed=3), str(tmp_path / "atrium.gltf"), index_dtype=np.uint32)
+    args = ["--tight-bounds", "--probes", "4x3x4", "--dirs", "64x32", "--light", "15,11,9"]
+    outs = []
+    for b in ("lbvh", "ploc", "auto"):
+        o = str(tmp_path / ("%s.gltf" % b))
+        r = _run(vlb, p, *args, "--builder", b, "--out", o)
+        assert r.returncode == 0, r.stderr + r.stdout
+        assert ("BVH (PLOC)" in r.stdout) == (b == "ploc")         # auto: 98 k rays through 8 k triangles -> LBVH
+        outs.append(vlb.deserialize_gltf(o)[0])
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
 
 
 @pytest.mark.gpu
