@@ -43,6 +43,7 @@ struct BakeParams {
     int ref_order, world_frame;
     WarpQueues* stream_scratch;  // k_bake_stream: per-warp radiance tile + ray queues, [grid * warps per block]
     int node_min;                // k_bake_stream: the node loop yields to the leaf phase below this many lanes
+    int refill_min;              // k_bake_stream: idle lanes are refilled once there are this many of them (or all)
     GatherView g;                // gather pass source (g.prev == NULL: direct pass)
     int* vis_ovf;                // gather passes: stack overflow slab of the visibility-ray batches, [grid * warps][kOvfStack][32]
 };
@@ -497,7 +498,7 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                 if (COUNT) ++u_outer;
                 // ---- 1. refill idle lanes: queued shadow rays first, then new directions ----
                 const unsigned idle = __ballot_sync(full, !busy);
-                if (idle != 0u && (n_sh > 0 || next < n_dirs)) {
+                if ((__popc(idle) >= p.refill_min || idle == full) && (n_sh > 0 || next < n_dirs)) {
                     const int n_idle = __popc(idle), rank = __popc(idle & lt_mask);
                     const int take_sh = min(n_idle, n_sh);
                     const int take_new = min(n_idle - take_sh, n_dirs - next);
@@ -821,7 +822,8 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     p.stats = ctx->d_stats.as<unsigned long long>();
     p.ref_order = (s->flags & VLB_BAKE_REFERENCE_PROBE_ORDER) ? 1 : 0;
     p.world_frame = (s->flags & VLB_BAKE_SH_WORLD_FRAME) ? 1 : 0;
-    p.node_min = std::max(1, std::min(32, env_flag("VLB_BAKE_NODE_MIN", 16)));
+    p.node_min = std::max(1, std::min(32, env_flag("VLB_BAKE_NODE_MIN", 6)));
+    p.refill_min = std::max(1, std::min(32, env_flag("VLB_BAKE_REFILL_MIN", 20)));
     p.g.prev = d_prev_full; p.g.px = p.px; p.g.py = p.py; p.g.pz = p.pz; p.g.Nx = Nx; p.g.Ny = Ny; p.g.Nz = Nz;
     for (int k = 0; k < 3; ++k) { p.g.origin[k] = s->origin[k]; p.g.step[k] = s->step[k]; }
     p.g.gain = s->indirect_gain; p.g.world_frame = p.world_frame;
