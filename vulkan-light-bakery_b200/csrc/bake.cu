@@ -44,6 +44,7 @@ struct BakeParams {
     WarpQueues* stream_scratch;  // k_bake_stream: per-warp radiance tile + ray queues, [grid * warps per block]
     int node_min;                // k_bake_stream: the node loop yields to the leaf phase below this many lanes
     int refill_min;              // k_bake_stream: idle lanes are refilled once there are this many of them (or all)
+    int refill_order;            // k_bake_stream: 0 shadow rays first, 1 homogeneous refill batches
     GatherView g;                // gather pass source (g.prev == NULL: direct pass)
     int* vis_ovf;                // gather passes: stack overflow slab of the visibility-ray batches, [grid * warps][kOvfStack][32]
 };
@@ -92,7 +93,10 @@ constexpr int kChunkTiles = VLB_BAKE_CHUNK_TILES;
 constexpr int kChunkDirs = kChunkTiles * 32;
 constexpr int kRayDone = kNoChild;          // traversal finished
 constexpr int kHitCap = 64;                 // queued hit records per warp (<= 31 waiting + 32 arriving)
-constexpr int kShadowCap = 64;              // queued shadow rays per warp (shading needs 32 free slots)
+#ifndef VLB_BAKE_SHADOW_CAP
+#define VLB_BAKE_SHADOW_CAP 64
+#endif
+constexpr int kShadowCap = VLB_BAKE_SHADOW_CAP;   // queued shadow rays per warp (shading needs 32 free slots)
 constexpr int kStreamWarps = kBakeBlock / 32;
 #ifndef VLB_BAKE_SMEM_STACK
 #define VLB_BAKE_SMEM_STACK 12              // stack entries per lane in shared memory; 0 = round-1 per-thread local array
@@ -500,7 +504,12 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                 const unsigned idle = __ballot_sync(full, !busy);
                 if ((__popc(idle) >= p.refill_min || idle == full) && (n_sh > 0 || next < n_dirs)) {
                     const int n_idle = __popc(idle), rank = __popc(idle & lt_mask);
-                    const int take_sh = min(n_idle, n_sh);
+                    // p.refill_order 0: queued shadow rays first, new directions for the lanes that are left. 1: homogeneous batches --
+                    // shadow rays only when they fill every idle lane (or must be drained before the next shading), else new
+                    // directions first and shadow rays for the rest.
+                    // 2 (needs a shadow queue as large as a chunk): all directions of the chunk first, then its shadow rays
+                    const bool sh_first = p.refill_order == 0 || (p.refill_order == 1 && n_sh >= n_idle) || n_sh > kShadowCap - 32 || next >= n_dirs;
+                    const int take_sh = sh_first ? min(n_idle, n_sh) : min(n_sh, max(0, n_idle - (n_dirs - next)));
                     const int take_new = min(n_idle - take_sh, n_dirs - next);
                     bool fresh = false;
                     if (!busy && rank < take_sh) {
@@ -824,6 +833,7 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     p.world_frame = (s->flags & VLB_BAKE_SH_WORLD_FRAME) ? 1 : 0;
     p.node_min = std::max(1, std::min(32, env_flag("VLB_BAKE_NODE_MIN", 6)));
     p.refill_min = std::max(1, std::min(32, env_flag("VLB_BAKE_REFILL_MIN", 20)));
+    p.refill_order = env_flag("VLB_BAKE_REFILL_ORDER", 1);
     p.g.prev = d_prev_full; p.g.px = p.px; p.g.py = p.py; p.g.pz = p.pz; p.g.Nx = Nx; p.g.Ny = Ny; p.g.Nz = Nz;
     for (int k = 0; k < 3; ++k) { p.g.origin[k] = s->origin[k]; p.g.step[k] = s->step[k]; }
     p.g.gain = s->indirect_gain; p.g.world_frame = p.world_frame;
