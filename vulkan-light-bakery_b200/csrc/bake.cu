@@ -45,6 +45,7 @@ struct BakeParams {
     int node_min;                // k_bake_stream: the node loop yields to the leaf phase below this many lanes
     int refill_min;              // k_bake_stream: idle lanes are refilled once there are this many of them (or all)
     int refill_order;            // k_bake_stream: 0 shadow rays first, 1 homogeneous refill batches
+    int vis_refill_min;          // gather passes: the same threshold inside a visibility-ray batch
     GatherView g;                // gather pass source (g.prev == NULL: direct pass)
     int* vis_ovf;                // gather passes: stack overflow slab of the visibility-ray batches, [grid * warps][kOvfStack][32]
 };
@@ -356,7 +357,7 @@ __global__ void k_cell_roots(BvhView b, const float* __restrict__ px, const floa
 // shading lane: 32 lanes in lockstep on unrelated rays, a gather pass cost 5.5 direct passes.) `hm`: lanes holding a hit.
 template <bool COUNT>
 __device__ __forceinline__ void trace_vis_batch(const BvhView& bvh, const GatherView& g, RayStack& stk, VisExchange& X, unsigned hm,
-                                                int lane, int node_min, TraceCounters& cnt) {
+                                                int lane, int node_min, int refill_min, TraceCounters& cnt) {
     const unsigned full = 0xffffffffu, lt_mask = (1u << lane) - 1u;
     const int n_hits = __popc(hm), n_rays = 8 * n_hits;
     int next = 0, cur = kRayDone, tag = 0;
@@ -365,7 +366,7 @@ __device__ __forceinline__ void trace_vis_batch(const BvhView& bvh, const Gather
     float tcull = 0.f;
     for (;;) {
         const unsigned idle = __ballot_sync(full, !busy);
-        if (idle != 0u && next < n_rays) {
+        if ((__popc(idle) >= refill_min || idle == full) && next < n_rays) {      // batched refills, as in the main loop
             const int cand = next + __popc(idle & lt_mask);
             if (!busy && cand < n_rays) {
 #if VLB_VIS_CORNER_MAJOR
@@ -581,7 +582,7 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                         X.occluded[lane] = 0u;
                         const unsigned hm = __ballot_sync(full, has_hit);
                         __syncwarp();
-                        if (hm != 0u && bvh.n_tris) trace_vis_batch<COUNT>(bvh, p.g, stk2, X, hm, lane, p.node_min, cnt);
+                        if (hm != 0u && bvh.n_tris) trace_vis_batch<COUNT>(bvh, p.g, stk2, X, hm, lane, p.node_min, p.vis_refill_min, cnt);
                         occluded = X.occluded[lane];
                         __syncwarp();
                     }
@@ -834,6 +835,7 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     p.node_min = std::max(1, std::min(32, env_flag("VLB_BAKE_NODE_MIN", 6)));
     p.refill_min = std::max(1, std::min(32, env_flag("VLB_BAKE_REFILL_MIN", 20)));
     p.refill_order = env_flag("VLB_BAKE_REFILL_ORDER", 1);
+    p.vis_refill_min = std::max(1, std::min(32, env_flag("VLB_BAKE_VIS_REFILL_MIN", 20)));
     p.g.prev = d_prev_full; p.g.px = p.px; p.g.py = p.py; p.g.pz = p.pz; p.g.Nx = Nx; p.g.Ny = Ny; p.g.Nz = Nz;
     for (int k = 0; k < 3; ++k) { p.g.origin[k] = s->origin[k]; p.g.step[k] = s->step[k]; }
     p.g.gain = s->indirect_gain; p.g.world_frame = p.world_frame;
