@@ -43,6 +43,7 @@ struct BakeParams {
     int ref_order, world_frame;
     WarpQueues* stream_scratch;  // k_bake_stream: per-warp radiance tile + ray queues, [grid * warps per block]
     int node_min;                // k_bake_stream: the node loop yields to the leaf phase below this many lanes
+    int leaf_min;                // ... and at least this many lanes wait at a leaf
     int refill_min;              // k_bake_stream: idle lanes are refilled once there are this many of them (or all)
     int refill_order;            // k_bake_stream: 0 shadow rays first, 1 homogeneous refill batches
     int vis_refill_min;          // gather passes: the same threshold inside a visibility-ray batch
@@ -639,7 +640,7 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                 for (;;) {
                     const bool at_node = busy && cur >= 0;
                     const unsigned nm = __ballot_sync(full, at_node);
-                    if (nm == 0u || (__popc(nm) < p.node_min && __popc(running) - __popc(nm) >= p.node_min)) break;
+                    if (nm == 0u || (__popc(nm) < p.node_min && __popc(running) - __popc(nm) >= p.leaf_min)) break;
                     if (COUNT) { ++u_node_it; u_node_ln += __popc(nm); }
                     if (at_node) {
                         if (COUNT) { cnt.nodes++; if (stk.sp > kSmemStack) ++u_ovf; }
@@ -833,6 +834,7 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     p.ref_order = (s->flags & VLB_BAKE_REFERENCE_PROBE_ORDER) ? 1 : 0;
     p.world_frame = (s->flags & VLB_BAKE_SH_WORLD_FRAME) ? 1 : 0;
     p.node_min = std::max(1, std::min(32, env_flag("VLB_BAKE_NODE_MIN", 6)));
+    p.leaf_min = std::max(1, std::min(32, env_flag("VLB_BAKE_LEAF_MIN", p.node_min)));
     p.refill_min = std::max(1, std::min(32, env_flag("VLB_BAKE_REFILL_MIN", 20)));
     p.refill_order = env_flag("VLB_BAKE_REFILL_ORDER", 1);
     p.vis_refill_min = std::max(1, std::min(32, env_flag("VLB_BAKE_VIS_REFILL_MIN", 20)));
