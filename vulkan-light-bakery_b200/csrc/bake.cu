@@ -23,6 +23,7 @@ __host__ __device__ inline int tile_x(int tile, int w, int tiles_x, int lw) { re
 __host__ __device__ inline int tile_y(int tile, int w, int tiles_x, int lw) { return ((tile / tiles_x) << (5 - lw)) + (w >> lw); }
 
 struct WarpQueues;
+struct WarpSpill;
 struct BakeParams {
     BvhView bvh;
     ShadeView shade;
@@ -41,7 +42,8 @@ struct BakeParams {
     unsigned int* work_counter;
     unsigned long long* stats;   // [0] shadow rays, [1] nodes visited, [2] triangles tested, [4..11] COUNT builds: phase utilisation
     int ref_order, world_frame;
-    WarpQueues* stream_scratch;  // k_bake_stream: per-warp radiance tile + ray queues, [grid * warps per block]
+    WarpQueues* stream_scratch;  // k_bake_stream: per-warp radiance tile + shadow-ray queue, [grid * warps per block]
+    WarpSpill* stream_spill;     // k_bake_stream: per-warp stack overflow rows (rarely touched), same indexing
     int node_min;                // k_bake_stream: the node loop yields to the leaf phase below this many lanes
     int leaf_min;                // ... and at least this many lanes wait at a leaf
     int refill_min;              // k_bake_stream: idle lanes are refilled once there are this many of them (or all)
@@ -62,20 +64,21 @@ __device__ __forceinline__ size_t out_slot(const BakeParams& p, uint32_t q) {
 // =========================================================================================
 // k_bake_stream — the production bake kernel: a warp is a small wavefront path tracer.
 //
-// A warp owns a work item = (probe, run of 256-direction chunks). Inside a chunk every LANE is a ray
-// slot: an idle lane first takes a queued shadow ray, otherwise the next direction of the chunk
-// (ballot + popc ranks; directions in tile order (32-texel tiles, square in angle: tile_x / tile_y) so the rays in flight stay angularly
-// adjacent), and traverses the LBVH. Primary (closest-hit) and shadow (any-hit) rays share one
-// "while-while" loop: all lanes step through internal nodes until most of them hold a leaf, then
-// the leaves are intersected. A finished primary ray only pushes its hit record into a per-warp
-// queue and frees its lane; once 32 records are queued the whole warp shades them
-// together (env_map.rchit / main.rmiss arithmetic at full SIMD width) and pushes the shadow rays
-// that are needed into a second queue. Shading stores the radiance of the OCCLUDED outcome in the
-// warp's radiance tile and hands the lit radiance to the shadow ray, which overwrites the tile entry
-// when it escapes. When the chunk is drained the warp projects its 256 radiances onto SH cooperatively
-// (lane l takes directions l, l+32, ... in a fixed order, so the result is bitwise reproducible
-// whatever the run-time ray scheduling was), reduces with shuffles and keeps one or two running
-// coefficients per lane. Radiance never leaves the SM; HBM sees 192 bytes per probe.
+// A warp owns a work item = (probe, run of direction chunks; a chunk = kChunkTiles tiles of 32 directions). Inside a
+// chunk every LANE is a ray slot; idle lanes are refilled in batches (ballot + popc ranks; directions in tile order
+// (32-texel tiles, square in angle: tile_x / tile_y) so the rays in flight stay angularly adjacent) and traverse the
+// BVH. Primary (closest-hit) and shadow (any-hit) rays share one "while-while" loop: all lanes step through internal
+// nodes until most of them hold a leaf, then the leaves are intersected. A chunk of full size runs in two phases
+// (refill order 3): A -- the chunk's closest-hit rays, nothing else in flight; a finished ray only drops its hit record
+// into its direction's slot of the warp's scratch, queues the direction index and frees its lane. B -- 32 queued hits
+// at a time are shaded by the whole warp (env_map.rchit / main.rmiss arithmetic at full SIMD width) whenever the shadow
+// queue cannot fill every idle lane; shading pushes the shadow rays that are needed, and the any-hit batches run as
+// full and as homogeneous as the closest-hit ones. (Short chunks interleave the two kinds, order 1: the drain between
+// phases would cost more than the mix.) Shading stores the radiance of the OCCLUDED outcome in the direction's slot and
+// hands the lit radiance to the shadow ray, which overwrites the slot when it escapes. When the chunk is drained the
+// warp projects its radiances onto SH cooperatively (lane l takes directions l, l+32, ... in a fixed order, so the
+// result is bitwise reproducible whatever the run-time ray scheduling was), reduces with shuffles and keeps one or two
+// running coefficients per lane. Radiance never goes to HBM by design; the result is 192 bytes per probe.
 //
 // Where the per-ray state lives (round 2; round 1 kept all of it in local / global memory behind the
 // L1 LSU pipe, which ncu showed to be the binding unit):
@@ -84,8 +87,10 @@ __device__ __forceinline__ size_t out_slot(const BakeParams& p, uint32_t q) {
 //                     however far the lanes' depths have diverged (a per-thread local array costs one
 //                     wavefront per distinct depth). Deeper entries overflow to a global scratch slab
 //                     (rare: the short stack covers > 99 % of pushes on the BASELINE scenes).
-//   hit queue         shared memory (SoA, 20 bytes per record).
-//   shadow-ray queue, radiance tile   global scratch, L1/L2-resident, touched with coalesced accesses.
+//   hit queue         the finishing ORDER (16-bit direction indices) in shared memory.
+//   direction slots   global scratch, L1/L2-resident, 16 bytes per direction of the chunk: the hit record until the
+//                     hit is shaded, the radiance from then on (one 128-bit access either way).
+//   shadow-ray queue  global scratch, L1/L2-resident, coalesced accesses.
 // The per-ray arithmetic is exactly that of probe_ray_radiance (vlb_shade.cuh).
 // =========================================================================================
 #ifndef VLB_BAKE_CHUNK_TILES
@@ -94,7 +99,7 @@ __device__ __forceinline__ size_t out_slot(const BakeParams& p, uint32_t q) {
 constexpr int kChunkTiles = VLB_BAKE_CHUNK_TILES;
 constexpr int kChunkDirs = kChunkTiles * 32;
 constexpr int kRayDone = kNoChild;          // traversal finished
-constexpr int kHitCap = 64;                 // queued hit records per warp (<= 31 waiting + 32 arriving)
+constexpr int kHitCap = kChunkDirs + 32;    // queued hits per warp: every direction of the chunk (deferred shading) + the 32 the invariant check allows for
 #ifndef VLB_BAKE_SHADOW_CAP
 #define VLB_BAKE_SHADOW_CAP 64
 #endif
@@ -106,16 +111,14 @@ constexpr int kStreamWarps = kBakeBlock / 32;
 #ifndef VLB_BAKE_FAST_PUSH
 #define VLB_BAKE_FAST_PUSH 1                // branch-free end of a node step in the shared short stack (WarpStack::advance)
 #endif
-#ifndef VLB_BAKE_SMEM_HQ
-#define VLB_BAKE_SMEM_HQ 1                  // hit queue in shared memory
-#endif
 constexpr int kSmemStack = VLB_BAKE_SMEM_STACK;
-constexpr bool kSmemHq = VLB_BAKE_SMEM_HQ != 0;
 constexpr int kOvfStack = kSmemStack > 0 ? kStackSize - kSmemStack : 1;
 
-// hit queue (SoA): flat triangle id (-1: miss), t, u, v, direction index
+// Hit queue: the ORDER in which the chunk's closest-hit rays finished, as direction indices (16 bits each, shared
+// memory); the hit record itself -- flat triangle id (-1: miss), t, u, v -- waits in the direction's slot of the warp's
+// global scratch (WarpQueues::slot) until it is shaded, and the radiance then takes its place.
 struct HitQueue {
-    int id[kHitCap]; float t[kHitCap], u[kHitCap], v[kHitCap]; int dir[kHitCap];
+    unsigned short dir[kHitCap];
 };
 #ifndef VLB_BAKE_DISCARD
 #define VLB_BAKE_DISCARD 1                  // discard.global.L2 of the radiance tile once a chunk is projected
@@ -130,11 +133,16 @@ template <class T> __device__ __forceinline__ T ld_scratch(const T* p) {
 #endif
 }
 struct alignas(128) WarpQueues {
-    float rad[3][kChunkDirs];      // radiance of the current chunk, by direction (whole 128-byte lines: see the discard below)
+    // one slot per direction of the current chunk: first the hit record of its closest-hit ray (bits(id), t, u, v), from
+    // the moment the hit is shaded its radiance (r, g, b, -). Whole 128-byte lines: see the discard below.
+    float4 slot[kChunkDirs];
     // shadow-ray queue: origin, unit direction, length, direction index, radiance if the light is visible
     float sq_o[3][kShadowCap], sq_d[3][kShadowCap], sq_len[kShadowCap]; int sq_dir[kShadowCap];
     float sq_rgb[3][kShadowCap];
-    HitQueue hq;                   // used when the hit queue is not in shared memory
+};
+// The cold part of a warp's scratch, in a slab of its own so that the hot part above is one dense range of a few tens
+// of MB (the L2 access-policy window of the launch, bake_device).
+struct alignas(128) WarpSpill {
     int ovf[kOvfStack * ((VLB_STACK_CULL || VLB_BVH8) ? 2 : 1)][32];   // stack entries beyond the shared-memory short stack, [entry][word][lane]
 };
 
@@ -434,7 +442,7 @@ __device__ __forceinline__ void trace_vis_batch(const BvhView& bvh, const Gather
 #define VLB_BAKE_MIN_BLOCKS 8      // resident 128-thread blocks per SM the register allocation is held to (8 -> 64 registers)
 #endif
 constexpr size_t kBakeSmemPerBlock = (kSmemStack > 0 ? (size_t)kStreamWarps * kSmemStack * kStackWords * 32 * sizeof(int) : 0) +
-                                     (kSmemHq ? (size_t)kStreamWarps * sizeof(HitQueue) : 0);
+                                     (size_t)kStreamWarps * sizeof(HitQueue);
 // gather passes add the second short stack and the exchange area of the visibility-ray batches
 constexpr size_t kBakeSmemPerBlockGather = kBakeSmemPerBlock + (kSmemStack > 0 ? (size_t)kStreamWarps * kSmemStack * kStackWords * 32 * sizeof(int) : 0) +
                                            (size_t)kStreamWarps * sizeof(VisExchange);
@@ -443,7 +451,7 @@ template <int K, bool COUNT, bool GATHER, bool TEX>
 __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) k_bake_stream(const BakeParams p) {
     constexpr int V = (K * 3 <= 32) ? 32 : 64;
     __shared__ int s_stack[kSmemStack > 0 ? kStreamWarps : 1][kSmemStack > 0 ? kSmemStack : 1][kStackWords][32];
-    __shared__ HitQueue s_hq[kSmemHq ? kStreamWarps : 1];
+    __shared__ HitQueue s_hq[kStreamWarps];
     __shared__ int s_stack2[GATHER && kSmemStack > 0 ? kStreamWarps : 1][GATHER && kSmemStack > 0 ? kSmemStack : 1][kStackWords][32];
     __shared__ VisExchange s_vis[GATHER ? kStreamWarps : 1];
     WarpQueues* s_all = p.stream_scratch + (size_t)blockIdx.x * kStreamWarps;
@@ -451,7 +459,8 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     WarpQueues& S = s_all[warp];
-    HitQueue& HQ = kSmemHq ? s_hq[warp] : S.hq;
+    WarpSpill& SP = p.stream_spill[(size_t)blockIdx.x * kStreamWarps + warp];
+    HitQueue& HQ = s_hq[warp];
     const BvhView& bvh = p.bvh;
     const bool want_shadow = (p.c.flags & 1u) != 0;
     TraceCounters cnt; cnt.nodes = 0; cnt.tris = 0;
@@ -460,7 +469,7 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
     uint32_t u_node_it = 0, u_node_ln = 0, u_leaf_it = 0, u_leaf_ln = 0, u_shade_it = 0, u_shade_ln = 0, u_outer = 0, u_ovf = 0;
 #if VLB_BAKE_SMEM_STACK > 0
     WarpStack stk;
-    stk.bind(&s_stack[warp][0][0][lane], &S.ovf[0][lane]);
+    stk.bind(&s_stack[warp][0][0][lane], &SP.ovf[0][lane]);
 #else
     LocalStack stk;
 #endif
@@ -504,7 +513,12 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                 if (COUNT) ++u_outer;
                 // ---- 1. refill idle lanes: queued shadow rays first, then new directions ----
                 const unsigned idle = __ballot_sync(full, !busy);
-                if ((__popc(idle) >= p.refill_min || idle == full) && (n_sh > 0 || next < n_dirs)) {
+                // p.refill_order 3 (needs a hit queue as large as a chunk): the hits of the chunk's directions are only queued while
+                // directions are left (phase A: closest-hit rays only); then (phase B) they are shaded 32 at a time whenever the
+                // shadow queue cannot fill every idle lane, so the any-hit batches are homogeneous and full as well
+                const bool deferred = p.refill_order == 3, phase_b = deferred && next >= n_dirs;
+                const bool shade_first = phase_b && n_hit > 0 && n_sh < __popc(idle);
+                if ((__popc(idle) >= p.refill_min || idle == full) && (n_sh > 0 || next < n_dirs) && !shade_first) {
                     const int n_idle = __popc(idle), rank = __popc(idle & lt_mask);
                     // p.refill_order 0: queued shadow rays first, new directions for the lanes that are left. 1: homogeneous batches --
                     // shadow rays only when they fill every idle lane (or must be drained before the next shading), else new
@@ -536,7 +550,7 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                             best.id = -1; best.t = tcull; best.u = 0.f; best.v = 0.f;
                             my_dir = cand; kind = 0; busy = true; fresh = true;
                         } else {
-                            S.rad[0][cand] = 0.f; S.rad[1][cand] = 0.f; S.rad[2][cand] = 0.f;   // outside the direction grid
+                            S.slot[cand] = make_float4(0.f, 0.f, 0.f, 0.f);                    // outside the direction grid
                         }
                     }
                     if (fresh) {
@@ -551,7 +565,10 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                 }
                 const unsigned running = __ballot_sync(full, busy);
                 // ---- 2. shade queued hits: a full warp of them, or whatever is left when nothing runs ----
-                if ((n_hit >= 32 && n_sh <= kShadowCap - 32) || (running == 0u && n_hit > 0)) {
+                const bool shade_now = deferred ? ((shade_first && (__popc(idle) >= p.refill_min || idle == full) && n_sh <= kShadowCap - 32) ||
+                                                   (n_hit > kHitCap - 32 && n_sh <= kShadowCap - 32))
+                                                : (n_hit >= 32 && n_sh <= kShadowCap - 32);
+                if (shade_now || (running == 0u && n_hit > 0)) {
                     const int take = min(n_hit, 32);
                     const int e = n_hit - take + lane;
                     if (COUNT) { ++u_shade_it; u_shade_ln += take; }
@@ -565,9 +582,10 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                         // shading below then only needs the 8-bit result per hit
                         VisExchange& X = s_vis[warp];
                         bool has_hit = false;
-                        if (lane < take && HQ.id[e] >= 0) {
-                            HitRec h; h.id = HQ.id[e]; h.t = HQ.t[e]; h.u = HQ.u[e]; h.v = HQ.v[e];
-                            const int hd = HQ.dir[e];
+                        const int hd = lane < take ? (int)HQ.dir[e] : 0;
+                        const float4 hrec = lane < take ? ld_scratch(&S.slot[hd]) : make_float4(__int_as_float(-1), 0.f, 0.f, 0.f);
+                        if (lane < take && __float_as_int(hrec.x) >= 0) {
+                            HitRec h; h.id = __float_as_int(hrec.x); h.t = hrec.y; h.u = hrec.z; h.v = hrec.w;
                             const int tile = base_tile + (hd >> 5), w = hd & 31;
                             const float2 row = __ldg(p.row_sc + tile_y(tile, w, p.tiles_x, p.tile_lw)), col = __ldg(p.col_cs + tile_x(tile, w, p.tiles_x, p.tile_lw));
                             const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);
@@ -588,8 +606,9 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                         __syncwarp();
                     }
                     if (lane < take) {
-                        HitRec h; h.id = HQ.id[e]; h.t = HQ.t[e]; h.u = HQ.u[e]; h.v = HQ.v[e];
                         dir = HQ.dir[e];
+                        const float4 hrec = ld_scratch(&S.slot[dir]);
+                        HitRec h; h.id = __float_as_int(hrec.x); h.t = hrec.y; h.u = hrec.z; h.v = hrec.w;
                         const int tile = base_tile + (dir >> 5), w = dir & 31;
                         const int x = tile_x(tile, w, p.tiles_x, p.tile_lw);
                         const int y = tile_y(tile, w, p.tiles_x, p.tile_lw);
@@ -615,7 +634,7 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                             if (p.c.flags & 4u) { rgb[0] = srgb_encode(rgb[0]); rgb[1] = srgb_encode(rgb[1]); rgb[2] = srgb_encode(rgb[2]); }
                         }
                         if (p.c.flags & 8u) { rgb[0] = quant8(rgb[0]); rgb[1] = quant8(rgb[1]); rgb[2] = quant8(rgb[2]); }
-                        S.rad[0][dir] = rgb[0]; S.rad[1][dir] = rgb[1]; S.rad[2][dir] = rgb[2];
+                        S.slot[dir] = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
                     }
                     const unsigned pm = __ballot_sync(full, push);
                     if (push) {
@@ -667,11 +686,12 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                 if (fin) {
                     if (kind == 0) {
                         const int e = n_hit + __popc(fp & lt_mask);
-                        HQ.id[e] = best.id; HQ.t[e] = best.t; HQ.u[e] = best.u; HQ.v[e] = best.v; HQ.dir[e] = my_dir;
+                        S.slot[my_dir] = make_float4(__int_as_float(best.id), best.t, best.u, best.v);
+                        HQ.dir[e] = (unsigned short)my_dir;
                     } else if (best.id < 0) {                                           // light visible: the lit radiance replaces the occluded one
                         float rgb[3] = {best.t, best.u, best.v};
                         if (p.c.flags & 8u) { rgb[0] = quant8(rgb[0]); rgb[1] = quant8(rgb[1]); rgb[2] = quant8(rgb[2]); }  // QUANTIZE_RGBA8
-                        S.rad[0][my_dir] = rgb[0]; S.rad[1][my_dir] = rgb[1]; S.rad[2][my_dir] = rgb[2];
+                        S.slot[my_dir] = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
                     }
                     busy = false;
                 }
@@ -694,7 +714,8 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                     const float w = p.pixel_area * row.x;                               // sh.comp:32-33
                     float b[K];
                     sh_basis<K>(p.world_frame ? mk3(t.x, t.z, t.y) : t, b);             // sh.comp:30,39
-                    const float r0 = ld_scratch(&S.rad[0][tt * 32 + lane]), r1 = ld_scratch(&S.rad[1][tt * 32 + lane]), r2 = ld_scratch(&S.rad[2][tt * 32 + lane]);
+                    const float4 rad = ld_scratch(&S.slot[tt * 32 + lane]);
+                    const float r0 = rad.x, r1 = rad.y, r2 = rad.z;
 #pragma unroll
                     for (int i = 0; i < K; ++i) {
                         const float bw = b[i] * w;
@@ -712,9 +733,9 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
             // The tile's radiances are dead now (the next chunk writes every entry before it reads any), but their
             // lines sit dirty in L2 and would be written back to HBM when the BVH / skybox traffic evicts them:
             // round 2 measured 4.2 GB of such write-backs per C3 launch. Tell L2 to drop them instead.
-            static_assert(sizeof(S.rad) % 128 == 0, "radiance tile must cover whole 128-byte lines");
-            for (uint32_t off = 128u * lane; off < sizeof(S.rad); off += 32u * 128u)
-                asm volatile("discard.global.L2 [%0], 128;" ::"l"(reinterpret_cast<char*>(&S.rad[0][0]) + off) : "memory");
+            static_assert(sizeof(S.slot) % 128 == 0, "radiance tile must cover whole 128-byte lines");
+            for (uint32_t off = 128u * lane; off < sizeof(S.slot); off += 32u * 128u)
+                asm volatile("discard.global.L2 [%0], 128;" ::"l"(reinterpret_cast<char*>(&S.slot[0]) + off) : "memory");
             __syncwarp();
 #endif
         }
@@ -836,7 +857,6 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     p.node_min = std::max(1, std::min(32, env_flag("VLB_BAKE_NODE_MIN", 6)));
     p.leaf_min = std::max(1, std::min(32, env_flag("VLB_BAKE_LEAF_MIN", p.node_min)));
     p.refill_min = std::max(1, std::min(32, env_flag("VLB_BAKE_REFILL_MIN", 20)));
-    p.refill_order = env_flag("VLB_BAKE_REFILL_ORDER", 1);
     p.vis_refill_min = std::max(1, std::min(32, env_flag("VLB_BAKE_VIS_REFILL_MIN", 20)));
     p.g.prev = d_prev_full; p.g.px = p.px; p.g.py = p.py; p.g.pz = p.pz; p.g.Nx = Nx; p.g.Ny = Ny; p.g.Nz = Nz;
     for (int k = 0; k < 3; ++k) { p.g.origin[k] = s->origin[k]; p.g.step[k] = s->step[k]; }
@@ -897,6 +917,10 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
                                      : std::min<uint64_t>(n_probes, (tail_waves * warps + p.chunks - 1) / p.chunks);
         n_whole = n_probes - tail_probes;
     }
+    // Ray-slot policy: chunks of full size are traced in two phases (3: all closest-hit rays first, their hits queued; then
+    // shading and any-hit batches) -- the drain between the phases only pays when a chunk is long; short chunks (small
+    // direction grids split into many items, C2: one tile per item) keep the interleaved order 1. Never changes a result.
+    p.refill_order = env_flag("VLB_BAKE_REFILL_ORDER", p.tiles_per_chunk >= kChunkTiles ? 3 : 1);
     const uint64_t n_items = n_whole + (n_probes - n_whole) * (uint64_t)p.chunks;
     if (n_items >= (1ull << 32)) return ctx->fail(VLB_ERR_UNSUPPORTED, "bake: too many work items");
     p.n_items = (uint32_t)n_items; p.n_whole = (uint32_t)n_whole;
@@ -908,6 +932,8 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
 
     VLB_CUDA(ctx, ctx->d_stream_scratch.reserve((size_t)grid * kStreamWarps * sizeof(WarpQueues)));
     p.stream_scratch = ctx->d_stream_scratch.as<WarpQueues>();
+    VLB_CUDA(ctx, ctx->d_stream_spill.reserve((size_t)grid * kStreamWarps * sizeof(WarpSpill)));
+    p.stream_spill = ctx->d_stream_spill.as<WarpSpill>();
     if (gather && Nx > 1 && Ny > 1 && Nz > 1 && env_flag("VLB_BAKE_CELL_ROOTS", 1)) {
         const int cx = Nx - 1, cy = Ny - 1, cz = Nz - 1;
         VLB_CUDA(ctx, ctx->d_cell_root.reserve((size_t)cx * cy * cz * sizeof(int)));
@@ -924,7 +950,40 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     }
     VLB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
     VLB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
-    kern<<<grid, kBakeBlock, 0, st>>>(p);
+    {
+        // The warps' radiance tiles and shadow-ray queues (the hot scratch: 8.75 KB per warp, 42 MB for 4,736 warps) are
+        // written and re-read all through the launch, while scene + skybox + scratch together just overflow the L2: ncu
+        // showed GBs of scratch lines written back to HBM and fetched again. The launch can carry an L2
+        // access-policy window over the hot scratch (persisting lines, as far as the device's set-aside reaches), so the
+        // capacity misses fall on the read-only scene instead. Measured (profiles/r02_bake_l2_persist_ab.log): no change
+        // in time, MORE write-backs (the set-aside evicts dirty lines earlier) -> off; VLB_BAKE_L2_PERSIST=<MB> turns it on.
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kBakeBlock); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        unsigned n_attr = 0;
+        const size_t hot_bytes = (size_t)grid * kStreamWarps * sizeof(WarpQueues);
+        const int persist_mb = env_flag("VLB_BAKE_L2_PERSIST", 0);
+        if (persist_mb > 0 && ctx->l2_persist_max > 0 && ctx->l2_window_max > 0) {
+            const size_t want = std::min<size_t>((size_t)persist_mb << 20, (size_t)ctx->l2_persist_max);
+            if (ctx->l2_persist_set != want) {
+                VLB_CUDA(ctx, cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+                ctx->l2_persist_set = want;
+            }
+            // VLB_BAKE_L2_WINDOW=1 (A/B): the window covers the BVH nodes instead of the scratch
+            const bool on_nodes = env_flag("VLB_BAKE_L2_WINDOW", 0) == 1;
+            const size_t win = std::min(on_nodes ? ctx->d_nodes.cap : hot_bytes, (size_t)ctx->l2_window_max);
+            attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+            attr[0].val.accessPolicyWindow.base_ptr = on_nodes ? ctx->d_nodes.p : (void*)p.stream_scratch;
+            attr[0].val.accessPolicyWindow.num_bytes = win;
+            attr[0].val.accessPolicyWindow.hitRatio = win <= want ? 1.0f : (float)((double)want / (double)win);
+            attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+            n_attr = 1;
+            ctx->l2_persist_dirty = true;
+        }
+        cfg.attrs = attr; cfg.numAttrs = n_attr;
+        VLB_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, p));
+    }
     VLB_LAUNCH_CHECK(ctx);
     VLB_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     if (p.n_whole < n_probes) {
@@ -956,6 +1015,10 @@ int bake_collect_stats(vlb_ctx* ctx) {
     if (!ctx->bake_pending) return VLB_OK;
     ctx->bake_pending = false;
     VLB_CUDA(ctx, cudaEventSynchronize(ctx->ev_done));
+    if (ctx->l2_persist_dirty) {        // hand the persisting lines of the bake's scratch back to the kernels that follow
+        ctx->l2_persist_dirty = false;
+        VLB_CUDA(ctx, cudaCtxResetPersistingL2Cache());
+    }
     vlb_bake_stats& b = ctx->last_bake;
     b.n_shadow_rays = ctx->h_bake_stats[0]; b.n_nodes_visited = ctx->h_bake_stats[1]; b.n_tris_tested = ctx->h_bake_stats[2];
     VLB_CUDA(ctx, cudaEventElapsedTime(&b.kernel_ms, ctx->ev[2], ctx->ev[3]));

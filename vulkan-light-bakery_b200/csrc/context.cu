@@ -155,6 +155,8 @@ int vlb_ctx_create(int device_id, vlb_ctx** out) {
         return VLB_ERR_CUDA;
     }
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->l2_persist_max = prop.persistingL2CacheMaxSize;
+    ctx->l2_window_max = prop.accessPolicyMaxWindowSize;
     ctx->stream = ctx->own_stream;
     *out = ctx;
     return VLB_OK;

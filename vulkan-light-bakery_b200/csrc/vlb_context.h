@@ -48,6 +48,9 @@ struct InstanceDev {       // device-side instance record used by the flatten ke
 struct vlb_ctx {
     int device = 0;
     int sm_count = 0;
+    int l2_persist_max = 0, l2_window_max = 0;   // device limits of the L2 set-aside and of one access-policy window (bytes)
+    size_t l2_persist_set = 0;                   // cudaLimitPersistingL2CacheSize as last set by the bake
+    bool l2_persist_dirty = false;               // a bake left persisting lines behind (reset when its stats are collected)
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -108,7 +111,7 @@ struct vlb_ctx {
     std::vector<ProjGraph> proj_graphs;
     cudaStream_t cap_stream = nullptr;
     // ---- bake ----
-    vlb::DevBuf d_bake_out, d_bake_prev, d_partials, d_work_counter, d_axis, d_row_sc, d_col_sc, d_stats, d_stream_scratch, d_vis_ovf, d_cell_root;
+    vlb::DevBuf d_bake_out, d_bake_prev, d_partials, d_work_counter, d_axis, d_row_sc, d_col_sc, d_stats, d_stream_scratch, d_stream_spill, d_vis_ovf, d_cell_root;
     int dir_w = 0, dir_h = 0;
     vlb_bake_stats last_bake{};
     bool bake_pending = false;             // a device bake was enqueued and its statistics not yet collected
