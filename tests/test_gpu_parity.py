@@ -438,6 +438,37 @@ def test_whole_probe_items_and_per_chunk_items_give_the_same_bits(vlb, scenes, m
         assert np.array_equal(part.cpu().numpy(), outs["default"][3 * 1024: 4 * 1024])
 
 
+def test_ray_slot_policies_give_the_same_bits(vlb, scenes, monkeypatch):
+    """How the warp schedules its ray slots -- interleaved refills (order 0 / 1), deferred shading in two phases per chunk
+    (order 3, the default for long chunks), refill thresholds -- never shows in the result: every policy gives the same coefficients bit for bit and the same shadow-ray count."""
+    import torch
+    sc = scenes.small_room()
+    sky = scenes.hdr_sky(64, 32, seed=4)
+    s = vlb.default_settings()
+    s.probes[:] = (12, 12, 8); s.dir_w, s.dir_h = 64, 64; s.sh_order = 2; s.light_pos[:] = (2.0, 3.5, 2.0)
+    s.flags = vlb.SHADOW_RAYS | vlb.SKYBOX_ON_MISS | vlb.SRGB_ENCODE
+    vlb.settings_from_bounds(s, (0.3, 0.3, 0.3, 3.7, 3.7, 3.7))
+    knobs = ("VLB_BAKE_REFILL_ORDER", "VLB_BAKE_REFILL_MIN", "VLB_BAKE_NODE_MIN")
+    policies = [{}, {"VLB_BAKE_REFILL_ORDER": "0"}, {"VLB_BAKE_REFILL_ORDER": "1"}, {"VLB_BAKE_REFILL_ORDER": "3"},
+                {"VLB_BAKE_REFILL_ORDER": "3", "VLB_BAKE_REFILL_MIN": "1", "VLB_BAKE_NODE_MIN": "1"},
+                {"VLB_BAKE_REFILL_ORDER": "1", "VLB_BAKE_REFILL_MIN": "32", "VLB_BAKE_NODE_MIN": "16"}]
+    with vlb.Context(0) as c:
+        c.set_scene(sc); c.build_bvh(); c.set_skybox(sky)
+        ref = None
+        for pol in policies:
+            for k in knobs:
+                monkeypatch.delenv(k, raising=False)
+            for k, v in pol.items():
+                monkeypatch.setenv(k, v)
+            out = torch.full((s.n_probes, 48), -1.0, device="cuda")
+            c.bake_probes_device(s, out.data_ptr()); c.synchronize()
+            got = (out.cpu().numpy(), c.last_bake_stats().n_shadow_rays)
+            if ref is None:
+                ref = got
+                assert np.abs(ref[0]).sum() > 0 and ref[1] > 0
+            assert np.array_equal(got[0], ref[0]) and got[1] == ref[1], pol
+
+
 def test_scene_with_an_index_past_its_vertex_range_is_refused(vlb, scenes):
     """Index validation and the per-instance bounds run on the device (k_instance_checks): a bad index fails the call with
     VLB_ERR_INVALID (never reads outside the vertex array), the context stays usable, and the reference-mode bounds of a

@@ -19,8 +19,9 @@ constexpr int kBakeBlock = 128;
 // per direction grid so that the tile is as square as possible in ANGLE (a texel spans 360/W x 180/H degrees): 4x8
 // texels for W = H (the 32x32 / 64x64 grids of the BASELINE configs; measured +1.4 % over 8x4 on C3), 8x4 for
 // W >= 2H (the reference's 3141x1000). Rays in flight in a warp then cover the smallest solid angle.
-__host__ __device__ inline int tile_x(int tile, int w, int tiles_x, int lw) { return ((tile % tiles_x) << lw) + (w & ((1 << lw) - 1)); }
-__host__ __device__ inline int tile_y(int tile, int w, int tiles_x, int lw) { return ((tile / tiles_x) << (5 - lw)) + (w >> lw); }
+// texel (x, y) of lane slot w of a tile: x = ((tile % tiles_x) << lw) + (w & (2^lw - 1)), y = ((tile / tiles_x) << (5 - lw)) + (w >> lw)
+// -- tile_xy() below, which divides with the host's reciprocal (an integer division is ~20 instructions, and the kernel
+// needs the pair in four places, one of them per ray).
 
 struct WarpQueues;
 struct WarpSpill;
@@ -33,6 +34,7 @@ struct BakeParams {
     const float2* col_cs;                                // (cos, sin) phi per direction column
     int Nx, Ny, Nz, k0, kstride;   // the call bakes z-slices k0, k0 + kstride, ...
     int W, H, tiles_x, n_tiles, tile_lw;   // tile_lw: log2 of the direction tile's width
+    unsigned long long tiles_x_rcp;        // floor(2^64 / tiles_x) + 1: umul64hi(tile, rcp) == tile / tiles_x for every 32-bit tile (tiles_x >= 2)
     int chunks, tiles_per_chunk;
     uint32_t n_items;
     uint32_t n_whole;            // items [0, n_whole) are whole probes; item n_whole + j is chunk run j % chunks of probe n_whole + j / chunks
@@ -52,6 +54,14 @@ struct BakeParams {
     GatherView g;                // gather pass source (g.prev == NULL: direct pass)
     int* vis_ovf;                // gather passes: stack overflow slab of the visibility-ray batches, [grid * warps][kOvfStack][32]
 };
+
+__device__ __forceinline__ void tile_xy(const BakeParams& p, int tile, int w, int& x, int& y) {
+    // exact: rcp = (2^64 + e) / d with 0 < e <= d, so tile * rcp / 2^64 = tile / d + tile * e / (d * 2^64) and tile * e < 2^64
+    const uint32_t row = p.tiles_x == 1 ? (uint32_t)tile : (uint32_t)__umul64hi((unsigned long long)(uint32_t)tile, p.tiles_x_rcp);
+    const uint32_t col = (uint32_t)tile - row * (uint32_t)p.tiles_x;
+    x = (int)(col << p.tile_lw) + (w & ((1 << p.tile_lw) - 1));
+    y = (int)(row << (5 - p.tile_lw)) + (w >> p.tile_lw);
+}
 
 __device__ __forceinline__ size_t out_slot(const BakeParams& p, uint32_t q) {
     if (!p.ref_order) return q;
@@ -539,8 +549,8 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                     } else if (!busy && rank - take_sh < take_new) {
                         const int cand = next + rank - take_sh;
                         const int tile = base_tile + (cand >> 5), w = cand & 31;
-                        const int x = tile_x(tile, w, p.tiles_x, p.tile_lw);
-                        const int y = tile_y(tile, w, p.tiles_x, p.tile_lw);
+                        int x, y;
+                        tile_xy(p, tile, w, x, y);
                         if (x < p.W && y < p.H) {
                             const float2 row = __ldg(p.row_sc + y), col = __ldg(p.col_cs + x);
                             const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);   // sh_common.h:8-12
@@ -587,7 +597,9 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                         if (lane < take && __float_as_int(hrec.x) >= 0) {
                             HitRec h; h.id = __float_as_int(hrec.x); h.t = hrec.y; h.u = hrec.z; h.v = hrec.w;
                             const int tile = base_tile + (hd >> 5), w = hd & 31;
-                            const float2 row = __ldg(p.row_sc + tile_y(tile, w, p.tiles_x, p.tile_lw)), col = __ldg(p.col_cs + tile_x(tile, w, p.tiles_x, p.tile_lw));
+                            int hx, hy;
+                            tile_xy(p, tile, w, hx, hy);
+                            const float2 row = __ldg(p.row_sc + hy), col = __ldg(p.col_cs + hx);
                             const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);
                             ShadePrelude q;
                             shade_prelude<TEX>(p.shade, p.c, h, po, mk3(t.x, t.z, t.y), q);
@@ -610,8 +622,8 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                         const float4 hrec = ld_scratch(&S.slot[dir]);
                         HitRec h; h.id = __float_as_int(hrec.x); h.t = hrec.y; h.u = hrec.z; h.v = hrec.w;
                         const int tile = base_tile + (dir >> 5), w = dir & 31;
-                        const int x = tile_x(tile, w, p.tiles_x, p.tile_lw);
-                        const int y = tile_y(tile, w, p.tiles_x, p.tile_lw);
+                        int x, y;
+                        tile_xy(p, tile, w, x, y);
                         const float2 row = __ldg(p.row_sc + y), col = __ldg(p.col_cs + x);
                         const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);
                         const Vec3 r = mk3(t.x, t.z, t.y);
@@ -620,15 +632,12 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                             const bool lit = shade_prelude<TEX>(p.shade, p.c, h, po, r, pre);
                             float ind[3] = {0.f, 0.f, 0.f};
                             if (GATHER) gather_accumulate<K>(p.g, pre, occluded, ind);         // main.rchit:156-165
-                            if (lit && want_shadow) {
-                                // radiance for both outcomes now, the shadow ray decides (env_map.rchit:83-99):
-                                // the tile gets the occluded one, the ray carries the lit one
-                                shade_finish(p.c, pre, r, false, ind, lit_rgb);
-                                shade_finish(p.c, pre, r, true, ind, rgb);
-                                push = true;
-                            } else {
-                                shade_finish(p.c, pre, r, !lit, ind, rgb);
-                            }
+                            // With a shadow ray to come, radiance for both outcomes now and the ray decides (env_map.rchit:83-99):
+                            // the slot gets the occluded one, the ray carries the lit one. (Two inlined copies of
+                            // shade_finish, not three: this is cold code that pays for every instruction-cache line.)
+                            push = lit && want_shadow;
+                            shade_finish(p.c, pre, r, !lit || want_shadow, ind, rgb);
+                            if (push) shade_finish(p.c, pre, r, false, ind, lit_rgb);
                         } else if ((p.c.flags & 2u) && p.shade.sky) {                   // VLB_BAKE_SKYBOX_ON_MISS
                             sky_lookup(p.shade, r, rgb);
                             if (p.c.flags & 4u) { rgb[0] = srgb_encode(rgb[0]); rgb[1] = srgb_encode(rgb[1]); rgb[2] = srgb_encode(rgb[2]); }
@@ -706,8 +715,8 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
             for (int i = 0; i < V; ++i) acc[i] = 0.f;
             for (int tt = 0; tt * 32 < n_dirs; ++tt) {
                 const int tile = base_tile + tt;
-                const int x = tile_x(tile, lane, p.tiles_x, p.tile_lw);
-                const int y = tile_y(tile, lane, p.tiles_x, p.tile_lw);
+                int x, y;
+                tile_xy(p, tile, lane, x, y);
                 if (x < p.W && y < p.H) {
                     const float2 row = __ldg(p.row_sc + y), col = __ldg(p.col_cs + x);
                     const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);
@@ -848,6 +857,7 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     const int tile_w = 1 << p.tile_lw, tile_h = 32 >> p.tile_lw;
     p.tiles_x = (W + tile_w - 1) / tile_w;
     p.n_tiles = p.tiles_x * ((H + tile_h - 1) / tile_h);
+    p.tiles_x_rcp = p.tiles_x > 1 ? ~0ull / (unsigned long long)p.tiles_x + ((~0ull % (unsigned long long)p.tiles_x) + 1 == (unsigned long long)p.tiles_x ? 2 : 1) : 0;
     p.tiles_per_chunk = 0;       // the work decomposition follows the kernel choice (it needs the resident warp count)
     p.pixel_area = (2.0f * kPi / (float)W) * (kPi / (float)H);            // sh.comp:32
     p.work_counter = ctx->d_work_counter.as<unsigned int>();
@@ -917,10 +927,11 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
                                      : std::min<uint64_t>(n_probes, (tail_waves * warps + p.chunks - 1) / p.chunks);
         n_whole = n_probes - tail_probes;
     }
-    // Ray-slot policy: chunks of full size are traced in two phases (3: all closest-hit rays first, their hits queued; then
-    // shading and any-hit batches) -- the drain between the phases only pays when a chunk is long; short chunks (small
-    // direction grids split into many items, C2: one tile per item) keep the interleaved order 1. Never changes a result.
-    p.refill_order = env_flag("VLB_BAKE_REFILL_ORDER", p.tiles_per_chunk >= kChunkTiles ? 3 : 1);
+    // Ray-slot policy: chunks of at least half the full size are traced in two phases (3: all closest-hit rays first, their
+    // hits queued; then shading and any-hit batches) -- the drain between the phases only pays when a chunk is long
+    // (measured on the atrium: 16 tiles -3.2 %, 8 tiles -2.8 %, 4 tiles -0.6 %, 2 tiles +8 %, 1 tile +32 %); short chunks
+    // (small grids split into many items, C2: one tile per item) keep the interleaved order 1. Never changes a result.
+    p.refill_order = env_flag("VLB_BAKE_REFILL_ORDER", 2 * p.tiles_per_chunk >= kChunkTiles ? 3 : 1);
     const uint64_t n_items = n_whole + (n_probes - n_whole) * (uint64_t)p.chunks;
     if (n_items >= (1ull << 32)) return ctx->fail(VLB_ERR_UNSUPPORTED, "bake: too many work items");
     p.n_items = (uint32_t)n_items; p.n_whole = (uint32_t)n_whole;

@@ -108,9 +108,23 @@ VLB_HD void sh_basis(Vec3 d, float* o) {
     }
 }
 
+// powf of the shading code: ONE out-of-line copy on the device. The hit shading calls it up to 14 times (sRGB of three
+// channels for the lit, the occluded and the sky outcome, the specular lobe), and inlined those expansions were a fifth of
+// k_bake_stream's instructions -- cold straight-line code that missed the instruction cache on every line (ncu round 2:
+// `no_instruction` = 45 % of the stall samples of the kernel's cold code). Same code, same bits; C3 148.7 -> 144.8 ms
+// (profiles/r02_bake_icache_ab.log). VLB_POW_OUTLINE=0 builds the inlined form.
+#ifndef VLB_POW_OUTLINE
+#define VLB_POW_OUTLINE 1
+#endif
+#if defined(__CUDA_ARCH__) && VLB_POW_OUTLINE
+static __device__ __noinline__ float pow_f(float a, float b) { return powf(a, b); }
+#else
+VLB_HD float pow_f(float a, float b) { return powf(a, b); }
+#endif
+
 // shaders/env_map.rchit:27-34, one channel
 VLB_HD float srgb_encode(float c) {
-    return c < 0.0031308f ? c * 12.92f : 1.055f * powf(c, 1.0f / 2.4f) - 0.055f;
+    return c < 0.0031308f ? c * 12.92f : 1.055f * pow_f(c, 1.0f / 2.4f) - 0.055f;
 }
 
 // ---- ray / triangle intersection: THE specification (oracle: intersect_tri) ------------------

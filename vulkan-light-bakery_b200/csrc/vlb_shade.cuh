@@ -132,8 +132,14 @@ float3 textured_base_color(const float4* tri_uv, const int4* tex_desc, const uch
     return make_float3(rgb[0], rgb[1], rgb[2]);
 }
 
-VLB_HD float quant8(float c) {
-    // imageStore to rgba8 (src/baker/env_map_generator.hpp:39): clamp, round-half-even to n/255
+// imageStore to rgba8 (src/baker/env_map_generator.hpp:39): clamp, round-half-even to n/255. One out-of-line copy on the
+// device (an IEEE division, nine call sites in the bake kernel's cold shading code; see pow_f).
+#if defined(__CUDA_ARCH__) && VLB_POW_OUTLINE
+static __device__ __noinline__
+#else
+VLB_HD
+#endif
+float quant8(float c) {
     return rintf(clampf(c, 0.0f, 1.0f) * 255.0f) / 255.0f;
 }
 
@@ -279,7 +285,7 @@ VLB_HD void shade_finish(const BakeConsts& c, const ShadePrelude& p, Vec3 r, boo
         const float dn = dot_exact(p.N, p.Ln);
         const Vec3 R = mk3(p.Ln.x - 2.0f * dn * p.N.x, p.Ln.y - 2.0f * dn * p.N.y, p.Ln.z - 2.0f * dn * p.N.z);
         const float rd = fmaxf(dot_exact(R, r), 0.0f);
-        specular = c.c_specular * powf(rd, c.gloss);
+        specular = c.c_specular * pow_f(rd, c.gloss);
     }
     const float k = c.ambient + diffuse + specular;
     for (int ch = 0; ch < 3; ++ch) {
