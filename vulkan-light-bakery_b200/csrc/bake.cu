@@ -6,6 +6,18 @@
 // chunk) items from a global counter, fires the probe's fixed equirect directions plus shadow
 // rays through the software LBVH, and projects the radiance onto SH in registers. Per-ray
 // radiance never goes to HBM; the only global writes are 192 bytes per probe.
+//
+// Two translation units are made of this file. bake.cu itself holds the direct-pass instantiations of k_bake_stream and
+// everything on the host side; bake_gather.cu includes it with VLB_BAKE_GATHER_TU to compile the gather-pass
+// instantiations (GATHER = true) alone, with the cold shading code's divisions and square roots out of line
+// (VLB_COLD_OUTLINE): the gather kernel is half as large again and gains 6 % from the smaller code, the direct kernel
+// loses 1.6 % to the calls (profiles/r02_bake_icache_ab.log, same box).
+#ifndef VLB_BAKE_GATHER_TU
+#define VLB_BAKE_GATHER_TU 0
+#endif
+#ifndef VLB_COLD_OUTLINE
+#define VLB_COLD_OUTLINE VLB_BAKE_GATHER_TU
+#endif
 #include <algorithm>
 
 #include "vlb_context.h"
@@ -341,6 +353,7 @@ struct VisExchange {
 // exactly ONE child box overlaps the cell's box; the node it stops at has every such triangle below it, and the ray may
 // start there -- on a scene much larger than a cell that skips the upper half of every descent. out[cell]: a node
 // index, a leaf ref (< 0) or kNoChild when nothing reaches into the cell at all. fp32 4-wide nodes only.
+#if !VLB_BAKE_GATHER_TU
 __global__ void k_cell_roots(BvhView b, const float* __restrict__ px, const float* __restrict__ py, const float* __restrict__ pz,
                              int cx, int cy, int cz, float margin, int* __restrict__ out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -367,6 +380,7 @@ __global__ void k_cell_roots(BvhView b, const float* __restrict__ px, const floa
 #endif
     out[c] = cur;
 }
+#endif
 
 // The 8 visibility rays of each of the (up to 32) hits a warp shades together (shaders/main.rchit:143-163), traced as
 // ONE batch by the whole warp: ray r = (hit r / 8, corner r % 8) goes to whichever lane is idle (the corner-major order,
@@ -400,7 +414,7 @@ __device__ __forceinline__ void trace_vis_batch(const BvhView& bvh, const Gather
                 gather_corner(g, P, X.cell[0][h], X.cell[1][h], X.cell[2][h], c, i, j, k, d, tmax);
                 if (tmax > 0.0f) {                                                     // main.rchit:154-155
                     ro = mk3(X.so[0][h], X.so[1][h], X.so[2][h]);
-                    rd = mk3(f_div(d.x, tmax), f_div(d.y, tmax), f_div(d.z, tmax));
+                    rd = mk3(f_div_c(d.x, tmax), f_div_c(d.y, tmax), f_div_c(d.z, tmax));
                     idir = mk3(safe_inv(rd.x), safe_inv(rd.y), safe_inv(rd.z));
                     ood = mk3(ro.x * idir.x, ro.y * idir.y, ro.z * idir.z);
                     tcull = tmax; tag = (h << 3) | c;
@@ -778,6 +792,18 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
     }
 }
 
+using BakeKernel = void (*)(const BakeParams);
+#if VLB_BAKE_GATHER_TU
+// bake_gather.cu: the gather-pass instantiation for (sh coefficients K, instrumented build, textured scene)
+BakeKernel bake_gather_kernel(int K, bool count, bool tex) {
+#define VLB_PICK(KK) (tex ? (count ? k_bake_stream<KK, true, true, true> : k_bake_stream<KK, false, true, true>)   \
+                          : (count ? k_bake_stream<KK, true, true, false> : k_bake_stream<KK, false, true, false>))
+    return K == 9 ? VLB_PICK(9) : VLB_PICK(16);
+#undef VLB_PICK
+}
+#else
+BakeKernel bake_gather_kernel(int K, bool count, bool tex);   // bake_gather.cu
+
 // Probes baked as chunk-run items: per-probe sum of the partials in chunk order (fixed order => deterministic).
 __global__ void k_sum_partials(const BakeParams p, uint32_t n_probes) {
     const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -878,11 +904,9 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     const int K = s->sh_order == 2 ? 9 : 16;
     // TEX: only scenes with a textured material pay for the texture branch of the hit shading
     const bool tex = ctx->max_tex_index >= 0;
-#define VLB_PICK(KK) (gather ? (tex ? (count ? k_bake_stream<KK, true, true, true> : k_bake_stream<KK, false, true, true>)     \
-                                    : (count ? k_bake_stream<KK, true, true, false> : k_bake_stream<KK, false, true, false>))   \
-                             : (tex ? (count ? k_bake_stream<KK, true, false, true> : k_bake_stream<KK, false, false, true>)   \
-                                    : (count ? k_bake_stream<KK, true, false, false> : k_bake_stream<KK, false, false, false>)))
-    void (*kern)(const BakeParams) = K == 9 ? VLB_PICK(9) : VLB_PICK(16);
+#define VLB_PICK(KK) (tex ? (count ? k_bake_stream<KK, true, false, true> : k_bake_stream<KK, false, false, true>)   \
+                          : (count ? k_bake_stream<KK, true, false, false> : k_bake_stream<KK, false, false, false>))
+    BakeKernel kern = gather ? bake_gather_kernel(K, count, tex) : (K == 9 ? VLB_PICK(9) : VLB_PICK(16));
 #undef VLB_PICK
     // Shared memory holds the short stacks and the hit queues (kBakeSmemPerBlock per block); everything else of the
     // SM's 228 KB stays L1 (BVH nodes, triangles, shadow-ray queues, radiance tiles).
@@ -1154,5 +1178,7 @@ int trace_rays(vlb_ctx* ctx, const float* o, const float* d, uint64_t n64, float
     if (overflow) return ctx->fail(VLB_ERR_UNSUPPORTED, "vlb_trace_rays: BVH traversal stack overflow");
     return VLB_OK;
 }
+
+#endif   // !VLB_BAKE_GATHER_TU
 
 }  // namespace vlb

@@ -65,6 +65,23 @@ VLB_HD float f_sqrt(float a) {
 #endif
 }
 
+// The same division / square root for the cold code of the bake kernel (hit shading, sky lookup, gather): one
+// out-of-line copy each on the device instead of ~10 inlined instructions per site (see pow_f below: cold straight-line
+// code pays for every instruction-cache line). The traversal (intersect_tri, safe_inv) keeps the inlined forms.
+#ifndef VLB_POW_OUTLINE
+#define VLB_POW_OUTLINE 1
+#endif
+#ifndef VLB_COLD_OUTLINE
+#define VLB_COLD_OUTLINE VLB_POW_OUTLINE
+#endif
+#if defined(__CUDA_ARCH__) && VLB_COLD_OUTLINE
+static __device__ __noinline__ float f_div_c(float a, float b) { return __fdiv_rn(a, b); }
+static __device__ __noinline__ float f_sqrt_c(float a) { return __fsqrt_rn(a); }
+#else
+VLB_HD float f_div_c(float a, float b) { return f_div(a, b); }
+VLB_HD float f_sqrt_c(float a) { return f_sqrt(a); }
+#endif
+
 struct Vec3 {
     float x, y, z;
 };
@@ -72,10 +89,18 @@ VLB_HD Vec3 mk3(float x, float y, float z) { Vec3 v; v.x = x; v.y = y; v.z = z; 
 VLB_HD float dot_exact(Vec3 a, Vec3 b) { return f_fma(a.z, b.z, f_fma(a.y, b.y, f_mul(a.x, b.x))); }
 
 // normalize(): v / sqrt(dot(v,v)), fixed operation order (oracle: normalize3).
-VLB_HD Vec3 normalize_exact(Vec3 v) {
+#ifndef VLB_NORMALIZE_OUTLINE
+#define VLB_NORMALIZE_OUTLINE 0
+#endif
+#if defined(__CUDA_ARCH__) && VLB_NORMALIZE_OUTLINE
+static __device__ __noinline__
+#else
+VLB_HD
+#endif
+Vec3 normalize_exact(Vec3 v) {
     const float l2 = f_fma(v.z, v.z, f_fma(v.y, v.y, f_mul(v.x, v.x)));
-    const float len = f_sqrt(l2);
-    return mk3(f_div(v.x, len), f_div(v.y, len), f_div(v.z, len));
+    const float len = f_sqrt_c(l2);
+    return mk3(f_div_c(v.x, len), f_div_c(v.y, len), f_div_c(v.z, len));
 }
 
 // shaders/sh_common.h:8-12 from tabulated sin/cos (tables are built on the host in double and
@@ -113,9 +138,6 @@ VLB_HD void sh_basis(Vec3 d, float* o) {
 // k_bake_stream's instructions -- cold straight-line code that missed the instruction cache on every line (ncu round 2:
 // `no_instruction` = 45 % of the stall samples of the kernel's cold code). Same code, same bits; C3 148.7 -> 144.8 ms
 // (profiles/r02_bake_icache_ab.log). VLB_POW_OUTLINE=0 builds the inlined form.
-#ifndef VLB_POW_OUTLINE
-#define VLB_POW_OUTLINE 1
-#endif
 #if defined(__CUDA_ARCH__) && VLB_POW_OUTLINE
 static __device__ __noinline__ float pow_f(float a, float b) { return powf(a, b); }
 #else

@@ -30,10 +30,17 @@ struct BakeConsts {
     uint32_t flags;
 };
 
-VLB_HD float glsl_mod(float x, float y) { return x - y * floorf(x / y); }
+VLB_HD float glsl_mod(float x, float y) { return x - y * floorf(f_div_c(x, y)); }
 VLB_HD float clampf(float x, float a, float b) { return fminf(fmaxf(x, a), b); }
 VLB_HD int wrapi(int i, int n) { int r = i % n; return r < 0 ? r + n : r; }
 VLB_HD int mini(int a, int b) { return a < b ? a : b; }
+// wrapi for an index no further than n outside [0, n) -- the sky lookup's texels are in [-1, n] -- without the integer
+// division (~20 instructions, four sites); anything else (NaN directions) is clamped into the map instead of wrapped.
+VLB_HD int wrap_near(int i, int n) {
+    i = i < 0 ? i + n : i;
+    i = i >= n ? i - n : i;
+    return i < 0 ? 0 : (i >= n ? n - 1 : i);
+}
 
 // main.rmiss:18-35 + bilinear / repeat lookup at LOD 0 (sampler: src/application.hpp:45-52)
 VLB_HD void sky_lookup(const ShadeView& s, Vec3 dir, float rgb[3]) {
@@ -44,13 +51,13 @@ VLB_HD void sky_lookup(const ShadeView& s, Vec3 dir, float rgb[3]) {
     if (theta > kPi) { theta = 2.0f * kPi - theta; phi += kPi; }
     phi = glsl_mod(phi, 2.0f * kPi);
     phi = clampf(phi, 0.0f, 2.0f * kPi);
-    const float u = phi / (2.0f * kPi), v = theta / kPi;
+    const float u = f_div_c(phi, 2.0f * kPi), v = f_div_c(theta, kPi);
     const int W = s.sky_w, H = s.sky_h;
     const float fx = u * (float)W - 0.5f, fy = v * (float)H - 0.5f;
     const float flx = floorf(fx), fly = floorf(fy);
     const float ax = fx - flx, ay = fy - fly;
-    const int x0 = wrapi((int)flx, W), x1 = wrapi((int)flx + 1, W);
-    const int y0 = wrapi((int)fly, H), y1 = wrapi((int)fly + 1, H);
+    const int x0 = wrap_near((int)flx, W), x1 = wrap_near((int)flx + 1, W);
+    const int y0 = wrap_near((int)fly, H), y1 = wrap_near((int)fly + 1, H);
     const float4 p00 = ld4_stream(s.sky + (size_t)y0 * W + x0);
     const float4 p10 = ld4_stream(s.sky + (size_t)y0 * W + x1);
     const float4 p01 = ld4_stream(s.sky + (size_t)y1 * W + x0);
@@ -194,8 +201,8 @@ VLB_HD bool shade_prelude(const ShadeView& s, const BakeConsts& c, const HitRec&
     p.N = normalize_exact(xform_normal(nm, nrm));                       // :68
     const Vec3 P = mk3(f_fma(r.x, h.t, o.x), f_fma(r.y, h.t, o.y), f_fma(r.z, h.t, o.z));  // :67
     const Vec3 L = mk3(c.light[0] - P.x, c.light[1] - P.y, c.light[2] - P.z);             // :73
-    p.llen = f_sqrt(dot_exact(L, L));
-    p.Ln = mk3(f_div(L.x, p.llen), f_div(L.y, p.llen), f_div(L.z, p.llen));
+    p.llen = f_sqrt_c(dot_exact(L, L));
+    p.Ln = mk3(f_div_c(L.x, p.llen), f_div_c(L.y, p.llen), f_div_c(L.z, p.llen));
     p.sDotN = fmaxf(dot_exact(p.Ln, p.N), 0.0f);                        // :79
     p.so = mk3(f_fma(c.shadow_bias, p.N.x, P.x), f_fma(c.shadow_bias, p.N.y, P.y),
                f_fma(c.shadow_bias, p.N.z, P.z));                       // :82
@@ -207,7 +214,7 @@ VLB_HD bool shade_prelude(const ShadeView& s, const BakeConsts& c, const HitRec&
 // (shaders/main.rchit:126 `floor(hitPosition / gridStep)`, for an arbitrary grid).
 VLB_HD int gather_cell(float p, float origin, float step, int n) {
     if (n < 2) return 0;
-    const float g = floorf(f_div(f_sub(p, origin), step));
+    const float g = floorf(f_div_c(f_sub(p, origin), step));
     if (!(g > 0.0f)) return 0;                                          // also NaN (step == 0)
     return g >= (float)(n - 2) ? n - 2 : (int)g;
 }
@@ -217,7 +224,7 @@ VLB_HD int gather_cell(float p, float origin, float step, int n) {
 VLB_HD void gather_corner(const GatherView& g, Vec3 P, int ci, int cj, int ck, int c, int& i, int& j, int& k, Vec3& d, float& tmax) {
     i = mini(ci + ((c >> 2) & 1), g.Nx - 1); j = mini(cj + ((c >> 1) & 1), g.Ny - 1); k = mini(ck + (c & 1), g.Nz - 1);
     d = mk3(f_sub(g.px[i], P.x), f_sub(g.py[j], P.y), f_sub(g.pz[k], P.z));
-    tmax = f_sqrt(dot_exact(d, d));
+    tmax = f_sqrt_c(dot_exact(d, d));
 }
 
 // The reference's run-time gather (shaders/main.rchit:124-163, probe lookup shaders/sh.rmiss:20-36)
@@ -230,7 +237,7 @@ VLB_HD void gather_accumulate(const GatherView& g, const ShadePrelude& p, unsign
     const int ci = gather_cell(p.P.x, g.origin[0], g.step[0], g.Nx);
     const int cj = gather_cell(p.P.y, g.origin[1], g.step[1], g.Ny);
     const int ck = gather_cell(p.P.z, g.origin[2], g.step[2], g.Nz);
-    const float weight_max = f_sqrt(dot_exact(mk3(g.step[0], g.step[1], g.step[2]), mk3(g.step[0], g.step[1], g.step[2])));  // :141
+    const float weight_max = f_sqrt_c(dot_exact(mk3(g.step[0], g.step[1], g.step[2]), mk3(g.step[0], g.step[1], g.step[2])));  // :141
     float basis[K];
     sh_basis<K>(g.world_frame ? p.N : mk3(p.N.x, p.N.z, p.N.y), basis);
     float sum[3] = {0.f, 0.f, 0.f}, wsum = 0.f;
@@ -256,7 +263,7 @@ VLB_HD void gather_accumulate(const GatherView& g, const ShadePrelude& p, unsign
         sum[0] = f_fma(w, v0, sum[0]); sum[1] = f_fma(w, v1, sum[1]); sum[2] = f_fma(w, v2, sum[2]);   // :160
         wsum = f_add(wsum, w);                                          // :161
     }
-    for (int c = 0; c < 3; ++c) out[c] = wsum > 0.0f ? f_mul(g.gain, f_div(sum[c], wsum)) : 0.0f;      // :164-165
+    for (int c = 0; c < 3; ++c) out[c] = wsum > 0.0f ? f_mul(g.gain, f_div_c(sum[c], wsum)) : 0.0f;      // :164-165
 }
 
 // Gather with the 8 visibility rays traced right here by the calling thread (tests/emu, probe_ray_radiance).
