@@ -374,6 +374,16 @@ def run_ours(args):
         l1_peak = 148 * 128 * sm_mhz * 1e6 / 1e9                          # 128 B per clock per SM through the L1 data pipe
         traffic = ncu_traffic(kname + ":" + which)
         pipes = ncu_pipes(kname + ":" + which)
+        # The ncu figures are static (a profiler cannot run inside a timed bench). They are only quoted when the capture is of
+        # THIS kernel: its duration under ncu must agree with the duration measured live, else they are dropped as stale.
+        if pipes and pipes.get("kernel_ms_under_ncu") and world == 1:
+            drift = abs(pipes["kernel_ms_under_ncu"] - kern_ms) / kern_ms
+            if drift > 0.05:
+                sys.stderr.write("[bench] profiles/ncu_pipes.json is stale for %s (%.1f ms under ncu, %.1f ms live): not quoted\n"
+                                 % (kname, pipes["kernel_ms_under_ncu"], kern_ms))
+                pipes, traffic = None, None
+            else:
+                pipes = dict(pipes, live_kernel_ms=kern_ms, drift_vs_capture=drift)
         roofline = {"bound": "l1", "kernel": kname, "achieved": achieved, "peak": l1_peak, "unit": "GB/s",
                     "frac": achieved / l1_peak, "traffic": traffic,
                     "peak_source": "148 SMs x 128 B/clk x %.0f MHz (SM clock sampled during the timed region): the L1 data pipe, the "
