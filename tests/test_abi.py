@@ -115,3 +115,18 @@ def test_header_is_plain_c(tmp_path):
                            "-lvlb_bake", "-Wl,-rpath," + lib_dir])
     out = subprocess.check_output([str(exe)]).decode().split()
     assert out == ["1", "7", "3141", "144"]
+
+
+def test_tile_reciprocal_is_exact():
+    """bake.cu divides a tile index by tiles_x with umul64hi(tile, rcp), rcp = floor(2^64 / tiles_x) + 1 as bake_device computes
+    it in 64-bit arithmetic. Exact for every 32-bit tile and every tiles_x >= 2 (tiles_x == 1 takes a branch)."""
+    rng = np.random.default_rng(5)
+    M = (1 << 64) - 1
+    ds = [2, 3, 5, 7, 16, 20, 393, 1024, 4097, 65535, 65536, (1 << 31) - 1, 1 << 31, (1 << 32) - 1] + [int(x) for x in rng.integers(2, 1 << 32, 200)]
+    for d in ds:
+        rcp = M // d + (2 if (M % d) + 1 == d else 1)          # the host expression of bake_device
+        assert rcp == (1 << 64) // d + 1 and rcp <= M
+        ns = [0, 1, d - 1, d, d + 1, 2 * d - 1, (1 << 32) - 1, ((1 << 32) - 1) // d * d, ((1 << 32) - 1) // d * d - 1] + [int(x) for x in rng.integers(0, 1 << 32, 50)]
+        for n in ns:
+            if 0 <= n < (1 << 32):
+                assert (n * rcp) >> 64 == n // d, (n, d)

@@ -259,6 +259,22 @@ def test_bake_room_vs_oracle(ctx, vlb, scenes, room, order, flags):
         assert np.all(got[:, 9:] == 0)
 
 
+@pytest.mark.parametrize("dirs", [(5, 3), (9, 7), (33, 17), (100, 37), (64, 64)])
+def test_bake_odd_direction_grids_vs_oracle(ctx, vlb, scenes, room, dirs):
+    """Direction grids that do not fill their 32-texel tiles, one tile column (W <= 8: the kernel's tile / tiles_x takes its
+    tiles_x == 1 branch), odd tile counts (the host reciprocal of tile_xy), and a grid of full-size chunks (two-phase schedule)."""
+    sc, osc = room
+    ctx.set_scene(sc)
+    sky = scenes.hdr_sky(64, 32, seed=4)
+    ctx.set_skybox(sky)
+    osc.set_skybox(sky)
+    s = _room_settings(vlb, ctx, vlb.SHADOW_RAYS | vlb.SKYBOX_ON_MISS | vlb.SRGB_ENCODE, 3, probes=(2, 1, 2), dirs=dirs)
+    got = ctx.bake_probes(s)
+    ref, n_shadow = osc.bake_probes(s)
+    assert rel_l2(got, ref) <= PROBE_TOL
+    assert ctx.last_bake_stats().n_shadow_rays == n_shadow
+
+
 def test_bake_slab_union_is_bitwise_full(ctx, vlb, scenes, room):
     sc, _ = room
     ctx.set_scene(sc)
