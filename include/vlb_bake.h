@@ -360,6 +360,21 @@ int vlb_bake_gather_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float
  * its traversal overflowed the per-ray stack (vlb_bake_probes reports that itself). */
 int vlb_bake_last_stats(vlb_ctx* ctx, vlb_bake_stats* out);
 
+/* --- diagnostics: measured ceilings for the traversal kernel's roofline ------------------
+ * The bake kernel is bound by the L1 data pipe (scattered 16-byte loads of L1/L2-resident BVH nodes), so bench.py divides
+ * its load rates by what THIS device delivers to three micro-kernels (csrc/diag.cu): an L2-resident stream (L1 bypassed),
+ * an L1-resident stream, and the traversal's own access shape (8 distinct 128-byte lines per warp-level load, 4 lanes per
+ * address). No reference counterpart (SURVEY 8(d) asks for the roofline the numbers are held against). */
+typedef struct vlb_cache_peaks {
+    double l2_read_gbs;                   /* GB/s, 48 MB buffer, ld.global.cg */
+    double l1_read_gbs;                   /* GB/s, 32 KB per block, coalesced */
+    double l1_scatter_lines_per_request;  /* 8 */
+    double l1_scatter_requests_per_s;     /* warp-level 16-byte load instructions per second, whole device */
+    double l1_scatter_wavefronts_per_s;   /* requests x lines */
+    double l1_scatter_gbs;                /* bytes delivered to the 32 lanes of those requests, GB/s */
+} vlb_cache_peaks;
+int vlb_diag_cache_peaks(vlb_ctx* ctx, vlb_cache_peaks* out);
+
 /* --- validation entry points (BVH hit IDs bit-exact vs brute force) --------------------- */
 enum { VLB_TRACE_BVH = 0, VLB_TRACE_BRUTE_FORCE = 1 };
 enum { VLB_TRACE_CLOSEST = 0, VLB_TRACE_ANY = 1 };

@@ -119,6 +119,12 @@ class BakeStats(ctypes.Structure):
                 ("total_ms", ctypes.c_float)]
 
 
+class CachePeaks(ctypes.Structure):      # vlb_cache_peaks
+    _fields_ = [("l2_read_gbs", ctypes.c_double), ("l1_read_gbs", ctypes.c_double), ("l1_scatter_lines_per_request", ctypes.c_double),
+                ("l1_scatter_requests_per_s", ctypes.c_double), ("l1_scatter_wavefronts_per_s", ctypes.c_double),
+                ("l1_scatter_gbs", ctypes.c_double)]
+
+
 class VlbError(RuntimeError):
     def __init__(self, code, message):
         super().__init__("vlb error %d: %s" % (code, message))
@@ -132,7 +138,7 @@ ABI_SYMBOLS = [
     "vlb_scene_set_textures", "vlb_gltf_texture", "vlb_image_load_rgba8", "vlb_image_load_rgba32f", "vlb_bake_probes_multi", "vlb_skybox_set", "vlb_skybox_set_async", "vlb_skybox_project_sh", "vlb_skybox_project_sh_batched", "vlb_skybox_project_sh_device",
     "vlb_skybox_project_sh_device_ptrs", "vlb_envmap_project_sh", "vlb_bake_settings_default", "vlb_bake_settings_from_bounds", "vlb_probe_positions",
     "vlb_bake_probes", "vlb_bake_probes_device", "vlb_bake_gather_device", "vlb_bake_last_stats", "vlb_trace_rays",
-    "vlb_bake_serialize_gltf", "vlb_bake_deserialize_gltf",
+    "vlb_bake_serialize_gltf", "vlb_bake_deserialize_gltf", "vlb_diag_cache_peaks",
     "vlb_comm_get_unique_id", "vlb_comm_init_rank", "vlb_comm_init_all", "vlb_comm_destroy", "vlb_comm_info",
     "vlb_comm_sharded_uploads", "vlb_bake_probes_sharded_device", "vlb_bake_probes_sharded", "vlb_bake_probes_sharded_rows",
 ]
@@ -189,6 +195,7 @@ def load_library():
         "vlb_trace_rays": (i32, [vp, vp, vp, u64, f32, f32, i32, i32, vp, vp]),
         "vlb_bake_serialize_gltf": (i32, [ctypes.c_char_p, ctypes.c_char_p, vp, u64, S]),
         "vlb_bake_deserialize_gltf": (i32, [ctypes.c_char_p, vp, u64, ctypes.POINTER(u64), vp]),
+        "vlb_diag_cache_peaks": (i32, [vp, ctypes.POINTER(CachePeaks)]),
         "vlb_comm_get_unique_id": (i32, [vp, u64]),
         "vlb_comm_init_rank": (i32, [vp, vp, i32, i32]),
         "vlb_comm_init_all": (i32, [vp, u32]),
@@ -382,6 +389,12 @@ class Context:
     def bake_gather_device(self, s, d_prev_full, d_out):
         """One gather pass: d_prev_full = previous pass over the WHOLE grid ([n_probes, 48] device floats) or 0."""
         self._check(self._lib.vlb_bake_gather_device(self._h, ctypes.byref(s), int(d_prev_full) if d_prev_full else None, int(d_out)))
+
+    def cache_peaks(self):
+        """Measured L2 / L1 read ceilings of this device (vlb_diag_cache_peaks), as a dict."""
+        pk = CachePeaks()
+        self._check(self._lib.vlb_diag_cache_peaks(self._h, ctypes.byref(pk)))
+        return {k: getattr(pk, k) for k, _ in CachePeaks._fields_}
 
     def last_bake_stats(self):
         st = BakeStats()

@@ -18,7 +18,7 @@ LIB = os.path.join(HERE, "libvlb_bake%s.so" % ("_" + TAG if TAG else ""))
 CLI = os.path.join(HERE, "vlb_baker")          # the reference's `baker` executable on top of the C ABI
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-SOURCES = ["context.cu", "bvh_build.cu", "bake.cu", "bake_gather.cu", "skybox_sh.cu", "comm.cu", "host_tables.cpp", "gltf_io.cpp", "gltf_scene.cpp", "png_decode.cpp", "jpeg_decode.cpp", "hdr_decode.cpp"]
+SOURCES = ["context.cu", "bvh_build.cu", "bake.cu", "bake_gather.cu", "diag.cu", "skybox_sh.cu", "comm.cu", "host_tables.cpp", "gltf_io.cpp", "gltf_scene.cpp", "png_decode.cpp", "jpeg_decode.cpp", "hdr_decode.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-ffp-contract=off,-Wall,-Wno-unknown-pragmas", "--expt-relaxed-constexpr"]
 NVCC_FLAGS += os.environ.get("VLB_NVCC_EXTRA", "").split()   # e.g. -DVLB_PROJ_TIMING for instrumented debug builds
