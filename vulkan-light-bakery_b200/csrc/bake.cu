@@ -345,6 +345,8 @@ struct VisExchange {
     float P[3][32], so[3][32];
     int cell[3][32];
     unsigned occluded[32];       // bit c: the ray from hit `lane` to corner c of its cell was blocked
+    int list[32];                // the lanes that hold a hit, in lane order (ray r belongs to hit list[r / 8])
+    int root[32];                // where the 8 rays of hit `lane` enter the tree: the root, or their cell's common ancestor (k_cell_roots)
 };
 
 // Entry points of the visibility rays (gather passes). A visibility ray runs from a hit inside grid cell (i, j, k) to
@@ -388,6 +390,18 @@ __global__ void k_cell_roots(BvhView b, const float* __restrict__ px, const floa
 // tree in the same while-while loop as the main rays and refill as they finish, so the warp stays full although the
 // rays are short and of very different lengths. (Round 1 traced the 8 rays of a hit one after the other inside the
 // shading lane: 32 lanes in lockstep on unrelated rays, a gather pass cost 5.5 direct passes.) `hm`: lanes holding a hit.
+// Entry point of the 8 visibility rays of a hit with biased origin `ro` in grid cell (ci, cj, ck): below the root when the
+// rays lie inside their cell's (grown) box -- origin inside, targets = the cell's corners -- else the root.
+__device__ __forceinline__ int vis_entry(const GatherView& g, Vec3 ro, int ci, int cj, int ck) {
+    if (!g.cell_root) return 0;
+    const float m = g.cell_margin;
+    const bool inside = g.Nx > 1 && g.Ny > 1 && g.Nz > 1 &&
+        ro.x >= fminf(g.px[ci], g.px[ci + 1]) - m && ro.x <= fmaxf(g.px[ci], g.px[ci + 1]) + m &&
+        ro.y >= fminf(g.py[cj], g.py[cj + 1]) - m && ro.y <= fmaxf(g.py[cj], g.py[cj + 1]) + m &&
+        ro.z >= fminf(g.pz[ck], g.pz[ck + 1]) - m && ro.z <= fmaxf(g.pz[ck], g.pz[ck + 1]) + m;
+    return inside ? __ldg(g.cell_root + ci + (g.Nx - 1) * (cj + (g.Ny - 1) * ck)) : 0;
+}
+
 template <bool COUNT>
 __device__ __forceinline__ void trace_vis_batch(const BvhView& bvh, const GatherView& g, RayStack& stk, VisExchange& X, unsigned hm,
                                                 int lane, int node_min, int refill_min, TraceCounters& cnt) {
@@ -405,9 +419,9 @@ __device__ __forceinline__ void trace_vis_batch(const BvhView& bvh, const Gather
 #if VLB_VIS_CORNER_MAJOR
                 // corner-major order: neighbouring lanes trace the rays of neighbouring hits towards the SAME corner of their
                 // cells (near-parallel rays from near-by origins) instead of the eight diverging rays of one hit
-                const int c = cand / n_hits, h = __fns(hm, 0, cand - c * n_hits + 1);
+                const int c = cand / n_hits, h = X.list[cand - c * n_hits];
 #else
-                const int h = __fns(hm, 0, (cand >> 3) + 1), c = cand & 7;
+                const int h = X.list[cand >> 3], c = cand & 7;     // (a table instead of __fns: ~50 instructions per ray)
 #endif
                 const Vec3 P = mk3(X.P[0][h], X.P[1][h], X.P[2][h]);
                 int i, j, k; Vec3 d; float tmax;
@@ -418,17 +432,8 @@ __device__ __forceinline__ void trace_vis_batch(const BvhView& bvh, const Gather
                     idir = mk3(safe_inv(rd.x), safe_inv(rd.y), safe_inv(rd.z));
                     ood = mk3(ro.x * idir.x, ro.y * idir.y, ro.z * idir.z);
                     tcull = tmax; tag = (h << 3) | c;
-                    stk.clear(); cur = 0;
-                    if (g.cell_root) {
-                        // start below the root when the ray lies inside its cell's (grown) box: origin inside, target = a corner
-                        const int ci = X.cell[0][h], cj = X.cell[1][h], ck = X.cell[2][h];
-                        const float m = g.cell_margin;
-                        const bool inside = g.Nx > 1 && g.Ny > 1 && g.Nz > 1 &&
-                            ro.x >= fminf(g.px[ci], g.px[ci + 1]) - m && ro.x <= fmaxf(g.px[ci], g.px[ci + 1]) + m &&
-                            ro.y >= fminf(g.py[cj], g.py[cj + 1]) - m && ro.y <= fmaxf(g.py[cj], g.py[cj + 1]) + m &&
-                            ro.z >= fminf(g.pz[ck], g.pz[ck + 1]) - m && ro.z <= fmaxf(g.pz[ck], g.pz[ck + 1]) + m;
-                        if (inside) cur = __ldg(g.cell_root + ci + (g.Nx - 1) * (cj + (g.Ny - 1) * ck));
-                    }
+                    stk.clear();
+                    cur = X.root[h];                 // the root, or below it (vis_entry: once per hit, not per ray)
                     busy = cur != kRayDone;          // kNoChild: nothing reaches into the cell, the corner is visible
                 }
             }
@@ -622,10 +627,12 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                             X.cell[0][lane] = gather_cell(q.P.x, p.g.origin[0], p.g.step[0], p.g.Nx);
                             X.cell[1][lane] = gather_cell(q.P.y, p.g.origin[1], p.g.step[1], p.g.Ny);
                             X.cell[2][lane] = gather_cell(q.P.z, p.g.origin[2], p.g.step[2], p.g.Nz);
+                            X.root[lane] = vis_entry(p.g, q.so, X.cell[0][lane], X.cell[1][lane], X.cell[2][lane]);
                             has_hit = true;
                         }
                         X.occluded[lane] = 0u;
                         const unsigned hm = __ballot_sync(full, has_hit);
+                        if (has_hit) X.list[__popc(hm & lt_mask)] = lane;
                         __syncwarp();
                         if (hm != 0u && bvh.n_tris) trace_vis_batch<COUNT>(bvh, p.g, stk2, X, hm, lane, p.node_min, p.vis_refill_min, cnt);
                         occluded = X.occluded[lane];

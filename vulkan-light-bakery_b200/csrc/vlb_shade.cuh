@@ -241,6 +241,7 @@ VLB_HD void gather_accumulate(const GatherView& g, const ShadePrelude& p, unsign
     float basis[K];
     sh_basis<K>(g.world_frame ? p.N : mk3(p.N.x, p.N.z, p.N.y), basis);
     float sum[3] = {0.f, 0.f, 0.f}, wsum = 0.f;
+#pragma unroll 1                                                        // one copy of the corner body: cold code (bake.cu: instruction cache)
     for (int c = 0; c < 8; ++c) {                                       // gridVertices order, :128-137
         if ((occluded >> c) & 1u) continue;
         int i, j, k; Vec3 d; float tmax;
