@@ -456,7 +456,7 @@ def test_whole_probe_items_and_per_chunk_items_give_the_same_bits(vlb, scenes, m
 
 def test_ray_slot_policies_give_the_same_bits(vlb, scenes, monkeypatch):
     """How the warp schedules its ray slots -- interleaved refills (order 0 / 1), deferred shading in two phases per chunk
-    (order 3, the default for long chunks), refill thresholds -- never shows in the result: every policy gives the same coefficients bit for bit and the same shadow-ray count."""
+    (order 3, the default for long chunks), refill thresholds, per-direction tables or the same values computed in place -- never shows in the result: every policy gives the same coefficients bit for bit and the same shadow-ray count."""
     import torch
     sc = scenes.small_room()
     sky = scenes.hdr_sky(64, 32, seed=4)
@@ -464,10 +464,11 @@ def test_ray_slot_policies_give_the_same_bits(vlb, scenes, monkeypatch):
     s.probes[:] = (12, 12, 8); s.dir_w, s.dir_h = 64, 64; s.sh_order = 2; s.light_pos[:] = (2.0, 3.5, 2.0)
     s.flags = vlb.SHADOW_RAYS | vlb.SKYBOX_ON_MISS | vlb.SRGB_ENCODE
     vlb.settings_from_bounds(s, (0.3, 0.3, 0.3, 3.7, 3.7, 3.7))
-    knobs = ("VLB_BAKE_REFILL_ORDER", "VLB_BAKE_REFILL_MIN", "VLB_BAKE_NODE_MIN")
+    knobs = ("VLB_BAKE_REFILL_ORDER", "VLB_BAKE_REFILL_MIN", "VLB_BAKE_NODE_MIN", "VLB_BAKE_DIR_TABLES")
     policies = [{}, {"VLB_BAKE_REFILL_ORDER": "0"}, {"VLB_BAKE_REFILL_ORDER": "1"}, {"VLB_BAKE_REFILL_ORDER": "3"},
                 {"VLB_BAKE_REFILL_ORDER": "3", "VLB_BAKE_REFILL_MIN": "1", "VLB_BAKE_NODE_MIN": "1"},
-                {"VLB_BAKE_REFILL_ORDER": "1", "VLB_BAKE_REFILL_MIN": "32", "VLB_BAKE_NODE_MIN": "16"}]
+                {"VLB_BAKE_REFILL_ORDER": "1", "VLB_BAKE_REFILL_MIN": "32", "VLB_BAKE_NODE_MIN": "16"},
+                {"VLB_BAKE_DIR_TABLES": "0"}, {"VLB_BAKE_DIR_TABLES": "0", "VLB_BAKE_REFILL_ORDER": "1"}]
     with vlb.Context(0) as c:
         c.set_scene(sc); c.build_bvh(); c.set_skybox(sky)
         ref = None

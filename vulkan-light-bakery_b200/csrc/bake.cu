@@ -18,7 +18,13 @@
 #ifndef VLB_COLD_OUTLINE
 #define VLB_COLD_OUTLINE VLB_BAKE_GATHER_TU
 #endif
+// Per-direction tables (k_dir_tables): compiled into the direct-pass kernels only. C3 -0.85 %, C2 -2.3 %, the direct pass of
+// C4 -2.6 %; the gather kernel, whose time is its visibility rays, lost 0.7 % to the extra code (profiles/r02_bake_dir_tables_ab.log).
+#ifndef VLB_DIR_TABLES
+#define VLB_DIR_TABLES (!VLB_BAKE_GATHER_TU)
+#endif
 #include <algorithm>
+#include <cstring>
 
 #include "vlb_context.h"
 #include "vlb_shade.cuh"
@@ -46,6 +52,9 @@ struct BakeParams {
     const float2* col_cs;                                // (cos, sin) phi per direction column
     int Nx, Ny, Nz, k0, kstride;   // the call bakes z-slices k0, k0 + kstride, ...
     int W, H, tiles_x, n_tiles, tile_lw;   // tile_lw: log2 of the direction tile's width
+    // Probe-independent per-direction work, hoisted into tables (k_dir_tables; NULL: computed in place, large direction grids):
+    const float4* dir_tab;                 // [n_tiles * 32]: unit ray direction (env_map.rgen:21) of slot w of a tile, w = 1 inside the grid / 0 outside
+    const float* proj_tab;                 // [n_tiles][K][32]: SH basis x quadrature weight of the slot's direction (sh.comp:30-39)
     unsigned long long tiles_x_rcp;        // floor(2^64 / tiles_x) + 1: umul64hi(tile, rcp) == tile / tiles_x for every 32-bit tile (tiles_x >= 2)
     int chunks, tiles_per_chunk;
     uint32_t n_items;
@@ -74,6 +83,49 @@ __device__ __forceinline__ void tile_xy(const BakeParams& p, int tile, int w, in
     x = (int)(col << p.tile_lw) + (w & ((1 << p.tile_lw) - 1));
     y = (int)(row << (5 - p.tile_lw)) + (w >> p.tile_lw);
 }
+
+// unit ray direction of slot w of a tile (env_map.rgen:19-21): from the table, or from the sin / cos tables
+__device__ __forceinline__ Vec3 slot_direction(const BakeParams& p, int tile, int w) {
+    if (VLB_DIR_TABLES && p.dir_tab) {
+        const float4 dt = __ldg(p.dir_tab + (size_t)tile * 32 + w);
+        return mk3(dt.x, dt.y, dt.z);
+    }
+    int x, y;
+    tile_xy(p, tile, w, x, y);
+    const float2 row = __ldg(p.row_sc + y), col = __ldg(p.col_cs + x);
+    const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);   // sh_common.h:8-12
+    return mk3(t.x, t.z, t.y);                                 // .xzy
+}
+
+#if !VLB_BAKE_GATHER_TU
+// The per-direction work that does not depend on the probe -- the ray direction and the projection weights basis x
+// sin(theta) x pixel area -- is the same for all probes of a call (131,072 at C3): computed once here with the very
+// expressions the kernel would use in place, so the bits are the same.
+template <int K>
+__global__ void k_dir_tables(const BakeParams p, float4* dir_tab, float* proj_tab) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= p.n_tiles * 32) return;
+    const int tile = d >> 5, w = d & 31;
+    int x, y;
+    tile_xy(p, tile, w, x, y);
+    const bool inside = x < p.W && y < p.H;
+    float4 dt = make_float4(0.f, 0.f, 0.f, 0.f);
+    float b[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) b[i] = 0.f;
+    float wgt = 0.f;
+    if (inside) {
+        const float2 row = __ldg(p.row_sc + y), col = __ldg(p.col_cs + x);
+        const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);
+        dt = make_float4(t.x, t.z, t.y, 1.0f);
+        wgt = p.pixel_area * row.x;                                         // sh.comp:32-33
+        sh_basis<K>(p.world_frame ? mk3(t.x, t.z, t.y) : t, b);             // sh.comp:30,39
+    }
+    dir_tab[d] = dt;
+#pragma unroll
+    for (int i = 0; i < K; ++i) proj_tab[(size_t)tile * (K * 32) + 32 * i + w] = b[i] * wgt;
+}
+#endif
 
 __device__ __forceinline__ size_t out_slot(const BakeParams& p, uint32_t q) {
     if (!p.ref_order) return q;
@@ -568,12 +620,22 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                     } else if (!busy && rank - take_sh < take_new) {
                         const int cand = next + rank - take_sh;
                         const int tile = base_tile + (cand >> 5), w = cand & 31;
-                        int x, y;
-                        tile_xy(p, tile, w, x, y);
-                        if (x < p.W && y < p.H) {
-                            const float2 row = __ldg(p.row_sc + y), col = __ldg(p.col_cs + x);
-                            const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);   // sh_common.h:8-12
-                            rd = mk3(t.x, t.z, t.y);                                   // env_map.rgen:21 .xzy
+                        bool inside;
+                        if (VLB_DIR_TABLES && p.dir_tab) {
+                            const float4 dt = __ldg(p.dir_tab + (size_t)tile * 32 + w);
+                            rd = mk3(dt.x, dt.y, dt.z);
+                            inside = dt.w != 0.0f;
+                        } else {
+                            int x, y;
+                            tile_xy(p, tile, w, x, y);
+                            inside = x < p.W && y < p.H;
+                            if (inside) {
+                                const float2 row = __ldg(p.row_sc + y), col = __ldg(p.col_cs + x);
+                                const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);   // sh_common.h:8-12
+                                rd = mk3(t.x, t.z, t.y);                                   // env_map.rgen:21 .xzy
+                            }
+                        }
+                        if (inside) {
                             ro = po;
                             tmin = p.c.tmin; tcull = p.c.tmax;
                             best.id = -1; best.t = tcull; best.u = 0.f; best.v = 0.f;
@@ -616,12 +678,8 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                         if (lane < take && __float_as_int(hrec.x) >= 0) {
                             HitRec h; h.id = __float_as_int(hrec.x); h.t = hrec.y; h.u = hrec.z; h.v = hrec.w;
                             const int tile = base_tile + (hd >> 5), w = hd & 31;
-                            int hx, hy;
-                            tile_xy(p, tile, w, hx, hy);
-                            const float2 row = __ldg(p.row_sc + hy), col = __ldg(p.col_cs + hx);
-                            const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);
                             ShadePrelude q;
-                            shade_prelude<TEX>(p.shade, p.c, h, po, mk3(t.x, t.z, t.y), q);
+                            shade_prelude<TEX>(p.shade, p.c, h, po, slot_direction(p, tile, w), q);
                             X.P[0][lane] = q.P.x; X.P[1][lane] = q.P.y; X.P[2][lane] = q.P.z;
                             X.so[0][lane] = q.so.x; X.so[1][lane] = q.so.y; X.so[2][lane] = q.so.z;
                             X.cell[0][lane] = gather_cell(q.P.x, p.g.origin[0], p.g.step[0], p.g.Nx);
@@ -643,11 +701,7 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                         const float4 hrec = ld_scratch(&S.slot[dir]);
                         HitRec h; h.id = __float_as_int(hrec.x); h.t = hrec.y; h.u = hrec.z; h.v = hrec.w;
                         const int tile = base_tile + (dir >> 5), w = dir & 31;
-                        int x, y;
-                        tile_xy(p, tile, w, x, y);
-                        const float2 row = __ldg(p.row_sc + y), col = __ldg(p.col_cs + x);
-                        const Vec3 t = to_vector_sc(row.x, row.y, col.x, col.y);
-                        const Vec3 r = mk3(t.x, t.z, t.y);
+                        const Vec3 r = slot_direction(p, tile, w);
                         float rgb[3] = {0.f, 0.f, 0.f};                                 // env_map.rgen:25
                         if (h.id >= 0) {
                             const bool lit = shade_prelude<TEX>(p.shade, p.c, h, po, r, pre);
@@ -736,6 +790,21 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
             for (int i = 0; i < V; ++i) acc[i] = 0.f;
             for (int tt = 0; tt * 32 < n_dirs; ++tt) {
                 const int tile = base_tile + tt;
+                if (VLB_DIR_TABLES && p.proj_tab) {
+                    if (__ldg(p.dir_tab + (size_t)tile * 32 + lane).w != 0.0f) {
+                        const float* bwp = p.proj_tab + (size_t)tile * (K * 32) + lane;
+                        const float4 rad = ld_scratch(&S.slot[tt * 32 + lane]);
+                        const float r0 = rad.x, r1 = rad.y, r2 = rad.z;
+#pragma unroll
+                        for (int i = 0; i < K; ++i) {
+                            const float bw = __ldg(bwp + 32 * i);
+                            acc[3 * i + 0] = fmaf(bw, r0, acc[3 * i + 0]);
+                            acc[3 * i + 1] = fmaf(bw, r1, acc[3 * i + 1]);
+                            acc[3 * i + 2] = fmaf(bw, r2, acc[3 * i + 2]);
+                        }
+                    }
+                    continue;
+                }
                 int x, y;
                 tile_xy(p, tile, lane, x, y);
                 if (x < p.W && y < p.H) {
@@ -909,6 +978,23 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
 
     const bool count = env_flag("VLB_BAKE_COUNTERS", 0) != 0;
     const int K = s->sh_order == 2 ? 9 : 16;
+    // per-direction tables (ray direction, projection weights): for direction grids up to 64 Ki slots -- beyond that the
+    // tables would be streamed from HBM once per probe, and the kernel computes the values in place as before
+    if (d_prev_full == nullptr && (uint64_t)p.n_tiles * 32 <= (1u << 16) && env_flag("VLB_BAKE_DIR_TABLES", 1)) {   // direct passes only
+        const int key[5] = {W, H, p.tile_lw, K, p.world_frame};
+        const size_t n_slots = (size_t)p.n_tiles * 32;
+        if (std::memcmp(key, ctx->dir_tab_key, sizeof key) != 0) {
+            VLB_CUDA(ctx, ctx->d_dir_tab.reserve(n_slots * sizeof(float4)));
+            VLB_CUDA(ctx, ctx->d_proj_tab.reserve(n_slots * 16 * sizeof(float)));
+            const unsigned blocks = (unsigned)((n_slots + 127) / 128);
+            if (K == 9) k_dir_tables<9><<<blocks, 128, 0, st>>>(p, ctx->d_dir_tab.as<float4>(), ctx->d_proj_tab.as<float>());
+            else        k_dir_tables<16><<<blocks, 128, 0, st>>>(p, ctx->d_dir_tab.as<float4>(), ctx->d_proj_tab.as<float>());
+            VLB_LAUNCH_CHECK(ctx);
+            std::memcpy(ctx->dir_tab_key, key, sizeof key);
+        }
+        p.dir_tab = ctx->d_dir_tab.as<float4>();
+        p.proj_tab = ctx->d_proj_tab.as<float>();
+    }
     // TEX: only scenes with a textured material pay for the texture branch of the hit shading
     const bool tex = ctx->max_tex_index >= 0;
 #define VLB_PICK(KK) (tex ? (count ? k_bake_stream<KK, true, false, true> : k_bake_stream<KK, false, false, true>)   \

@@ -380,10 +380,11 @@ int vlb_bvh_set_builder(vlb_ctx* ctx, int builder, int ploc_radius) {
 }
 
 int vlb_bvh_recommend_builder(uint64_t n_triangles, uint64_t n_primary_rays) {
-    // PLOC costs ~2.5 ns per triangle more than the LBVH and takes ~4.2 % off ~0.31 ns per primary ray (C3, shadow rays
-    // included): worth it above ~190 primary rays per triangle. Measured without gain at 1 M and 3 M triangles.
+    // PLOC costs ~2.3 ns per triangle more than the LBVH (1.06 vs 0.46 ms at 262,144 triangles) and takes ~4.2 % off
+    // ~0.26 ns per primary ray (C3 at 138 ms, shadow rays included): worth it above ~215 primary rays per triangle.
+    // Measured without gain at 1 M and 3 M triangles.
     if (n_triangles < 4096 || n_triangles > (1u << 20)) return VLB_BVH_BUILDER_LBVH;    // a tiny tree has nothing to gain
-    return n_primary_rays > 190ull * n_triangles ? VLB_BVH_BUILDER_PLOC : VLB_BVH_BUILDER_LBVH;
+    return n_primary_rays > 215ull * n_triangles ? VLB_BVH_BUILDER_PLOC : VLB_BVH_BUILDER_LBVH;
 }
 
 int vlb_bvh_build(vlb_ctx* ctx, vlb_bvh_stats* stats) {

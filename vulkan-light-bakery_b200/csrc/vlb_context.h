@@ -113,6 +113,8 @@ struct vlb_ctx {
     // ---- bake ----
     vlb::DevBuf d_bake_out, d_bake_prev, d_partials, d_work_counter, d_axis, d_row_sc, d_col_sc, d_stats, d_stream_scratch, d_stream_spill, d_vis_ovf, d_cell_root;
     int dir_w = 0, dir_h = 0;
+    vlb::DevBuf d_dir_tab, d_proj_tab;            // per-direction tables of the bake (k_dir_tables)
+    int dir_tab_key[5] = {0, 0, 0, 0, -1};        // (W, H, tile_lw, K, world_frame) the tables were built for
     vlb_bake_stats last_bake{};
     bool bake_pending = false;             // a device bake was enqueued and its statistics not yet collected
     unsigned long long* h_bake_stats = nullptr;   // pinned: [0] shadow rays, [1] nodes, [2] triangles, [3] stack overflow
