@@ -983,7 +983,7 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     if (d_prev_full == nullptr && (uint64_t)p.n_tiles * 32 <= (1u << 16) && env_flag("VLB_BAKE_DIR_TABLES", 1)) {   // direct passes only
         const int key[5] = {W, H, p.tile_lw, K, p.world_frame};
         const size_t n_slots = (size_t)p.n_tiles * 32;
-        if (std::memcmp(key, ctx->dir_tab_key, sizeof key) != 0) {
+        if (std::memcmp(key, ctx->dir_tab_key, sizeof key) != 0 || ctx->dir_tab_stream != st) {
             VLB_CUDA(ctx, ctx->d_dir_tab.reserve(n_slots * sizeof(float4)));
             VLB_CUDA(ctx, ctx->d_proj_tab.reserve(n_slots * 16 * sizeof(float)));
             const unsigned blocks = (unsigned)((n_slots + 127) / 128);
@@ -991,6 +991,7 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
             else        k_dir_tables<16><<<blocks, 128, 0, st>>>(p, ctx->d_dir_tab.as<float4>(), ctx->d_proj_tab.as<float>());
             VLB_LAUNCH_CHECK(ctx);
             std::memcpy(ctx->dir_tab_key, key, sizeof key);
+            ctx->dir_tab_stream = st;
         }
         p.dir_tab = ctx->d_dir_tab.as<float4>();
         p.proj_tab = ctx->d_proj_tab.as<float>();

@@ -115,6 +115,7 @@ struct vlb_ctx {
     int dir_w = 0, dir_h = 0;
     vlb::DevBuf d_dir_tab, d_proj_tab;            // per-direction tables of the bake (k_dir_tables)
     int dir_tab_key[5] = {0, 0, 0, 0, -1};        // (W, H, tile_lw, K, world_frame) the tables were built for
+    cudaStream_t dir_tab_stream = nullptr;        // ... and the stream that built them (another stream rebuilds: no cross-stream order is assumed)
     vlb_bake_stats last_bake{};
     bool bake_pending = false;             // a device bake was enqueued and its statistics not yet collected
     unsigned long long* h_bake_stats = nullptr;   // pinned: [0] shadow rays, [1] nodes, [2] triangles, [3] stack overflow
