@@ -65,7 +65,7 @@ struct BakeParams {
     unsigned int* work_counter;
     unsigned long long* stats;   // [0] shadow rays, [1] nodes visited, [2] triangles tested, [4..11] COUNT builds: phase utilisation
     int ref_order, world_frame;
-    WarpQueues* stream_scratch;  // k_bake_stream: per-warp radiance tile + shadow-ray queue, [grid * warps per block]
+    WarpQueues* stream_scratch;  // k_bake_stream: per-warp direction slots (hit record, then radiance) + shadow-ray queue, [grid * warps per block]
     WarpSpill* stream_spill;     // k_bake_stream: per-warp stack overflow rows (rarely touched), same indexing
     int node_min;                // k_bake_stream: the node loop yields to the leaf phase below this many lanes
     int leaf_min;                // ... and at least this many lanes wait at a leaf
@@ -195,10 +195,10 @@ struct HitQueue {
     unsigned short dir[kHitCap];
 };
 #ifndef VLB_BAKE_DISCARD
-#define VLB_BAKE_DISCARD 1                  // discard.global.L2 of the radiance tile once a chunk is projected
+#define VLB_BAKE_DISCARD 1                  // discard.global.L2 of the direction slots once a chunk is projected
 #endif
 // Loads of the per-warp scratch (written by other lanes of the warp): with VLB_L1_HINTS through L2 only, so that the
-// queues and radiance tiles do not compete with the BVH for L1 lines.
+// queues and direction slots do not compete with the BVH for L1 lines.
 template <class T> __device__ __forceinline__ T ld_scratch(const T* p) {
 #if VLB_L1_HINTS
     return __ldcg(p);
@@ -832,7 +832,7 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
             // The tile's radiances are dead now (the next chunk writes every entry before it reads any), but their
             // lines sit dirty in L2 and would be written back to HBM when the BVH / skybox traffic evicts them:
             // round 2 measured 4.2 GB of such write-backs per C3 launch. Tell L2 to drop them instead.
-            static_assert(sizeof(S.slot) % 128 == 0, "radiance tile must cover whole 128-byte lines");
+            static_assert(sizeof(S.slot) % 128 == 0, "the direction slots must cover whole 128-byte lines");
             for (uint32_t off = 128u * lane; off < sizeof(S.slot); off += 32u * 128u)
                 asm volatile("discard.global.L2 [%0], 128;" ::"l"(reinterpret_cast<char*>(&S.slot[0]) + off) : "memory");
             __syncwarp();
@@ -1003,7 +1003,7 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     BakeKernel kern = gather ? bake_gather_kernel(K, count, tex) : (K == 9 ? VLB_PICK(9) : VLB_PICK(16));
 #undef VLB_PICK
     // Shared memory holds the short stacks and the hit queues (kBakeSmemPerBlock per block); everything else of the
-    // SM's 228 KB stays L1 (BVH nodes, triangles, shadow-ray queues, radiance tiles).
+    // SM's 228 KB stays L1 (BVH nodes, triangles, shadow-ray queues, direction slots).
     const int min_blocks = gather ? 6 : VLB_BAKE_MIN_BLOCKS;
     int carve = (int)((min_blocks * ((gather ? kBakeSmemPerBlockGather : kBakeSmemPerBlock) + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
     carve = env_flag("VLB_BAKE_CARVEOUT", std::min(100, carve));
@@ -1013,7 +1013,7 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     per_sm = std::max(per_sm, 1);
     const uint32_t full_grid = (uint32_t)(ctx->sm_count * per_sm);
 
-    // Work decomposition. A probe's directions are traced in chunks of 8 tiles = 256 directions whose SH sums are
+    // Work decomposition. A probe's directions are traced in chunks of kChunkTiles tiles = 512 directions whose SH sums are
     // added up in chunk order, so a probe can be ONE work item (a warp walks all its chunks and writes the 192-byte
     // result itself) or one item PER CHUNK (each writes a partial, k_sum_partials adds them in chunk order): both
     // give bit-identical coefficients, because 0 + a_0 + a_1 + ... is evaluated left to right either way. Whole-probe
@@ -1080,7 +1080,7 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     VLB_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
     VLB_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     {
-        // The warps' radiance tiles and shadow-ray queues (the hot scratch: 8.75 KB per warp, 42 MB for 4,736 warps) are
+        // The warps' direction slots and shadow-ray queues (the hot scratch: 10.75 KB per warp, 51 MB for 4,736 warps) are
         // written and re-read all through the launch, while scene + skybox + scratch together just overflow the L2: ncu
         // showed GBs of scratch lines written back to HBM and fetched again. The launch can carry an L2
         // access-policy window over the hot scratch (persisting lines, as far as the device's set-aside reaches), so the
