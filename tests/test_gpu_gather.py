@@ -56,7 +56,9 @@ def test_gather_pass_device_slabs_are_bitwise_rows_of_the_full_pass(ctx, vlb, sc
     import torch
     sc, osc = room
     ctx.set_scene(sc)
-    ctx.set_skybox(scenes.hdr_sky(64, 32, seed=4))
+    sky = scenes.hdr_sky(64, 32, seed=4)
+    ctx.set_skybox(sky)
+    osc.set_skybox(sky)          # (the oracle scene is shared by the module: do not rely on an earlier test having set it)
     s = _settings(vlb, ctx, vlb.SHADOW_RAYS | vlb.SKYBOX_ON_MISS, order=2, probes=(3, 2, 4))
     prev = torch.from_numpy(ctx.bake_probes(s).reshape(-1, 48)).cuda()
     full = torch.zeros((s.n_probes, 48), device="cuda")
