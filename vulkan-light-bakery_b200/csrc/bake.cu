@@ -23,6 +23,15 @@
 #ifndef VLB_DIR_TABLES
 #define VLB_DIR_TABLES (!VLB_BAKE_GATHER_TU)
 #endif
+// Two small layout choices measured together (profiles/r02_bake_dir_tables_ab.log): shadow-ray queue records as three float4s
+// instead of eleven scalars, and 1 / direction carried by the direction table. Each alone lost ~0.7 % at C3, both together
+// gain 1.25 % (136.6 -> 134.9 ms) -- the kernel's register allocation under the 64-register cap decides, not the idea.
+#ifndef VLB_SQ_PACKED
+#define VLB_SQ_PACKED 1
+#endif
+#ifndef VLB_IDIR_TAB
+#define VLB_IDIR_TAB 1
+#endif
 #include <algorithm>
 #include <cstring>
 
@@ -76,6 +85,7 @@ struct BakeParams {
     int* vis_ovf;                // gather passes: stack overflow slab of the visibility-ray batches, [grid * warps][kOvfStack][32]
 };
 
+constexpr int kDirTabQuads = VLB_IDIR_TAB ? 2 : 1;   // float4s per slot of the direction table
 __device__ __forceinline__ void tile_xy(const BakeParams& p, int tile, int w, int& x, int& y) {
     // exact: rcp = (2^64 + e) / d with 0 < e <= d, so tile * rcp / 2^64 = tile / d + tile * e / (d * 2^64) and tile * e < 2^64
     const uint32_t row = p.tiles_x == 1 ? (uint32_t)tile : (uint32_t)__umul64hi((unsigned long long)(uint32_t)tile, p.tiles_x_rcp);
@@ -87,7 +97,7 @@ __device__ __forceinline__ void tile_xy(const BakeParams& p, int tile, int w, in
 // unit ray direction of slot w of a tile (env_map.rgen:19-21): from the table, or from the sin / cos tables
 __device__ __forceinline__ Vec3 slot_direction(const BakeParams& p, int tile, int w) {
     if (VLB_DIR_TABLES && p.dir_tab) {
-        const float4 dt = __ldg(p.dir_tab + (size_t)tile * 32 + w);
+        const float4 dt = __ldg(p.dir_tab + ((size_t)tile * 32 + w) * kDirTabQuads);
         return mk3(dt.x, dt.y, dt.z);
     }
     int x, y;
@@ -121,7 +131,10 @@ __global__ void k_dir_tables(const BakeParams p, float4* dir_tab, float* proj_ta
         wgt = p.pixel_area * row.x;                                         // sh.comp:32-33
         sh_basis<K>(p.world_frame ? mk3(t.x, t.z, t.y) : t, b);             // sh.comp:30,39
     }
-    dir_tab[d] = dt;
+    dir_tab[(size_t)d * kDirTabQuads] = dt;
+#if VLB_IDIR_TAB
+    dir_tab[(size_t)d * kDirTabQuads + 1] = make_float4(safe_inv(dt.x), safe_inv(dt.y), safe_inv(dt.z), 0.f);
+#endif
 #pragma unroll
     for (int i = 0; i < K; ++i) proj_tab[(size_t)tile * (K * 32) + 32 * i + w] = b[i] * wgt;
 }
@@ -211,8 +224,12 @@ struct alignas(128) WarpQueues {
     // the moment the hit is shaded its radiance (r, g, b, -). Whole 128-byte lines: see the discard below.
     float4 slot[kChunkDirs];
     // shadow-ray queue: origin, unit direction, length, direction index, radiance if the light is visible
+#if VLB_SQ_PACKED
+    float4 sq_a[kShadowCap], sq_b[kShadowCap], sq_c[kShadowCap];   // (origin, length), (unit direction, bits(direction index)), (lit radiance, -)
+#else
     float sq_o[3][kShadowCap], sq_d[3][kShadowCap], sq_len[kShadowCap]; int sq_dir[kShadowCap];
     float sq_rgb[3][kShadowCap];
+#endif
 };
 // The cold part of a warp's scratch, in a slab of its own so that the hot part above is one dense range of a few tens
 // of MB (the L2 access-policy window of the launch, bake_device).
@@ -609,22 +626,38 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                     const int take_sh = sh_first ? min(n_idle, n_sh) : min(n_sh, max(0, n_idle - (n_dirs - next)));
                     const int take_new = min(n_idle - take_sh, n_dirs - next);
                     bool fresh = false;
+                    bool tab_idir = false;      // VLB_IDIR_TAB: idir came from the direction table
                     if (!busy && rank < take_sh) {
                         const int e = n_sh - 1 - rank;
+#if VLB_SQ_PACKED
+                        const float4 qa = ld_scratch(&S.sq_a[e]), qb = ld_scratch(&S.sq_b[e]), qc = ld_scratch(&S.sq_c[e]);
+                        ro = mk3(qa.x, qa.y, qa.z); rd = mk3(qb.x, qb.y, qb.z);
+                        tmin = 0.0f; tcull = qa.w;                                      // env_map.rchit:87
+                        my_dir = __float_as_int(qb.w);
+                        best.id = -1; best.t = qc.x; best.u = qc.y; best.v = qc.z;
+#else
                         ro = mk3(ld_scratch(&S.sq_o[0][e]), ld_scratch(&S.sq_o[1][e]), ld_scratch(&S.sq_o[2][e]));
                         rd = mk3(ld_scratch(&S.sq_d[0][e]), ld_scratch(&S.sq_d[1][e]), ld_scratch(&S.sq_d[2][e]));
                         tmin = 0.0f; tcull = ld_scratch(&S.sq_len[e]);                  // env_map.rchit:87
                         my_dir = ld_scratch(&S.sq_dir[e]);
                         best.id = -1; best.t = ld_scratch(&S.sq_rgb[0][e]); best.u = ld_scratch(&S.sq_rgb[1][e]); best.v = ld_scratch(&S.sq_rgb[2][e]);
+#endif
                         kind = 1; busy = true; fresh = true;
                     } else if (!busy && rank - take_sh < take_new) {
                         const int cand = next + rank - take_sh;
                         const int tile = base_tile + (cand >> 5), w = cand & 31;
                         bool inside;
                         if (VLB_DIR_TABLES && p.dir_tab) {
-                            const float4 dt = __ldg(p.dir_tab + (size_t)tile * 32 + w);
+                            const float4 dt = __ldg(p.dir_tab + ((size_t)tile * 32 + w) * kDirTabQuads);
                             rd = mk3(dt.x, dt.y, dt.z);
                             inside = dt.w != 0.0f;
+#if VLB_IDIR_TAB
+                            if (inside) {
+                                const float4 it = __ldg(p.dir_tab + ((size_t)tile * 32 + w) * kDirTabQuads + 1);
+                                idir = mk3(it.x, it.y, it.z);
+                                tab_idir = true;
+                            }
+#endif
                         } else {
                             int x, y;
                             tile_xy(p, tile, w, x, y);
@@ -645,7 +678,7 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                         }
                     }
                     if (fresh) {
-                        idir = mk3(safe_inv(rd.x), safe_inv(rd.y), safe_inv(rd.z));
+                        if (!(VLB_IDIR_TAB && tab_idir)) idir = mk3(safe_inv(rd.x), safe_inv(rd.y), safe_inv(rd.z));
                         ood = mk3(ro.x * idir.x, ro.y * idir.y, ro.z * idir.z);
                         stk.clear();
                         cur = bvh.n_tris ? 0 : kRayDone;
@@ -723,11 +756,17 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                     const unsigned pm = __ballot_sync(full, push);
                     if (push) {
                         const int d = n_sh + __popc(pm & lt_mask);
+#if VLB_SQ_PACKED
+                        S.sq_a[d] = make_float4(pre.so.x, pre.so.y, pre.so.z, pre.llen);             // env_map.rchit:82
+                        S.sq_b[d] = make_float4(pre.Ln.x, pre.Ln.y, pre.Ln.z, __int_as_float(dir));
+                        S.sq_c[d] = make_float4(lit_rgb[0], lit_rgb[1], lit_rgb[2], 0.f);
+#else
                         S.sq_o[0][d] = pre.so.x; S.sq_o[1][d] = pre.so.y; S.sq_o[2][d] = pre.so.z;   // env_map.rchit:82
                         S.sq_d[0][d] = pre.Ln.x; S.sq_d[1][d] = pre.Ln.y; S.sq_d[2][d] = pre.Ln.z;
                         S.sq_len[d] = pre.llen; S.sq_dir[d] = dir;
 #pragma unroll
                         for (int k = 0; k < 3; ++k) S.sq_rgb[k][d] = lit_rgb[k];
+#endif
                         ++shadow;
                     }
                     n_sh += __popc(pm);
@@ -791,7 +830,7 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
             for (int tt = 0; tt * 32 < n_dirs; ++tt) {
                 const int tile = base_tile + tt;
                 if (VLB_DIR_TABLES && p.proj_tab) {
-                    if (__ldg(p.dir_tab + (size_t)tile * 32 + lane).w != 0.0f) {
+                    if (__ldg(p.dir_tab + ((size_t)tile * 32 + lane) * kDirTabQuads).w != 0.0f) {
                         const float* bwp = p.proj_tab + (size_t)tile * (K * 32) + lane;
                         const float4 rad = ld_scratch(&S.slot[tt * 32 + lane]);
                         const float r0 = rad.x, r1 = rad.y, r2 = rad.z;
@@ -984,7 +1023,7 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
         const int key[5] = {W, H, p.tile_lw, K, p.world_frame};
         const size_t n_slots = (size_t)p.n_tiles * 32;
         if (std::memcmp(key, ctx->dir_tab_key, sizeof key) != 0 || ctx->dir_tab_stream != st) {
-            VLB_CUDA(ctx, ctx->d_dir_tab.reserve(n_slots * sizeof(float4)));
+            VLB_CUDA(ctx, ctx->d_dir_tab.reserve(n_slots * kDirTabQuads * sizeof(float4)));
             VLB_CUDA(ctx, ctx->d_proj_tab.reserve(n_slots * 16 * sizeof(float)));
             const unsigned blocks = (unsigned)((n_slots + 127) / 128);
             if (K == 9) k_dir_tables<9><<<blocks, 128, 0, st>>>(p, ctx->d_dir_tab.as<float4>(), ctx->d_proj_tab.as<float>());
