@@ -50,7 +50,6 @@ constexpr int kBakeBlock = 128;
 // -- tile_xy() below, which divides with the host's reciprocal (an integer division is ~20 instructions, and the kernel
 // needs the pair in four places, one of them per ray).
 
-struct WarpQueues;
 struct WarpSpill;
 struct BakeParams {
     BvhView bvh;
@@ -74,7 +73,7 @@ struct BakeParams {
     unsigned int* work_counter;
     unsigned long long* stats;   // [0] shadow rays, [1] nodes visited, [2] triangles tested, [4..11] COUNT builds: phase utilisation
     int ref_order, world_frame;
-    WarpQueues* stream_scratch;  // k_bake_stream: per-warp direction slots (hit record, then radiance) + shadow-ray queue, [grid * warps per block]
+    void* stream_scratch;         // k_bake_stream: per-warp direction slots (hit record, then radiance) + shadow-ray queue, [grid * warps per block]
     WarpSpill* stream_spill;     // k_bake_stream: per-warp stack overflow rows (rarely touched), same indexing
     int node_min;                // k_bake_stream: the node loop yields to the leaf phase below this many lanes
     int leaf_min;                // ... and at least this many lanes wait at a leaf
@@ -219,18 +218,25 @@ template <class T> __device__ __forceinline__ T ld_scratch(const T* p) {
     return *p;
 #endif
 }
-struct alignas(128) WarpQueues {
+// PACKED: the shadow-ray queue records as three float4s (the direct-pass kernels) or as eleven scalar arrays (the gather
+// kernels, which measured 2 % slower with the packed form); everything else is the same.
+template <bool PACKED> struct WarpQueuesT;
+template <> struct alignas(128) WarpQueuesT<true> {
+    static constexpr bool kPacked = true;
     // one slot per direction of the current chunk: first the hit record of its closest-hit ray (bits(id), t, u, v), from
     // the moment the hit is shaded its radiance (r, g, b, -). Whole 128-byte lines: see the discard below.
     float4 slot[kChunkDirs];
+    // shadow-ray queue: (origin, length), (unit direction, bits(direction index)), (radiance if the light is visible, -)
+    float4 sq_a[kShadowCap], sq_b[kShadowCap], sq_c[kShadowCap];
+};
+template <> struct alignas(128) WarpQueuesT<false> {
+    static constexpr bool kPacked = false;
+    float4 slot[kChunkDirs];
     // shadow-ray queue: origin, unit direction, length, direction index, radiance if the light is visible
-#if VLB_SQ_PACKED
-    float4 sq_a[kShadowCap], sq_b[kShadowCap], sq_c[kShadowCap];   // (origin, length), (unit direction, bits(direction index)), (lit radiance, -)
-#else
     float sq_o[3][kShadowCap], sq_d[3][kShadowCap], sq_len[kShadowCap]; int sq_dir[kShadowCap];
     float sq_rgb[3][kShadowCap];
-#endif
 };
+constexpr size_t kWarpQueuesBytes = sizeof(WarpQueuesT<true>) > sizeof(WarpQueuesT<false>) ? sizeof(WarpQueuesT<true>) : sizeof(WarpQueuesT<false>);
 // The cold part of a warp's scratch, in a slab of its own so that the hot part above is one dense range of a few tens
 // of MB (the L2 access-policy window of the launch, bake_device).
 struct alignas(128) WarpSpill {
@@ -552,7 +558,9 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
     __shared__ HitQueue s_hq[kStreamWarps];
     __shared__ int s_stack2[GATHER && kSmemStack > 0 ? kStreamWarps : 1][GATHER && kSmemStack > 0 ? kSmemStack : 1][kStackWords][32];
     __shared__ VisExchange s_vis[GATHER ? kStreamWarps : 1];
-    WarpQueues* s_all = p.stream_scratch + (size_t)blockIdx.x * kStreamWarps;
+    using WarpQueues = WarpQueuesT<(VLB_SQ_PACKED != 0) && !GATHER>;
+    // (the host sizes the slab for the larger form; each kernel strides it by its own)
+    WarpQueues* s_all = static_cast<WarpQueues*>(p.stream_scratch) + (size_t)blockIdx.x * kStreamWarps;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -629,19 +637,19 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                     bool tab_idir = false;      // VLB_IDIR_TAB: idir came from the direction table
                     if (!busy && rank < take_sh) {
                         const int e = n_sh - 1 - rank;
-#if VLB_SQ_PACKED
-                        const float4 qa = ld_scratch(&S.sq_a[e]), qb = ld_scratch(&S.sq_b[e]), qc = ld_scratch(&S.sq_c[e]);
-                        ro = mk3(qa.x, qa.y, qa.z); rd = mk3(qb.x, qb.y, qb.z);
-                        tmin = 0.0f; tcull = qa.w;                                      // env_map.rchit:87
-                        my_dir = __float_as_int(qb.w);
-                        best.id = -1; best.t = qc.x; best.u = qc.y; best.v = qc.z;
-#else
-                        ro = mk3(ld_scratch(&S.sq_o[0][e]), ld_scratch(&S.sq_o[1][e]), ld_scratch(&S.sq_o[2][e]));
-                        rd = mk3(ld_scratch(&S.sq_d[0][e]), ld_scratch(&S.sq_d[1][e]), ld_scratch(&S.sq_d[2][e]));
-                        tmin = 0.0f; tcull = ld_scratch(&S.sq_len[e]);                  // env_map.rchit:87
-                        my_dir = ld_scratch(&S.sq_dir[e]);
-                        best.id = -1; best.t = ld_scratch(&S.sq_rgb[0][e]); best.u = ld_scratch(&S.sq_rgb[1][e]); best.v = ld_scratch(&S.sq_rgb[2][e]);
-#endif
+                        if constexpr (WarpQueues::kPacked) {
+                            const float4 qa = ld_scratch(&S.sq_a[e]), qb = ld_scratch(&S.sq_b[e]), qc = ld_scratch(&S.sq_c[e]);
+                            ro = mk3(qa.x, qa.y, qa.z); rd = mk3(qb.x, qb.y, qb.z);
+                            tmin = 0.0f; tcull = qa.w;                                      // env_map.rchit:87
+                            my_dir = __float_as_int(qb.w);
+                            best.id = -1; best.t = qc.x; best.u = qc.y; best.v = qc.z;
+                        } else {
+                            ro = mk3(ld_scratch(&S.sq_o[0][e]), ld_scratch(&S.sq_o[1][e]), ld_scratch(&S.sq_o[2][e]));
+                            rd = mk3(ld_scratch(&S.sq_d[0][e]), ld_scratch(&S.sq_d[1][e]), ld_scratch(&S.sq_d[2][e]));
+                            tmin = 0.0f; tcull = ld_scratch(&S.sq_len[e]);                  // env_map.rchit:87
+                            my_dir = ld_scratch(&S.sq_dir[e]);
+                            best.id = -1; best.t = ld_scratch(&S.sq_rgb[0][e]); best.u = ld_scratch(&S.sq_rgb[1][e]); best.v = ld_scratch(&S.sq_rgb[2][e]);
+                        }
                         kind = 1; busy = true; fresh = true;
                     } else if (!busy && rank - take_sh < take_new) {
                         const int cand = next + rank - take_sh;
@@ -756,17 +764,17 @@ __global__ void __launch_bounds__(kBakeBlock, GATHER ? 6 : VLB_BAKE_MIN_BLOCKS) 
                     const unsigned pm = __ballot_sync(full, push);
                     if (push) {
                         const int d = n_sh + __popc(pm & lt_mask);
-#if VLB_SQ_PACKED
-                        S.sq_a[d] = make_float4(pre.so.x, pre.so.y, pre.so.z, pre.llen);             // env_map.rchit:82
-                        S.sq_b[d] = make_float4(pre.Ln.x, pre.Ln.y, pre.Ln.z, __int_as_float(dir));
-                        S.sq_c[d] = make_float4(lit_rgb[0], lit_rgb[1], lit_rgb[2], 0.f);
-#else
-                        S.sq_o[0][d] = pre.so.x; S.sq_o[1][d] = pre.so.y; S.sq_o[2][d] = pre.so.z;   // env_map.rchit:82
-                        S.sq_d[0][d] = pre.Ln.x; S.sq_d[1][d] = pre.Ln.y; S.sq_d[2][d] = pre.Ln.z;
-                        S.sq_len[d] = pre.llen; S.sq_dir[d] = dir;
+                        if constexpr (WarpQueues::kPacked) {
+                            S.sq_a[d] = make_float4(pre.so.x, pre.so.y, pre.so.z, pre.llen);             // env_map.rchit:82
+                            S.sq_b[d] = make_float4(pre.Ln.x, pre.Ln.y, pre.Ln.z, __int_as_float(dir));
+                            S.sq_c[d] = make_float4(lit_rgb[0], lit_rgb[1], lit_rgb[2], 0.f);
+                        } else {
+                            S.sq_o[0][d] = pre.so.x; S.sq_o[1][d] = pre.so.y; S.sq_o[2][d] = pre.so.z;   // env_map.rchit:82
+                            S.sq_d[0][d] = pre.Ln.x; S.sq_d[1][d] = pre.Ln.y; S.sq_d[2][d] = pre.Ln.z;
+                            S.sq_len[d] = pre.llen; S.sq_dir[d] = dir;
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) S.sq_rgb[k][d] = lit_rgb[k];
-#endif
+                            for (int k = 0; k < 3; ++k) S.sq_rgb[k][d] = lit_rgb[k];
+                        }
                         ++shadow;
                     }
                     n_sh += __popc(pm);
@@ -1098,8 +1106,8 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
     }
     const uint32_t grid = std::max(1u, std::min(full_grid, (p.n_items + kStreamWarps - 1) / kStreamWarps));
 
-    VLB_CUDA(ctx, ctx->d_stream_scratch.reserve((size_t)grid * kStreamWarps * sizeof(WarpQueues)));
-    p.stream_scratch = ctx->d_stream_scratch.as<WarpQueues>();
+    VLB_CUDA(ctx, ctx->d_stream_scratch.reserve((size_t)grid * kStreamWarps * kWarpQueuesBytes));
+    p.stream_scratch = ctx->d_stream_scratch.p;
     VLB_CUDA(ctx, ctx->d_stream_spill.reserve((size_t)grid * kStreamWarps * sizeof(WarpSpill)));
     p.stream_spill = ctx->d_stream_spill.as<WarpSpill>();
     if (gather && Nx > 1 && Ny > 1 && Nz > 1 && env_flag("VLB_BAKE_CELL_ROOTS", 1)) {
@@ -1129,7 +1137,7 @@ int bake_device(vlb_ctx* ctx, const vlb_bake_settings* s, const float* d_prev_fu
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kBakeBlock); cfg.dynamicSmemBytes = 0; cfg.stream = st;
         cudaLaunchAttribute attr[1];
         unsigned n_attr = 0;
-        const size_t hot_bytes = (size_t)grid * kStreamWarps * sizeof(WarpQueues);
+        const size_t hot_bytes = (size_t)grid * kStreamWarps * kWarpQueuesBytes;
         const int persist_mb = env_flag("VLB_BAKE_L2_PERSIST", 0);
         if (persist_mb > 0 && ctx->l2_persist_max > 0 && ctx->l2_window_max > 0) {
             const size_t want = std::min<size_t>((size_t)persist_mb << 20, (size_t)ctx->l2_persist_max);
