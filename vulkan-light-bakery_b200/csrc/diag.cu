@@ -88,13 +88,18 @@ extern "C" int vlb_diag_cache_peaks(vlb_ctx* ctx, vlb_cache_peaks* out) {
     cudaStream_t st = ctx->stream;
     const size_t l2_bytes = 48ull << 20;
     const uint32_t n_quads = (uint32_t)(l2_bytes / 16);
-    DevBuf buf;
+    struct Scratch {                 // released on every path out of this function
+        DevBuf buf;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        ~Scratch() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); buf.release(); }
+    } sc;
+    DevBuf& buf = sc.buf;
     VLB_CUDA(ctx, buf.reserve(l2_bytes + 64));
     VLB_CUDA(ctx, cudaMemsetAsync(buf.p, 0, l2_bytes, st));
     float* sink = reinterpret_cast<float*>(static_cast<char*>(buf.p) + l2_bytes);
-    cudaEvent_t e0, e1;
-    VLB_CUDA(ctx, cudaEventCreate(&e0));
-    VLB_CUDA(ctx, cudaEventCreate(&e1));
+    VLB_CUDA(ctx, cudaEventCreate(&sc.e0));
+    VLB_CUDA(ctx, cudaEventCreate(&sc.e1));
+    cudaEvent_t e0 = sc.e0, e1 = sc.e1;
     float ms = 0.f;
     const int sms = ctx->sm_count;
     auto timed = [&](auto&& launch) -> cudaError_t {
@@ -123,8 +128,6 @@ extern "C" int vlb_diag_cache_peaks(vlb_ctx* ctx, vlb_cache_peaks* out) {
     out->l1_scatter_requests_per_s = requests / (ms * 1e-3);
     out->l1_scatter_wavefronts_per_s = out->l1_scatter_requests_per_s * lines;
     out->l1_scatter_gbs = out->l1_scatter_requests_per_s * 32 * 16 / 1e9;   // bytes the 32 lanes receive
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    buf.release();
     ctx->launches += 6;
     return VLB_OK;
 }
