@@ -73,9 +73,15 @@ struct ivec2 {
     ivec2(uint a, uint b) : x((int)a), y((int)b) {}
     explicit ivec2(const uvec2& v) : x((int)v.x), y((int)v.y) {}
 };
-struct ivec3 { int x, y, z; };
+struct ivec3 {
+    int x, y, z;
+    ivec3() : x(0), y(0), z(0) {}
+    ivec3(int a, int b, int c) : x(a), y(b), z(c) {}
+    explicit ivec3(const vec3& v) : x((int)v.x), y((int)v.y), z((int)v.z) {}      // GLSL float -> int: truncation
+};
 static_assert(sizeof(ivec3) == 12, "Indices buffer stride");
 struct bvec4 { bool x, y, z, w; };
+struct bvec3 { bool x, y, z; };
 
 // ---- arithmetic -------------------------------------------------------------------------------------------
 #define GLSL_OPS(V, EXPR2, EXPRS, EXPRS_L)                                                     \
@@ -121,6 +127,10 @@ inline vec3 normalize(const vec3& v) { const float l = length(v); return vec3(v.
 inline vec3 reflect(const vec3& i, const vec3& n) { return i - 2.0f * dot(n, i) * n; }
 inline vec4 pow(const vec4& a, const vec4& b) { return vec4(pow(a.x, b.x), pow(a.y, b.y), pow(a.z, b.z), pow(a.w, b.w)); }
 inline bvec4 lessThan(const vec4& a, const vec4& b) { return bvec4{a.x < b.x, a.y < b.y, a.z < b.z, a.w < b.w}; }
+inline vec3 pow(const vec3& a, const vec3& b) { return vec3(pow(a.x, b.x), pow(a.y, b.y), pow(a.z, b.z)); }
+inline bvec3 lessThan(const vec3& a, const vec3& b) { return bvec3{a.x < b.x, a.y < b.y, a.z < b.z}; }
+inline vec3 mix(const vec3& x, const vec3& y, const bvec3& a) { return vec3(a.x ? y.x : x.x, a.y ? y.y : x.y, a.z ? y.z : x.z); }
+inline vec3 floor(const vec3& v) { return vec3(std::floor(v.x), std::floor(v.y), std::floor(v.z)); }
 inline vec4 mix(const vec4& x, const vec4& y, const bvec4& a) { return vec4(a.x ? y.x : x.x, a.y ? y.y : x.y, a.z ? y.z : x.z, a.w ? y.w : x.w); }
 
 // mat4x3: 4 columns of vec3 (gl_WorldToObjectEXT). v * M = row vector times matrix = (dot(v, column j))_j.

@@ -1,13 +1,15 @@
 """Compiles the REFERENCE's own shader sources as C++ (TEST INFRASTRUCTURE; outputs only into oracle/_ref/).
 
-For each shader of the bake / skybox path the file is read from where it lies under /root/reference/shaders and
+For each shader of the bake / skybox path -- and the viewer's main.rchit + sh.rmiss, whose gather the multi-bounce passes
+iterate -- the file is read from where it lies under /root/reference/shaders and
 only its INTERFACE syntax is touched:
   * `#version` / `#extension` lines are dropped,
   * `layout(...) ... ;` declarations and `hitAttributeEXT ... ;` are dropped; the first one is replaced by
     `#include GLUE_DECLS` (the C++ stand-ins for those resources, oracle/ref_glue/<shader>_decls.inc),
   * `#include "structures.h"` gets `using namespace shader;` appended (the header's C++ side wraps its structs in
     a namespace),
-  * `main` is renamed `shader_main`.
+  * `main` is renamed `shader_main`,
+  * a GLSL array constructor `T[](a, b, ...)` becomes the C++ aggregate `{a, b, ...}` (main.rchit's gridVertices).
 Every function BODY -- sRGB, getBaseColor, dir2SkyboxUV, all main()s, sh_common.h, structures.h -- is compiled from
 the reference's text, unmodified, behind oracle/glsl_shim.h. The filtered text only ever exists in a temporary
 directory; no reference source is written into the repository.
@@ -35,6 +37,9 @@ SHADERS = {
     "shadow.rmiss": "shadow_rmiss.cpp",
     "sh.comp": "sh_comp.cpp",
     "skybox_sh.comp": "skybox_sh_comp.cpp",
+    # the viewer's gather operator, which the multi-bounce passes iterate (main.rchit:124-167 + sh.rmiss:20-36)
+    "main.rchit": "main_rchit.cpp",
+    "sh.rmiss": "sh_rmiss.cpp",
 }
 
 _DECL = re.compile(r"^[ \t]*(?:layout\s*\([^)]*\)|hitAttributeEXT)[^;{]*(?:\{[^}]*\})?[^;]*;[ \t]*\n", re.M | re.S)
@@ -54,6 +59,8 @@ def filter_shader(text):
     if first[0]:
         raise RuntimeError("no interface declaration found")
     text = re.sub(r'(#include\s+"structures\.h"[^\n]*\n)', r"\1using namespace shader;\n", text)
+    # GLSL array constructor `T name[N] = T[]( ... );` (main.rchit:128-137) -> C++ aggregate `T name[N] = { ... };`: syntax only
+    text = re.sub(r"=\s*(\w+)\[\]\s*\(((?:[^()]|\([^()]*\))*)\)\s*;", r"= {\2};", text, flags=re.S)
     text, n = re.subn(r"\bvoid\s+main\s*\(\s*\)", "void shader_main()", text)
     if n != 1:
         raise RuntimeError("expected exactly one main()")
@@ -77,6 +84,7 @@ def build(force=False):
         return OUT_SO
     os.makedirs(REF_DIR, exist_ok=True)
     flags = ["-std=c++17", "-O2", "-fsingle-precision-constant", "-ffp-contract=off", "-fPIC", "-w"]
+    flags += os.environ.get("VLB_REF_CFLAGS", "").split()          # e.g. "-g -fsanitize=address" when debugging the glue
     with tempfile.TemporaryDirectory(prefix="vlb_refshaders_") as tmp:
         objs = []
         for shader, glue in SHADERS.items():
@@ -92,7 +100,7 @@ def build(force=False):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-Wall", "-I", HERE, "-I", os.path.join(HERE, "..", "include"),
                                "-c", os.path.join(HERE, "ref_pipeline.cpp"), "-o", obj])
         objs.append(obj)
-        subprocess.check_call(["g++", "-shared", "-o", OUT_SO] + objs)
+        subprocess.check_call(["g++", "-shared", "-o", OUT_SO] + objs + os.environ.get("VLB_REF_LDFLAGS", "").split())
     return OUT_SO
 
 

@@ -63,6 +63,7 @@ def lib():
         L.vo_bake_gather.restype = _u64
         L.vo_bake_gather.argtypes = [_vp, _vp, _vp, _vp, _u64, _i32, _vp]
         L.vo_probe_envmap.argtypes = [_vp, _vp, _vp, _i32, _vp, _vp]
+        L.vo_probe_envmap_gather.argtypes = [_vp, _vp, _vp, _vp, _i32, _vp, _vp]
         _lib = L
     return _lib
 
@@ -88,7 +89,7 @@ _refsh = None
 
 
 def ref_shaders_lib():
-    """The reference's own shaders (env_map.rgen/.rchit, main.rmiss, shadow.rmiss, sh.comp, skybox_sh.comp) compiled
+    """The reference's own shaders (env_map.rgen/.rchit, main.rmiss, shadow.rmiss, sh.comp, skybox_sh.comp, main.rchit, sh.rmiss) compiled
     as C++ by oracle/make_ref_shaders.py into oracle/_ref/libvlb_refshaders.so; None if unavailable."""
     global _refsh
     if _refsh is None and os.path.exists(REF_SHADERS_SO):
@@ -107,6 +108,11 @@ def ref_shaders_lib():
         R.rp_set_textures.argtypes = [_vp, _vp, _vp, ctypes.c_uint32]
         R.rp_bake_probe.restype = _u64
         R.rp_bake_probe.argtypes = [_vp, _vp, _i32, _i32, ctypes.c_uint32, _vp, _vp, _vp]
+        if hasattr(R, "rp_bake_probe_viewer_hit"):
+            f32 = ctypes.c_float
+            R.rp_bake_probe_viewer_hit.restype = _u64
+            R.rp_bake_probe_viewer_hit.argtypes = [_vp, _vp, _i32, _i32, ctypes.c_uint32, _vp, _vp, ctypes.c_uint32, f32, f32, f32, f32, f32,
+                                                   _vp, _vp, _vp]
         _refsh = R
     return _refsh
 
@@ -208,6 +214,28 @@ class RefPipeline:
         img = np.zeros((H, W, 4), np.float32)
         out = np.zeros((16, 3), np.float64)
         n = self.R.rp_bake_probe(self._h, _p(o), W, H, int(flags), _p(l), _p(img), _p(out))
+        return out, img, int(n)
+
+    def bake_probe_viewer_hit(self, origin, W, H, flags, light, grid_step, lmax, shadow_bias, ambient, c_diffuse, c_specular, c_gloss,
+                              sh_coeffs):
+        """The same probe with the VIEWER's closest-hit shader (shaders/main.rchit: direct light + the gather over the baked
+        probes, probe-visibility rays answered by shaders/sh.rmiss). sh_coeffs: [343, (lmax+1)^2, 3] float32, the SHCoeffs buffer
+        of a 7x7x7 grid. -> (coeffs [16,3] float64, image [H,W,4] float32, flagged rays)"""
+        o = np.ascontiguousarray(origin, np.float32).reshape(3)
+        l = np.ascontiguousarray(light, np.float32).reshape(3)
+        g = np.ascontiguousarray(grid_step, np.float32).reshape(3)
+        sh = np.ascontiguousarray(sh_coeffs, np.float32)
+        assert sh.shape == (343, (lmax + 1) ** 2, 3)
+        # The shader indexes the buffer with floor(hitPosition / gridStep) unclamped (main.rchit:126, sh.rmiss:25): a hit a hair
+        # outside the grid reads one probe layer before / after it. A Vulkan buffer tolerates that; here the buffer gets a margin
+        # of 64 probes on either side (a copy of the first / last probe) and the shader sees the interior.
+        pad = 64
+        buf = np.concatenate([np.repeat(sh[:1], pad, 0), sh, np.repeat(sh[-1:], pad, 0)], 0)
+        inner = ctypes.c_void_p(buf.ctypes.data + pad * sh.shape[1] * 3 * 4)
+        img = np.zeros((H, W, 4), np.float32)
+        out = np.zeros((16, 3), np.float64)
+        n = self.R.rp_bake_probe_viewer_hit(self._h, _p(o), W, H, int(flags), _p(l), _p(g), int(lmax), float(shadow_bias), float(ambient),
+                                            float(c_diffuse), float(c_specular), float(c_gloss), inner, _p(img), _p(out))
         return out, img, int(n)
 
     def close(self):
@@ -369,6 +397,16 @@ class Scene:
         for _ in range(1 + max(0, settings.bounces)):
             prev, _sr = self.bake_gather(settings, prev, brute=brute)
         return prev
+
+    def probe_envmap_gather(self, settings, pos, prev_full, brute=False):
+        """Environment image of one probe position in a gather pass over prev_full ([n_probes,16,3], whole grid)."""
+        img = np.zeros((settings.dir_h, settings.dir_w, 3), np.float32)
+        sh = np.zeros((16, 3), np.float32)
+        p = np.ascontiguousarray(pos, np.float32).reshape(3)
+        prev = np.ascontiguousarray(prev_full, np.float32).reshape(-1, 48)
+        assert prev.shape[0] == settings.n_probes
+        lib().vo_probe_envmap_gather(self._h, ctypes.byref(settings), _p(p), _p(prev), int(bool(brute)), _p(img), _p(sh))
+        return img, sh
 
     def probe_envmap(self, settings, pos, brute=False):
         img = np.zeros((settings.dir_h, settings.dir_w, 3), np.float32)

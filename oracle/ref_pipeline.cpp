@@ -31,6 +31,15 @@ int ref_shadow_rmiss_run(void);
 void ref_rgen_set_color(const float rgb[3]);
 void ref_rgen_run(int x, int y, int W, int H, const float origin[3], float* image_texels, int rgba8);
 void ref_sh_comp_dispatch(float* texels, int W, int H, double* out48);
+// the viewer's closest-hit shader (main.rchit) and the miss shader of its probe-visibility rays (sh.rmiss)
+void ref_main_rchit_set_constants(const float grid_step[3], unsigned lmax, const float light[3], float shadow_bias, float ambient,
+                                  float c_diffuse, float c_specular, float c_gloss);
+void ref_main_rchit_set_in_shadow(int v);
+void ref_main_rchit_get_sh_payload(float sum[3], float normal[3], int ijk[3], unsigned* lmax, int* occluded);
+void ref_main_rchit_set_sh_payload(const float sum[3], int occluded);
+void ref_main_rchit_run(const void* instance_infos, const void* materials, const void* samplers, int instance, int primitive,
+                        const float bary_uv[2], const float origin[3], const float dir[3], float t, const float w2o[12], float color_out[3]);
+void ref_sh_rmiss_run(float sum[3], const float normal[3], const int ijk[3], unsigned lmax, int* occluded, const float* sh);
 }
 
 typedef void (*vo_trace_fn)(void* h, const float* o, const float* d, uint64_t n, float tmin, float tmax, int accel, int kind,
@@ -50,6 +59,8 @@ struct Pipeline {
     vo_trace_fn trace = nullptr; void* oracle_scene = nullptr;
     uint32_t flags = 0;
     uint64_t shadow_rays = 0;
+    bool viewer_hit = false;                             // closest-hit shader: env_map.rchit (the bake) or main.rchit (the viewer's gather)
+    const float* sh_coeffs = nullptr;                    // SHCoeffs buffer of sh.rmiss: (lmax+1)^2 vec3 per probe of the 7x7x7 grid
 };
 Pipeline* g_cur = nullptr;
 
@@ -73,7 +84,16 @@ void pipeline_trace(unsigned flags, unsigned miss_index, const float* o, float t
     if (flags & 4u) {                                    // gl_RayFlagsTerminateOnFirstHitEXT | SkipClosestHitShader: shadow ray
         ++p->shadow_rays;
         p->trace(p->oracle_scene, o, d, 1, tmin, tmax, VLB_TRACE_BVH, VLB_TRACE_ANY, &id, tuv);
-        if (id < 0 && miss_index == 1) ref_rchit_set_in_shadow(ref_shadow_rmiss_run());     // shadow.rmiss -> payload 1
+        if (id >= 0) return;                             // occluded: no shader runs (SkipClosestHitShader)
+        if (miss_index == 1) {                           // shadow.rmiss -> payload 1 of whichever hit shader is bound
+            if (p->viewer_hit) ref_main_rchit_set_in_shadow(ref_shadow_rmiss_run());
+            else ref_rchit_set_in_shadow(ref_shadow_rmiss_run());
+        } else if (miss_index == 2 && p->viewer_hit) {   // sh.rmiss -> payload 2 (main.rchit:153)
+            float sum[3], normal[3]; int ijk[3], occ; unsigned lmax;
+            ref_main_rchit_get_sh_payload(sum, normal, ijk, &lmax, &occ);
+            ref_sh_rmiss_run(sum, normal, ijk, lmax, &occ, p->sh_coeffs);
+            ref_main_rchit_set_sh_payload(sum, occ);
+        }                                                // miss 3 (skybox_sh.rmiss, main.rchit:121): only read when gridStep == 0
         return;
     }
     p->trace(p->oracle_scene, o, d, 1, tmin, tmax, VLB_TRACE_BVH, VLB_TRACE_CLOSEST, &id, tuv);
@@ -82,8 +102,8 @@ void pipeline_trace(unsigned flags, unsigned miss_index, const float* o, float t
         size_t inst = 0;
         while (inst + 1 < p->tri_offset.size() && p->tri_offset[inst + 1] <= (uint32_t)id) ++inst;
         const float bary[2] = {tuv[1], tuv[2]};
-        ref_rchit_run(p->instance_info.data(), p->materials, p->samplers.data(), (int)inst, id - (int)p->tri_offset[inst], bary, o, d, tuv[0],
-                      &p->w2o[12 * inst], rgb);
+        (p->viewer_hit ? ref_main_rchit_run : ref_rchit_run)(p->instance_info.data(), p->materials, p->samplers.data(), (int)inst,
+                                                             id - (int)p->tri_offset[inst], bary, o, d, tuv[0], &p->w2o[12 * inst], rgb);
         ref_rgen_set_color(rgb);
     } else if ((p->flags & VLB_BAKE_SKYBOX_ON_MISS) && p->sky && miss_index == 0) {
         ref_rmiss_run(d, p->sky, p->sky_w, p->sky_h, rgb);                                  // main.rmiss -> payload 0
@@ -135,6 +155,27 @@ uint64_t rp_bake_probe(void* h, const float origin[3], int W, int H, uint32_t fl
     for (int y = 0; y < H; ++y)
         for (int x = 0; x < W; ++x) ref_rgen_run(x, y, W, H, origin, image, (flags & VLB_BAKE_QUANTIZE_RGBA8) ? 1 : 0);
     ref_sh_comp_dispatch(image, W, H, coeffs48);
+    g_cur = nullptr;
+    return p->shadow_rays;
+}
+
+// The same probe with the VIEWER's closest-hit shader bound instead of the bake's: main.rchit shades every hit with direct
+// light plus its gather over the probe grid (main.rchit:124-167; probe-visibility rays with sh.rmiss as their miss shader).
+// This is the reference code the multi-bounce passes of BASELINE configs[3] iterate. sh_coeffs: the SHCoeffs buffer the
+// shader indexes -- (lmax + 1)^2 vec3 per probe, 7 x 7 x 7 probes, x-fastest (sh.rmiss:22-25). Push constants as
+// main.rchit:38-48.
+uint64_t rp_bake_probe_viewer_hit(void* h, const float origin[3], int W, int H, uint32_t flags, const float light[3], const float grid_step[3],
+                                  unsigned lmax, float shadow_bias, float ambient, float c_diffuse, float c_specular, float c_gloss,
+                                  const float* sh_coeffs, float* image, double* coeffs48) {
+    Pipeline* p = static_cast<Pipeline*>(h);
+    g_cur = p; glsl::g_trace = pipeline_trace;
+    p->flags = flags; p->shadow_rays = 0; p->viewer_hit = true; p->sh_coeffs = sh_coeffs;
+    ref_main_rchit_set_constants(grid_step, lmax, light, shadow_bias, ambient, c_diffuse, c_specular, c_gloss);
+    std::memset(image, 0, sizeof(float) * 4 * (size_t)W * H);
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) ref_rgen_run(x, y, W, H, origin, image, (flags & VLB_BAKE_QUANTIZE_RGBA8) ? 1 : 0);
+    ref_sh_comp_dispatch(image, W, H, coeffs48);
+    p->viewer_hit = false; p->sh_coeffs = nullptr;
     g_cur = nullptr;
     return p->shadow_rays;
 }

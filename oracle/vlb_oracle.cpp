@@ -557,9 +557,11 @@ static void base_color(const Scene& s, const vlb_material& m, float u, float v, 
 }
 
 // ---- multi-bounce gather: the reference's run-time operator, shaders/main.rchit:124-163 with the
-// probe lookup of shaders/sh.rmiss:20-36, restated for an arbitrary grid. "Parity unpinned": the
-// reference never runs this inside the bake (it bakes direct light only), so this restatement is the
-// specification of BASELINE configs[3]. Deviations from the literal shader, all documented in
+// probe lookup of shaders/sh.rmiss:20-36, restated for an arbitrary grid. The reference never runs this
+// inside the bake (it bakes direct light only), so as a bake pass this restatement is the specification of
+// BASELINE configs[3]; as an operator it is pinned to the reference's own main.rchit + sh.rmiss, compiled from
+// /root/reference/shaders (tests/test_ref_shaders.py: *_viewer_hit_shader, under the conditions in which the
+// deviations below vanish). Deviations from the literal shader, all documented in
 // include/vlb_bake.h: the grid origin is honoured (main.rchit:126 assumes 0); the cell is clamped into
 // the grid (the shader hard-codes 7x7x7, sh.rmiss:22); each corner reads ITS probe (sh.rmiss:25 reads
 // the cell's base probe for all eight -- evident defect); weights are clamped at 0 and an empty
@@ -1000,6 +1002,22 @@ void vo_probe_envmap(void* h, const vlb_bake_settings* st, const float pos[3], i
     const DirTable dt = make_dirs(st->dir_w, st->dir_h);
     double acc[48] = {0};
     bake_one(*s, *st, dt, v3(pos[0], pos[1], pos[2]), brute != 0, acc, image_rgb, nullptr);
+    if (out48) for (int c = 0; c < 48; ++c) out48[c] = (float)acc[c];
+}
+
+// The same for a gather pass: every hit adds the gather of prev_full over the settings' grid (the image the viewer's
+// main.rchit would shade from this position; tests/test_ref_shaders.py holds it to that shader).
+void vo_probe_envmap_gather(void* h, const vlb_bake_settings* st, const float pos[3], const float* prev_full, int brute,
+                            float* image_rgb, float* out48) {
+    Scene* s = (Scene*)h;
+    std::vector<float> px, py, pz;
+    axis_coords(st->origin[0], st->step[0], st->probes[0], px);
+    axis_coords(st->origin[1], st->step[1], st->probes[1], py);
+    axis_coords(st->origin[2], st->step[2], st->probes[2], pz);
+    GatherCtx gctx{prev_full, px.data(), py.data(), pz.data(), st->probes[0], st->probes[1], st->probes[2]};
+    const DirTable dt = make_dirs(st->dir_w, st->dir_h);
+    double acc[48] = {0};
+    bake_one(*s, *st, dt, v3(pos[0], pos[1], pos[2]), brute != 0, acc, image_rgb, nullptr, prev_full ? &gctx : nullptr);
     if (out48) for (int c = 0; c < 48; ++c) out48[c] = (float)acc[c];
 }
 

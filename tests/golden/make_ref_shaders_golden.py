@@ -36,6 +36,48 @@ def cube_case(vlb, scenes):
     return scenes.default_cube(), scenes.hdr_sky(32, 16, seed=6), s
 
 
+def viewer_gather_case(vlb, scenes):
+    """The conditions under which the oracle's gather (its documented deviations from the literal shader, oracle/vlb_oracle.cpp:
+    gather_indirect) and the viewer's main.rchit + sh.rmiss compute the same thing: a 7x7x7 grid with origin 0 (the shader
+    hard-codes both) that contains the room with a cell to spare on every side (the room is moved by (1, 1, 1) into positive
+    coordinates: the shader's floor(hitPosition / gridStep) indexes the buffer unclamped), every probe holding the SAME
+    coefficients (the shader reads the cell's base probe for all eight corners), the SH argument in world frame (the shader
+    passes hitNormal), no ambient term of the bake's own (the viewer has none), indirect_gain = ambient * 1250 (main.rchit:166).
+    -> (scene, settings, the viewer's `ambient` push constant, prev [343,16,3], probe origins [4,3])"""
+    s = vlb.default_settings()
+    s.probes[:] = (7, 7, 7)
+    s.origin[:] = (0.0, 0.0, 0.0)
+    s.step[:] = (1.0, 1.0, 1.0)
+    s.dir_w, s.dir_h = 48, 24
+    s.sh_order = 3
+    s.light_pos[:] = (3.0, 4.5, 3.0)
+    s.ambient = 0.0
+    amb = np.float32(0.0008)
+    s.indirect_gain = float(amb * np.float32(1250.0))
+    s.flags = vlb.SHADOW_RAYS | vlb.SRGB_ENCODE | vlb.SH_WORLD_FRAME
+    rng = np.random.default_rng(21)
+    one = (rng.uniform(0.05, 0.6, (16, 3)) * np.array([1.0] + [0.3] * 15)[:, None]).astype(np.float32)   # a positive DC, smaller bands
+    prev = np.broadcast_to(one, (343, 16, 3)).copy()
+    sc = scenes.small_room()
+    sc = dict(sc, instances=sc["instances"].copy())
+    sc["instances"]["transform"][:, [3, 7, 11]] += 1.0                 # the room, one cell into the grid
+    origins = np.random.default_rng(22).uniform(1.5, 4.5, (4, 3)).astype(np.float32)
+    return sc, s, float(amb), prev, origins
+
+
+def viewer_gather_images(vlb, scenes, P, case):
+    """One environment image per origin from env_map.rgen + the VIEWER's main.rchit + sh.rmiss (reference code)."""
+    sc, s, amb, prev, origins = case
+    sh25 = np.zeros((343, 25, 3), np.float32)
+    sh25[:, :16] = prev
+    imgs = []
+    for o in origins:
+        _sh, img, _n = P.bake_probe_viewer_hit(o, s.dir_w, s.dir_h, s.flags & ~vlb.SH_WORLD_FRAME, tuple(s.light_pos), tuple(s.step), 4,
+                                               s.shadow_bias, amb, s.c_diffuse, s.c_specular, s.gloss, sh25)
+        imgs.append(img[..., :3].copy())
+    return np.stack(imgs)
+
+
 def main():
     build_oracle.build_ref(force=True)
     vlb = importlib.import_module("vulkan-light-bakery_b200")
@@ -83,6 +125,13 @@ def main():
             g["bake_%s_%s_shadow" % (name, tag)] = np.int64(shadow)
         P.close()
         osc.close()
+    # the viewer's gather operator (main.rchit:124-167 + sh.rmiss), which the multi-bounce passes iterate
+    case = viewer_gather_case(vlb, scenes)
+    osc = oa.Scene(case[0])
+    P = oa.RefPipeline(case[0], osc)
+    g["gather_viewer_images"] = viewer_gather_images(vlb, scenes, P, case)       # NaN where the shader divides 0 / 0 (no corner visible)
+    P.close()
+    osc.close()
     out = os.path.join(ROOT, "tests", "golden", "ref_shaders_golden.npz")
     np.savez_compressed(out, **g)
     print("wrote", out, os.path.getsize(out), "bytes")

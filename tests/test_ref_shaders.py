@@ -6,7 +6,9 @@ text). The oracle is checked against
   (b) the library itself when oracle/_ref/libvlb_refshaders.so is present (this container; it also travels to the GPU box).
 Covered: sRGB (env_map.rchit:27-34, main.rmiss:9-16), dir2SkyboxUV (main.rmiss:18-35), getBaseColor
 (env_map.rchit:36-49), the whole dispatches of skybox_sh.comp:25-41 and sh.comp:25-41 (double accumulation), and whole
-probes through env_map.rgen:18-28 -> env_map.rchit:51-102 / main.rmiss:37-41 / shadow.rmiss:6-9 -> sh.comp.
+probes through env_map.rgen:18-28 -> env_map.rchit:51-102 / main.rmiss:37-41 / shadow.rmiss:6-9 -> sh.comp; and the
+multi-bounce operator: environment images of env_map.rgen with the VIEWER's main.rchit:75-171 bound as the closest-hit shader
+and sh.rmiss:20-36 answering its probe-visibility rays, against the oracle's gather pass.
 Left to the oracle's own definition (driver-defined in the reference): ray/triangle intersection, bilinear filtering."""
 import importlib
 import os
@@ -235,3 +237,44 @@ def test_bake_live_reference_pipeline_room_probes(oa, vlb, live, scenes):
         assert rel(got, want) <= BAKE_TOL_Q and n == n_ref          # default flags include QUANTIZE_RGBA8
     P.close()
     osc.close()
+
+
+def _check_viewer_gather(oa, vlb, scenes, ref_images):
+    """The oracle's gather pass against images of env_map.rgen + the VIEWER's main.rchit + sh.rmiss (reference code): the
+    multi-bounce operator pinned to the reference's own text. Pinned this way: the direct terms under push constants, the
+    probe-visibility rays' origin / direction / length (through who is occluded), the SH evaluation on the normal
+    (sh.rmiss:27-34), the weight normalisation, the combination ambient * 1250 * gather + diffuse + specular and the sRGB
+    encode. Where no corner is visible the literal shader divides 0 / 0 (NaN); the oracle defines the gather as 0 there
+    (include/vlb_bake.h), i.e. the direct-only radiance. Not pinnable: the corner weights (the literal shader reads one probe
+    for all corners, so they cancel)."""
+    import make_ref_shaders_golden as mk
+    sc, s, _amb, prev, origins = mk.viewer_gather_case(vlb, scenes)
+    osc = oa.Scene(sc)
+    lo_hi = osc.bounds(tight=True)
+    assert min(lo_hi[:3]) > 0.5 and max(lo_hi[3:]) < 5.5                    # the room sits inside the grid, a cell to spare
+    for o, ref in zip(origins, ref_images):
+        got, _sh = osc.probe_envmap_gather(s, o, prev)
+        direct, _ = osc.probe_envmap(s, o)
+        fin = np.isfinite(ref).all(-1)
+        assert fin.mean() > 0.95 and ref[fin].max() > 0.05
+        assert np.abs(got - ref)[fin].max() <= 2e-6
+        assert np.abs(direct - ref)[fin].max() > 0.05                       # the gather term really is in there
+        assert np.array_equal(got[~fin], direct[~fin])                      # 0 / 0 in the shader = no indirect term here
+    osc.close()
+
+
+def test_gather_vs_golden_viewer_hit_shader(oa, vlb, scenes, gold):
+    _check_viewer_gather(oa, vlb, scenes, gold["gather_viewer_images"])
+
+
+def test_gather_live_viewer_hit_shader(oa, vlb, live, scenes):
+    if not hasattr(live.R, "rp_bake_probe_viewer_hit"):
+        pytest.skip("oracle/_ref/libvlb_refshaders.so predates the viewer shaders")
+    import make_ref_shaders_golden as mk
+    case = mk.viewer_gather_case(vlb, scenes)
+    osc = oa.Scene(case[0])
+    P = oa.RefPipeline(case[0], osc)
+    images = mk.viewer_gather_images(vlb, scenes, P, case)
+    P.close()
+    osc.close()
+    _check_viewer_gather(oa, vlb, scenes, images)
